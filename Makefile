@@ -1,0 +1,69 @@
+# Top-level build.  Everything is built IN-TREE so the .so files travel to the GPU box.
+#
+#   make cuda     convolutionalencdec_b200/libced_cuda.so      sm_100a kernels + extern "C" ABI
+#   make host     convolutionalencdec_b200/libconvencdec_{k7,k3}.so   the C drop-in library
+#   make drivers  drivers/_bin/*   the reference's UNCHANGED driver sources ($(CED_REF)/*/X.c)
+#                 compiled against include/ and linked to the drop-in library
+#   make oracle   oracle/libced_oracle.so, oracle/_ref/*   (test infrastructure)
+#   make hostsim  tests/hostsim/libswar_sim.so             (test infrastructure)
+CED_REF ?= /root/reference
+NVCC ?= nvcc
+CC ?= gcc
+PKG := convolutionalencdec_b200
+CSRC := $(PKG)/csrc
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+CFLAGS := -O2 -g -std=gnu11 -fPIC -Wall -Iinclude
+HOST_SRCS := $(CSRC)/host/convEncode.c $(CSRC)/host/convHelpers.c $(CSRC)/host/viterbiDecoder.c $(CSRC)/host/ced_introspect.c
+CUDA_HDRS := $(wildcard $(CSRC)/*.cuh) include/ced_abi.h
+
+all: cuda host oracle hostsim drivers
+
+cuda: $(PKG)/libced_cuda.so
+$(PKG)/libced_cuda.so: $(CSRC)/ced_abi.cu $(CUDA_HDRS)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $<
+
+host: $(PKG)/libconvencdec_k7.so $(PKG)/libconvencdec_k3.so
+$(PKG)/libconvencdec_k7.so: $(HOST_SRCS) $(CSRC)/host/params/default/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)
+	$(CC) $(CFLAGS) -Iinclude/params/default -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/default/convCodeParams.c \
+	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
+$(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)
+	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
+	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
+
+oracle:
+	$(MAKE) -C oracle CED_REF=$(CED_REF) all
+
+hostsim: tests/hostsim/libswar_sim.so
+tests/hostsim/libswar_sim.so: tests/hostsim/swar_sim.cpp $(CSRC)/trellis_swar.cuh
+	g++ -O2 -std=c++17 -Wno-unknown-pragmas -fPIC -shared -x c++ -I$(CSRC) -o $@ $<
+
+# Reference drivers, sources untouched.  speedDecode/speedEncode pin their worker
+# to CPU 16 (speedDecode.c:23,147); drivers/affinity_wrap.c makes that call
+# succeed on boxes with fewer CPUs (link-time --wrap, no source change).
+DRV := drivers/_bin
+DRV_FLAGS := -O2 -g -std=gnu11 -Iinclude -w
+ifneq ($(wildcard $(CED_REF)/speedDecode/speedDecode.c),)
+drivers: $(DRV)/handTraced $(DRV)/berTestK7 $(DRV)/speedDecode $(DRV)/speedEncode
+$(DRV)/handTraced: $(CED_REF)/handTracedTest/handTraced.c $(PKG)/libconvencdec_k3.so | $(DRV)
+	$(CC) $(DRV_FLAGS) -Iinclude/params/handTraced -o $@ $< -L$(PKG) -lconvencdec_k3 -lced_cuda -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
+$(DRV)/berTestK7: $(CED_REF)/berTestK7/berTestK7.c $(PKG)/libconvencdec_k7.so | $(DRV)
+	$(CC) $(DRV_FLAGS) -Iinclude/params/default -o $@ $< -L$(PKG) -lconvencdec_k7 -lced_cuda -lm -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
+$(DRV)/speedDecode: $(CED_REF)/speedDecode/speedDecode.c drivers/affinity_wrap.c $(PKG)/libconvencdec_k7.so | $(DRV)
+	$(CC) $(DRV_FLAGS) -Iinclude/params/default -o $@ $< drivers/affinity_wrap.c -Wl,--wrap=pthread_attr_setaffinity_np \
+	    -L$(PKG) -lconvencdec_k7 -lced_cuda -pthread -lm -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
+$(DRV)/speedEncode: $(CED_REF)/speedEncode/speedEncode.c drivers/affinity_wrap.c $(PKG)/libconvencdec_k7.so | $(DRV)
+	$(CC) $(DRV_FLAGS) -Iinclude/params/default -o $@ $< drivers/affinity_wrap.c -Wl,--wrap=pthread_attr_setaffinity_np \
+	    -L$(PKG) -lconvencdec_k7 -lced_cuda -pthread -lm -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
+$(DRV):
+	mkdir -p $@
+else
+drivers:
+	@echo "drivers: $(CED_REF) not present; using prebuilt drivers/_bin if any"
+endif
+
+clean:
+	rm -f $(PKG)/*.so tests/hostsim/*.so
+	rm -rf $(DRV)
+	$(MAKE) -C oracle clean
+
+.PHONY: all cuda host oracle hostsim drivers clean

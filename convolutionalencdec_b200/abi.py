@@ -1,0 +1,211 @@
+"""ctypes binding of include/ced_abi.h (libced_cuda.so).
+
+Device buffers are torch CUDA uint8 tensors; only their ``data_ptr()`` crosses
+the ABI.  Every wrapper raises :class:`CedError` on a non-zero return code --
+nothing here computes an encode or a decode on the host.
+"""
+import ctypes as C
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+_u8p = C.c_void_p
+
+
+class CedError(RuntimeError):
+    pass
+
+
+class _CodeStruct(C.Structure):
+    _fields_ = [("constraintLen", C.c_int32), ("codedBits", C.c_int32), ("gen", C.c_uint64 * 8)]
+
+
+class Code:
+    """Code parameters (Proakis convention, src/defaultParams/convCodeParams.c:6)."""
+
+    def __init__(self, K, g):
+        self.K, self.n, self.g = int(K), len(g), tuple(int(x) for x in g)
+        self.S = self.K - 1
+        self._c = _CodeStruct(self.K, self.n, (C.c_uint64 * 8)(*self.g))
+
+    def segments(self, frame_bits):
+        return frame_bits + self.S
+
+    def __repr__(self):
+        return "Code(K=%d, g=(%s))" % (self.K, ", ".join(oct(x) for x in self.g))
+
+
+K7_DEFAULT = Code(7, (0o113, 0o171))    # the reference's defaultParams
+K7_TEXTBOOK = Code(7, (0o133, 0o171))   # the MATLAB scripts' generators (scripts/matlab/viterbiBEREstimate.m:11)
+
+
+def lib_path(name="libced_cuda.so"):
+    return os.path.join(HERE, name)
+
+
+def exported_abi_symbols():
+    """Function names declared in include/ced_abi.h."""
+    with open(os.path.join(ROOT, "include", "ced_abi.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ced_[a-z_0-9]+)\s*\(", text)))
+
+
+_LIB = None
+
+
+def load_abi():
+    """Load libced_cuda.so; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise CedError("%s is missing: run `make cuda host` (or __graft_entry__.build()); "
+                       "there is no CPU fallback" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    sz, i, vp, u64 = C.c_size_t, C.c_int, C.c_void_p, C.c_uint64
+    codep = C.POINTER(_CodeStruct)
+    lib.ced_device_count.restype = i
+    lib.ced_last_error.restype = C.c_char_p
+    lib.ced_ctx_create.argtypes = [i, C.POINTER(vp)]
+    lib.ced_ctx_destroy.argtypes = [vp]
+    lib.ced_ctx_destroy.restype = None
+    lib.ced_ctx_device.argtypes = [vp]
+    lib.ced_default_ctx.restype = vp
+    lib.ced_sync.argtypes = [vp, vp]
+    lib.ced_launch_count.argtypes = [vp]
+    lib.ced_launch_count.restype = u64
+    lib.ced_ctx_set_profiling.argtypes = [vp, i]
+    lib.ced_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ced_probe_int_peak.argtypes = [vp, i, C.POINTER(C.c_double)]
+    lib.ced_decode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_encode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
+    lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
+    lib.ced_decode_scratch_bytes.argtypes = [i, i]
+    lib.ced_decode_scratch_bytes.restype = sz
+    lib.ced_ber_count.argtypes = [vp, _u8p, sz, _u8p, sz, i, i, vp, vp]
+    lib.ced_bsc_channel.argtypes = [vp, _u8p, sz, i, i, i, C.c_double, u64, u64, vp, vp]
+    lib.ced_random_bytes.argtypes = [vp, _u8p, sz, i, i, u64, u64, vp]
+    lib.ced_stream_surv_words.argtypes = [i]
+    lib.ced_stream_decode.argtypes = [i, i, _u8p, _u8p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp,
+                                      C.c_uint32, _u8p, i, _u8p, i]
+    lib.ced_stream_encode.argtypes = [i, i, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _u8p, i, _u8p, i]
+    _LIB = lib
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise CedError("%s failed (%d): %s" % (what, rc, lib.ced_last_error().decode()))
+
+
+def _stream_handle(stream):
+    if stream is None:
+        return None
+    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+class Context:
+    """One per GPU (ced_ctx): owns the compute/copy streams and survivor scratch."""
+
+    def __init__(self, device=0):
+        self.lib = load_abi()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.ced_ctx_create(int(device), C.byref(h)), "ced_ctx_create")
+        self.h, self.device = h, int(device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ced_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self, stream=None):
+        _check(self.lib, self.lib.ced_sync(self.h, _stream_handle(stream)), "ced_sync")
+
+    def set_profiling(self, enable=True):
+        _check(self.lib, self.lib.ced_ctx_set_profiling(self.h, int(bool(enable))), "ced_ctx_set_profiling")
+
+    def last_kernel_ms(self):
+        """(forward_ms, traceback_ms) of the most recent decode_batch, CUDA-event timed."""
+        ms = (C.c_float * 2)()
+        _check(self.lib, self.lib.ced_ctx_last_kernel_ms(self.h, ms), "ced_ctx_last_kernel_ms")
+        return float(ms[0]), float(ms[1])
+
+    def probe_int_peak(self, mode=0):
+        """32-bit lane-ops/s of a dependent-free LOP3 stream (mode 1: with IMAD co-issue)."""
+        v = C.c_double(0)
+        _check(self.lib, self.lib.ced_probe_int_peak(self.h, int(mode), C.byref(v)), "ced_probe_int_peak")
+        return v.value
+
+    @property
+    def launches(self):
+        return int(self.lib.ced_launch_count(self.h))
+
+    # ---- device-resident batches (torch uint8 CUDA tensors, 2-D [frames, stride]) ----
+    def decode_batch(self, code, segs, frame_bits, out=None, stream=None, n_frames=None):
+        import torch
+        nf = segs.shape[0] if n_frames is None else n_frames
+        if out is None:
+            out = torch.empty((nf, frame_bits // 8), dtype=torch.uint8, device=segs.device)
+        _check(self.lib, self.lib.ced_decode_batch(self.h, C.byref(code._c), segs.data_ptr(), segs.stride(0), nf,
+                                                   frame_bits, out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_decode_batch")
+        return out
+
+    def encode_batch(self, code, msgs, out=None, stream=None, seg_stride=None):
+        import torch
+        nf, nb = msgs.shape
+        T = 8 * nb + code.S
+        if out is None:
+            out = torch.empty((nf, seg_stride or T), dtype=torch.uint8, device=msgs.device)
+        _check(self.lib, self.lib.ced_encode_batch(self.h, C.byref(code._c), msgs.data_ptr(), msgs.stride(0), nf, nb,
+                                                   out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_encode_batch")
+        return out
+
+    def ber_count(self, a, b, counters, stream=None):
+        nf, nb = a.shape
+        _check(self.lib, self.lib.ced_ber_count(self.h, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), nf, nb,
+                                                counters.data_ptr(), _stream_handle(stream)), "ced_ber_count")
+
+    def bsc_channel(self, segs, segs_per_frame, n, p, seed, first_frame=0, counters=None, stream=None):
+        _check(self.lib, self.lib.ced_bsc_channel(self.h, segs.data_ptr(), segs.stride(0), segs.shape[0],
+                                                  segs_per_frame, n, float(p), int(seed), int(first_frame),
+                                                  counters.data_ptr() if counters is not None else None,
+                                                  _stream_handle(stream)), "ced_bsc_channel")
+
+    def random_bytes(self, msgs, seed, first_frame=0, stream=None):
+        _check(self.lib, self.lib.ced_random_bytes(self.h, msgs.data_ptr(), msgs.stride(0), msgs.shape[0],
+                                                   msgs.shape[1], int(seed), int(first_frame),
+                                                   _stream_handle(stream)), "ced_random_bytes")
+
+    # ---- host buffers (numpy arrays or pinned torch CPU tensors) ----
+    @staticmethod
+    def _host(a):
+        if hasattr(a, "data_ptr"):
+            return a.data_ptr(), a.stride(0), a.shape
+        return a.ctypes.data, a.strides[0], a.shape
+
+    def decode_batch_host(self, code, segs, frame_bits, out):
+        sp, ss, sshape = self._host(segs)
+        op, os_, _ = self._host(out)
+        _check(self.lib, self.lib.ced_decode_batch_host(self.h, C.byref(code._c), sp, ss, sshape[0], frame_bits, op,
+                                                        os_), "ced_decode_batch_host")
+        return out
+
+    def encode_batch_host(self, code, msgs, out):
+        mp, ms, mshape = self._host(msgs)
+        op, os_, _ = self._host(out)
+        _check(self.lib, self.lib.ced_encode_batch_host(self.h, C.byref(code._c), mp, ms, mshape[0], mshape[1], op,
+                                                        os_), "ced_encode_batch_host")
+        return out

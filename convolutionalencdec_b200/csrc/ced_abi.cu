@@ -1,0 +1,727 @@
+/*
+ * ced_abi.cu -- implementation of include/ced_abi.h: per-GPU context, launch
+ * logic for the batched hot path and the stateless per-frame streaming path.
+ * Everything here runs kernels; there is no host implementation of any
+ * encode/decode arithmetic in this file.
+ */
+#include "../../include/ced_abi.h"
+#include "channel_kernels.cuh"
+#include "decode_batch.cuh"
+#include "encode_batch.cuh"
+#include "probe_kernels.cuh"
+#include "stream_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace {
+
+thread_local char gLastError[512] = "";
+
+void setError(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(gLastError, sizeof(gLastError), fmt, ap);
+    va_end(ap);
+}
+
+#define CED_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            setError("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return CED_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave            */
+constexpr int kHostChunkFrames = 16384;           /* frames per H2D/kernel/D2H pipeline stage */
+constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
+
+template <typename T>
+struct DeviceBuf {
+    T *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes)
+            return CED_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), need);
+        if (e != cudaSuccess) {
+            setError("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+            return CED_ERR_NOMEM;
+        }
+        bytes = need;
+        return CED_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct PinnedBuf {
+    uint8_t *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes)
+            return CED_OK;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), need);
+        if (e != cudaSuccess) {
+            setError("cudaMallocHost(%zu) failed: %s", need, cudaGetErrorString(e));
+            return CED_ERR_NOMEM;
+        }
+        bytes = need;
+        return CED_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171 };
+
+CodeId classify(const ced_code_t *c)
+{
+    if (!c || c->constraintLen != 7 || c->codedBits != 2)
+        return CodeId::Unsupported;
+    if (c->gen[0] == 0113 && c->gen[1] == 0171)
+        return CodeId::K7_0113_0171;
+    if (c->gen[0] == 0133 && c->gen[1] == 0171)
+        return CodeId::K7_0133_0171;
+    return CodeId::Unsupported;
+}
+
+uint32_t reverseBits(uint64_t g, int K)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < K; i++)
+        r |= (uint32_t)((g >> i) & 1u) << (K - 1 - i);
+    return r;
+}
+
+} // namespace
+
+struct ced_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;   /* compute */
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t inReady[2] = {}, inFree[2] = {}, outReady[2] = {}, outFree[2] = {};
+    DeviceBuf<uint4> scratch;        /* survivor words of the wave in flight */
+    DeviceBuf<uint8_t> hostIn[2], hostOut[2];
+    /* streaming path */
+    DeviceBuf<uint8_t> sIn, sOut;
+    DeviceBuf<uint32_t> sSurv;
+    PinnedBuf sPinIn, sPinOut;
+    std::recursive_mutex mu;
+    uint64_t launches = 0;
+    ced::BmTable bm0113, bm0133;
+    /* optional kernel timing (ced_ctx_set_profiling) */
+    bool profiling = false;
+    static constexpr int kMaxProfWaves = 64;
+    cudaEvent_t prof[kMaxProfWaves][3] = {};
+    int profWaves = 0;
+};
+
+using Code0113 = ced::K7Code<0113, 0171>;
+using Code0133 = ced::K7Code<0133, 0171>;
+static_assert(Code0113::symmetric && Code0133::symmetric, "SWAR butterflies need symmetric generators");
+static_assert(Code0113::tap0 == 0x69 && Code0113::tap1 == 0x4F, "SURVEY 8(c) KAT: taps of 0113/0171");
+
+extern "C" {
+
+int ced_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+const char *ced_last_error(void)
+{
+    return gLastError;
+}
+
+int ced_ctx_create(int device, ced_ctx **out)
+{
+    if (!out)
+        return CED_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    CED_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        setError("device %d out of range (%d visible)", device, n);
+        return CED_ERR_ARG;
+    }
+    CED_CUDA(cudaSetDevice(device));
+    ced_ctx *c = new ced_ctx();
+    c->device = device;
+    c->bm0113 = ced::makeBmTable<Code0113>();
+    c->bm0133 = ced::makeBmTable<Code0133>();
+    CED_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CED_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
+    CED_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CED_CUDA(cudaEventCreateWithFlags(&c->inReady[i], cudaEventDisableTiming));
+        CED_CUDA(cudaEventCreateWithFlags(&c->inFree[i], cudaEventDisableTiming));
+        CED_CUDA(cudaEventCreateWithFlags(&c->outReady[i], cudaEventDisableTiming));
+        CED_CUDA(cudaEventCreateWithFlags(&c->outFree[i], cudaEventDisableTiming));
+    }
+    for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
+        for (int e = 0; e < 3; e++)
+            CED_CUDA(cudaEventCreate(&c->prof[w][e]));
+    *out = c;
+    return CED_OK;
+}
+
+void ced_ctx_destroy(ced_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->scratch.release();
+    for (int i = 0; i < 2; i++) {
+        c->hostIn[i].release();
+        c->hostOut[i].release();
+        cudaEventDestroy(c->inReady[i]);
+        cudaEventDestroy(c->inFree[i]);
+        cudaEventDestroy(c->outReady[i]);
+        cudaEventDestroy(c->outFree[i]);
+    }
+    c->sIn.release();
+    c->sOut.release();
+    c->sSurv.release();
+    c->sPinIn.release();
+    c->sPinOut.release();
+    for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
+        for (int e = 0; e < 3; e++)
+            cudaEventDestroy(c->prof[w][e]);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->h2d);
+    cudaStreamDestroy(c->d2h);
+    delete c;
+}
+
+int ced_ctx_device(const ced_ctx *c)
+{
+    return c ? c->device : -1;
+}
+
+ced_ctx *ced_default_ctx(void)
+{
+    static std::once_flag once;
+    static ced_ctx *ctx = nullptr;
+    std::call_once(once, [] {
+        const char *env = getenv("CED_DEVICE");
+        int dev = env ? atoi(env) : 0;
+        if (ced_ctx_create(dev, &ctx) != CED_OK)
+            ctx = nullptr;
+    });
+    return ctx;
+}
+
+int ced_sync(ced_ctx *c, void *stream)
+{
+    if (!c)
+        return CED_ERR_ARG;
+    CED_CUDA(cudaSetDevice(c->device));
+    CED_CUDA(cudaStreamSynchronize(stream ? (cudaStream_t)stream : c->stream));
+    return CED_OK;
+}
+
+uint64_t ced_launch_count(const ced_ctx *c)
+{
+    return c ? c->launches : 0;
+}
+
+size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
+{
+    if (nFrames <= 0 || frameBits <= 0)
+        return 0;
+    const size_t T = (size_t)frameBits + ced::kTailSteps;
+    const size_t perFrame = (T / 2) * sizeof(uint4);
+    size_t wave = std::min<size_t>((size_t)nFrames, std::max<size_t>(ced::kFwdThreads, kMaxScratchBytes / perFrame));
+    wave = (wave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
+    return wave * perFrame;
+}
+
+int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                     int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    if (!c || !dSegs || !dOut || nFrames < 0 || frameBits <= 0 || (frameBits & 7)) {
+        setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
+        return CED_ERR_ARG;
+    }
+    const int T = frameBits + ced::kTailSteps;
+    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    const CodeId id = classify(code);
+    if (id == CodeId::Unsupported) {
+        setError("ced_decode_batch: only K=7 n=2 g={0113,0171} or {0133,0171} is built");
+        return CED_ERR_UNSUPPORTED;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const size_t perFrame = (size_t)(T / 2) * sizeof(uint4);
+    size_t waveMax = std::max<size_t>(ced::kFwdThreads, kMaxScratchBytes / perFrame);
+    waveMax = waveMax / ced::kFwdThreads * ced::kFwdThreads;
+    const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
+    const size_t firstPad = (firstWave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
+    if (c->scratch.bytes < firstPad * perFrame) {
+        /* growing means freeing: make sure nothing still uses the old block */
+        CED_CUDA(cudaDeviceSynchronize());
+        int rc = c->scratch.ensure(firstPad * perFrame);
+        if (rc != CED_OK)
+            return rc;
+    }
+    const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
+    c->profWaves = 0;
+    for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
+        const bool prof = c->profiling && c->profWaves < ced_ctx::kMaxProfWaves;
+        const int pw = c->profWaves;
+        if (prof)
+            CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
+        const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
+        const int framesPad = (wave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
+        const int blocks = framesPad / ced::kFwdThreads;
+        const uint8_t *in = dSegs + f0 * segStride;
+        uint8_t *out = dOut + f0 * outStride;
+        if (id == CodeId::K7_0113_0171)
+            ced::k7ForwardKernel<Code0113><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                             framesPad, aligned16, c->bm0113);
+        else
+            ced::k7ForwardKernel<Code0133><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                             framesPad, aligned16, c->bm0133);
+        if (prof)
+            CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
+        ced::k7TracebackKernel<<<(wave + 127) / 128, 128, 0, s>>>(c->scratch.p, framesPad, wave, T, out, outStride);
+        if (prof) {
+            CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
+            c->profWaves++;
+        }
+        c->launches += 2;
+    }
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int ced_ctx_set_profiling(ced_ctx *c, int enable)
+{
+    if (!c)
+        return CED_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    c->profiling = enable != 0;
+    c->profWaves = 0;
+    return CED_OK;
+}
+
+int ced_ctx_last_kernel_ms(ced_ctx *c, float *ms2)
+{
+    if (!c || !ms2)
+        return CED_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    ms2[0] = ms2[1] = 0.f;
+    for (int w = 0; w < c->profWaves; w++) {
+        float a = 0.f, b = 0.f;
+        CED_CUDA(cudaEventSynchronize(c->prof[w][2]));
+        CED_CUDA(cudaEventElapsedTime(&a, c->prof[w][0], c->prof[w][1]));
+        CED_CUDA(cudaEventElapsedTime(&b, c->prof[w][1], c->prof[w][2]));
+        ms2[0] += a;
+        ms2[1] += b;
+    }
+    return CED_OK;
+}
+
+int ced_probe_int_peak(ced_ctx *c, int mode, double *laneOpsPerSecond)
+{
+    if (!c || !laneOpsPerSecond || mode < 0 || mode > 1)
+        return CED_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    int sms = 0;
+    CED_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+    uint32_t *sink = nullptr;
+    CED_CUDA(cudaMalloc(reinterpret_cast<void **>(&sink), 64));
+    cudaEvent_t e0, e1;
+    CED_CUDA(cudaEventCreate(&e0));
+    CED_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CED_CUDA(cudaEventRecord(e0, c->stream));
+        if (mode == 0)
+            ced::intProbeKernel<0><<<blocks, threads, 0, c->stream>>>(sink, iters, 0x9E3779B9u + rep, 0x7F4A7C15u);
+        else
+            ced::intProbeKernel<1><<<blocks, threads, 0, c->stream>>>(sink, iters, 0x9E3779B9u + rep, 0x7F4A7C15u);
+        CED_CUDA(cudaEventRecord(e1, c->stream));
+        CED_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CED_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * (double)iters * ced::kProbeUnroll * ced::kProbeChains;
+        if (rep > 0)
+            best = std::max(best, ops / (ms * 1e-3));
+        c->launches += 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *laneOpsPerSecond = best;
+    return CED_OK;
+}
+
+static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
+                        int frameBytes, uint8_t *dSegs, size_t segStride, int tailSegs, uint32_t hist, cudaStream_t s)
+{
+    ced::EncTaps taps;
+    for (int i = 0; i < 8; i++)
+        taps.tap[i] = i < code->codedBits ? reverseBits(code->gen[i], code->constraintLen) : 0u;
+    const int T = 8 * frameBytes + tailSegs;
+    if (T == 0)
+        return CED_OK;
+    const long long threads = (long long)nFrames * ((T + 15) / 16);
+    const int blocks = (int)((threads + 255) / 256);
+    const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
+    ced::encodeBatchKernel<<<blocks, 256, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs,
+                                                  code->constraintLen, code->codedBits, taps, hist, aligned16);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int ced_encode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
+                     int frameBytes, uint8_t *dSegs, size_t segStride, void *stream)
+{
+    if (!c || !code || !dMsg || !dSegs || nFrames < 0 || frameBytes <= 0) {
+        setError("ced_encode_batch: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (code->constraintLen < 2 || code->constraintLen > 9 || code->codedBits < 1 || code->codedBits > CED_MAX_N) {
+        setError("ced_encode_batch: K must be 2..9 and n 1..8");
+        return CED_ERR_UNSUPPORTED;
+    }
+    if (msgStride < (size_t)frameBytes || segStride < (size_t)(8 * frameBytes + code->constraintLen - 1)) {
+        setError("ced_encode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    return launchEncode(c, code, dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, code->constraintLen - 1, 0u,
+                        stream ? (cudaStream_t)stream : c->stream);
+}
+
+/* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
+static int hostPipeline(ced_ctx *c, const ced_code_t *code, bool encode, const uint8_t *hIn, size_t inStride,
+                        size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
+                        size_t outRowBytes)
+{
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const int chunk = std::min(nFrames, kHostChunkFrames);
+    for (int b = 0; b < 2; b++) {
+        int rc = c->hostIn[b].ensure((size_t)chunk * inStride + 16);
+        if (rc == CED_OK)
+            rc = c->hostOut[b].ensure((size_t)chunk * outStride + 16);
+        if (rc != CED_OK)
+            return rc;
+    }
+    int idx = 0;
+    for (int f0 = 0; f0 < nFrames; f0 += chunk, idx++) {
+        const int b = idx & 1;
+        const int cnt = std::min(chunk, nFrames - f0);
+        const size_t inBytes = (size_t)(cnt - 1) * inStride + inRowBytes;
+        const size_t outBytes = (size_t)(cnt - 1) * outStride + outRowBytes;
+        if (idx >= 2)
+            CED_CUDA(cudaStreamWaitEvent(c->h2d, c->inFree[b], 0));
+        CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, hIn + (size_t)f0 * inStride, inBytes, cudaMemcpyHostToDevice, c->h2d));
+        CED_CUDA(cudaEventRecord(c->inReady[b], c->h2d));
+        CED_CUDA(cudaStreamWaitEvent(c->stream, c->inReady[b], 0));
+        if (idx >= 2)
+            CED_CUDA(cudaStreamWaitEvent(c->stream, c->outFree[b], 0));
+        int rc;
+        if (encode)
+            rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride,
+                                  c->stream);
+        else
+            rc = ced_decode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride,
+                                  c->stream);
+        if (rc != CED_OK)
+            return rc;
+        CED_CUDA(cudaEventRecord(c->inFree[b], c->stream));
+        CED_CUDA(cudaEventRecord(c->outReady[b], c->stream));
+        CED_CUDA(cudaStreamWaitEvent(c->d2h, c->outReady[b], 0));
+        CED_CUDA(cudaMemcpyAsync(hOut + (size_t)f0 * outStride, c->hostOut[b].p, outBytes, cudaMemcpyDeviceToHost,
+                                 c->d2h));
+        CED_CUDA(cudaEventRecord(c->outFree[b], c->d2h));
+    }
+    CED_CUDA(cudaStreamSynchronize(c->d2h));
+    CED_CUDA(cudaStreamSynchronize(c->stream));
+    return CED_OK;
+}
+
+int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSegs, size_t segStride, int nFrames,
+                          int frameBits, uint8_t *hOut, size_t outStride)
+{
+    if (!c || !code || !hSegs || !hOut || nFrames < 0 || frameBits <= 0 || (frameBits & 7)) {
+        setError("ced_decode_batch_host: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    return hostPipeline(c, code, false, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames, frameBits, hOut,
+                        outStride, (size_t)frameBits / 8);
+}
+
+int ced_encode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride, int nFrames,
+                          int frameBytes, uint8_t *hSegs, size_t segStride)
+{
+    if (!c || !code || !hMsg || !hSegs || nFrames < 0 || frameBytes <= 0) {
+        setError("ced_encode_batch_host: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    return hostPipeline(c, code, true, hMsg, msgStride, (size_t)frameBytes, nFrames, frameBytes, hSegs, segStride,
+                        (size_t)frameBytes * 8 + code->constraintLen - 1);
+}
+
+int ced_ber_count(ced_ctx *c, const uint8_t *dA, size_t strideA, const uint8_t *dB, size_t strideB, int nFrames,
+                  int bytesPerFrame, uint64_t *dCounters, void *stream)
+{
+    if (!c || !dA || !dB || !dCounters || nFrames < 0 || bytesPerFrame <= 0) {
+        setError("ced_ber_count: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const int aligned4 = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | strideA | strideB |
+                           (size_t)bytesPerFrame) & 3u) == 0;
+    const long long work = (long long)nFrames * (aligned4 ? bytesPerFrame / 4 : bytesPerFrame);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    ced::berCountKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        dA, strideA, dB, strideB, nFrames, bytesPerFrame, reinterpret_cast<unsigned long long *>(dCounters), aligned4);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int ced_bsc_channel(ced_ctx *c, uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame, int n, double p,
+                    uint64_t seed, uint64_t firstFrameIndex, uint64_t *dCounters, void *stream)
+{
+    if (!c || !dSegs || nFrames < 0 || segsPerFrame <= 0 || n < 1 || n > CED_MAX_N || !(p >= 0.0) || !(p < 1.0)) {
+        setError("ced_bsc_channel: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const uint32_t threshold = (uint32_t)(p * 4294967296.0);
+    const long long work = (long long)nFrames * segsPerFrame;
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    ced::bscChannelKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        dSegs, segStride, nFrames, segsPerFrame, n, threshold, seed, firstFrameIndex,
+        reinterpret_cast<unsigned long long *>(dCounters));
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int ced_random_bytes(ced_ctx *c, uint8_t *dMsg, size_t msgStride, int nFrames, int frameBytes, uint64_t seed,
+                     uint64_t firstFrameIndex, void *stream)
+{
+    if (!c || !dMsg || nFrames < 0 || frameBytes <= 0 || msgStride < (size_t)frameBytes) {
+        setError("ced_random_bytes: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const long long work = (long long)nFrames * ((frameBytes + 7) / 8);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    ced::randomBytesKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(dMsg, msgStride, nFrames,
+                                                                                         frameBytes, seed,
+                                                                                         firstFrameIndex);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+/* ------------------------------------------------------------- streaming */
+
+int ced_stream_surv_words(int nStates)
+{
+    const int H = nStates / 2;
+    return 2 * ((H + 31) / 32);
+}
+
+int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint32_t *iteration,
+                      uint32_t *renormCounter, uint32_t *surv, uint32_t survCapacitySteps, const uint8_t *segs,
+                      int segmentsIn, uint8_t *uncoded, int last)
+{
+    if (K < 2 || K > 9 || n < 1 || n > CED_MAX_N || !edge || !metrics || !iteration || !renormCounter || !surv ||
+        segmentsIn < 0 || (segmentsIn > 0 && !segs) || (last && !uncoded)) {
+        setError("ced_stream_decode: bad argument");
+        return CED_ERR_ARG;
+    }
+    ced_ctx *c = ced_default_ctx();
+    if (!c) {
+        setError("ced_stream_decode: no CUDA context (%s)", gLastError);
+        return CED_ERR_CUDA;
+    }
+    const int N = 1 << (K - 1), W = ced_stream_surv_words(N), S = K - 1;
+    const uint32_t it0 = *iteration;
+    const uint64_t total = (uint64_t)it0 + (uint64_t)segmentsIn;
+    if (total > survCapacitySteps || total > kStreamMaxSteps) {
+        setError("ced_stream_decode: packet longer than the survivor buffer (%llu steps)", (unsigned long long)total);
+        return CED_ERR_ARG;
+    }
+    if (last && total <= (uint64_t)S) {
+        setError("ced_stream_decode: last=true with no information bits");
+        return CED_ERR_ARG;
+    }
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const size_t inBytes = 1024 + (size_t)segmentsIn;
+    const size_t survBytes = (size_t)kStreamMaxSteps * W * sizeof(uint32_t);
+    const size_t outBytes = 1024 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
+    int rc = c->sIn.ensure(1024 + kStreamMaxSteps);
+    if (rc == CED_OK) rc = c->sOut.ensure(16 + kStreamMaxSteps / 8 + 16);
+    if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
+    if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
+    if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
+    if (rc != CED_OK)
+        return rc;
+
+    /* mailbox: [0,512) edge  [512,768) metrics  [1024,...) segments */
+    memcpy(c->sPinIn.p, edge, (size_t)2 * N);
+    memcpy(c->sPinIn.p + 512, metrics, (size_t)N);
+    if (segmentsIn)
+        memcpy(c->sPinIn.p + 1024, segs, (size_t)segmentsIn);
+    CED_CUDA(cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream));
+    if (last && it0 > 0) /* chunked packet: bring the earlier decisions back */
+        CED_CUDA(cudaMemcpyAsync(c->sSurv.p, surv, (size_t)it0 * W * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                 c->stream));
+    ced::StreamArgs a;
+    a.K = K;
+    a.n = n;
+    a.N = N;
+    a.W = W;
+    a.iteration = it0;
+    a.renormCounter = *renormCounter;
+    a.segmentsIn = segmentsIn;
+    a.last = last;
+    a.edge = c->sIn.p;
+    a.metrics = c->sIn.p + 512;
+    a.segs = c->sIn.p + 1024;
+    a.surv = c->sSurv.p;
+    a.stateOut = reinterpret_cast<uint32_t *>(c->sOut.p); /* [0,16) state word, then decoded bytes */
+    a.out = c->sOut.p + 16;
+    const size_t decodedBytes = last ? (size_t)((total - S - 1) / 8 + 1) : 0;
+    const int threads = std::max(32, N / 2);
+    ced::streamDecodeKernel<<<1, threads, 0, c->stream>>>(a);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    /* results: metrics | renormCounter | decoded bytes or the new survivor rows */
+    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->sIn.p + 512, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 512, c->sOut.p, 16 + decodedBytes, cudaMemcpyDeviceToHost, c->stream));
+    if (!last && segmentsIn)
+        CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 1024, c->sSurv.p + (size_t)it0 * W,
+                                 (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CED_CUDA(cudaStreamSynchronize(c->stream));
+    if (last) {
+        memcpy(uncoded, c->sPinOut.p + 512 + 16, decodedBytes);
+        /* src/viterbiDecoderButterflyk1.c:259 -- the caller's reset restores metrics/counters */
+        return (int)decodedBytes;
+    }
+    memcpy(metrics, c->sPinOut.p, (size_t)N);
+    memcpy(renormCounter, c->sPinOut.p + 512, sizeof(uint32_t));
+    if (segmentsIn)
+        memcpy(surv + (size_t)it0 * W, c->sPinOut.p + 1024, (size_t)segmentsIn * W * sizeof(uint32_t));
+    *iteration = it0 + (uint32_t)segmentsIn;
+    return 0;
+}
+
+int ced_stream_encode(int K, int n, const uint32_t *taps, uint32_t *reg, const uint8_t *in, int bytesIn,
+                      uint8_t *segs, int last)
+{
+    if (K < 2 || K > 9 || n < 1 || n > CED_MAX_N || !taps || !reg || bytesIn < 0 || (bytesIn > 0 && !in) || !segs) {
+        setError("ced_stream_encode: bad argument");
+        return CED_ERR_ARG;
+    }
+    ced_ctx *c = ced_default_ctx();
+    if (!c) {
+        setError("ced_stream_encode: no CUDA context (%s)", gLastError);
+        return CED_ERR_CUDA;
+    }
+    const int tail = last ? K - 1 : 0;
+    const int T = 8 * bytesIn + tail;
+    if (T == 0)
+        return 0;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const size_t need = (size_t)std::max(bytesIn, 1) + 16;
+    int rc = c->hostIn[0].ensure(need);
+    if (rc == CED_OK) rc = c->hostOut[0].ensure((size_t)T + 16);
+    if (rc == CED_OK) rc = c->sPinIn.ensure(std::max<size_t>(need, 1024 + kStreamMaxSteps));
+    if (rc == CED_OK) rc = c->sPinOut.ensure(std::max<size_t>((size_t)T + 16, 4096));
+    if (rc != CED_OK)
+        return rc;
+    if (bytesIn) {
+        memcpy(c->sPinIn.p, in, (size_t)bytesIn);
+        CED_CUDA(cudaMemcpyAsync(c->hostIn[0].p, c->sPinIn.p, (size_t)bytesIn, cudaMemcpyHostToDevice, c->stream));
+    }
+    ced::EncTaps t;
+    for (int i = 0; i < 8; i++)
+        t.tap[i] = i < n ? taps[i] : 0u;
+    const int threads = (T + 15) / 16;
+    ced::encodeBatchKernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(c->hostIn[0].p, (size_t)std::max(bytesIn, 1),
+                                                                         1, bytesIn, c->hostOut[0].p, (size_t)T + 16,
+                                                                         tail, K, n, t, *reg, 1);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->hostOut[0].p, (size_t)T, cudaMemcpyDeviceToHost, c->stream));
+    CED_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(segs, c->sPinOut.p, (size_t)T);
+    /* shift-register bookkeeping only (src/convEncode.c:93,122): which input bits are still in the window */
+    uint32_t r = *reg;
+    for (int i = std::max(0, bytesIn - 2); i < bytesIn; i++)
+        r = (r << 8) | in[i];
+    *reg = last ? 0u : (r & ((1u << K) - 1u));
+    return T;
+}
+
+} // extern "C"

@@ -1,0 +1,106 @@
+/*
+ * channel_kernels.cuh -- the BER-mode helpers around the decoder:
+ *   berCountKernel   <- bitErrors()          berTestK7/berTestK7.c:45-53
+ *   bscChannelKernel <- corruptCodedArray()  berTestK7/berTestK7.c:29-43 (IID flips;
+ *                       the generator is counter-based instead of rand(), so the
+ *                       stream is independent of batch sharding)
+ *   randomBytesKernel<- the `(uint8_t) rand()` message fill, berTestK7.c:135-138
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ced {
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+__host__ __device__ __forceinline__ uint64_t keyed(uint64_t seed, uint64_t frame, uint64_t idx)
+{
+    return mix64(mix64(seed * 0x9E3779B97F4A7C15ULL + frame) + idx * 0xD1B54A32D192ED03ULL);
+}
+
+__global__ void __launch_bounds__(256)
+berCountKernel(const uint8_t *__restrict__ a, size_t strideA, const uint8_t *__restrict__ b, size_t strideB,
+               int nFrames, int bytesPerFrame, unsigned long long *counters, int aligned4)
+{
+    unsigned long long errs = 0;
+    const long long total = (long long)nFrames * (aligned4 ? bytesPerFrame / 4 : bytesPerFrame);
+    const int per = aligned4 ? bytesPerFrame / 4 : bytesPerFrame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / per;
+        const int c = (int)(i - f * per);
+        if (aligned4) {
+            const uint32_t x = __ldg(reinterpret_cast<const uint32_t *>(a + (size_t)f * strideA) + c);
+            const uint32_t y = __ldg(reinterpret_cast<const uint32_t *>(b + (size_t)f * strideB) + c);
+            errs += __popc(x ^ y);
+        } else {
+            errs += __popc((uint32_t)(a[(size_t)f * strideA + c] ^ b[(size_t)f * strideB + c]));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        errs += __shfl_xor_sync(0xFFFFFFFFu, errs, o);
+    if ((threadIdx.x & 31) == 0 && errs)
+        atomicAdd(&counters[0], errs);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&counters[1], (unsigned long long)nFrames * (unsigned long long)bytesPerFrame * 8ULL);
+}
+
+__global__ void __launch_bounds__(256)
+bscChannelKernel(uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame, int n, uint32_t threshold,
+                 uint64_t seed, uint64_t firstFrame, unsigned long long *counters)
+{
+    unsigned long long flipsTotal = 0;
+    const long long total = (long long)nFrames * segsPerFrame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / segsPerFrame;
+        const int t = (int)(i - f * segsPerFrame);
+        uint32_t flips = 0;
+        for (int j = 0; j < n; j += 2) {
+            const uint64_t h = keyed(seed, firstFrame + (uint64_t)f, (uint64_t)t * 4u + (uint64_t)(j >> 1));
+            flips |= ((uint32_t)h < threshold ? 1u : 0u) << j;
+            if (j + 1 < n)
+                flips |= ((uint32_t)(h >> 32) < threshold ? 1u : 0u) << (j + 1);
+        }
+        if (flips) {
+            segs[(size_t)f * segStride + t] ^= (uint8_t)flips;
+            flipsTotal += __popc(flips);
+        }
+    }
+    if (counters) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            flipsTotal += __shfl_xor_sync(0xFFFFFFFFu, flipsTotal, o);
+        if ((threadIdx.x & 31) == 0 && flipsTotal)
+            atomicAdd(&counters[0], flipsTotal);
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicAdd(&counters[1], (unsigned long long)total * (unsigned long long)n);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+randomBytesKernel(uint8_t *msg, size_t msgStride, int nFrames, int frameBytes, uint64_t seed, uint64_t firstFrame)
+{
+    const int wordsPerFrame = (frameBytes + 7) / 8;
+    const long long total = (long long)nFrames * wordsPerFrame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / wordsPerFrame;
+        const int w = (int)(i - f * wordsPerFrame);
+        const uint64_t h = keyed(seed ^ 0x6D657373616765ULL, firstFrame + (uint64_t)f, (uint64_t)w);
+        uint8_t *dst = msg + (size_t)f * msgStride + 8 * (size_t)w;
+        for (int b = 0; b < 8 && 8 * w + b < frameBytes; b++)
+            dst[b] = (uint8_t)(h >> (8 * b));
+    }
+}
+
+} // namespace ced

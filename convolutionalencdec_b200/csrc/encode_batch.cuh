@@ -1,0 +1,69 @@
+/*
+ * encode_batch.cuh -- bit-parallel rate-1/n convolutional encoder, sm_100a.
+ *
+ * Replaces convEnc + computeEncOutputSegment (src/convEncode.c:46-161): the
+ * reference shifts one bit at a time and takes two popcount parities per bit;
+ * here one thread produces 16 consecutive segments from a 24-bit window of the
+ * message with shift/XOR (generator i's tap d contributes window << d), then
+ * spreads each 4-bit group to 4 bytes with one multiply.  Output is the
+ * reference's wire format: one byte per segment, generator i in bit i.
+ *
+ * The same kernel serves the per-frame streaming call (nFrames == 1): `hist`
+ * carries the previous call's shift register (convEncoderState_t.tappedDelay)
+ * and `tailSegs` is K-1 when `last` (src/convEncode.c:108-119), else 0.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ced {
+
+struct EncTaps {
+    uint32_t tap[8]; /* bit d taps the input bit d steps back (bit 0 = newest) */
+};
+
+__global__ void __launch_bounds__(256)
+encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
+                  uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
+                  uint32_t hist, int aligned16)
+{
+    const int T = 8 * frameBytes + tailSegs;
+    const int chunksPerFrame = (T + 15) / 16;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long f = gid / chunksPerFrame;
+    const int c = (int)(gid - f * chunksPerFrame);
+    if (f >= nFrames)
+        return;
+    const uint8_t *m = msg + (size_t)f * msgStride;
+    /* message bytes 2c-1, 2c, 2c+1; byte -1 is the carried shift register, bytes
+     * past the end are the zero tail */
+    const int i0 = 2 * c - 1;
+    const uint32_t b0 = (i0 < 0) ? (hist & 0xFFu) : (i0 < frameBytes ? __ldg(m + i0) : 0u);
+    const uint32_t b1 = (i0 + 1 < frameBytes) ? __ldg(m + i0 + 1) : 0u;
+    const uint32_t b2 = (i0 + 2 < frameBytes) ? __ldg(m + i0 + 2) : 0u;
+    /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, :91) */
+    const uint32_t win = __brev(((b0 << 16) | (b1 << 8) | b2) << 8);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    for (int g = 0; g < n; g++) {
+        const uint32_t tap = taps.tap[g];
+        uint32_t c16 = 0;
+        for (int d = 0; d < K; d++)
+            if ((tap >> d) & 1u)
+                c16 ^= win << d;
+        c16 >>= 8; /* bit s = coded bit g of segment 16c + s */
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t nib = (c16 >> (4 * q)) & 0xFu;
+            w[q] |= ((nib * 0x00204081u) & 0x01010101u) << g;
+        }
+    }
+    uint8_t *dst = segs + (size_t)f * segStride + 16 * (size_t)c;
+    if (aligned16 && 16 * c + 16 <= T) {
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int s = 0; s < 16 && 16 * c + s < T; s++)
+            dst[s] = (uint8_t)(w[s >> 2] >> (8 * (s & 3)));
+    }
+}
+
+} // namespace ced

@@ -1,0 +1,248 @@
+/*
+ * trellis_swar.cuh -- SIMD-in-word add-compare-select for the K=7 rate-1/2 trellis.
+ *
+ * One thread owns one frame.  The 64 path metrics are unsigned bytes packed four
+ * to a 32-bit register (16 registers R[0..15]); all arithmetic is 8-bit and the
+ * decisions are identical to src/viterbiDecoderButterflyk1.c:101-149 of the
+ * reference (strict '>' compare, tie -> lower predecessor).  See DESIGN.md 4.
+ *
+ * In-place butterflies with a rotating state labelling
+ * -----------------------------------------------------
+ * A "position" p in [0,64) names byte lane (p & 3) of register (p >> 2).  Before
+ * trellis step t, with phase ph = t mod 6, state s lives at position rotr6(s, ph)
+ * (so position p holds state rotl6(p, ph)).  Butterfly j reads states j and j+32
+ * -- two positions that differ only in position bit q = 5 - ph -- and writes the
+ * successors 2j and 2j+1 back to the same two positions; that is exactly the
+ * phase ph+1 labelling, so no data moves between steps and after 6 steps the
+ * labelling is the identity again.
+ *   ph 0..3: q is a register bit -> pairs are (R[r], R[r | 1<<(q-2)]), same lanes.
+ *   ph 4,5 : q is a lane bit     -> partner = same register with lanes swapped
+ *            (one PRMT); each lane computes min(self + d, partner + (2-d)).
+ *
+ * Branch metrics: d(j) = HD(sym[j], rx) with sym[] the reference's
+ * edgeCodedBitsSymm (src/viterbiDecoderButterflyk1.c:24-29).  sym is GF(2)-linear
+ * in j, so the class of lane l of register r is regCls(r) ^ laneCls(l): per phase
+ * and received symbol only 4 distinct packed words X[0..3] exist (X[k] lane l =
+ * HD(rx, k ^ laneCls(l, ph))), and the complement 2-d of X[k] is X[k^3].
+ *
+ * Compare/select without byte-min hardware: all candidates are < 128, so
+ *   diff = cand1 + 0x80 - cand0   (per byte, never borrows across lanes)
+ * has bit 7 set iff cand1 >= cand0; PRMT replicates that bit over the byte and
+ * one LOP3 selects.  Decision bits (1 = predecessor j+32 won, as stored in the
+ * reference's tracebackBufs, :145-149,185-187) are gathered with one LOP3 per
+ * register into two 32-bit survivor words: position p -> word p>>5,
+ * bit 8*(p&3) + ((p>>2)&7).
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CED_HD __host__ __device__ __forceinline__
+#define CED_HDC __host__ __device__ constexpr
+#else
+#define CED_HD inline
+#define CED_HDC constexpr
+#endif
+
+namespace ced {
+
+CED_HDC uint32_t rotl6(uint32_t x, int r)
+{
+    return r == 0 ? (x & 63u) : (((x << r) | (x >> (6 - r))) & 63u);
+}
+CED_HDC uint32_t rotr6(uint32_t x, int r)
+{
+    return r == 0 ? (x & 63u) : (((x >> r) | (x << (6 - r))) & 63u);
+}
+CED_HDC uint32_t parity32(uint32_t x)
+{
+    x ^= x >> 16;
+    x ^= x >> 8;
+    x ^= x >> 4;
+    x ^= x >> 2;
+    x ^= x >> 1;
+    return x & 1u;
+}
+CED_HDC uint32_t hd2(uint32_t a, uint32_t b)
+{
+    return ((a ^ b) & 1u) + (((a ^ b) >> 1) & 1u);
+}
+
+/* A K=7, n=2 code given by its two Proakis-convention generators (octal 0113,
+ * 0171 for src/defaultParams/convCodeParams.c:6). */
+template <uint32_t G0, uint32_t G1>
+struct K7Code {
+    static constexpr int K = 7;
+    static constexpr uint32_t g0 = G0, g1 = G1;
+    /* src/convEncode.c:163-175: bit-reverse so bit 0 taps the newest input */
+    static CED_HDC uint32_t rev7(uint32_t g)
+    {
+        uint32_t r = 0;
+        for (int i = 0; i < 7; i++)
+            r |= ((g >> i) & 1u) << (6 - i);
+        return r;
+    }
+    static constexpr uint32_t tap0 = rev7(G0), tap1 = rev7(G1);
+    /* both generators tap the newest and the oldest bit (src/viterbiDecoder.c:20-24) */
+    static constexpr bool symmetric = (G0 & 1u) && ((G0 >> 6) & 1u) && (G1 & 1u) && ((G1 >> 6) & 1u);
+    /* output segment for shift-register contents reg (src/convEncode.c:132-161) */
+    static CED_HDC uint32_t segment(uint32_t reg)
+    {
+        return parity32(reg & tap0) | (parity32(reg & tap1) << 1);
+    }
+    /* edgeCodedBitsSymm[j], j < 32 (src/viterbiDecoderButterflyk1.c:24-29) */
+    static CED_HDC uint32_t sym(uint32_t j) { return segment((j << 1) & 127u); }
+    /* class of position p at phase ph: sym of the butterfly index (state bit 5 dropped) */
+    static CED_HDC uint32_t cls(uint32_t p, int ph) { return sym(rotl6(p, ph) & 31u); }
+    static CED_HDC uint32_t regCls(int r, int ph) { return cls((uint32_t)r << 2, ph); }
+    static CED_HDC uint32_t laneCls(int l, int ph) { return cls((uint32_t)l, ph); }
+    /* packed branch-metric word X[k] for phase ph and received symbol rx */
+    static CED_HDC uint32_t bmWord(int ph, uint32_t rx, uint32_t k)
+    {
+        uint32_t w = 0;
+        for (int l = 0; l < 4; l++)
+            w |= hd2(rx & 3u, k ^ laneCls(l, ph)) << (8 * l);
+        return w;
+    }
+};
+
+using DefaultK7 = K7Code<0113, 0171>;
+
+/* ---- byte-lane primitives ---- */
+CED_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    /* host model of PRMT (default mode), used only by tests/hostsim */
+    uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t out = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t nib = (sel >> (4 * i)) & 0xFu;
+        uint32_t byte = (uint32_t)(src >> (8 * (nib & 7u))) & 0xFFu;
+        if (nib & 8u)
+            byte = (byte & 0x80u) ? 0xFFu : 0x00u;
+        out |= byte << (8 * i);
+    }
+    return out;
+#endif
+}
+
+/* 0xFF in every byte whose bit 7 is set */
+CED_HD uint32_t signMask(uint32_t x) { return prmt(x, 0u, 0xba98u); }
+CED_HD uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
+
+constexpr uint32_t kGuard = 0x80808080u;
+constexpr uint32_t kInitMetricWord = 0x41414141u; /* NUM_STATES+1 = 65 in every lane (:59-67) */
+
+CED_HD void initMetrics(uint32_t (&R)[16])
+{
+#pragma unroll
+    for (int r = 0; r < 16; r++)
+        R[r] = kInitMetricWord;
+    R[0] = kInitMetricWord & 0xFFFFFF00u; /* STARTING_STATE 0 -> metric 0 */
+}
+
+/*
+ * One trellis step at compile-time phase PH.  X = the 4 packed branch-metric
+ * words for (PH, rx).  On return T0/T1 hold the 64 decision bits of this step.
+ */
+template <class Code, int PH>
+CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], uint32_t &T0, uint32_t &T1)
+{
+    constexpr int q = 5 - PH;
+    uint32_t t0 = 0, t1 = 0;
+    if constexpr (q >= 2) {
+        constexpr int rb = q - 2;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            if ((r >> rb) & 1)
+                continue;
+            const int rh = r | (1 << rb);
+            const uint32_t k = Code::regCls(r, PH);
+            const uint32_t d = X[k], dc = X[k ^ 3u];
+            const uint32_t lo = R[r], hi = R[rh];
+            const uint32_t a0 = lo + d, a1 = hi + dc;   /* successors 2j   (:109-110) */
+            const uint32_t b0 = lo + dc, b1 = hi + d;   /* successors 2j+1 (:113-114) */
+            const uint32_t ma = signMask(a1 + kGuard - a0); /* FF: a1 >= a0 -> keep a0 */
+            const uint32_t mb = signMask(b1 + kGuard - b0);
+            R[r] = sel(ma, a0, a1);
+            R[rh] = sel(mb, b0, b1);
+            const uint32_t ca = 0x01010101u << (r & 7), cb = 0x01010101u << (rh & 7);
+            if (r < 8) t0 |= ~ma & ca; else t1 |= ~ma & ca;
+            if (rh < 8) t0 |= ~mb & cb; else t1 |= ~mb & cb;
+        }
+    } else {
+        /* lanes with position bit q set hold the upper state (j+32) of their pair */
+        constexpr uint32_t swapSel = (q == 1) ? 0x1032u : 0x2301u;
+        constexpr uint32_t guard = (q == 1) ? 0x7F7F8080u : 0x7F807F80u;
+        constexpr uint32_t upper = (q == 1) ? 0xFFFF0000u : 0xFF00FF00u;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+            const uint32_t k = Code::regCls(r, PH);
+            const uint32_t self = R[r] + X[k];
+            const uint32_t cross = prmt(R[r], 0u, swapSel) + X[k ^ 3u];
+            /* lower lanes: FF iff cross >= self (keep self, decision 0)
+             * upper lanes: FF iff cross >  self (keep self, decision 1) */
+            const uint32_t m = signMask(cross + guard - self);
+            R[r] = sel(m, self, cross);
+            const uint32_t c = 0x01010101u << (r & 7);
+            if (r < 8) t0 |= ~m & c; else t1 |= ~m & c;
+        }
+        t0 ^= upper;
+        t1 ^= upper;
+    }
+    T0 = t0;
+    T1 = t1;
+}
+
+/* Subtract the minimum of the 64 metrics from all of them.  Decisions do not
+ * depend on when this happens as long as no candidate reaches 128 (DESIGN.md
+ * 4.3); the reference does it every 121 steps (:159-183), the batch kernel
+ * every kRenormPeriod steps. */
+CED_HD uint32_t byteMin(uint32_t a, uint32_t b)
+{
+    return sel(signMask(b + kGuard - a), a, b);
+}
+CED_HD void renorm(uint32_t (&R)[16])
+{
+    uint32_t m[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        m[i] = byteMin(R[i], R[i + 8]);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        m[i] = byteMin(m[i], m[i + 4]);
+    uint32_t v = byteMin(byteMin(m[0], m[2]), byteMin(m[1], m[3]));
+    v = byteMin(v, prmt(v, 0u, 0x1032u));
+    v = byteMin(v, prmt(v, 0u, 0x2301u));
+#pragma unroll
+    for (int r = 0; r < 16; r++)
+        R[r] -= v;
+}
+constexpr int kRenormPeriod = 96;
+
+/* ---- traceback bookkeeping (position in "survivor bit index" form) ----
+ * b = 32*(p>>5) + 8*(p&3) + ((p>>2)&7).  Position bit q = 5-ph maps to b bit
+ * kPairBitInB[ph]. */
+CED_HDC int pairBitInB(int ph)
+{
+    /* q = 5-ph: 5,4,3,2,1,0 -> b bit 5,2,1,0,4,3 (one nibble per phase) */
+    return (int)((0x340125u >> (4 * ph)) & 7u);
+}
+
+/* One backward step through trellis step t (phase ph).  On entry b locates the
+ * survivor state after step t; returns that state's newest bit (the decoded bit
+ * of step t, src/viterbiDecoderButterflyk1.c:244-249) and moves b to the
+ * predecessor (:252). */
+CED_HD uint32_t tracebackStep(uint32_t &b, uint32_t w0, uint32_t w1, int ph)
+{
+    const int qb = pairBitInB(ph);
+    const uint32_t word = (b & 32u) ? w1 : w0;
+    const uint32_t dec = (word >> (b & 31u)) & 1u;
+    const uint32_t bit = (b >> qb) & 1u;
+    b = (b & ~(1u << qb)) | (dec << qb);
+    return bit;
+}
+
+} // namespace ced

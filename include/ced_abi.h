@@ -1,0 +1,158 @@
+/*
+ * ced_abi.h -- the C ABI between the host-side C library (the drop-in for
+ * convEncode.h / viterbiDecoder.h / viterbiDecoderButterflyk1.h) and the
+ * sm_100a CUDA kernels.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * The reference (ucb-cyarp/ConvolutionalEncDec) has no FFI layer: its boundary
+ * is the three public headers plus the link line.  Every entry
+ * point below therefore names the reference interface it stands behind:
+ *
+ *   ced_stream_encode   <- convEnc                         src/convEncode.h:74
+ *   ced_stream_decode   <- viterbiDecoderHardButterflyk1   src/viterbiDecoderButterflyk1.h:6
+ *                          (VITERBI_DECODER_HARD,           src/viterbiDecoder.h:87-95)
+ *   ced_encode_batch    <- the loop `for pkt: convEnc(..., last=true)`
+ *                                                          speedEncode/speedEncode.c:65-67
+ *   ced_decode_batch    <- the loop `for pkt: VITERBI_DECODER_HARD(..., last=true)`
+ *                                                          speedDecode/speedDecode.c:78-79
+ *   ced_ber_count       <- bitErrors()                     berTestK7/berTestK7.c:45-53
+ *   ced_bsc_channel     <- corruptCodedArray()             berTestK7/berTestK7.c:29-43
+ *
+ * There is no CPU implementation behind any of these: every call either runs
+ * on the GPU or returns an error code (text in ced_last_error()).
+ */
+#ifndef CED_ABI_H
+#define CED_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CED_OK 0
+#define CED_ERR_CUDA (-1)        /* a CUDA runtime call or kernel failed           */
+#define CED_ERR_ARG (-2)         /* bad pointer / size / alignment argument        */
+#define CED_ERR_UNSUPPORTED (-3) /* code parameters outside what the kernels cover */
+#define CED_ERR_NOMEM (-4)
+
+#define CED_MAX_N 8        /* coded bits per segment (one byte per segment on the wire) */
+#define CED_MAX_STATES 256 /* K <= 9 for the streaming kernel                            */
+
+/* Code parameters, Proakis convention as in src/defaultParams/convCodeParams.c:6:
+ * g[i] has its MSb (bit K-1) on the newest input bit.  k is always 1. */
+typedef struct {
+    int32_t constraintLen;      /* K */
+    int32_t codedBits;          /* n */
+    uint64_t gen[CED_MAX_N];    /* g[] */
+} ced_code_t;
+
+/* NOTE: no identifier in this header is a bare K, k, n, S or g -- the reference's
+ * parameter headers #define those (src/defaultParams/convCodeParams.h:8-17). */
+
+typedef struct ced_ctx ced_ctx; /* one per GPU: stream, scratch, staging buffers */
+
+/* ---------------------------------------------------------------- contexts */
+int ced_device_count(void);
+const char *ced_last_error(void);
+int ced_ctx_create(int device, ced_ctx **out);
+void ced_ctx_destroy(ced_ctx *ctx);
+int ced_ctx_device(const ced_ctx *ctx);
+/* Lazily-created context on device $CED_DEVICE (default 0) used by the
+ * streaming entry points; NULL on failure. */
+ced_ctx *ced_default_ctx(void);
+/* Block until everything queued on `stream` (NULL: the context's stream) ran. */
+int ced_sync(ced_ctx *ctx, void *stream);
+/* Number of kernel launches issued through this context so far. */
+uint64_t ced_launch_count(const ced_ctx *ctx);
+
+/* ------------------------------------------------------------ measurement
+ * ced_ctx_set_profiling(ctx, 1): ced_decode_batch brackets its forward (ACS)
+ * and traceback kernels with CUDA events on the launching stream;
+ * ced_ctx_last_kernel_ms then returns their summed durations for the most
+ * recent call ([0] forward, [1] traceback) after synchronising those events.
+ * ced_probe_int_peak runs a dependent-free LOP3 stream (mode 0: ALU pipe only,
+ * mode 1: LOP3 + IMAD co-issued) and reports 32-bit lane-operations per second
+ * of the LOP3 stream -- the INT roofline denominator of SURVEY 8(d). */
+int ced_ctx_set_profiling(ced_ctx *ctx, int enable);
+int ced_ctx_last_kernel_ms(ced_ctx *ctx, float *ms2);
+int ced_probe_int_peak(ced_ctx *ctx, int mode, double *laneOpsPerSecond);
+
+/* ------------------------------------------------------- batched hot path
+ * Frames are independent packets, each encoded from state 0 and terminated
+ * with K-1 zero bits.  A frame of frameBits information bits (multiple of 8)
+ * is frameBits+K-1 coded segments, one byte per segment holding c0 | c1<<1
+ * (src/viterbiDecoder.h:154), at dSegs[frame*segStride + t].  Decoded / message
+ * bits are MSb-first bytes at d*[frame*stride + t/8].
+ *
+ * Pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL: the context's
+ * own stream).  Calls are asynchronous with respect to the host.
+ * Fastest when base pointers and strides are multiples of 16 bytes; any
+ * alignment is accepted.
+ */
+int ced_decode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
+                     int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream);
+
+int ced_encode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride,
+                     int nFrames, int frameBytes, uint8_t *dSegs, size_t segStride, void *stream);
+
+/* Same operations on HOST buffers: pinned staging, chunked H2D / kernel / D2H
+ * pipelined on two streams.  Synchronous: returns when hOut / hSegs is complete. */
+int ced_decode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hSegs, size_t segStride,
+                          int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
+
+int ced_encode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride,
+                          int nFrames, int frameBytes, uint8_t *hSegs, size_t segStride);
+
+/* Bytes of survivor scratch ced_decode_batch keeps inside the context for a
+ * batch of this shape (grown on demand, reused across calls). */
+size_t ced_decode_scratch_bytes(int nFrames, int frameBits);
+
+/* dCounters[0] += popcount(dA ^ dB) over nFrames x bytesPerFrame; dCounters[1] +=
+ * bits compared.  Device-side uint64 counters, so a BER sweep can all-reduce
+ * them (NCCL sum) without a host round trip. */
+int ced_ber_count(ced_ctx *ctx, const uint8_t *dA, size_t strideA, const uint8_t *dB, size_t strideB,
+                  int nFrames, int bytesPerFrame, uint64_t *dCounters, void *stream);
+
+/* Binary symmetric channel on byte-per-segment symbols: each of the codedBits coded
+ * bits of every segment is flipped with probability p using a counter-based
+ * generator keyed by (seed, frame index, segment index), so the result does
+ * not depend on how frames are sharded.  dCounters (may be NULL):
+ * [0] += flips, [1] += coded bits. */
+int ced_bsc_channel(ced_ctx *ctx, uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame, int codedBits,
+                    double p, uint64_t seed, uint64_t firstFrameIndex, uint64_t *dCounters, void *stream);
+
+/* Uniform random message bytes keyed by (seed, frame index, byte index). */
+int ced_random_bytes(ced_ctx *ctx, uint8_t *dMsg, size_t msgStride, int nFrames, int frameBytes,
+                     uint64_t seed, uint64_t firstFrameIndex, void *stream);
+
+/* ------------------------------------------------ per-frame streaming path
+ * One frame, fed in arbitrary chunks exactly like the reference API
+ * (SURVEY A.6).  All decoder state lives in caller memory (the host struct
+ * viterbiHardState_t); the device side is stateless between calls.
+ *
+ *   edge[b*nStates + s] : coded segment on the edge leaving state s with input b
+ *   metrics             : nStates path metrics, updated in place, with the
+ *                         reference's uint8 arithmetic and renormalisation
+ *                         schedule (src/viterbiDecoderButterflyk1.c:159-183)
+ *   iteration, renorm   : viterbiHardState_t.iteration / .renormCounter
+ *   surv                : host mirror of the packed survivor decisions,
+ *                         survWordsPerStep uint32 per trellis step
+ *                         (ced_stream_surv_words(nStates)), capacity in steps
+ * Returns the number of decoded bytes written (0 unless last), <0 on error.
+ */
+int ced_stream_surv_words(int nStates);
+
+int ced_stream_decode(int constraintLen, int codedBits, const uint8_t *edge, uint8_t *metrics, uint32_t *iteration,
+                      uint32_t *renormCounter, uint32_t *surv, uint32_t survCapacitySteps,
+                      const uint8_t *segs, int segmentsIn, uint8_t *uncoded, int last);
+
+/* taps[i]: generator i with bit 0 on the newest input bit (convEncoderState_t.
+ * polynomials).  *reg is convEncoderState_t.tappedDelay.  Returns segments written. */
+int ced_stream_encode(int constraintLen, int codedBits, const uint32_t *taps, uint32_t *reg, const uint8_t *in, int bytesIn,
+                      uint8_t *segs, int last);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CED_ABI_H */

@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def bsc(rng, segs, p, junk_upper_bits=False):
+    """Flip each of the 2 coded bits of every byte-per-segment symbol with probability p."""
+    flips = rng.random(segs.shape + (2,)) < p
+    out = segs ^ (flips[..., 0].astype(np.uint8) | (flips[..., 1].astype(np.uint8) << 1))
+    if junk_upper_bits:
+        out = out | (rng.integers(0, 64, segs.shape, dtype=np.uint8) << 2)
+    return out
+
+
+@pytest.fixture(scope="session")
+def port():
+    import oracle
+    return oracle.port()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    import oracle
+    r = oracle.ref()
+    if r is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    return r
+
+
+@pytest.fixture(scope="session")
+def golden():
+    path = os.path.join(ROOT, "tests", "golden", "k7_reference_vectors.npz")
+    return np.load(path)

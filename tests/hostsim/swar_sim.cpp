@@ -1,0 +1,67 @@
+// TEST INFRASTRUCTURE ONLY: runs the exact SWAR step / traceback functions of
+// convolutionalencdec_b200/csrc/trellis_swar.cuh for ONE frame on the host so the
+// rotating-label algebra can be checked against the oracle without a GPU.
+// It is never linked into the product library.
+#include "trellis_swar.cuh"
+#include <vector>
+
+using Code = ced::DefaultK7;
+
+template <int PH>
+static void stepPhase(uint32_t (&R)[16], uint32_t rx, uint32_t &t0, uint32_t &t1)
+{
+    uint32_t X[4];
+    for (uint32_t k = 0; k < 4; k++)
+        X[k] = Code::bmWord(PH, rx, k);
+    ced::acsStep<Code, PH>(R, X, t0, t1);
+}
+
+extern "C" int swar_sim_decode(const uint8_t *segs, int T, uint8_t *out, uint32_t *survOut, uint8_t *maxMetric,
+                               int renormPeriod)
+{
+    uint32_t R[16];
+    ced::initMetrics(R);
+    std::vector<uint32_t> surv(2 * (size_t)T);
+    uint8_t mx = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t t0 = 0, t1 = 0, rx = segs[t];
+        switch (t % 6) {
+        case 0: stepPhase<0>(R, rx, t0, t1); break;
+        case 1: stepPhase<1>(R, rx, t0, t1); break;
+        case 2: stepPhase<2>(R, rx, t0, t1); break;
+        case 3: stepPhase<3>(R, rx, t0, t1); break;
+        case 4: stepPhase<4>(R, rx, t0, t1); break;
+        default: stepPhase<5>(R, rx, t0, t1); break;
+        }
+        surv[2 * t] = t0;
+        surv[2 * t + 1] = t1;
+        for (int r = 0; r < 16; r++)
+            for (int l = 0; l < 4; l++) {
+                uint8_t v = (R[r] >> (8 * l)) & 0xFF;
+                if (v > mx) mx = v;
+            }
+        if ((t + 1) % renormPeriod == 0)
+            ced::renorm(R);
+    }
+    if (maxMetric) *maxMetric = mx;
+    if (survOut)
+        for (size_t i = 0; i < surv.size(); i++) survOut[i] = surv[i];
+    const int L = T - 6;
+    uint32_t b = 0;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        uint32_t bit = ced::tracebackStep(b, surv[2 * t], surv[2 * t + 1], t % 6);
+        if (t < L)
+            out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
+    }
+    return (L + 7) / 8;
+}
+
+// decision of state s after step t from the packed words (for comparing with the oracle's survivors)
+extern "C" int swar_sim_decision(const uint32_t *surv, int t, int s)
+{
+    uint32_t p = ced::rotr6((uint32_t)s, (t + 1) % 6);
+    uint32_t word = surv[2 * t + (p >> 5)];
+    uint32_t bit = 8 * (p & 3) + ((p >> 2) & 7);
+    return (word >> bit) & 1;
+}

@@ -1,0 +1,298 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/ced_abi.h)
+and through the reference-named host C API, against the oracle, the committed
+reference fixtures and size-independent properties.  Bit-exact everywhere: all
+arithmetic on this path is 8-bit integer."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import convolutionalencdec_b200 as ced
+import oracle
+from conftest import ROOT, bsc
+
+pytestmark = pytest.mark.gpu
+K7 = oracle.K7_G
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch_cuda):
+    c = ced.Context(0)
+    yield c
+    c.close()
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ batch decode
+@pytest.mark.parametrize("bits", [8, 64, 256, 2048, 4096])
+def test_decode_batch_matches_reference_fixtures(torch_cuda, ctx, golden, bits):
+    for tag in ("p0", "p02", "p06", "p50"):
+        noisy = golden["noisy_%d_%s" % (bits, tag)]
+        out = ctx.decode_batch(ced.K7_DEFAULT, dev(torch_cuda, noisy), bits)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), golden["dec_%d_%s" % (bits, tag)]), (bits, tag)
+
+
+@pytest.mark.parametrize("bits,frames,stride_pad,offset", [
+    (8, 1, 0, 0), (16, 3, 0, 0), (40, 33, 0, 0), (96, 127, 10, 0), (104, 128, 2, 0), (192, 129, 6, 0),
+    (1000 // 8 * 8, 200, 0, 0), (2048, 257, 16 - (2054 % 16), 0), (4096, 300, 10, 0), (4096, 64, 0, 0),
+    (4096, 70, 0, 3), (264, 500, 5, 1), (16384, 9, 10, 0),
+])
+def test_decode_batch_vs_oracle_shapes_and_alignment(torch_cuda, ctx, port, bits, frames, stride_pad, offset):
+    """Ragged sizes: frame counts off the 32/128 grid, rows 16-byte aligned (fast staging path) and
+    not (generic path), base pointer misaligned, max packet length, junk in the unused symbol bits."""
+    torch = torch_cuda
+    rng = np.random.default_rng(bits * 131 + frames)
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    clean = port.encode_batch(7, K7, msgs)
+    for p in (0.0, 0.05, 0.5):
+        noisy = bsc(rng, clean, p, junk_upper_bits=True)
+        want = port.decode_batch(7, K7, noisy, T)
+        stride = T + stride_pad
+        flat = torch.zeros(frames * stride + offset + 64, dtype=torch.uint8, device="cuda")
+        view = flat[offset:offset + frames * stride].view(frames, stride)
+        view[:, :T] = dev(torch, noisy)
+        view[:, T:] = 0xFF  # padding must never influence the result
+        out = ctx.decode_batch(ced.K7_DEFAULT, view, bits)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), want), (bits, frames, p)
+        if p == 0.0:
+            assert np.array_equal(want, msgs)
+
+
+def test_decode_batch_textbook_generators(torch_cuda, ctx, port):
+    g = (0o133, 0o171)
+    rng = np.random.default_rng(9)
+    msgs = rng.integers(0, 256, (150, 64), dtype=np.uint8)
+    noisy = bsc(rng, port.encode_batch(7, g, msgs), 0.06)
+    out = ctx.decode_batch(ced.K7_TEXTBOOK, dev(torch_cuda, noisy), 512)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), port.decode_batch(7, g, noisy, 518))
+
+
+def test_decode_batch_rejects_what_it_cannot_do(torch_cuda, ctx):
+    torch = torch_cuda
+    segs = torch.zeros((4, 70), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ced.CedError):
+        ctx.decode_batch(ced.Code(7, (0o117, 0o155)), segs, 64)      # generators not built
+    with pytest.raises(ced.CedError):
+        ctx.decode_batch(ced.K7_DEFAULT, segs, 60)                    # not a multiple of 8
+    with pytest.raises(ced.CedError):
+        ctx.decode_batch(ced.K7_DEFAULT, segs, 128)                   # stride shorter than a frame
+    out = ctx.decode_batch(ced.K7_DEFAULT, segs, 64, n_frames=0)      # empty batch is a no-op
+    assert out.shape[0] == 0
+
+
+# ------------------------------------------------------------------ batch encode
+@pytest.mark.parametrize("nbytes,frames,stride_pad", [(1, 1, 0), (2, 5, 0), (3, 40, 3), (32, 100, 10), (256, 257, 10),
+                                                      (512, 300, 10), (512, 64, 0), (2048, 7, 10)])
+def test_encode_batch_vs_oracle(torch_cuda, ctx, port, golden, nbytes, frames, stride_pad):
+    torch = torch_cuda
+    rng = np.random.default_rng(nbytes + frames)
+    msgs = rng.integers(0, 256, (frames, nbytes), dtype=np.uint8)
+    T = 8 * nbytes + 6
+    out = torch.full((frames, T + stride_pad), 0xEE, dtype=torch.uint8, device="cuda")
+    ctx.encode_batch(ced.K7_DEFAULT, dev(torch, msgs), out=out)
+    ctx.sync()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, :T], port.encode_batch(7, K7, msgs))
+    assert (got[:, T:] == 0xEE).all()  # padding untouched
+
+
+def test_encode_batch_matches_reference_fixtures_and_other_codes(torch_cuda, ctx, port, golden):
+    torch = torch_cuda
+    for bits in (8, 64, 256, 2048, 4096):
+        out = ctx.encode_batch(ced.K7_DEFAULT, dev(torch, golden["msg_%d" % bits]))
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), golden["segs_%d" % bits])
+    rng = np.random.default_rng(4)
+    msgs = rng.integers(0, 256, (50, 33), dtype=np.uint8)
+    for K, g in ((3, (0b111, 0b110)), (7, (0o133, 0o171)), (9, (0o561, 0o753)), (7, (0o133, 0o145, 0o175))):
+        out = ctx.encode_batch(ced.Code(K, g), dev(torch, msgs))
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), port.encode_batch(K, g, msgs)), (K, g)
+
+
+# ------------------------------------------------------------------ host-buffer (e2e) entry points
+def test_host_buffer_pipeline_roundtrip(torch_cuda, ctx, port):
+    torch = torch_cuda
+    rng = np.random.default_rng(21)
+    frames, bits = 40000, 256     # > 2 pipeline chunks of 16384 frames
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    T = bits + 6
+    segs = torch.empty((frames, T + 10), dtype=torch.uint8).pin_memory()
+    ctx.encode_batch_host(ced.K7_DEFAULT, torch.from_numpy(msgs).pin_memory(), segs)
+    sample = rng.choice(frames, 300, replace=False)
+    assert np.array_equal(segs.numpy()[sample, :T], port.encode_batch(7, K7, msgs[sample]))
+    noisy = segs.numpy().copy()
+    noisy[:, :T] = bsc(rng, noisy[:, :T], 0.04)
+    out = np.zeros((frames, bits // 8), dtype=np.uint8)       # pageable host memory also works
+    ctx.decode_batch_host(ced.K7_DEFAULT, noisy, bits, out)
+    assert np.array_equal(out[sample], port.decode_batch(7, K7, noisy[sample, :T], T))
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_roundtrip_and_sampled_parity(torch_cuda, ctx, port):
+    """BASELINE config 2 shape: 2^16 frames x 4096 bits.  encode -> decode must be the identity;
+    encode -> BSC(5 dB) -> decode must equal the oracle on a random sample of frames, and the
+    on-device error counter must equal a host recount."""
+    torch = torch_cuda
+    frames, bits, stride = 1 << 16, 4096, 4112
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=314)
+    segs = torch.zeros((frames, stride), dtype=torch.uint8, device="cuda")
+    ctx.encode_batch(ced.K7_DEFAULT, msgs, out=segs)
+    dec = ctx.decode_batch(ced.K7_DEFAULT, segs, bits)
+    ctx.sync()
+    assert torch.equal(dec, msgs)
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ctx.bsc_channel(segs, bits + 6, 2, 0.0377, seed=7, counters=counters[:2])
+    dec = ctx.decode_batch(ced.K7_DEFAULT, segs, bits)
+    ctx.ber_count(dec, msgs, counters[2:])
+    ctx.sync()
+    c = counters.cpu().numpy()
+    assert c[1] == frames * (bits + 6) * 2 and c[3] == frames * bits
+    assert abs(c[0] / c[1] - 0.0377) < 2e-4
+    assert c[2] == int(np.bitwise_count((dec ^ msgs).cpu().numpy()).sum())
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(frames, 256, replace=False))
+    noisy = segs[torch.from_numpy(sample).cuda()].cpu().numpy()[:, :bits + 6]
+    assert np.array_equal(dec[torch.from_numpy(sample).cuda()].cpu().numpy(),
+                          port.decode_batch(7, K7, noisy, bits + 6))
+
+
+def test_channel_is_independent_of_sharding(torch_cuda, ctx):
+    torch = torch_cuda
+    frames, T = 1000, 262
+    whole = torch.zeros((frames, T), dtype=torch.uint8, device="cuda")
+    ctx.bsc_channel(whole, T, 2, 0.1, seed=5)
+    parts = torch.zeros((frames, T), dtype=torch.uint8, device="cuda")
+    for lo, hi in ((0, 333), (333, 334), (334, 1000)):
+        ctx.bsc_channel(parts[lo:hi], T, 2, 0.1, seed=5, first_frame=lo)
+    ctx.sync()
+    assert torch.equal(whole, parts)
+    assert 0.09 < (whole & 1).float().mean().item() < 0.11 and int(whole.max()) <= 3
+
+
+# ------------------------------------------------------------------ reference-named per-frame API
+def test_handtraced_sequence_through_the_dropin_api():
+    """handTracedTest/handTraced.c:29-111 step for step (K=3 testParams)."""
+    api = ced.RefApi("k3")
+    enc = api.encoder()
+    enc.resetConvEncoder()
+    enc.initConvEncoder()
+    assert enc.convEnc(np.array([0b01101000], dtype=np.uint8), True).tolist() == [0, 3, 0, 2, 2, 3, 1, 0, 0, 0]
+    dec = api.decoder()
+    dec.VITERBI_RESET()
+    dec.VITERBI_INIT()
+    api.viterbiConfigCheck()
+    corrupted = np.array([1, 3, 1, 2, 2, 3, 1, 0, 0, 0], dtype=np.uint8)
+    assert dec.VITERBI_DECODER_HARD(corrupted, True).tolist() == [0b01101000]
+    dec.VITERBI_RESET()
+    assert dec.nodeMetricsCur().tolist() == [0, 5, 5, 5]
+    for i, want in enumerate([[1, 1, 6, 5], [3, 1, 1, 3], [1, 3, 2, 2], [2, 2, 2, 4]]):
+        assert dec.VITERBI_DECODER_HARD(corrupted[i:i + 1], False).size == 0
+        assert dec.nodeMetricsCur().tolist() == want
+
+
+def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
+    api = ced.RefApi("k7")
+    dec = api.decoder()
+    dec.VITERBI_RESET()
+    dec.VITERBI_INIT()
+    noise, want_dec, want_metrics = golden["stream_noise"], golden["stream_dec"], golden["stream_metrics"]
+    for c in range(want_metrics.shape[0]):
+        assert dec.VITERBI_DECODER_HARD(noise[64 * c:64 * c + 64], False).size == 0
+        assert np.array_equal(dec.nodeMetricsCur(), want_metrics[c]), c     # exact 121-step renorm schedule
+    assert np.array_equal(dec.VITERBI_DECODER_HARD(noise[:0], True), want_dec)  # last with segmentsIn == 0
+    assert dec.nodeMetricsCur().tolist() == [0] + [65] * 63                   # reset after last
+    assert np.array_equal(dec.VITERBI_DECODER_HARD(noise, True), want_dec)     # one-shot == chunked
+    # ragged chunking, maximum packet length
+    rng = np.random.default_rng(8)
+    big = rng.integers(0, 4, 16384 + 6, dtype=np.uint8)
+    want = port.decode_batch(7, K7, big[None, :], big.size)[0]
+    pos = 0
+    for step in (1, 5, 121, 4097, 3000, 9166):
+        assert dec.VITERBI_DECODER_HARD(big[pos:pos + step], False).size == 0
+        pos += step
+    assert pos == big.size
+    assert np.array_equal(dec.VITERBI_DECODER_HARD(big[:0], True, max_bytes=4096), want)
+
+
+def test_streaming_encoder_chunks_and_kat(golden, port):
+    api = ced.RefApi("k7")
+    enc = api.encoder()
+    enc.resetConvEncoder()
+    enc.initConvEncoder()
+    assert np.array_equal(enc.convEnc(golden["kat_msg"], True), golden["kat_segs"])
+    rng = np.random.default_rng(2)
+    msg = rng.integers(0, 256, 1000, dtype=np.uint8)
+    parts, pos = [], 0
+    for step in (1, 2, 3, 250, 744):
+        parts.append(enc.convEnc(msg[pos:pos + step], pos + step == msg.size))
+        pos += step
+    assert np.array_equal(np.concatenate(parts), port.encode(7, K7, msg)[0])
+    # encoder state was reset by last=true: a second packet encodes from state 0
+    assert np.array_equal(enc.convEnc(golden["kat_msg"], True), golden["kat_segs"])
+
+
+def test_bertest_first_packets_through_the_dropin_api(golden):
+    """The first 64 packets of berTestK7's first configuration (same rand() stream as the reference
+    binary) decoded through VITERBI_DECODER_HARD: same decoded-error count as the reference."""
+    api = ced.RefApi("k7")
+    dec = api.decoder()
+    dec.VITERBI_RESET()
+    dec.VITERBI_INIT()
+    noisy, msgs, counts = golden["ber64_noisy"], golden["ber64_msgs"], golden["ber64_counts"]
+    errs = 0
+    for f in range(noisy.shape[0]):
+        out = dec.VITERBI_DECODER_HARD(noisy[f], True)
+        errs += int(np.unpackbits(out ^ msgs[f]).sum())
+    assert errs == int(counts[2])
+
+
+# ------------------------------------------------------------------ the reference's own drivers, unchanged
+def _driver(name):
+    path = os.path.join(ROOT, "drivers", "_bin", name)
+    if not os.path.exists(path):
+        pytest.skip("drivers/_bin/%s not built" % name)
+    return path
+
+
+def test_driver_handtraced_passes():
+    r = subprocess.run([_driver("handTraced")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "++++ Test Passed! ++++" in r.stdout and "Decoded 0x68, Expected 0x68" in r.stdout
+
+
+def test_driver_bertestk7_reproduces_golden_integers():
+    r = subprocess.run([_driver("berTestK7")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "Success!" in r.stdout
+    rows = [l for l in r.stdout.splitlines() if "|" in l and l.strip()[0] in "-0123456789"]
+    got = [[int(x) for x in l.replace("|", " ").split() if x.isdigit()] for l in rows]
+    assert got == [[2296339, 41080000, 92418, 20480000], [1525431, 41080000, 9655, 20480000],
+                   [928843, 41080000, 655, 20480000]], r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("name,word", [("speedDecode", "Decoded"), ("speedEncode", "Encoded")])
+def test_speed_drivers_run(name, word):
+    path = _driver(name)
+    try:
+        r = subprocess.run(["timeout", "-s", "INT", "6", "stdbuf", "-oL", path], capture_output=True, text=True, timeout=60)
+    except subprocess.TimeoutExpired:
+        pytest.fail("%s did not stop" % name)
+    assert "Could not" not in r.stdout, r.stdout
+    assert "Rate:" in r.stdout and "Mbps" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]

@@ -1,0 +1,73 @@
+"""The SIMD-in-word ACS algebra of csrc/trellis_swar.cuh (rotating state labels,
+lane-phase compare constants, packed survivor layout, traceback bookkeeping) run
+on the host for single frames and compared with the oracle -- decoded bytes and
+every per-state decision."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, bsc
+
+u8p, u32p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    path = os.path.join(ROOT, "tests", "hostsim", "libswar_sim.so")
+    subprocess.run(["make", "-C", ROOT, "hostsim"], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.swar_sim_decode.argtypes = [u8p, C.c_int, u8p, u32p, u8p, C.c_int]
+    lib.swar_sim_decision.argtypes = [u32p, C.c_int, C.c_int]
+    return lib
+
+
+def run(sim, row, period=96):
+    T = row.size
+    out = np.zeros((T - 6) // 8, dtype=np.uint8)
+    surv = np.zeros(2 * T, dtype=np.uint32)
+    mx = C.c_uint8(0)
+    row = np.ascontiguousarray(row)
+    sim.swar_sim_decode(row.ctypes.data_as(u8p), T, out.ctypes.data_as(u8p), surv.ctypes.data_as(u32p), C.byref(mx),
+                        period)
+    return out, surv, mx.value
+
+
+@pytest.mark.parametrize("bits", [8, 16, 24, 48, 96, 512, 4096])
+def test_decoded_bytes_match_oracle(sim, port, bits):
+    rng = np.random.default_rng(bits)
+    msgs = rng.integers(0, 256, (6, bits // 8), dtype=np.uint8)
+    segs = port.encode_batch(7, oracle.K7_G, msgs)
+    for p in (0.0, 0.04, 0.12, 0.5):
+        noisy = bsc(rng, segs, p, junk_upper_bits=True)
+        want = port.decode_batch(7, oracle.K7_G, noisy, bits + 6)
+        for f in range(noisy.shape[0]):
+            got, _, mx = run(sim, noisy[f])
+            assert np.array_equal(got, want[f])
+            assert mx < 126  # candidates must stay below 128 for the guard-bit compare
+
+
+def test_every_decision_matches_oracle(sim, port):
+    rng = np.random.default_rng(77)
+    for p in (0.0, 0.1, 0.5):
+        row = bsc(rng, port.encode_batch(7, oracle.K7_G, rng.integers(0, 256, (1, 32), dtype=np.uint8)), p)[0]
+        T = row.size
+        _, surv, _ = run(sim, row)
+        d = port.decoder(7, oracle.K7_G)
+        d.step(row, False)
+        sp = surv.ctypes.data_as(u32p)
+        for t in range(T):
+            got = [sim.swar_sim_decision(sp, t, s) for s in range(64)]
+            assert got == d.survivors(t).tolist(), t
+
+
+def test_renorm_period_does_not_change_decisions(sim, port):
+    rng = np.random.default_rng(3)
+    row = rng.integers(0, 4, 1030, dtype=np.uint8)
+    base, _, _ = run(sim, row, 96)
+    for period in (6, 24, 48, 102):
+        got, _, mx = run(sim, row, period)
+        assert np.array_equal(got, base) and mx < 126
