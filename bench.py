@@ -98,7 +98,31 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class c_stdout_to_stderr:
+    """The reference's init prints a banner with printf (src/viterbiDecoderButterflyk1.c:16);
+    keep the process's stdout clean for the single JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference_rate(seconds, threads=None, frames=None):
+    with c_stdout_to_stderr():
+        return _cpu_reference_rate(seconds, threads, frames)
+
+
+def _cpu_reference_rate(seconds, threads=None, frames=None):
     """speedDecode-style loop (speedDecode/speedDecode.c:72-110) over the reference's own decoder."""
     import numpy as np
     import oracle
