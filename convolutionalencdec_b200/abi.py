@@ -104,9 +104,15 @@ def _check(lib, rc, what):
 
 
 def _stream_handle(stream):
+    """cudaStream_t to launch on.  None means torch's CURRENT stream, so calls are ordered with
+    the torch ops that produced the tensors.  Handle 0 (the legacy default stream) is passed as
+    cudaStreamLegacy (1) because NULL means "the context's own stream" in ced_abi.h."""
     if stream is None:
-        return None
-    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+        import torch
+        handle = int(torch.cuda.current_stream().cuda_stream)
+    else:
+        handle = int(getattr(stream, "cuda_stream", stream))
+    return C.c_void_p(handle if handle != 0 else 1)
 
 
 class Context:

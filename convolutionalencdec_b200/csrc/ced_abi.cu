@@ -271,7 +271,7 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
 int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                      int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    if (!c || !dSegs || !dOut || nFrames < 0 || frameBits <= 0 || (frameBits & 7)) {
+    if (!c || nFrames < 0 || frameBits <= 0 || (frameBits & 7) || (nFrames > 0 && (!dSegs || !dOut))) {
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
     }
@@ -420,7 +420,7 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
 int ced_encode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
                      int frameBytes, uint8_t *dSegs, size_t segStride, void *stream)
 {
-    if (!c || !code || !dMsg || !dSegs || nFrames < 0 || frameBytes <= 0) {
+    if (!c || !code || nFrames < 0 || frameBytes <= 0 || (nFrames > 0 && (!dMsg || !dSegs))) {
         setError("ced_encode_batch: bad argument");
         return CED_ERR_ARG;
     }

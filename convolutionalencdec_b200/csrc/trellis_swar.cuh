@@ -112,7 +112,11 @@ using DefaultK7 = K7Code<0113, 0171>;
 CED_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, sel);
+    /* PTX prmt (default mode): selector nibble bit 3 replicates the selected byte's sign bit.
+     * The __byte_perm() intrinsic masks that bit away, so it cannot be used here. */
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
 #else
     /* host model of PRMT (default mode), used only by tests/hostsim */
     uint64_t src = ((uint64_t)b << 32) | a;

@@ -85,8 +85,10 @@ int ced_probe_int_peak(ced_ctx *ctx, int mode, double *laneOpsPerSecond);
  * (src/viterbiDecoder.h:154), at dSegs[frame*segStride + t].  Decoded / message
  * bits are MSb-first bytes at d*[frame*stride + t/8].
  *
- * Pointers are DEVICE pointers; `stream` is a cudaStream_t (NULL: the context's
- * own stream).  Calls are asynchronous with respect to the host.
+ * Pointers are DEVICE pointers; `stream` is a cudaStream_t.  NULL selects the
+ * context's own stream, which is non-blocking: it does NOT synchronise with
+ * the legacy default stream -- pass cudaStreamLegacy ((cudaStream_t)0x1) to
+ * launch there.  Calls are asynchronous with respect to the host.
  * Fastest when base pointers and strides are multiples of 16 bytes; any
  * alignment is accepted.
  */
