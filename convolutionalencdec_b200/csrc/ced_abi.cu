@@ -322,7 +322,7 @@ int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, s
                                                                              framesPad, aligned16, c->bm0133);
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
-        ced::k7TracebackKernel<<<(wave + 127) / 128, 128, 0, s>>>(c->scratch.p, framesPad, wave, T, out, outStride);
+        ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(c->scratch.p, framesPad, wave, T, out, outStride);
         if (prof) {
             CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
             c->profWaves++;

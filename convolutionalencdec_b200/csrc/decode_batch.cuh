@@ -28,7 +28,8 @@ constexpr int kPitch = kChunk + 16;       /* bytes per tile row in shared memory
 constexpr int kTailSteps = 6;             /* S = K-1                                     */
 
 struct BmTable {
-    uint4 x[6 * 4]; /* [phase][rx] -> X[0..3] */
+    uint4 x[6 * 4 * 2]; /* [phase][rx] -> X[0..3], E[0..3] (E[k] = X[k^3] - X[k] + guardWord(phase)) */
+    uint32_t minusOne;  /* 0xFFFFFFFF, opaque to the compiler (trellis_swar.cuh subOnFma) */
 };
 
 template <class Code>
@@ -42,76 +43,94 @@ inline BmTable makeBmTable()
             v.y = Code::bmWord(ph, rx, 1);
             v.z = Code::bmWord(ph, rx, 2);
             v.w = Code::bmWord(ph, rx, 3);
-            t.x[ph * 4 + rx] = v;
+            t.x[(ph * 4 + rx) * 2] = v;
+            const uint32_t g = guardWord(ph);
+            t.x[(ph * 4 + rx) * 2 + 1] = make_uint4(v.w - v.x + g, v.z - v.y + g, v.y - v.z + g, v.x - v.w + g);
         }
+    t.minusOne = 0xFFFFFFFFu;
     return t;
 }
 
 __device__ __forceinline__ uint32_t toBmOffset(uint32_t w)
 {
     /* four segments per word: keep the n=2 low bits (calcHammingDist(..., n),
-     * src/viterbiDecoder.c:279-283) and scale by sizeof(uint4) */
-    return (w & 0x03030303u) << 4;
+     * src/viterbiDecoder.c:279-283) and scale by the 32-byte table entry */
+    return (w & 0x03030303u) << 5;
 }
 
-/* Stage segments [t0, t0+kChunk) of the warp's 32 frames into `tile`. */
-__device__ __forceinline__ void stageTile(uint8_t *tile, const uint8_t *__restrict__ segs, size_t stride,
-                                          long long frame0, int nFrames, int t0, int T, int lane, bool aligned16)
+constexpr int kPieces = (32 * (kChunk / 16)) / 32; /* 16-byte pieces per lane and tile (6) */
+
+/* Fast path (rows 16-byte aligned): fetch this lane's 6 pieces of segments [t0, t0+kChunk) of the
+ * warp's 32 frames into registers.  Issued one chunk ahead of use so the HBM latency (18 % of warp
+ * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current chunk. */
+__device__ __forceinline__ void loadTileAligned(uint4 (&v)[kPieces], const uint8_t *__restrict__ segs, size_t stride,
+                                                long long frame0, int nFrames, int t0, int T, int lane)
 {
-    if (aligned16) {
-        /* 6 x 16 bytes per row; 32 rows -> 192 pieces over 32 lanes */
 #pragma unroll
-        for (int i = 0; i < (32 * (kChunk / 16)) / 32; i++) {
-            const int piece = i * 32 + lane;
-            const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
-            const long long f = frame0 + row;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            /* rows are padded to a multiple of 16 by the aligned16 contract only up
-             * to `stride`; never read beyond the row */
-            if (f < nFrames && t0 + col < T) {
-                const uint8_t *src = segs + (size_t)f * stride + (size_t)(t0 + col);
-                if ((size_t)(t0 + col + 16) <= stride)
-                    v = __ldg(reinterpret_cast<const uint4 *>(src));
-                else {
-                    uint32_t w[4] = {0, 0, 0, 0};
-                    for (int b = 0; b < 16 && t0 + col + b < T; b++)
-                        w[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
-                    v = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+    for (int i = 0; i < kPieces; i++) {
+        const int piece = i * 32 + lane;
+        const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
+        const long long f = frame0 + row;
+        v[i] = make_uint4(0, 0, 0, 0);
+        if (f < nFrames && t0 + col < T) {
+            const uint8_t *src = segs + (size_t)f * stride + (size_t)(t0 + col);
+            if ((size_t)(t0 + col + 16) <= stride) {
+                v[i] = __ldg(reinterpret_cast<const uint4 *>(src));
+            } else { /* last piece of a row whose stride is not padded: never read past the row */
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int b = 0; b < 16 && t0 + col + b < T; b++)
+                    w[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
+                v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            v.x = toBmOffset(v.x);
-            v.y = toBmOffset(v.y);
-            v.z = toBmOffset(v.z);
-            v.w = toBmOffset(v.w);
-            *reinterpret_cast<uint4 *>(tile + row * kPitch + col) = v;
         }
-    } else {
-        /* any alignment: lane l fetches bytes col = 4*(i*32+l) .. +3 of each row pass */
-        for (int row = 0; row < 32; row++) {
-            const long long f = frame0 + row;
-            if (lane < kChunk / 4) {
-                uint32_t w = 0;
-                if (f < nFrames) {
-                    const uint8_t *src = segs + (size_t)f * stride + (size_t)t0 + 4 * lane;
+    }
+}
+
+__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[kPieces], int lane)
+{
 #pragma unroll
-                    for (int b = 0; b < 4; b++)
-                        if (t0 + 4 * lane + b < T)
-                            w |= (uint32_t)__ldg(src + b) << (8 * b);
-                }
-                *reinterpret_cast<uint32_t *>(tile + row * kPitch + 4 * lane) = toBmOffset(w);
+    for (int i = 0; i < kPieces; i++) {
+        const int piece = i * 32 + lane;
+        const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
+        uint4 w = v[i];
+        w.x = toBmOffset(w.x);
+        w.y = toBmOffset(w.y);
+        w.z = toBmOffset(w.z);
+        w.w = toBmOffset(w.w);
+        *reinterpret_cast<uint4 *>(tile + row * kPitch + col) = w;
+    }
+}
+
+/* Generic path (any base / stride alignment): byte loads, staged just in time. */
+__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, const uint8_t *__restrict__ segs, size_t stride,
+                                                   long long frame0, int nFrames, int t0, int T, int lane)
+{
+    for (int row = 0; row < 32; row++) {
+        const long long f = frame0 + row;
+        if (lane < kChunk / 4) {
+            uint32_t w = 0;
+            if (f < nFrames) {
+                const uint8_t *src = segs + (size_t)f * stride + (size_t)t0 + 4 * lane;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (t0 + 4 * lane + b < T)
+                        w |= (uint32_t)__ldg(src + b) << (8 * b);
             }
+            *reinterpret_cast<uint32_t *>(tile + row * kPitch + 4 * lane) = toBmOffset(w);
         }
     }
 }
 
 template <class Code, int PH>
 __device__ __forceinline__ void fwdStep(uint32_t (&R)[16], const uint8_t *bmBase, const uint8_t *symPtr,
-                                        uint32_t &t0, uint32_t &t1)
+                                        uint32_t minusOne, uint32_t &t0, uint32_t &t1)
 {
     const uint32_t off = symPtr[PH];
-    const uint4 x = *reinterpret_cast<const uint4 *>(bmBase + PH * 64 + off);
+    const uint4 x = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + off);
+    const uint4 xg = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + 16 + off);
     const uint32_t X[4] = {x.x, x.y, x.z, x.w};
-    acsStep<Code, PH>(R, X, t0, t1);
+    const uint32_t E[4] = {xg.x, xg.y, xg.z, xg.w};
+    acsStep<Code, PH>(R, X, E, minusOne, t0, t1);
 }
 
 template <class Code>
@@ -119,10 +138,10 @@ __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
                 int framesPad, int aligned16, BmTable table)
 {
-    __shared__ uint4 sBm[6 * 4];
+    __shared__ uint4 sBm[6 * 4 * 2];
     __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
 
-    if (threadIdx.x < 24)
+    if (threadIdx.x < 48)
         sBm[threadIdx.x] = table.x[threadIdx.x];
     __syncthreads();
 
@@ -133,47 +152,62 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     uint8_t *tile = sTile[warp];
     const uint8_t *myRow = tile + lane * kPitch;
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
-    uint4 *out = surv + frame;
+    /* survivor layout: warp-major.  Each warp owns (T/2) consecutive 512-byte rows (one uint4 per
+     * lane and step pair), so both this kernel's stores and the traceback's loads are sequential
+     * streams per warp. */
+    const size_t pairs = (size_t)(T / 2);
+    uint4 *out = surv + ((size_t)(frame0 / 32) * pairs) * 32 + lane;
 
+    const uint32_t minusOne = table.minusOne;
     uint32_t R[16];
     initMetrics(R);
     int sinceRenorm = 0;
 
+    uint4 pre[kPieces];
+    if (aligned16)
+        loadTileAligned(pre, segs, stride, frame0, nFrames, 0, T, lane);
+
     for (int t0 = 0; t0 < T; t0 += kChunk) {
         __syncwarp();
-        stageTile(tile, segs, stride, frame0, nFrames, t0, T, lane, aligned16 != 0);
+        if (aligned16) {
+            storeTileAligned(tile, pre, lane);
+            if (t0 + kChunk < T)
+                loadTileAligned(pre, segs, stride, frame0, nFrames, t0 + kChunk, T, lane);
+        } else {
+            stageTileUnaligned(tile, segs, stride, frame0, nFrames, t0, T, lane);
+        }
         __syncwarp();
         const int steps = min(kChunk, T - t0);
         const int full = steps / 6;
         const uint8_t *p = myRow;
-        uint4 *o = out + (size_t)(t0 / 2) * framesPad;
+        uint4 *o = out + (size_t)(t0 / 2) * 32;
         for (int it = 0; it < full; it++) {
             uint4 s;
-            fwdStep<Code, 0>(R, bmBase, p, s.x, s.y);
-            fwdStep<Code, 1>(R, bmBase, p, s.z, s.w);
+            fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
+            fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
             if (live) o[0] = s;
-            fwdStep<Code, 2>(R, bmBase, p, s.x, s.y);
-            fwdStep<Code, 3>(R, bmBase, p, s.z, s.w);
-            if (live) o[framesPad] = s;
-            fwdStep<Code, 4>(R, bmBase, p, s.x, s.y);
-            fwdStep<Code, 5>(R, bmBase, p, s.z, s.w);
-            if (live) o[2 * (size_t)framesPad] = s;
+            fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
+            fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
+            if (live) o[32] = s;
+            fwdStep<Code, 4>(R, bmBase, p, minusOne, s.x, s.y);
+            fwdStep<Code, 5>(R, bmBase, p, minusOne, s.z, s.w);
+            if (live) o[64] = s;
             p += 6;
-            o += 3 * (size_t)framesPad;
+            o += 96;
         }
         /* T is even, so the remainder is 0, 2 or 4 steps (last chunk only) */
         const int rem = steps - 6 * full;
         if (rem >= 2) {
             uint4 s;
-            fwdStep<Code, 0>(R, bmBase, p, s.x, s.y);
-            fwdStep<Code, 1>(R, bmBase, p, s.z, s.w);
+            fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
+            fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
             if (live) o[0] = s;
         }
         if (rem >= 4) {
             uint4 s;
-            fwdStep<Code, 2>(R, bmBase, p, s.x, s.y);
-            fwdStep<Code, 3>(R, bmBase, p, s.z, s.w);
-            if (live) o[framesPad] = s;
+            fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
+            fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
+            if (live) o[32] = s;
         }
         sinceRenorm += kChunk;
         if (sinceRenorm >= kRenormPeriod) {
@@ -183,45 +217,116 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     }
 }
 
-/* Full-frame traceback from state 0 (src/viterbiDecoderButterflyk1.c:205-254). */
-__global__ void __launch_bounds__(128)
+/* backward step with the phase known at compile time */
+template <int PH>
+__device__ __forceinline__ uint32_t tracebackStepC(uint32_t &b, uint32_t w0, uint32_t w1)
+{
+    constexpr int qb = pairBitInB(PH);
+    const uint32_t word = (b & 32u) ? w1 : w0;
+    const uint32_t dec = (word >> (b & 31u)) & 1u;
+    const uint32_t bit = (b >> qb) & 1u;
+    b = (b & ~(1u << qb)) | (dec << qb);
+    return bit;
+}
+
+/* 8 steps = 4 pairs = one output byte; pair i of the group holds steps (base+6-2i, base+7-2i),
+ * PH0 = phase of the group's first step (step base, a multiple of 8 inside a 24-step block). */
+template <int PH0>
+__device__ __forceinline__ uint32_t tracebackByteC(uint32_t &b, const uint4 (&w)[4])
+{
+    uint32_t acc = 0;
+    acc |= tracebackStepC<(PH0 + 7) % 6>(b, w[0].z, w[0].w) << 0;
+    acc |= tracebackStepC<(PH0 + 6) % 6>(b, w[0].x, w[0].y) << 1;
+    acc |= tracebackStepC<(PH0 + 5) % 6>(b, w[1].z, w[1].w) << 2;
+    acc |= tracebackStepC<(PH0 + 4) % 6>(b, w[1].x, w[1].y) << 3;
+    acc |= tracebackStepC<(PH0 + 3) % 6>(b, w[2].z, w[2].w) << 4;
+    acc |= tracebackStepC<(PH0 + 2) % 6>(b, w[2].x, w[2].y) << 5;
+    acc |= tracebackStepC<(PH0 + 1) % 6>(b, w[3].z, w[3].w) << 6;
+    acc |= tracebackStepC<(PH0 + 0) % 6>(b, w[3].x, w[3].y) << 7;
+    return acc;
+}
+
+constexpr int kTbThreads = 64;
+
+__device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmemSrc));
+}
+
+/*
+ * Full-frame traceback from state 0 (src/viterbiDecoderButterflyk1.c:205-254), one thread per
+ * frame.  The survivor words a thread needs do not depend on the path, only which bit of them
+ * does, so the kernel is a pure HBM-read stream: the 12 uint4 of the NEXT 24-step block are
+ * fetched with cp.async (LDGSTS, no registers held) into the thread's private shared-memory
+ * slots while the current block is walked -- 192..384 bytes in flight per thread.
+ * Steps [24*floor(L/24), T) -- the S tail steps plus at most two bytes -- take the generic path.
+ */
+__global__ void __launch_bounds__(kTbThreads)
 k7TracebackKernel(const uint4 *__restrict__ surv, int framesPad, int nFrames, int T, uint8_t *__restrict__ out,
                   size_t outStride)
 {
+    __shared__ uint4 sW[2][12][kTbThreads];
     const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (frame >= nFrames)
         return;
-    const uint4 *s = surv + frame;
+    const size_t pairs = (size_t)(T / 2);
+    const uint4 *s = surv + ((size_t)(frame / 32) * pairs) * 32 + (frame & 31);   /* warp-major, see k7ForwardKernel */
     uint8_t *dst = out + (size_t)frame * outStride;
+    const int L = T - kTailSteps;
+    const int blocks24 = L / 24;
+    const int tid = threadIdx.x;
+
+    auto prefetch = [&](int blk, int buf) {
+        const uint4 *p = s + (size_t)(blk * 12) * 32;
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+            cpAsync16(&sW[buf][i][tid], p + (size_t)(11 - i) * 32);   /* slot 0 = highest pair of the block */
+        asm volatile("cp.async.commit_group;");
+    };
+    if (blocks24 > 0)
+        prefetch(blocks24 - 1, 0);
+
     uint32_t b = 0;                 /* state 0 sits at position 0 in every phase */
-    int m = T / 2 - 1;              /* index of the step pair (2m, 2m+1)         */
     int ph = (T - 1) % 6;           /* phase of step 2m+1                        */
-    /* the S = 6 tail steps carry no output (:208-223) */
-#pragma unroll
-    for (int i = 0; i < kTailSteps / 2; i++, m--) {
-        const uint4 w = __ldg(s + (size_t)m * framesPad);
-        tracebackStep(b, w.z, w.w, ph);
+    uint32_t acc = 0;
+    for (int m = T / 2 - 1; m >= blocks24 * 12; m--) {
+        const uint4 w = __ldg(s + (size_t)m * 32);
+        const int t = 2 * m;
+        const uint32_t b1 = tracebackStep(b, w.z, w.w, ph);
         ph = ph ? ph - 1 : 5;
-        tracebackStep(b, w.x, w.y, ph);
+        const uint32_t b0 = tracebackStep(b, w.x, w.y, ph);
         ph = ph ? ph - 1 : 5;
-    }
-    /* L = T-6 is a multiple of 8: one output byte per 4 pairs */
-    for (int byteIdx = (T - kTailSteps) / 8 - 1; byteIdx >= 0; byteIdx--, m -= 4) {
-        uint4 w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            w[i] = __ldg(s + (size_t)(m - i) * framesPad);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            /* step 2(m-i)+1 = bit (6 - 2i ... ) of the byte: steps are visited in
-             * descending order, the first visited (t%8 == 7) is the LSb (:249) */
-            acc |= tracebackStep(b, w[i].z, w[i].w, ph) << (2 * i);
-            ph = ph ? ph - 1 : 5;
-            acc |= tracebackStep(b, w[i].x, w[i].y, ph) << (2 * i + 1);
-            ph = ph ? ph - 1 : 5;
+        if (t < L) {                /* the S = 6 tail steps carry no output (:208-223) */
+            acc = (acc >> 2) | (b1 << 6) | (b0 << 7);   /* first visited (t%8 == 7) ends as the LSb (:249) */
+            if ((t & 7) == 0) {
+                dst[t >> 3] = (uint8_t)acc;
+                acc = 0;
+            }
         }
-        dst[byteIdx] = (uint8_t)acc;
+    }
+    int buf = 0;
+    for (int blk = blocks24 - 1; blk >= 0; blk--, buf ^= 1) {
+        if (blk > 0) {
+            prefetch(blk - 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        /* only the issuing thread reads its slots: no barrier needed */
+        uint4 g[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = sW[buf][i][tid];          /* steps 24blk+16 .. +23 */
+        const uint32_t o2 = tracebackByteC<16 % 6>(b, g);
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = sW[buf][4 + i][tid];      /* steps 24blk+8  .. +15 */
+        const uint32_t o1 = tracebackByteC<8 % 6>(b, g);
+#pragma unroll
+        for (int i = 0; i < 4; i++) g[i] = sW[buf][8 + i][tid];      /* steps 24blk    .. +7  */
+        const uint32_t o0 = tracebackByteC<0>(b, g);
+        dst[3 * blk + 2] = (uint8_t)o2;
+        dst[3 * blk + 1] = (uint8_t)o1;
+        dst[3 * blk + 0] = (uint8_t)o0;
     }
 }
 

@@ -108,6 +108,14 @@ struct K7Code {
 
 using DefaultK7 = K7Code<0113, 0171>;
 
+/* Guard word added to the "upper predecessor" candidate before the compare (see acsStep):
+ * 0x80 per lane; in the lane phases the lanes holding the upper state use 0x7F so that a tie
+ * still goes to the lower predecessor. */
+CED_HDC uint32_t guardWord(int ph)
+{
+    return ph == 4 ? 0x7F7F8080u : ph == 5 ? 0x7F807F80u : 0x80808080u;
+}
+
 /* ---- byte-lane primitives ---- */
 CED_HD uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
 {
@@ -147,12 +155,34 @@ CED_HD void initMetrics(uint32_t (&R)[16])
     R[0] = kInitMetricWord & 0xFFFFFF00u; /* STARTING_STATE 0 -> metric 0 */
 }
 
+/* a - b issued as a true multiply-add (b * minusOne + a) so that it runs on the FMA pipe;
+ * `minusOne` is 0xFFFFFFFF passed at run time so the compiler cannot fold it back into an
+ * ALU-pipe IADD3. */
+CED_HD uint32_t subOnFma(uint32_t a, uint32_t b, uint32_t minusOne)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(minusOne), "r"(a));
+    return d;
+#else
+    return b * minusOne + a;
+#endif
+}
+
 /*
- * One trellis step at compile-time phase PH.  X = the 4 packed branch-metric
- * words for (PH, rx).  On return T0/T1 hold the 64 decision bits of this step.
+ * One trellis step at compile-time phase PH.  X = the 4 packed branch-metric words for
+ * (PH, rx); E[k] = X[k^3] - X[k] + guardWord(PH).  On return T0/T1 hold the 64 decision bits.
+ *
+ * Compare words.  For a butterfly (lo = metrics of states j, hi = of j+32, d = X[k], dc = X[k^3]):
+ *   a1 + G - a0 = (hi - lo) + E[k]       b1 + G - b0 = (hi - lo) + E[k^3]
+ * (byte-wise identical to the direct form because every true per-lane result lies in [0,255]).
+ * Pipe balance: profiles/r1_v1_* showed the ALU pipe 82 % busy and the FMA pipe 19 % with the
+ * direct 3-input IADD3 form; hi - lo is therefore issued once per butterfly as an IMAD and the
+ * two + E as 2-input adds, which ptxas places on the FMA pipe (IMAD.IADD).
  */
 template <class Code, int PH>
-CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], uint32_t &T0, uint32_t &T1)
+CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], const uint32_t (&E)[4], uint32_t minusOne,
+                    uint32_t &T0, uint32_t &T1)
 {
     constexpr int q = 5 - PH;
     uint32_t t0 = 0, t1 = 0;
@@ -168,8 +198,10 @@ CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], uint32_t &T0, uin
             const uint32_t lo = R[r], hi = R[rh];
             const uint32_t a0 = lo + d, a1 = hi + dc;   /* successors 2j   (:109-110) */
             const uint32_t b0 = lo + dc, b1 = hi + d;   /* successors 2j+1 (:113-114) */
-            const uint32_t ma = signMask(a1 + kGuard - a0); /* FF: a1 >= a0 -> keep a0 */
-            const uint32_t mb = signMask(b1 + kGuard - b0);
+            const uint32_t delta = subOnFma(hi, lo, minusOne);
+            /* FF: candidate from j+32 >= candidate from j -> keep the lower predecessor */
+            const uint32_t ma = signMask(delta + E[k]);
+            const uint32_t mb = signMask(delta + E[k ^ 3u]);
             R[r] = sel(ma, a0, a1);
             R[rh] = sel(mb, b0, b1);
             const uint32_t ca = 0x01010101u << (r & 7), cb = 0x01010101u << (rh & 7);
@@ -179,16 +211,17 @@ CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], uint32_t &T0, uin
     } else {
         /* lanes with position bit q set hold the upper state (j+32) of their pair */
         constexpr uint32_t swapSel = (q == 1) ? 0x1032u : 0x2301u;
-        constexpr uint32_t guard = (q == 1) ? 0x7F7F8080u : 0x7F807F80u;
         constexpr uint32_t upper = (q == 1) ? 0xFFFF0000u : 0xFF00FF00u;
 #pragma unroll
         for (int r = 0; r < 16; r++) {
             const uint32_t k = Code::regCls(r, PH);
             const uint32_t self = R[r] + X[k];
-            const uint32_t cross = prmt(R[r], 0u, swapSel) + X[k ^ 3u];
-            /* lower lanes: FF iff cross >= self (keep self, decision 0)
-             * upper lanes: FF iff cross >  self (keep self, decision 1) */
-            const uint32_t m = signMask(cross + guard - self);
+            const uint32_t swapped = prmt(R[r], 0u, swapSel);
+            const uint32_t cross = swapped + X[k ^ 3u];
+            /* cross + guard - self; guardWord(PH) makes it
+             *   lower lanes: FF iff cross >= self (keep self, decision 0)
+             *   upper lanes: FF iff cross >  self (keep self, decision 1) */
+            const uint32_t m = signMask(subOnFma(swapped, R[r], minusOne) + E[k]);
             R[r] = sel(m, self, cross);
             const uint32_t c = 0x01010101u << (r & 7);
             if (r < 8) t0 |= ~m & c; else t1 |= ~m & c;

@@ -10,10 +10,12 @@ using Code = ced::DefaultK7;
 template <int PH>
 static void stepPhase(uint32_t (&R)[16], uint32_t rx, uint32_t &t0, uint32_t &t1)
 {
-    uint32_t X[4];
+    uint32_t X[4], E[4];
     for (uint32_t k = 0; k < 4; k++)
         X[k] = Code::bmWord(PH, rx, k);
-    ced::acsStep<Code, PH>(R, X, t0, t1);
+    for (uint32_t k = 0; k < 4; k++)
+        E[k] = X[k ^ 3u] - X[k] + ced::guardWord(PH);
+    ced::acsStep<Code, PH>(R, X, E, 0xFFFFFFFFu, t0, t1);
 }
 
 extern "C" int swar_sim_decode(const uint8_t *segs, int T, uint8_t *out, uint32_t *survOut, uint8_t *maxMetric,
