@@ -7,14 +7,14 @@
  *
  * k7ForwardKernel  : one thread per frame, metrics in 16 registers (trellis_swar.cuh).
  *   - symbols: each warp stages a tile of 32 frames x kChunk segments through shared
- *     memory with coalesced 128-bit loads (8-byte-per-lane fallback path for rows
- *     that are not 16-byte aligned), already converted to "(rx & 3) * 16", the
+ *     memory with coalesced 128-bit loads prefetched one tile ahead (byte-load fallback
+ *     for rows that are not 16-byte aligned), already converted to "(rx & 3) * 32", the
  *     byte offset into the branch-metric table;
- *   - branch metrics: one LDS.128 per step from a 384-byte table [phase][rx][4 words];
- *   - survivors: 64 decision bits per step, two steps per 128-bit store, layout
- *     surv[(t/2) * framesPad + frame] so a warp writes 512 contiguous bytes.
- * k7TracebackKernel: one thread per frame walks the survivor words backwards (loads
- *     are independent of the state, so 4 are kept in flight), emits one byte per 8 steps.
+ *   - branch metrics: two LDS.128 per step from a 768-byte table [phase][rx] -> {X[4], E[4]};
+ *   - survivors: 64 decision bits per step, two steps per 128-bit store, warp-major
+ *     layout surv[((frame/32) * T/2 + t/2) * 32 + lane]: one sequential stream per warp.
+ * k7TracebackKernel: one thread per frame walks its survivor stream backwards; the next
+ *     24-step block is fetched with cp.async while the current one is walked.
  */
 #pragma once
 #include "trellis_swar.cuh"
