@@ -184,7 +184,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="decode", choices=["decode", "encode", "ber"])
@@ -213,7 +213,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with c_stdout_to_stderr():   # NCCL prints its version banner on stdout at communicator creation
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -356,6 +360,9 @@ def main():
 
     # ---- decoded bit-error count, summed over ranks with NCCL (BER mode's only collective) ----
     cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    if args.mode == "encode":   # nothing was decoded in this mode: decode the freshly encoded (noise-free) symbols
+        ctx.decode_batch(code, segs, bits, out=out, stream=stream)
     ctx.ber_count(out, msgs, cnt, stream=stream)
     stream.synchronize()
     allreduce_counts(cnt)

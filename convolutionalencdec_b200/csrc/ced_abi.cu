@@ -40,6 +40,7 @@ void setError(const char *fmt, ...)
     } while (0)
 
 constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave            */
+constexpr size_t kMaxWaveFrames = 1u << 20;       /* bounds the scheduler state (2 KB per 32 frames) */
 constexpr int kHostChunkFrames = 16384;           /* frames per H2D/kernel/D2H pipeline stage */
 constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
 
@@ -129,6 +130,11 @@ struct ced_ctx {
     cudaStream_t h2d = nullptr, d2h = nullptr;
     cudaEvent_t inReady[2] = {}, inFree[2] = {}, outReady[2] = {}, outFree[2] = {};
     DeviceBuf<uint4> scratch;        /* survivor words of the wave in flight */
+    DeviceBuf<uint4> schedState;     /* FwdSched.state */
+    DeviceBuf<int> schedFlags;       /* [0] unit counter, [1 + g] FwdSched.done */
+    int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel */
+    int fwdFramesPerThread = 1;      /* NF template parameter in use (CED_FWD_FRAMES_PER_THREAD) */
+    size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
     DeviceBuf<uint8_t> hostIn[2], hostOut[2];
     /* streaming path */
     DeviceBuf<uint8_t> sIn, sOut;
@@ -192,6 +198,26 @@ int ced_ctx_create(int device, ced_ctx **out)
     for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
         for (int e = 0; e < 3; e++)
             CED_CUDA(cudaEventCreate(&c->prof[w][e]));
+    {
+        /* persistent forward grid: CED_FWD_BLOCKS_PER_SM CTAs of 4 warps per SM (default 4 = 4 warps per
+         * sub-partition), never more than the kernel's resident capacity */
+        int sms = 0, resident = 0;
+        CED_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES");
+        c->maxWaveFrames = (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
+        const char *nfEnv = getenv("CED_FWD_FRAMES_PER_THREAD");
+        c->fwdFramesPerThread = (nfEnv && atoi(nfEnv) == 2) ? 2 : 1; /* 2 measured slower: DESIGN.md 6 */
+        if (c->fwdFramesPerThread == 1)
+            CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ced::k7ForwardKernel<Code0113, 1>,
+                                                                   ced::kFwdThreads, 0));
+        else
+            CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ced::k7ForwardKernel<Code0113, 2>,
+                                                                   ced::kFwdThreads, 0));
+        const char *env = getenv("CED_FWD_BLOCKS_PER_SM");
+        int perSm = env ? atoi(env) : (c->fwdFramesPerThread == 1 ? 3 : 2);
+        perSm = std::max(1, std::min(perSm, std::max(1, resident)));
+        c->fwdBlocks = sms * perSm;
+    }
     *out = c;
     return CED_OK;
 }
@@ -203,6 +229,8 @@ void ced_ctx_destroy(ced_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->scratch.release();
+    c->schedState.release();
+    c->schedFlags.release();
     for (int i = 0; i < 2; i++) {
         c->hostIn[i].release();
         c->hostOut[i].release();
@@ -263,9 +291,10 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
         return 0;
     const size_t T = (size_t)frameBits + ced::kTailSteps;
     const size_t perFrame = (T / 2) * sizeof(uint4);
-    size_t wave = std::min<size_t>((size_t)nFrames, std::max<size_t>(ced::kFwdThreads, kMaxScratchBytes / perFrame));
-    wave = (wave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
-    return wave * perFrame;
+    size_t wave = std::min<size_t>(kMaxWaveFrames, std::max<size_t>(32, kMaxScratchBytes / perFrame));
+    wave = std::min<size_t>((size_t)nFrames, wave / 32 * 32);
+    const size_t groups = (wave + 63) / 64 * 2;
+    return groups * 32 * perFrame + groups * 4 * 32 * sizeof(uint4) + (groups + 1) * sizeof(int);
 }
 
 int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
@@ -291,14 +320,17 @@ int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, s
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     const size_t perFrame = (size_t)(T / 2) * sizeof(uint4);
-    size_t waveMax = std::max<size_t>(ced::kFwdThreads, kMaxScratchBytes / perFrame);
-    waveMax = waveMax / ced::kFwdThreads * ced::kFwdThreads;
+    size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
+    waveMax = waveMax / 64 * 64;
     const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
-    const size_t firstPad = (firstWave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
-    if (c->scratch.bytes < firstPad * perFrame) {
-        /* growing means freeing: make sure nothing still uses the old block */
+    const size_t firstGroups = (firstWave + 63) / 64 * 2; /* 32-frame subgroups, whole 64-frame groups */
+    if (c->scratch.bytes < firstGroups * 32 * perFrame || c->schedState.bytes < firstGroups * 4 * 32 * sizeof(uint4) ||
+        c->schedFlags.bytes < (firstGroups + 1) * sizeof(int)) {
+        /* growing means freeing: make sure nothing still uses the old blocks */
         CED_CUDA(cudaDeviceSynchronize());
-        int rc = c->scratch.ensure(firstPad * perFrame);
+        int rc = c->scratch.ensure(firstGroups * 32 * perFrame);
+        if (rc == CED_OK) rc = c->schedState.ensure(firstGroups * 4 * 32 * sizeof(uint4));
+        if (rc == CED_OK) rc = c->schedFlags.ensure((firstGroups + 1) * sizeof(int));
         if (rc != CED_OK)
             return rc;
     }
@@ -307,22 +339,36 @@ int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, s
     for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
         const bool prof = c->profiling && c->profWaves < ced_ctx::kMaxProfWaves;
         const int pw = c->profWaves;
-        if (prof)
-            CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
         const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
-        const int framesPad = (wave + ced::kFwdThreads - 1) / ced::kFwdThreads * ced::kFwdThreads;
-        const int blocks = framesPad / ced::kFwdThreads;
+        const int nf = c->fwdFramesPerThread;
+        const int groups = (wave + 32 * nf - 1) / (32 * nf);
+        const int warpsNeeded = groups; /* more persistent warps than groups would only spin */
+        const int blocks = std::max(1, std::min(c->fwdBlocks, (warpsNeeded + 3) / 4));
         const uint8_t *in = dSegs + f0 * segStride;
         uint8_t *out = dOut + f0 * outStride;
-        if (id == CodeId::K7_0113_0171)
-            ced::k7ForwardKernel<Code0113><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                             framesPad, aligned16, c->bm0113);
+        ced::FwdSched sched;
+        sched.counter = reinterpret_cast<unsigned int *>(c->schedFlags.p);
+        sched.done = c->schedFlags.p + 1;
+        sched.state = c->schedState.p;
+        CED_CUDA(cudaMemsetAsync(c->schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
+        if (prof)
+            CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
+        if (id == CodeId::K7_0113_0171 && nf == 2)
+            ced::k7ForwardKernel<Code0113, 2><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                                aligned16, c->bm0113, sched);
+        else if (id == CodeId::K7_0113_0171)
+            ced::k7ForwardKernel<Code0113, 1><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                                aligned16, c->bm0113, sched);
+        else if (nf == 2)
+            ced::k7ForwardKernel<Code0133, 2><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                                aligned16, c->bm0133, sched);
         else
-            ced::k7ForwardKernel<Code0133><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                             framesPad, aligned16, c->bm0133);
+            ced::k7ForwardKernel<Code0133, 1><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
+                                                                                aligned16, c->bm0133, sched);
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
-        ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(c->scratch.p, framesPad, wave, T, out, outStride);
+        ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+            c->scratch.p, wave, T, out, outStride);
         if (prof) {
             CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
             c->profWaves++;
@@ -407,11 +453,15 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
     const int T = 8 * frameBytes + tailSegs;
     if (T == 0)
         return CED_OK;
-    const long long threads = (long long)nFrames * ((T + 15) / 16);
-    const int blocks = (int)((threads + 255) / 256);
+    const int blocks = (nFrames + ced::kEncFramesPerBlock - 1) / ced::kEncFramesPerBlock;
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
-    ced::encodeBatchKernel<<<blocks, 256, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs,
-                                                  code->constraintLen, code->codedBits, taps, hist, aligned16);
+    if (code->constraintLen == 7 && code->codedBits == 2)
+        ced::encodeBatchKernel<7, 2><<<blocks, ced::kEncThreads, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs,
+                                                                         segStride, tailSegs, 7, 2, taps, hist, aligned16);
+    else
+        ced::encodeBatchKernel<0, 0><<<blocks, ced::kEncThreads, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs,
+                                                                         segStride, tailSegs, code->constraintLen,
+                                                                         code->codedBits, taps, hist, aligned16);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
@@ -537,10 +587,11 @@ int ced_ber_count(ced_ctx *c, const uint8_t *dA, size_t strideA, const uint8_t *
     return CED_OK;
 }
 
-int ced_bsc_channel(ced_ctx *c, uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame, int n, double p,
+int ced_bsc_channel(ced_ctx *c, uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame, int codedBits, double p,
                     uint64_t seed, uint64_t firstFrameIndex, uint64_t *dCounters, void *stream)
 {
-    if (!c || !dSegs || nFrames < 0 || segsPerFrame <= 0 || n < 1 || n > CED_MAX_N || !(p >= 0.0) || !(p < 1.0)) {
+    if (!c || !dSegs || nFrames < 0 || segsPerFrame <= 0 || codedBits < 1 || codedBits > CED_MAX_N || !(p >= 0.0) ||
+        !(p < 1.0)) {
         setError("ced_bsc_channel: bad argument");
         return CED_ERR_ARG;
     }
@@ -549,11 +600,12 @@ int ced_bsc_channel(ced_ctx *c, uint8_t *dSegs, size_t segStride, int nFrames, i
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     const uint32_t threshold = (uint32_t)(p * 4294967296.0);
-    const long long work = (long long)nFrames * segsPerFrame;
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
     ced::bscChannelKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
-        dSegs, segStride, nFrames, segsPerFrame, n, threshold, seed, firstFrameIndex,
-        reinterpret_cast<unsigned long long *>(dCounters));
+        dSegs, segStride, nFrames, segsPerFrame, codedBits, threshold, seed, firstFrameIndex,
+        reinterpret_cast<unsigned long long *>(dCounters), aligned16);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
@@ -707,10 +759,9 @@ int ced_stream_encode(int K, int n, const uint32_t *taps, uint32_t *reg, const u
     ced::EncTaps t;
     for (int i = 0; i < 8; i++)
         t.tap[i] = i < n ? taps[i] : 0u;
-    const int threads = (T + 15) / 16;
-    ced::encodeBatchKernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(c->hostIn[0].p, (size_t)std::max(bytesIn, 1),
-                                                                         1, bytesIn, c->hostOut[0].p, (size_t)T + 16,
-                                                                         tail, K, n, t, *reg, 1);
+    ced::encodeBatchKernel<0, 0><<<1, ced::kEncThreads, 0, c->stream>>>(c->hostIn[0].p, (size_t)std::max(bytesIn, 1), 1,
+                                                                        bytesIn, c->hostOut[0].p, (size_t)T + 16, tail,
+                                                                        K, n, t, *reg, 1);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
     CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->hostOut[0].p, (size_t)T, cudaMemcpyDeviceToHost, c->stream));

@@ -54,26 +54,49 @@ berCountKernel(const uint8_t *__restrict__ a, size_t strideA, const uint8_t *__r
         atomicAdd(&counters[1], (unsigned long long)nFrames * (unsigned long long)bytesPerFrame * 8ULL);
 }
 
+__device__ __forceinline__ uint32_t bscFlips(uint64_t seed, uint64_t frame, int t, int n, uint32_t threshold)
+{
+    uint32_t flips = 0;
+    for (int j = 0; j < n; j += 2) {
+        const uint64_t h = keyed(seed, frame, (uint64_t)t * 4u + (uint64_t)(j >> 1));
+        flips |= ((uint32_t)h < threshold ? 1u : 0u) << j;
+        if (j + 1 < n)
+            flips |= ((uint32_t)(h >> 32) < threshold ? 1u : 0u) << (j + 1);
+    }
+    return flips;
+}
+
+/* One thread handles 16 consecutive segments of one frame (one 128-bit load/store when the rows are
+ * 16-byte aligned, byte accesses otherwise). */
 __global__ void __launch_bounds__(256)
 bscChannelKernel(uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame, int n, uint32_t threshold,
-                 uint64_t seed, uint64_t firstFrame, unsigned long long *counters)
+                 uint64_t seed, uint64_t firstFrame, unsigned long long *counters, int aligned16)
 {
     unsigned long long flipsTotal = 0;
-    const long long total = (long long)nFrames * segsPerFrame;
+    const int chunksPerFrame = (segsPerFrame + 15) / 16;
+    const long long total = (long long)nFrames * chunksPerFrame;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long f = i / segsPerFrame;
-        const int t = (int)(i - f * segsPerFrame);
-        uint32_t flips = 0;
-        for (int j = 0; j < n; j += 2) {
-            const uint64_t h = keyed(seed, firstFrame + (uint64_t)f, (uint64_t)t * 4u + (uint64_t)(j >> 1));
-            flips |= ((uint32_t)h < threshold ? 1u : 0u) << j;
-            if (j + 1 < n)
-                flips |= ((uint32_t)(h >> 32) < threshold ? 1u : 0u) << (j + 1);
+        const long long f = i / chunksPerFrame;
+        const int t0 = (int)(i - f * chunksPerFrame) * 16;
+        uint8_t *p = segs + (size_t)f * segStride + t0;
+        const int cnt = min(16, segsPerFrame - t0);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        for (int s = 0; s < cnt; s++) {
+            const uint32_t fl = bscFlips(seed, firstFrame + (uint64_t)f, t0 + s, n, threshold);
+            w[s >> 2] |= fl << (8 * (s & 3));
+            flipsTotal += __popc(fl);
         }
-        if (flips) {
-            segs[(size_t)f * segStride + t] ^= (uint8_t)flips;
-            flipsTotal += __popc(flips);
+        if (aligned16 && (size_t)(t0 + 16) <= segStride) {
+            uint4 v = *reinterpret_cast<uint4 *>(p);
+            v.x ^= w[0];
+            v.y ^= w[1];
+            v.z ^= w[2];
+            v.w ^= w[3];
+            *reinterpret_cast<uint4 *>(p) = v;   /* bytes past segsPerFrame are XORed with 0 */
+        } else {
+            for (int s = 0; s < cnt; s++)
+                p[s] ^= (uint8_t)(w[s >> 2] >> (8 * (s & 3)));
         }
     }
     if (counters) {
@@ -83,7 +106,8 @@ bscChannelKernel(uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame,
         if ((threadIdx.x & 31) == 0 && flipsTotal)
             atomicAdd(&counters[0], flipsTotal);
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            atomicAdd(&counters[1], (unsigned long long)total * (unsigned long long)n);
+            atomicAdd(&counters[1], (unsigned long long)nFrames * (unsigned long long)segsPerFrame *
+                                        (unsigned long long)n);
     }
 }
 

@@ -58,16 +58,17 @@ __device__ __forceinline__ uint32_t toBmOffset(uint32_t w)
     return (w & 0x03030303u) << 5;
 }
 
-constexpr int kPieces = (32 * (kChunk / 16)) / 32; /* 16-byte pieces per lane and tile (6) */
+constexpr int kPiecesPerRow = kChunk / 16;             /* 16-byte pieces per tile row (6) = pieces per lane per 32 rows */
 
 /* Fast path (rows 16-byte aligned): fetch this lane's 6 pieces of segments [t0, t0+kChunk) of the
  * warp's 32 frames into registers.  Issued one chunk ahead of use so the HBM latency (18 % of warp
  * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current chunk. */
-__device__ __forceinline__ void loadTileAligned(uint4 (&v)[kPieces], const uint8_t *__restrict__ segs, size_t stride,
+template <int NP>
+__device__ __forceinline__ void loadTileAligned(uint4 (&v)[NP], const uint8_t *__restrict__ segs, size_t stride,
                                                 long long frame0, int nFrames, int t0, int T, int lane)
 {
 #pragma unroll
-    for (int i = 0; i < kPieces; i++) {
+    for (int i = 0; i < NP; i++) {
         const int piece = i * 32 + lane;
         const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
         const long long f = frame0 + row;
@@ -86,10 +87,11 @@ __device__ __forceinline__ void loadTileAligned(uint4 (&v)[kPieces], const uint8
     }
 }
 
-__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[kPieces], int lane)
+template <int NP>
+__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[NP], int lane)
 {
 #pragma unroll
-    for (int i = 0; i < kPieces; i++) {
+    for (int i = 0; i < NP; i++) {
         const int piece = i * 32 + lane;
         const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
         uint4 w = v[i];
@@ -102,10 +104,10 @@ __device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)
 }
 
 /* Generic path (any base / stride alignment): byte loads, staged just in time. */
-__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, const uint8_t *__restrict__ segs, size_t stride,
-                                                   long long frame0, int nFrames, int t0, int T, int lane)
+__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, int rows, const uint8_t *__restrict__ segs,
+                                                   size_t stride, long long frame0, int nFrames, int t0, int T, int lane)
 {
-    for (int row = 0; row < 32; row++) {
+    for (int row = 0; row < rows; row++) {
         const long long f = frame0 + row;
         if (lane < kChunk / 4) {
             uint32_t w = 0;
@@ -133,87 +135,192 @@ __device__ __forceinline__ void fwdStep(uint32_t (&R)[16], const uint8_t *bmBase
     acsStep<Code, PH>(R, X, E, minusOne, t0, t1);
 }
 
-template <class Code>
+/* Work distribution of the forward kernel.  A unit is (group of 32 frames, chunk of kChunk steps);
+ * units are numbered chunk-major and handed out with one atomic counter, so a unit's predecessor
+ * (same group, previous chunk) was always handed out earlier, to a warp that is running. */
+struct FwdSched {
+    unsigned int *counter;  /* next unit to hand out (zeroed before every launch)            */
+    int *done;              /* [groups] number of chunks finished per group (zeroed likewise) */
+    uint4 *state;           /* [groups][4][32] path metrics handed from chunk c to chunk c+1  */
+};
+
+__device__ __forceinline__ int ldAcquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelease(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+/*
+ * Persistent forward kernel: gridDim.x * 4 warps, each looping over units.  Why not simply one
+ * thread per frame for the whole frame: 2^16 frames are 2048 warps for 592 SM sub-partitions,
+ * 3.46 per SMSP, so a static assignment leaves the 3-warp SMSPs idle for the last 13.5 % of the
+ * launch (profiles/r1_v4: ALU pipe 77 % while active, 67 % of elapsed).  With units of 96 steps the
+ * tail shrinks to one chunk in 43.
+ *
+ * NF = frames per thread.  With NF = 2 a lane runs two independent frames (lane and lane+32 of a
+ * 64-frame group) through the same straight-line code: the two dependency chains interleave, so a
+ * single warp can issue nearly every cycle and alternate ALU- and FMA-pipe instructions even when a
+ * sub-partition holds only one or two warps.
+ */
+template <class Code, int NF>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                int framesPad, int aligned16, BmTable table)
+                int aligned16, BmTable table, FwdSched sched)
 {
+    constexpr int kRows = 32 * NF;             /* tile rows (frames) per warp */
+    constexpr int kPieces = kPiecesPerRow * NF; /* 16-byte pieces per lane and tile */
     __shared__ uint4 sBm[6 * 4 * 2];
-    __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
+    __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][kRows * kPitch];
 
     if (threadIdx.x < 48)
         sBm[threadIdx.x] = table.x[threadIdx.x];
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long frame = (long long)blockIdx.x * kFwdThreads + threadIdx.x;
-    const long long frame0 = frame - lane;
-    const bool live = frame < nFrames;
     uint8_t *tile = sTile[warp];
     const uint8_t *myRow = tile + lane * kPitch;
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
-    /* survivor layout: warp-major.  Each warp owns (T/2) consecutive 512-byte rows (one uint4 per
-     * lane and step pair), so both this kernel's stores and the traceback's loads are sequential
-     * streams per warp. */
-    const size_t pairs = (size_t)(T / 2);
-    uint4 *out = surv + ((size_t)(frame0 / 32) * pairs) * 32 + lane;
-
     const uint32_t minusOne = table.minusOne;
-    uint32_t R[16];
-    initMetrics(R);
-    int sinceRenorm = 0;
+    const size_t pairs = (size_t)(T / 2);
+    const unsigned groups = (unsigned)((nFrames + kRows - 1) / kRows);
+    const unsigned chunks = (unsigned)((T + kChunk - 1) / kChunk);
+    const unsigned total = groups * chunks;
 
+    auto grab = [&]() -> unsigned {
+        unsigned v = 0;
+        if (lane == 0)
+            v = atomicAdd(sched.counter, 1u);
+        return __shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+
+    unsigned u = grab();
     uint4 pre[kPieces];
-    if (aligned16)
-        loadTileAligned(pre, segs, stride, frame0, nFrames, 0, T, lane);
+    if (u < total && aligned16)
+        loadTileAligned(pre, segs, stride, (long long)kRows * (u % groups), nFrames, (int)(u / groups) * kChunk, T,
+                        lane);
 
-    for (int t0 = 0; t0 < T; t0 += kChunk) {
-        __syncwarp();
-        if (aligned16) {
-            storeTileAligned(tile, pre, lane);
-            if (t0 + kChunk < T)
-                loadTileAligned(pre, segs, stride, frame0, nFrames, t0 + kChunk, T, lane);
+    while (u < total) {
+        const unsigned g = u % groups, c = u / groups;
+        const long long frame0 = (long long)kRows * g;
+        const int t0 = (int)c * kChunk;
+        bool live[NF];
+#pragma unroll
+        for (int f = 0; f < NF; f++)
+            live[f] = frame0 + 32 * f + lane < nFrames;
+        /* 32-frame subgroup g*NF + f owns state slot and survivor stream number g*NF + f */
+        uint4 *stateSlot = sched.state + ((size_t)g * NF * 4) * 32 + lane;
+
+        uint32_t R[NF][16];
+        if (c == 0) {
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                initMetrics(R[f]);
         } else {
-            stageTileUnaligned(tile, segs, stride, frame0, nFrames, t0, T, lane);
+            if (lane == 0)
+                while (ldAcquire(sched.done + g) < (int)c)
+                    __nanosleep(200);
+            __syncwarp();
+            __threadfence();
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint4 v = __ldcg(stateSlot + (f * 4 + i) * 32);
+                    R[f][4 * i] = v.x;
+                    R[f][4 * i + 1] = v.y;
+                    R[f][4 * i + 2] = v.z;
+                    R[f][4 * i + 3] = v.w;
+                }
         }
+
         __syncwarp();
+        if (aligned16)
+            storeTileAligned(tile, pre, lane);
+        else
+            stageTileUnaligned(tile, kRows, segs, stride, frame0, nFrames, t0, T, lane);
+        /* next unit: claim it now so its symbol tile streams in during this chunk's ACS work */
+        const unsigned un = grab();
+        if (un < total && aligned16)
+            loadTileAligned(pre, segs, stride, (long long)kRows * (un % groups), nFrames, (int)(un / groups) * kChunk,
+                            T, lane);
+        __syncwarp();
+
+        /* survivor layout: one stream per 32-frame subgroup, (T/2) consecutive 512-byte rows (one uint4
+         * per lane and step pair), so this kernel's stores and the traceback's loads are sequential. */
+        uint4 *o = surv + ((size_t)g * NF * pairs + (size_t)(t0 / 2)) * 32 + lane;
+        const size_t oStride = pairs * 32; /* between the subgroups of this thread */
         const int steps = min(kChunk, T - t0);
         const int full = steps / 6;
         const uint8_t *p = myRow;
-        uint4 *o = out + (size_t)(t0 / 2) * 32;
         for (int it = 0; it < full; it++) {
-            uint4 s;
-            fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
-            fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
-            if (live) o[0] = s;
-            fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
-            fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
-            if (live) o[32] = s;
-            fwdStep<Code, 4>(R, bmBase, p, minusOne, s.x, s.y);
-            fwdStep<Code, 5>(R, bmBase, p, minusOne, s.z, s.w);
-            if (live) o[64] = s;
+            uint4 s[NF];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                fwdStep<Code, 0>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
+                fwdStep<Code, 1>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                if (live[f]) o[f * oStride] = s[f];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                fwdStep<Code, 2>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
+                fwdStep<Code, 3>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                if (live[f]) o[f * oStride + 32] = s[f];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                fwdStep<Code, 4>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
+                fwdStep<Code, 5>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
+            }
+#pragma unroll
+            for (int f = 0; f < NF; f++)
+                if (live[f]) o[f * oStride + 64] = s[f];
             p += 6;
             o += 96;
         }
         /* T is even, so the remainder is 0, 2 or 4 steps (last chunk only) */
         const int rem = steps - 6 * full;
         if (rem >= 2) {
-            uint4 s;
-            fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
-            fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
-            if (live) o[0] = s;
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                uint4 s;
+                fwdStep<Code, 0>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.x, s.y);
+                fwdStep<Code, 1>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.z, s.w);
+                if (live[f]) o[f * oStride] = s;
+            }
         }
         if (rem >= 4) {
-            uint4 s;
-            fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
-            fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
-            if (live) o[32] = s;
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                uint4 s;
+                fwdStep<Code, 2>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.x, s.y);
+                fwdStep<Code, 3>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.z, s.w);
+                if (live[f]) o[f * oStride + 32] = s;
+            }
         }
-        sinceRenorm += kChunk;
-        if (sinceRenorm >= kRenormPeriod) {
-            renorm(R);
-            sinceRenorm = 0;
+        if (c + 1 < chunks) {
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                renorm(R[f]); /* every kChunk = kRenormPeriod steps, see DESIGN.md 4.3 */
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    __stcg(stateSlot + (f * 4 + i) * 32,
+                           make_uint4(R[f][4 * i], R[f][4 * i + 1], R[f][4 * i + 2], R[f][4 * i + 3]));
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                stRelease(sched.done + g, (int)c + 1);
         }
+        u = un;
     }
 }
 
@@ -263,8 +370,7 @@ __device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
  * Steps [24*floor(L/24), T) -- the S tail steps plus at most two bytes -- take the generic path.
  */
 __global__ void __launch_bounds__(kTbThreads)
-k7TracebackKernel(const uint4 *__restrict__ surv, int framesPad, int nFrames, int T, uint8_t *__restrict__ out,
-                  size_t outStride)
+k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride)
 {
     __shared__ uint4 sW[2][12][kTbThreads];
     const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;

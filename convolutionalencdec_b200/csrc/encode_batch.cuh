@@ -22,47 +22,73 @@ struct EncTaps {
     uint32_t tap[8]; /* bit d taps the input bit d steps back (bit 0 = newest) */
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int kEncThreads = 256;
+constexpr int kEncFramesPerBlock = 4;
+
+/* 16 coded segments (one uint4) from the 24-bit window `win` (bit i = input bit u[16c - 8 + i]). */
+template <int KK, int NN>
+__device__ __forceinline__ uint4 encode16(uint32_t win, const EncTaps &taps, int K, int n)
+{
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    const int kk = KK ? KK : K, nn = NN ? NN : n;
+#pragma unroll
+    for (int g = 0; g < (NN ? NN : 8); g++) {
+        if (g >= nn)
+            break;
+        const uint32_t tap = taps.tap[g];
+        uint32_t c16 = 0;
+#pragma unroll
+        for (int d = 0; d < (KK ? KK : 9); d++)
+            if (d < kk)
+                c16 ^= (0u - ((tap >> d) & 1u)) & (win << d);   /* tap d contributes u[t-d] */
+        c16 >>= 8; /* bit s = coded bit g of segment 16c + s */
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t nib = (c16 >> (4 * q)) & 0xFu;
+            w[q] |= ((nib * 0x00204081u) & 0x01010101u) << g;   /* bit i of nib -> byte i */
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+/*
+ * A CTA encodes kEncFramesPerBlock consecutive frames; its threads stride over the 16-segment
+ * chunks of those frames (32-bit index math only).  KK/NN != 0 fix the constraint length and the
+ * number of generators at compile time (the K=7 n=2 production code), 0 = run-time values.
+ */
+template <int KK, int NN>
+__global__ void __launch_bounds__(kEncThreads)
 encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
                   uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
                   uint32_t hist, int aligned16)
 {
     const int T = 8 * frameBytes + tailSegs;
-    const int chunksPerFrame = (T + 15) / 16;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long f = gid / chunksPerFrame;
-    const int c = (int)(gid - f * chunksPerFrame);
-    if (f >= nFrames)
-        return;
-    const uint8_t *m = msg + (size_t)f * msgStride;
-    /* message bytes 2c-1, 2c, 2c+1; byte -1 is the carried shift register, bytes
-     * past the end are the zero tail */
-    const int i0 = 2 * c - 1;
-    const uint32_t b0 = (i0 < 0) ? (hist & 0xFFu) : (i0 < frameBytes ? __ldg(m + i0) : 0u);
-    const uint32_t b1 = (i0 + 1 < frameBytes) ? __ldg(m + i0 + 1) : 0u;
-    const uint32_t b2 = (i0 + 2 < frameBytes) ? __ldg(m + i0 + 2) : 0u;
-    /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, :91) */
-    const uint32_t win = __brev(((b0 << 16) | (b1 << 8) | b2) << 8);
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    for (int g = 0; g < n; g++) {
-        const uint32_t tap = taps.tap[g];
-        uint32_t c16 = 0;
-        for (int d = 0; d < K; d++)
-            if ((tap >> d) & 1u)
-                c16 ^= win << d;
-        c16 >>= 8; /* bit s = coded bit g of segment 16c + s */
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint32_t nib = (c16 >> (4 * q)) & 0xFu;
-            w[q] |= ((nib * 0x00204081u) & 0x01010101u) << g;
+    const unsigned chunksPerFrame = (unsigned)(T + 15) / 16;
+    const long long frameBase = (long long)blockIdx.x * kEncFramesPerBlock;
+    const unsigned framesHere = (unsigned)min((long long)kEncFramesPerBlock, (long long)nFrames - frameBase);
+    const unsigned items = framesHere * chunksPerFrame;
+    for (unsigned item = threadIdx.x; item < items; item += kEncThreads) {
+        const unsigned fl = item / chunksPerFrame;
+        const int c = (int)(item - fl * chunksPerFrame);
+        const long long f = frameBase + fl;
+        const uint8_t *m = msg + (size_t)f * msgStride;
+        /* message bytes 2c-1, 2c, 2c+1; byte -1 is the carried shift register, bytes past the end are
+         * the zero tail (src/convEncode.c:108-119) */
+        const int i0 = 2 * c - 1;
+        const uint32_t b0 = (i0 < 0) ? (hist & 0xFFu) : (i0 < frameBytes ? __ldg(m + i0) : 0u);
+        const uint32_t b1 = (i0 + 1 < frameBytes) ? __ldg(m + i0 + 1) : 0u;
+        const uint32_t b2 = (i0 + 2 < frameBytes) ? __ldg(m + i0 + 2) : 0u;
+        /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, src/convEncode.c:91) */
+        const uint32_t win = __brev(((b0 << 16) | (b1 << 8) | b2) << 8);
+        const uint4 v = encode16<KK, NN>(win, taps, K, n);
+        uint8_t *dst = segs + (size_t)f * segStride + 16 * (size_t)c;
+        if (aligned16 && 16 * c + 16 <= T) {
+            *reinterpret_cast<uint4 *>(dst) = v;
+        } else {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            for (int s2 = 0; s2 < 16 && 16 * c + s2 < T; s2++)
+                dst[s2] = (uint8_t)(w[s2 >> 2] >> (8 * (s2 & 3)));
         }
-    }
-    uint8_t *dst = segs + (size_t)f * segStride + 16 * (size_t)c;
-    if (aligned16 && 16 * c + 16 <= T) {
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-    } else {
-        for (int s = 0; s < 16 && 16 * c + s < T; s++)
-            dst[s] = (uint8_t)(w[s >> 2] >> (8 * (s & 3)));
     }
 }
 

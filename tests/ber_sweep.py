@@ -1,0 +1,128 @@
+"""BASELINE config 4: BPSK+AWGN (hard-sliced => BSC) Eb/N0 sweep, GPU BER vs the reference's decoder.
+
+For every Eb/N0 point the whole chain runs on the GPU through the C ABI
+(random messages -> ced_encode_batch -> ced_bsc_channel -> ced_decode_batch -> ced_ber_count); the four
+counters {channel flips, coded bits, decoded errors, decoded bits} stay on the device and are summed
+over ranks with ONE all-reduce (NCCL when launched under torchrun).  "Identical to the reference"
+is checked on a subset of each point: the very same noisy symbols are copied to the host, decoded by
+the unmodified reference (oracle/_ref; the oracle port if it is absent) and the decoded-error counts
+must be equal as integers.  berTestK7's own three points (berTestK7/berTestK7.c:95-96) lie on this
+curve at Eb/N0 = 4.03 / 5.03 / 6.03 dB.
+
+    python tests/ber_sweep.py [--frames-per-gpu N] [--subset M] [--out profiles/ber_sweep_r1.json]
+    python -m torch.distributed.run --nproc-per-node 2 ... tests/ber_sweep.py
+
+This file lives under tests/ because it uses the oracle as its checker.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+PKT_BITS = 2048  # berTestK7.c:8 ENCODE_PKT_BYTE_LEN = 2048/8
+
+
+def q_function(x):
+    return 0.5 * math.erfc(x / math.sqrt(2.0))
+
+
+def bsc_probability(ebn0_db, rate=0.5):
+    """Hard-sliced BPSK over AWGN: p = Q(sqrt(2 * Rc * Eb/N0))."""
+    return q_function(math.sqrt(2.0 * rate * 10.0 ** (ebn0_db / 10.0)))
+
+
+def run_point(ctx, code, p, frames, seed, first_frame, subset, checker):
+    import numpy as np
+    import torch
+    T = PKT_BITS + code.S
+    stride = (T + 15) // 16 * 16
+    msgs = torch.empty((frames, PKT_BITS // 8), dtype=torch.uint8, device="cuda")
+    segs = torch.zeros((frames, stride), dtype=torch.uint8, device="cuda")
+    counters = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ctx.random_bytes(msgs, seed=seed, first_frame=first_frame)
+    ctx.encode_batch(code, msgs, out=segs)
+    ctx.bsc_channel(segs, T, code.n, p, seed=seed + 1, first_frame=first_frame, counters=counters[:2])
+    dec = ctx.decode_batch(code, segs, PKT_BITS)
+    ctx.ber_count(dec, msgs, counters[2:])
+    ctx.sync()
+    check = None
+    if subset and checker is not None:
+        m = min(subset, frames)
+        noisy = segs[:m, :T].cpu().numpy()
+        want = checker(noisy, T)
+        ref_errs = int(np.bitwise_count(want ^ msgs[:m].cpu().numpy()).sum())
+        gpu_errs = int(np.bitwise_count((dec[:m] ^ msgs[:m]).cpu().numpy()).sum())
+        check = {"frames": m, "reference_decoded_errors": ref_errs, "gpu_decoded_errors": gpu_errs,
+                 "bytes_identical": bool(np.array_equal(want, dec[:m].cpu().numpy()))}
+    return counters, check
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames-per-gpu", type=int, default=1 << 18)
+    ap.add_argument("--subset", type=int, default=10000, help="frames per point re-decoded by the reference (rank 0)")
+    ap.add_argument("--points", default="0,1,2,3,4,5,6,7,8")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args(argv)
+
+    import torch
+    import torch.distributed as dist
+    import convolutionalencdec_b200 as ced
+    from convolutionalencdec_b200.sharding import allreduce_counts
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    checker, kind = None, None
+    if rank == 0 and args.subset:
+        import oracle
+        R = oracle.ref()
+        if R is not None:
+            checker, kind = (lambda noisy, T: R.decode_batch(noisy, T)), "reference (oracle/_ref)"
+        else:
+            P = oracle.port()
+            checker, kind = (lambda noisy, T: P.decode_batch(7, oracle.K7_G, noisy, T)), "port (oracle/ced_oracle.c)"
+    ctx = ced.Context(local_rank)
+    code = ced.K7_DEFAULT
+    rows = []
+    for i, db in enumerate(float(x) for x in args.points.split(",")):
+        p = bsc_probability(db)
+        counters, check = run_point(ctx, code, p, args.frames_per_gpu, seed=1000 + 10 * i,
+                                    first_frame=rank * args.frames_per_gpu, subset=args.subset if rank == 0 else 0,
+                                    checker=checker)
+        allreduce_counts(counters)   # the only collective of BER mode: 4 x int64
+        c = [int(x) for x in counters.cpu().tolist()]
+        rows.append({"ebn0_db": db, "bsc_p": p, "channel_flips": c[0], "coded_bits": c[1], "decoded_errors": c[2],
+                     "decoded_bits": c[3], "channel_ber": c[0] / c[1], "decoded_ber": c[2] / c[3],
+                     "subset_check": check})
+        if rank == 0:
+            print("Eb/N0 %4.1f dB  p=%.5f  channel BER %.5e  decoded BER %.5e  (%d errors / %d bits)%s"
+                  % (db, p, c[0] / c[1], c[2] / c[3], c[2], c[3],
+                     "" if not check else "  subset %d frames: ref %d == gpu %d : %s"
+                     % (check["frames"], check["reference_decoded_errors"], check["gpu_decoded_errors"],
+                        check["bytes_identical"])), file=sys.stderr)
+    result = {"config": "K=7 r=1/2 g=(0113,0171), %d-bit packets, hard-decision BSC from BPSK+AWGN" % PKT_BITS,
+              "n_gpus": world, "frames_per_gpu": args.frames_per_gpu, "checker": kind, "points": rows}
+    if rank == 0:
+        text = json.dumps(result, indent=1)
+        if args.out:
+            with open(os.path.join(ROOT, args.out) if not os.path.isabs(args.out) else args.out, "w") as f:
+                f.write(text + "\n")
+        print(json.dumps(result))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,7 @@ reference fixtures and size-independent properties.  Bit-exact everywhere: all
 arithmetic on this path is 8-bit integer."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -261,6 +262,44 @@ def test_bertest_first_packets_through_the_dropin_api(golden):
         out = dec.VITERBI_DECODER_HARD(noisy[f], True)
         errs += int(np.unpackbits(out ^ msgs[f]).sum())
     assert errs == int(counts[2])
+
+
+def test_ber_sweep_subset_identical_to_reference_decoder(torch_cuda):
+    """BASELINE config 4 in miniature: per Eb/N0 point the GPU's decoded bytes equal the reference
+    decoder's on the same hard symbols, so the BER curves are identical."""
+    import ber_sweep
+    res = ber_sweep.main(["--frames-per-gpu", "4096", "--subset", "512", "--points", "0,3,5,8"])
+    ps = [r["bsc_p"] for r in res["points"]]
+    assert abs(ps[0] - 0.1587) < 2e-4 and abs(ps[2] - 0.0377) < 2e-4       # SURVEY 8(d) table
+    for r in res["points"]:
+        chk = r["subset_check"]
+        assert chk["bytes_identical"] and chk["reference_decoded_errors"] == chk["gpu_decoded_errors"]
+        assert abs(r["channel_ber"] - r["bsc_p"]) < 0.02 * r["bsc_p"] + 1e-4
+    bers = [r["decoded_ber"] for r in res["points"]]
+    assert bers[0] > bers[1] > bers[2] > bers[3]
+
+
+def test_multi_wave_batches(torch_cuda, port):
+    """Batches larger than one wave of survivor scratch are decoded wave by wave (forced small here)."""
+    code = ("import os, sys, numpy as np, torch\n"
+            "sys.path.insert(0, %r)\n"
+            "import convolutionalencdec_b200 as ced\n"
+            "ctx = ced.Context(0)\n"
+            "msgs = torch.empty((1000, 32), dtype=torch.uint8, device='cuda'); ctx.random_bytes(msgs, seed=3)\n"
+            "segs = ctx.encode_batch(ced.K7_DEFAULT, msgs, seg_stride=272)\n"
+            "ctx.bsc_channel(segs, 262, 2, 0.05, seed=4)\n"
+            "dec = ctx.decode_batch(ced.K7_DEFAULT, segs, 256); ctx.sync()\n"
+            "np.save(sys.argv[1], dec.cpu().numpy()); np.save(sys.argv[2], segs.cpu().numpy())\n" % ROOT)
+    import tempfile
+    outs = []
+    for wave in ("128", "1048576"):
+        with tempfile.TemporaryDirectory() as d:
+            a, b = os.path.join(d, "dec.npy"), os.path.join(d, "segs.npy")
+            env = dict(os.environ, CED_MAX_WAVE_FRAMES=wave)
+            subprocess.run([sys.executable, "-c", code, a, b], check=True, env=env, timeout=300)
+            outs.append((np.load(a), np.load(b)))
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][0], port.decode_batch(7, K7, outs[0][1][:, :262], 262))
 
 
 # ------------------------------------------------------------------ the reference's own drivers, unchanged
