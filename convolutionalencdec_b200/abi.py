@@ -83,6 +83,9 @@ def load_abi():
     lib.ced_probe_int_peak.argtypes = [vp, i, C.POINTER(C.c_double)]
     lib.ced_decode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_encode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_packed_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
+    lib.ced_pack_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_decode_scratch_bytes.argtypes = [i, i]
@@ -168,6 +171,27 @@ class Context:
                "ced_decode_batch")
         return out
 
+    def decode_batch_packed(self, code, packed, frame_bits, out=None, stream=None):
+        import torch
+        nf = packed.shape[0]
+        if out is None:
+            out = torch.empty((nf, frame_bits // 8), dtype=torch.uint8, device=packed.device)
+        _check(self.lib, self.lib.ced_decode_batch_packed(self.h, C.byref(code._c), packed.data_ptr(),
+                                                          packed.stride(0), nf, frame_bits, out.data_ptr(),
+                                                          out.stride(0), _stream_handle(stream)),
+               "ced_decode_batch_packed")
+        return out
+
+    def pack_symbols(self, segs, segs_per_frame, out=None, stream=None, packed_stride=None):
+        import torch
+        nf = segs.shape[0]
+        if out is None:
+            out = torch.zeros((nf, packed_stride or (segs_per_frame + 3) // 4), dtype=torch.uint8, device=segs.device)
+        _check(self.lib, self.lib.ced_pack_symbols(self.h, segs.data_ptr(), segs.stride(0), nf, segs_per_frame,
+                                                   out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_pack_symbols")
+        return out
+
     def encode_batch(self, code, msgs, out=None, stream=None, seg_stride=None):
         import torch
         nf, nb = msgs.shape
@@ -207,6 +231,13 @@ class Context:
         op, os_, _ = self._host(out)
         _check(self.lib, self.lib.ced_decode_batch_host(self.h, C.byref(code._c), sp, ss, sshape[0], frame_bits, op,
                                                         os_), "ced_decode_batch_host")
+        return out
+
+    def decode_batch_packed_host(self, code, packed, frame_bits, out):
+        sp, ss, sshape = self._host(packed)
+        op, os_, _ = self._host(out)
+        _check(self.lib, self.lib.ced_decode_batch_packed_host(self.h, C.byref(code._c), sp, ss, sshape[0],
+                                                               frame_bits, op, os_), "ced_decode_batch_packed_host")
         return out
 
     def encode_batch_host(self, code, msgs, out):

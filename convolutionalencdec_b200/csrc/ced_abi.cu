@@ -41,7 +41,8 @@ void setError(const char *fmt, ...)
 
 constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave            */
 constexpr size_t kMaxWaveFrames = 1u << 20;       /* bounds the scheduler state (2 KB per 32 frames) */
-constexpr int kHostChunkFrames = 16384;           /* frames per H2D/kernel/D2H pipeline stage */
+constexpr int kHostChunkFrames = 8192;            /* frames per H2D/kernel/D2H pipeline stage */
+constexpr int kPipeDepth = 4;                     /* chunks in flight in the host pipeline      */
 constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
 
 template <typename T>
@@ -128,14 +129,18 @@ struct ced_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;   /* compute */
     cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t inReady[2] = {}, inFree[2] = {}, outReady[2] = {}, outFree[2] = {};
-    DeviceBuf<uint4> scratch;        /* survivor words of the wave in flight */
-    DeviceBuf<uint4> schedState;     /* FwdSched.state */
-    DeviceBuf<int> schedFlags;       /* [0] unit counter, [1 + g] FwdSched.done */
+    cudaEvent_t inReady[kPipeDepth] = {}, inFree[kPipeDepth] = {}, outReady[kPipeDepth] = {}, outFree[kPipeDepth] = {};
+    /* decode working set: slot 0 serves direct calls, slots 1-2 the two chunks the host pipeline keeps
+     * in flight on its two compute streams */
+    struct Work {
+        DeviceBuf<uint4> scratch;    /* survivor words of the wave in flight */
+        DeviceBuf<uint4> schedState; /* FwdSched.state */
+        DeviceBuf<int> schedFlags;   /* [0] unit counter, [1 + g] FwdSched.done */
+    } work[1 + kPipeDepth];
+    cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
     int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel */
-    int fwdFramesPerThread = 1;      /* NF template parameter in use (CED_FWD_FRAMES_PER_THREAD) */
     size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
-    DeviceBuf<uint8_t> hostIn[2], hostOut[2];
+    DeviceBuf<uint8_t> hostIn[kPipeDepth], hostOut[kPipeDepth];
     /* streaming path */
     DeviceBuf<uint8_t> sIn, sOut;
     DeviceBuf<uint32_t> sSurv;
@@ -189,7 +194,8 @@ int ced_ctx_create(int device, ced_ctx **out)
     CED_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CED_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CED_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kPipeDepth; i++) {
+        CED_CUDA(cudaStreamCreateWithFlags(&c->pipe[i], cudaStreamNonBlocking));
         CED_CUDA(cudaEventCreateWithFlags(&c->inReady[i], cudaEventDisableTiming));
         CED_CUDA(cudaEventCreateWithFlags(&c->inFree[i], cudaEventDisableTiming));
         CED_CUDA(cudaEventCreateWithFlags(&c->outReady[i], cudaEventDisableTiming));
@@ -205,16 +211,10 @@ int ced_ctx_create(int device, ced_ctx **out)
         CED_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES");
         c->maxWaveFrames = (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
-        const char *nfEnv = getenv("CED_FWD_FRAMES_PER_THREAD");
-        c->fwdFramesPerThread = (nfEnv && atoi(nfEnv) == 2) ? 2 : 1; /* 2 measured slower: DESIGN.md 6 */
-        if (c->fwdFramesPerThread == 1)
-            CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ced::k7ForwardKernel<Code0113, 1>,
-                                                                   ced::kFwdThreads, 0));
-        else
-            CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, ced::k7ForwardKernel<Code0113, 2>,
-                                                                   ced::kFwdThreads, 0));
+        CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &resident, ced::k7ForwardKernel<Code0113, ced::PackedSymbols>, ced::kFwdThreads, 0));
         const char *env = getenv("CED_FWD_BLOCKS_PER_SM");
-        int perSm = env ? atoi(env) : (c->fwdFramesPerThread == 1 ? 3 : 2);
+        int perSm = env ? atoi(env) : 3; /* 3 warps per sub-partition measured best */
         perSm = std::max(1, std::min(perSm, std::max(1, resident)));
         c->fwdBlocks = sms * perSm;
     }
@@ -228,10 +228,15 @@ void ced_ctx_destroy(ced_ctx *c)
         return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    c->scratch.release();
-    c->schedState.release();
-    c->schedFlags.release();
-    for (int i = 0; i < 2; i++) {
+    for (auto &w : c->work) {
+        w.scratch.release();
+        w.schedState.release();
+        w.schedFlags.release();
+    }
+    for (int i = 0; i < kPipeDepth; i++)
+        if (c->pipe[i])
+            cudaStreamDestroy(c->pipe[i]);
+    for (int i = 0; i < kPipeDepth; i++) {
         c->hostIn[i].release();
         c->hostOut[i].release();
         cudaEventDestroy(c->inReady[i]);
@@ -297,15 +302,16 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
     return groups * 32 * perFrame + groups * 4 * 32 * sizeof(uint4) + (groups + 1) * sizeof(int);
 }
 
-int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                     int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
+                           int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0)
 {
     if (!c || nFrames < 0 || frameBits <= 0 || (frameBits & 7) || (nFrames > 0 && (!dSegs || !dOut))) {
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
     }
     const int T = frameBits + ced::kTailSteps;
-    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+    const size_t rowBytes = packed ? (size_t)(T + 3) / 4 : (size_t)T;
+    if (segStride < rowBytes || outStride < (size_t)(frameBits / 8)) {
         setError("ced_decode_batch: stride shorter than a frame");
         return CED_ERR_ARG;
     }
@@ -323,14 +329,15 @@ int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, s
     size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
     waveMax = waveMax / 64 * 64;
     const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
-    const size_t firstGroups = (firstWave + 63) / 64 * 2; /* 32-frame subgroups, whole 64-frame groups */
-    if (c->scratch.bytes < firstGroups * 32 * perFrame || c->schedState.bytes < firstGroups * 4 * 32 * sizeof(uint4) ||
-        c->schedFlags.bytes < (firstGroups + 1) * sizeof(int)) {
+    const size_t firstGroups = (firstWave + 31) / 32;
+    ced_ctx::Work &wk = c->work[slot];
+    if (wk.scratch.bytes < firstGroups * 32 * perFrame || wk.schedState.bytes < firstGroups * 4 * 32 * sizeof(uint4) ||
+        wk.schedFlags.bytes < (firstGroups + 1) * sizeof(int)) {
         /* growing means freeing: make sure nothing still uses the old blocks */
         CED_CUDA(cudaDeviceSynchronize());
-        int rc = c->scratch.ensure(firstGroups * 32 * perFrame);
-        if (rc == CED_OK) rc = c->schedState.ensure(firstGroups * 4 * 32 * sizeof(uint4));
-        if (rc == CED_OK) rc = c->schedFlags.ensure((firstGroups + 1) * sizeof(int));
+        int rc = wk.scratch.ensure(firstGroups * 32 * perFrame);
+        if (rc == CED_OK) rc = wk.schedState.ensure(firstGroups * 4 * 32 * sizeof(uint4));
+        if (rc == CED_OK) rc = wk.schedFlags.ensure((firstGroups + 1) * sizeof(int));
         if (rc != CED_OK)
             return rc;
     }
@@ -340,41 +347,76 @@ int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, s
         const bool prof = c->profiling && c->profWaves < ced_ctx::kMaxProfWaves;
         const int pw = c->profWaves;
         const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
-        const int nf = c->fwdFramesPerThread;
-        const int groups = (wave + 32 * nf - 1) / (32 * nf);
-        const int warpsNeeded = groups; /* more persistent warps than groups would only spin */
-        const int blocks = std::max(1, std::min(c->fwdBlocks, (warpsNeeded + 3) / 4));
+        const int groups = (wave + 31) / 32;
+        /* more persistent warps than groups would only spin */
+        const int blocks = std::max(1, std::min(c->fwdBlocks, (groups + 3) / 4));
         const uint8_t *in = dSegs + f0 * segStride;
         uint8_t *out = dOut + f0 * outStride;
         ced::FwdSched sched;
-        sched.counter = reinterpret_cast<unsigned int *>(c->schedFlags.p);
-        sched.done = c->schedFlags.p + 1;
-        sched.state = c->schedState.p;
-        CED_CUDA(cudaMemsetAsync(c->schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
+        sched.counter = reinterpret_cast<unsigned int *>(wk.schedFlags.p);
+        sched.done = wk.schedFlags.p + 1;
+        sched.state = wk.schedState.p;
+        CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
-        if (id == CodeId::K7_0113_0171 && nf == 2)
-            ced::k7ForwardKernel<Code0113, 2><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                                aligned16, c->bm0113, sched);
+        const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
+#define CED_LAUNCH_FWD(CODE, FMT)                                                                              \
+    ced::k7ForwardKernel<CODE, ced::FMT><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, wk.scratch.p, \
+                                                                              aligned16, bm, sched)
+        if (id == CodeId::K7_0113_0171 && !packed)
+            CED_LAUNCH_FWD(Code0113, ByteSymbols);
         else if (id == CodeId::K7_0113_0171)
-            ced::k7ForwardKernel<Code0113, 1><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                                aligned16, c->bm0113, sched);
-        else if (nf == 2)
-            ced::k7ForwardKernel<Code0133, 2><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                                aligned16, c->bm0133, sched);
+            CED_LAUNCH_FWD(Code0113, PackedSymbols);
+        else if (!packed)
+            CED_LAUNCH_FWD(Code0133, ByteSymbols);
         else
-            ced::k7ForwardKernel<Code0133, 1><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, c->scratch.p,
-                                                                                aligned16, c->bm0133, sched);
+            CED_LAUNCH_FWD(Code0133, PackedSymbols);
+#undef CED_LAUNCH_FWD
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
         ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
-            c->scratch.p, wave, T, out, outStride);
+            wk.scratch.p, wave, T, out, outStride);
         if (prof) {
             CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
             c->profWaves++;
         }
         c->launches += 2;
     }
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                     int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    return decodeBatchImpl(c, code, false, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+}
+
+int ced_decode_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
+                            int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    return decodeBatchImpl(c, code, true, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
+}
+
+int ced_pack_symbols(ced_ctx *c, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
+                     uint8_t *dPacked, size_t packedStride, void *stream)
+{
+    if (!c || nFrames < 0 || segsPerFrame <= 0 || (nFrames > 0 && (!dSegs || !dPacked)) ||
+        segStride < (size_t)segsPerFrame || packedStride < (size_t)(segsPerFrame + 3) / 4) {
+        setError("ced_pack_symbols: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int aligned = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(dPacked) & 3u) == 0 && (packedStride & 3u) == 0) ? 1 : 0;
+    ced::packSymbolsKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        dSegs, segStride, nFrames, segsPerFrame, dPacked, packedStride, aligned);
+    c->launches += 1;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
 }
@@ -491,14 +533,16 @@ int ced_encode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, si
 }
 
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
-static int hostPipeline(ced_ctx *c, const ced_code_t *code, bool encode, const uint8_t *hIn, size_t inStride,
+enum class HostOp { Encode, Decode, DecodePacked };
+
+static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
                         size_t outRowBytes)
 {
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     const int chunk = std::min(nFrames, kHostChunkFrames);
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < kPipeDepth; b++) {
         int rc = c->hostIn[b].ensure((size_t)chunk * inStride + 16);
         if (rc == CED_OK)
             rc = c->hostOut[b].ensure((size_t)chunk * outStride + 16);
@@ -507,35 +551,37 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, bool encode, const u
     }
     int idx = 0;
     for (int f0 = 0; f0 < nFrames; f0 += chunk, idx++) {
-        const int b = idx & 1;
+        const int b = idx % kPipeDepth;
+        cudaStream_t cs = c->pipe[b]; /* consecutive chunks run on different compute streams, so their
+                                         (small, latency-bound) kernels overlap on the GPU */
         const int cnt = std::min(chunk, nFrames - f0);
         const size_t inBytes = (size_t)(cnt - 1) * inStride + inRowBytes;
         const size_t outBytes = (size_t)(cnt - 1) * outStride + outRowBytes;
-        if (idx >= 2)
+        if (idx >= kPipeDepth)
             CED_CUDA(cudaStreamWaitEvent(c->h2d, c->inFree[b], 0));
         CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, hIn + (size_t)f0 * inStride, inBytes, cudaMemcpyHostToDevice, c->h2d));
         CED_CUDA(cudaEventRecord(c->inReady[b], c->h2d));
-        CED_CUDA(cudaStreamWaitEvent(c->stream, c->inReady[b], 0));
-        if (idx >= 2)
-            CED_CUDA(cudaStreamWaitEvent(c->stream, c->outFree[b], 0));
+        CED_CUDA(cudaStreamWaitEvent(cs, c->inReady[b], 0));
+        if (idx >= kPipeDepth)
+            CED_CUDA(cudaStreamWaitEvent(cs, c->outFree[b], 0));
         int rc;
-        if (encode)
-            rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride,
-                                  c->stream);
+        if (op == HostOp::Encode)
+            rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride, cs);
         else
-            rc = ced_decode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride,
-                                  c->stream);
+            rc = decodeBatchImpl(c, code, op == HostOp::DecodePacked, c->hostIn[b].p, inStride, cnt, frameParam,
+                                 c->hostOut[b].p, outStride, cs, 1 + b);
         if (rc != CED_OK)
             return rc;
-        CED_CUDA(cudaEventRecord(c->inFree[b], c->stream));
-        CED_CUDA(cudaEventRecord(c->outReady[b], c->stream));
+        CED_CUDA(cudaEventRecord(c->inFree[b], cs));
+        CED_CUDA(cudaEventRecord(c->outReady[b], cs));
         CED_CUDA(cudaStreamWaitEvent(c->d2h, c->outReady[b], 0));
         CED_CUDA(cudaMemcpyAsync(hOut + (size_t)f0 * outStride, c->hostOut[b].p, outBytes, cudaMemcpyDeviceToHost,
                                  c->d2h));
         CED_CUDA(cudaEventRecord(c->outFree[b], c->d2h));
     }
     CED_CUDA(cudaStreamSynchronize(c->d2h));
-    CED_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < kPipeDepth; i++)
+        CED_CUDA(cudaStreamSynchronize(c->pipe[i]));
     return CED_OK;
 }
 
@@ -548,8 +594,22 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     }
     if (nFrames == 0)
         return CED_OK;
-    return hostPipeline(c, code, false, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames, frameBits, hOut,
-                        outStride, (size_t)frameBits / 8);
+    return hostPipeline(c, code, HostOp::Decode, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
+                        frameBits, hOut, outStride, (size_t)frameBits / 8);
+}
+
+int ced_decode_batch_packed_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hPacked, size_t packedStride,
+                                 int nFrames, int frameBits, uint8_t *hOut, size_t outStride)
+{
+    if (!c || !code || !hPacked || !hOut || nFrames < 0 || frameBits <= 0 || (frameBits & 7)) {
+        setError("ced_decode_batch_packed_host: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    return hostPipeline(c, code, HostOp::DecodePacked, hPacked, packedStride,
+                        ((size_t)frameBits + code->constraintLen - 1 + 3) / 4, nFrames, frameBits, hOut, outStride,
+                        (size_t)frameBits / 8);
 }
 
 int ced_encode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride, int nFrames,
@@ -561,7 +621,7 @@ int ced_encode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hMs
     }
     if (nFrames == 0)
         return CED_OK;
-    return hostPipeline(c, code, true, hMsg, msgStride, (size_t)frameBytes, nFrames, frameBytes, hSegs, segStride,
+    return hostPipeline(c, code, HostOp::Encode, hMsg, msgStride, (size_t)frameBytes, nFrames, frameBytes, hSegs, segStride,
                         (size_t)frameBytes * 8 + code->constraintLen - 1);
 }
 

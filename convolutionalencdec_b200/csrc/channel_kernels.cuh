@@ -111,6 +111,46 @@ bscChannelKernel(uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame,
     }
 }
 
+/* byte-per-segment symbols -> packed symbols (4 per byte, segment t in bits 2*(t%4).. of byte t/4).
+ * One thread packs 16 segments into one 32-bit word. */
+__global__ void __launch_bounds__(256)
+packSymbolsKernel(const uint8_t *__restrict__ segs, size_t segStride, int nFrames, int segsPerFrame,
+                  uint8_t *__restrict__ packed, size_t packedStride, int aligned)
+{
+    const int chunksPerFrame = (segsPerFrame + 15) / 16;
+    const long long total = (long long)nFrames * chunksPerFrame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / chunksPerFrame;
+        const int c = (int)(i - f * chunksPerFrame);
+        const uint8_t *src = segs + (size_t)f * segStride + 16 * (size_t)c;
+        const int cnt = min(16, segsPerFrame - 16 * c);
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (aligned && (size_t)(16 * c + 16) <= segStride) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            for (int s2 = 0; s2 < cnt; s2++)
+                w[s2 >> 2] |= (uint32_t)src[s2] << (8 * (s2 & 3));
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t m = w[q] & 0x03030303u;                 /* 4 segments, 2 bits each, one per byte */
+            const uint32_t b = (m | (m >> 6) | (m >> 12) | (m >> 18)) & 0xFFu;
+            out |= b << (8 * q);
+        }
+        uint8_t *dst = packed + (size_t)f * packedStride + 4 * (size_t)c;
+        const int bytes = (cnt + 3) / 4;
+        if (aligned && bytes == 4) {
+            *reinterpret_cast<uint32_t *>(dst) = out;
+        } else {
+            for (int b2 = 0; b2 < bytes; b2++)
+                dst[b2] = (uint8_t)(out >> (8 * b2));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 randomBytesKernel(uint8_t *msg, size_t msgStride, int nFrames, int frameBytes, uint64_t seed, uint64_t firstFrame)
 {

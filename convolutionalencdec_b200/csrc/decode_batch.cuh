@@ -23,9 +23,25 @@
 namespace ced {
 
 constexpr int kFwdThreads = 128;          /* 4 warps, one per SM sub-partition          */
-constexpr int kChunk = 96;                /* segments staged per tile row (16 x 6 steps) */
-constexpr int kPitch = kChunk + 16;       /* bytes per tile row in shared memory         */
 constexpr int kTailSteps = 6;             /* S = K-1                                     */
+
+/*
+ * Wire formats of the coded symbols.
+ *   ByteSymbols  : the reference's format, one byte per 2-bit segment, c0 | c1<<1
+ *                  (src/viterbiDecoder.h:154); only bits 0-1 of a byte are used.
+ *   PackedSymbols: four segments per byte, segment t in bits 2*(t%4)..2*(t%4)+1 of byte t/4
+ *                  (a quarter of the HBM / PCIe bytes).
+ * kChunk = trellis steps per work unit / per staged tile row; one 16-byte global piece carries
+ * 16 (byte) or 64 (packed) segments, and kChunk is a whole number of pieces and of 96 steps.
+ */
+struct ByteSymbols {
+    static constexpr int kSegsPerByte = 1;
+    static constexpr int kChunk = 96;
+};
+struct PackedSymbols {
+    static constexpr int kSegsPerByte = 4;
+    static constexpr int kChunk = 192;
+};
 
 struct BmTable {
     uint4 x[6 * 4 * 2]; /* [phase][rx] -> X[0..3], E[0..3] (E[k] = X[k^3] - X[k] + guardWord(phase)) */
@@ -51,35 +67,54 @@ inline BmTable makeBmTable()
     return t;
 }
 
+/* four byte-format segments per word -> four table offsets: keep the n=2 low bits
+ * (calcHammingDist(..., n), src/viterbiDecoder.c:279-283) and scale by the 32-byte table entry */
 __device__ __forceinline__ uint32_t toBmOffset(uint32_t w)
 {
-    /* four segments per word: keep the n=2 low bits (calcHammingDist(..., n),
-     * src/viterbiDecoder.c:279-283) and scale by the 32-byte table entry */
     return (w & 0x03030303u) << 5;
 }
-
-constexpr int kPiecesPerRow = kChunk / 16;             /* 16-byte pieces per tile row (6) = pieces per lane per 32 rows */
-
-/* Fast path (rows 16-byte aligned): fetch this lane's 6 pieces of segments [t0, t0+kChunk) of the
- * warp's 32 frames into registers.  Issued one chunk ahead of use so the HBM latency (18 % of warp
- * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current chunk. */
-template <int NP>
-__device__ __forceinline__ void loadTileAligned(uint4 (&v)[NP], const uint8_t *__restrict__ segs, size_t stride,
-                                                long long frame0, int nFrames, int t0, int T, int lane)
+/* one packed byte b = [s3 s2 s1 s0] -> four table offsets (s_j * 32 in byte j).  The even and the odd
+ * segments are spread by separate multiplies so that the shifted copies never overlap (a single
+ * multiply would carry between them). */
+__device__ __forceinline__ uint32_t packedToBmOffsets(uint32_t b)
 {
+    const uint32_t x = (b & 0x33u) * (0x1001u << 5);   /* s0 -> bits 5-6,   s2 -> bits 21-22 */
+    const uint32_t y = (b & 0xCCu) * (0x40040u << 5);  /* s1 -> bits 13-14, s3 -> bits 29-30 */
+    return (x & 0x00600060u) | (y & 0x60006000u);
+}
+
+template <class Fmt>
+struct TileGeom {
+    static constexpr int kChunk = Fmt::kChunk;
+    static constexpr int kPitch = kChunk + 16;                         /* bytes per tile row in shared memory */
+    static constexpr int kSegsPerPiece = 16 * Fmt::kSegsPerByte;       /* segments in one 16-byte global piece */
+    static constexpr int kPiecesPerRow = kChunk / kSegsPerPiece;       /* = pieces per lane per 32-row tile    */
+    static constexpr int kBytesPerRow = kChunk / Fmt::kSegsPerByte;    /* wire bytes of one tile row           */
+};
+
+/* Fast path (rows 16-byte aligned): fetch this lane's pieces of segments [t0, t0+kChunk) of the
+ * group's 32 frames into registers.  Issued one unit ahead of use so the HBM latency (18 % of warp
+ * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current unit. */
+template <class Fmt>
+__device__ __forceinline__ void loadTileAligned(uint4 (&v)[TileGeom<Fmt>::kPiecesPerRow], const uint8_t *__restrict__ segs,
+                                                size_t stride, long long frame0, int nFrames, int t0, int T, int lane)
+{
+    using G = TileGeom<Fmt>;
+    const int rowBytes = (T + Fmt::kSegsPerByte - 1) / Fmt::kSegsPerByte;   /* valid wire bytes per frame */
 #pragma unroll
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < G::kPiecesPerRow; i++) {
         const int piece = i * 32 + lane;
-        const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
+        const int row = piece / G::kPiecesPerRow, pc = piece % G::kPiecesPerRow;
         const long long f = frame0 + row;
+        const int byteOff = t0 / Fmt::kSegsPerByte + pc * 16;
         v[i] = make_uint4(0, 0, 0, 0);
-        if (f < nFrames && t0 + col < T) {
-            const uint8_t *src = segs + (size_t)f * stride + (size_t)(t0 + col);
-            if ((size_t)(t0 + col + 16) <= stride) {
+        if (f < nFrames && byteOff < rowBytes) {
+            const uint8_t *src = segs + (size_t)f * stride + (size_t)byteOff;
+            if ((size_t)(byteOff + 16) <= stride) {
                 v[i] = __ldg(reinterpret_cast<const uint4 *>(src));
             } else { /* last piece of a row whose stride is not padded: never read past the row */
                 uint32_t w[4] = {0, 0, 0, 0};
-                for (int b = 0; b < 16 && t0 + col + b < T; b++)
+                for (int b = 0; b < 16 && byteOff + b < rowBytes; b++)
                     w[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
                 v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -87,38 +122,47 @@ __device__ __forceinline__ void loadTileAligned(uint4 (&v)[NP], const uint8_t *_
     }
 }
 
-template <int NP>
-__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[NP], int lane)
+template <class Fmt>
+__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[TileGeom<Fmt>::kPiecesPerRow], int lane)
 {
+    using G = TileGeom<Fmt>;
 #pragma unroll
-    for (int i = 0; i < NP; i++) {
+    for (int i = 0; i < G::kPiecesPerRow; i++) {
         const int piece = i * 32 + lane;
-        const int row = piece / (kChunk / 16), col = (piece % (kChunk / 16)) * 16;
-        uint4 w = v[i];
-        w.x = toBmOffset(w.x);
-        w.y = toBmOffset(w.y);
-        w.z = toBmOffset(w.z);
-        w.w = toBmOffset(w.w);
-        *reinterpret_cast<uint4 *>(tile + row * kPitch + col) = w;
+        const int row = piece / G::kPiecesPerRow, pc = piece % G::kPiecesPerRow;
+        uint8_t *dst = tile + row * G::kPitch + pc * G::kSegsPerPiece;
+        const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        if (Fmt::kSegsPerByte == 1) {
+            *reinterpret_cast<uint4 *>(dst) =
+                make_uint4(toBmOffset(w[0]), toBmOffset(w[1]), toBmOffset(w[2]), toBmOffset(w[3]));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) /* each word: 4 packed bytes = 16 segments = one uint4 of offsets */
+                *reinterpret_cast<uint4 *>(dst + 16 * q) =
+                    make_uint4(packedToBmOffsets(w[q] & 0xFFu), packedToBmOffsets((w[q] >> 8) & 0xFFu),
+                               packedToBmOffsets((w[q] >> 16) & 0xFFu), packedToBmOffsets(w[q] >> 24));
+        }
     }
 }
 
 /* Generic path (any base / stride alignment): byte loads, staged just in time. */
-__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, int rows, const uint8_t *__restrict__ segs,
-                                                   size_t stride, long long frame0, int nFrames, int t0, int T, int lane)
+template <class Fmt>
+__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, const uint8_t *__restrict__ segs, size_t stride,
+                                                   long long frame0, int nFrames, int t0, int T, int lane)
 {
-    for (int row = 0; row < rows; row++) {
+    using G = TileGeom<Fmt>;
+    const int rowBytes = (T + Fmt::kSegsPerByte - 1) / Fmt::kSegsPerByte;
+    for (int row = 0; row < 32; row++) {
         const long long f = frame0 + row;
-        if (lane < kChunk / 4) {
-            uint32_t w = 0;
-            if (f < nFrames) {
-                const uint8_t *src = segs + (size_t)f * stride + (size_t)t0 + 4 * lane;
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (t0 + 4 * lane + b < T)
-                        w |= (uint32_t)__ldg(src + b) << (8 * b);
-            }
-            *reinterpret_cast<uint32_t *>(tile + row * kPitch + 4 * lane) = toBmOffset(w);
+        for (int b = lane; b < G::kBytesPerRow; b += 32) {
+            const int byteOff = t0 / Fmt::kSegsPerByte + b;
+            uint32_t v = 0;
+            if (f < nFrames && byteOff < rowBytes)
+                v = __ldg(segs + (size_t)f * stride + (size_t)byteOff);
+            if (Fmt::kSegsPerByte == 1)
+                tile[row * G::kPitch + b] = (uint8_t)((v & 3u) << 5);
+            else
+                *reinterpret_cast<uint32_t *>(tile + row * G::kPitch + 4 * b) = packedToBmOffsets(v);
         }
     }
 }
@@ -159,23 +203,19 @@ __device__ __forceinline__ void stRelease(int *p, int v)
  * Persistent forward kernel: gridDim.x * 4 warps, each looping over units.  Why not simply one
  * thread per frame for the whole frame: 2^16 frames are 2048 warps for 592 SM sub-partitions,
  * 3.46 per SMSP, so a static assignment leaves the 3-warp SMSPs idle for the last 13.5 % of the
- * launch (profiles/r1_v4: ALU pipe 77 % while active, 67 % of elapsed).  With units of 96 steps the
- * tail shrinks to one chunk in 43.
- *
- * NF = frames per thread.  With NF = 2 a lane runs two independent frames (lane and lane+32 of a
- * 64-frame group) through the same straight-line code: the two dependency chains interleave, so a
- * single warp can issue nearly every cycle and alternate ALU- and FMA-pipe instructions even when a
- * sub-partition holds only one or two warps.
+ * launch (profiles/r1_v4: ALU pipe 77 % while active, 67 % of elapsed).  With 3 persistent warps per
+ * SMSP pulling 96-step units the tail shrinks to one unit in 43+.  (Two frames per thread to double
+ * the ILP of the few warps was measured slower: 1.61 ms vs 1.25 ms)
  */
-template <class Code, int NF>
+template <class Code, class Fmt>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
                 int aligned16, BmTable table, FwdSched sched)
 {
-    constexpr int kRows = 32 * NF;             /* tile rows (frames) per warp */
-    constexpr int kPieces = kPiecesPerRow * NF; /* 16-byte pieces per lane and tile */
+    using G = TileGeom<Fmt>;
+    constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
     __shared__ uint4 sBm[6 * 4 * 2];
-    __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][kRows * kPitch];
+    __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
 
     if (threadIdx.x < 48)
         sBm[threadIdx.x] = table.x[threadIdx.x];
@@ -187,7 +227,7 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
     const uint32_t minusOne = table.minusOne;
     const size_t pairs = (size_t)(T / 2);
-    const unsigned groups = (unsigned)((nFrames + kRows - 1) / kRows);
+    const unsigned groups = (unsigned)((nFrames + 31) / 32);
     const unsigned chunks = (unsigned)((T + kChunk - 1) / kChunk);
     const unsigned total = groups * chunks;
 
@@ -199,27 +239,20 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     };
 
     unsigned u = grab();
-    uint4 pre[kPieces];
+    uint4 pre[G::kPiecesPerRow];
     if (u < total && aligned16)
-        loadTileAligned(pre, segs, stride, (long long)kRows * (u % groups), nFrames, (int)(u / groups) * kChunk, T,
-                        lane);
+        loadTileAligned<Fmt>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)(u / groups) * kChunk, T, lane);
 
     while (u < total) {
         const unsigned g = u % groups, c = u / groups;
-        const long long frame0 = (long long)kRows * g;
+        const long long frame0 = 32LL * g;
         const int t0 = (int)c * kChunk;
-        bool live[NF];
-#pragma unroll
-        for (int f = 0; f < NF; f++)
-            live[f] = frame0 + 32 * f + lane < nFrames;
-        /* 32-frame subgroup g*NF + f owns state slot and survivor stream number g*NF + f */
-        uint4 *stateSlot = sched.state + ((size_t)g * NF * 4) * 32 + lane;
+        const bool live = frame0 + lane < nFrames;
+        uint4 *stateSlot = sched.state + ((size_t)g * 4) * 32 + lane;
 
-        uint32_t R[NF][16];
+        uint32_t R[16];
         if (c == 0) {
-#pragma unroll
-            for (int f = 0; f < NF; f++)
-                initMetrics(R[f]);
+            initMetrics(R);
         } else {
             if (lane == 0)
                 while (ldAcquire(sched.done + g) < (int)c)
@@ -227,94 +260,71 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
             __syncwarp();
             __threadfence();
 #pragma unroll
-            for (int f = 0; f < NF; f++)
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint4 v = __ldcg(stateSlot + (f * 4 + i) * 32);
-                    R[f][4 * i] = v.x;
-                    R[f][4 * i + 1] = v.y;
-                    R[f][4 * i + 2] = v.z;
-                    R[f][4 * i + 3] = v.w;
-                }
+            for (int i = 0; i < 4; i++) {
+                const uint4 v = __ldcg(stateSlot + i * 32);
+                R[4 * i] = v.x;
+                R[4 * i + 1] = v.y;
+                R[4 * i + 2] = v.z;
+                R[4 * i + 3] = v.w;
+            }
         }
 
         __syncwarp();
         if (aligned16)
-            storeTileAligned(tile, pre, lane);
+            storeTileAligned<Fmt>(tile, pre, lane);
         else
-            stageTileUnaligned(tile, kRows, segs, stride, frame0, nFrames, t0, T, lane);
-        /* next unit: claim it now so its symbol tile streams in during this chunk's ACS work */
+            stageTileUnaligned<Fmt>(tile, segs, stride, frame0, nFrames, t0, T, lane);
+        /* next unit: claim it now so its symbol tile streams in during this unit's ACS work */
         const unsigned un = grab();
         if (un < total && aligned16)
-            loadTileAligned(pre, segs, stride, (long long)kRows * (un % groups), nFrames, (int)(un / groups) * kChunk,
-                            T, lane);
+            loadTileAligned<Fmt>(pre, segs, stride, 32LL * (un % groups), nFrames, (int)(un / groups) * kChunk, T,
+                                 lane);
         __syncwarp();
 
-        /* survivor layout: one stream per 32-frame subgroup, (T/2) consecutive 512-byte rows (one uint4
-         * per lane and step pair), so this kernel's stores and the traceback's loads are sequential. */
-        uint4 *o = surv + ((size_t)g * NF * pairs + (size_t)(t0 / 2)) * 32 + lane;
-        const size_t oStride = pairs * 32; /* between the subgroups of this thread */
+        /* survivor layout: one stream per 32-frame group, (T/2) consecutive 512-byte rows (one uint4 per
+         * lane and step pair), so this kernel's stores and the traceback's loads are sequential. */
+        uint4 *o = surv + ((size_t)g * pairs + (size_t)(t0 / 2)) * 32 + lane;
         const int steps = min(kChunk, T - t0);
-        const int full = steps / 6;
         const uint8_t *p = myRow;
-        for (int it = 0; it < full; it++) {
-            uint4 s[NF];
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
-                fwdStep<Code, 0>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
-                fwdStep<Code, 1>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
-            }
-#pragma unroll
-            for (int f = 0; f < NF; f++)
-                if (live[f]) o[f * oStride] = s[f];
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
-                fwdStep<Code, 2>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
-                fwdStep<Code, 3>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
-            }
-#pragma unroll
-            for (int f = 0; f < NF; f++)
-                if (live[f]) o[f * oStride + 32] = s[f];
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
-                fwdStep<Code, 4>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].x, s[f].y);
-                fwdStep<Code, 5>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s[f].z, s[f].w);
-            }
-#pragma unroll
-            for (int f = 0; f < NF; f++)
-                if (live[f]) o[f * oStride + 64] = s[f];
-            p += 6;
-            o += 96;
-        }
-        /* T is even, so the remainder is 0, 2 or 4 steps (last chunk only) */
-        const int rem = steps - 6 * full;
-        if (rem >= 2) {
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
+        for (int done = 0; done < steps;) {
+            const int n = min(kRenormPeriod, steps - done);
+            const int full = n / 6;
+            for (int it = 0; it < full; it++) {
                 uint4 s;
-                fwdStep<Code, 0>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.x, s.y);
-                fwdStep<Code, 1>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.z, s.w);
-                if (live[f]) o[f * oStride] = s;
+                fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
+                fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
+                if (live) o[0] = s;
+                fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
+                fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
+                if (live) o[32] = s;
+                fwdStep<Code, 4>(R, bmBase, p, minusOne, s.x, s.y);
+                fwdStep<Code, 5>(R, bmBase, p, minusOne, s.z, s.w);
+                if (live) o[64] = s;
+                p += 6;
+                o += 96;
             }
-        }
-        if (rem >= 4) {
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
+            /* T is even, so the remainder is 0, 2 or 4 steps (end of the frame only) */
+            const int rem = n - 6 * full;
+            if (rem >= 2) {
                 uint4 s;
-                fwdStep<Code, 2>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.x, s.y);
-                fwdStep<Code, 3>(R[f], bmBase, p + f * 32 * kPitch, minusOne, s.z, s.w);
-                if (live[f]) o[f * oStride + 32] = s;
+                fwdStep<Code, 0>(R, bmBase, p, minusOne, s.x, s.y);
+                fwdStep<Code, 1>(R, bmBase, p, minusOne, s.z, s.w);
+                if (live) o[0] = s;
             }
+            if (rem >= 4) {
+                uint4 s;
+                fwdStep<Code, 2>(R, bmBase, p, minusOne, s.x, s.y);
+                fwdStep<Code, 3>(R, bmBase, p, minusOne, s.z, s.w);
+                if (live) o[32] = s;
+            }
+            done += n;
+            if (done < steps || c + 1 < chunks)
+                renorm(R); /* every kRenormPeriod = 96 steps, see DESIGN.md 4.3 */
         }
         if (c + 1 < chunks) {
 #pragma unroll
-            for (int f = 0; f < NF; f++) {
-                renorm(R[f]); /* every kChunk = kRenormPeriod steps, see DESIGN.md 4.3 */
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    __stcg(stateSlot + (f * 4 + i) * 32,
-                           make_uint4(R[f][4 * i], R[f][4 * i + 1], R[f][4 * i + 2], R[f][4 * i + 3]));
-            }
+            for (int i = 0; i < 4; i++)
+                __stcg(stateSlot + i * 32, make_uint4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]));
             __threadfence();
             __syncwarp();
             if (lane == 0)

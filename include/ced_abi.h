@@ -98,6 +98,17 @@ int ced_decode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs,
 int ced_encode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride,
                      int nFrames, int frameBytes, uint8_t *dSegs, size_t segStride, void *stream);
 
+/* Packed wire format (not in the reference): four 2-bit segments per byte, segment t
+ * in bits 2*(t%4)..2*(t%4)+1 of byte t/4, rows of ceil((frameBits+K-1)/4) valid bytes.  A quarter of
+ * the HBM and PCIe bytes of the byte-per-segment format; decoded output is identical.
+ * ced_pack_symbols converts byte-per-segment symbols (low 2 bits) to this format on the device. */
+int ced_decode_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
+                            int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream);
+int ced_decode_batch_packed_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hPacked, size_t packedStride,
+                                 int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
+int ced_pack_symbols(ced_ctx *ctx, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
+                     uint8_t *dPacked, size_t packedStride, void *stream);
+
 /* Same operations on HOST buffers: pinned staging, chunked H2D / kernel / D2H
  * pipelined on two streams.  Synchronous: returns when hOut / hSegs is complete. */
 int ced_decode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hSegs, size_t segStride,

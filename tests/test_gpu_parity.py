@@ -96,6 +96,58 @@ def test_decode_batch_rejects_what_it_cannot_do(torch_cuda, ctx):
     assert out.shape[0] == 0
 
 
+# ------------------------------------------------------------------ packed wire format
+def np_pack(segs, T):
+    """numpy model of the packed format: segment t -> bits 2*(t%4).. of byte t/4."""
+    nf = segs.shape[0]
+    padded = np.zeros((nf, (T + 3) // 4 * 4), dtype=np.uint8)
+    padded[:, :T] = segs[:, :T] & 3
+    q = padded.reshape(nf, -1, 4)
+    return (q[..., 0] | (q[..., 1] << 2) | (q[..., 2] << 4) | (q[..., 3] << 6)).astype(np.uint8)
+
+
+@pytest.mark.parametrize("bits,frames,stride_pad,offset", [
+    (8, 1, 0, 0), (16, 5, 0, 0), (40, 33, 1, 0), (184, 127, 3, 0), (192, 128, 0, 0), (376, 129, 2, 1),
+    (2048, 257, 16 - (514 % 16), 0), (4096, 300, 16 - (1026 % 16), 0), (4096, 70, 0, 0), (16384, 9, 7, 0),
+])
+def test_packed_format_pack_and_decode(torch_cuda, ctx, port, bits, frames, stride_pad, offset):
+    """No reference oracle exists for this format; it is pinned by: device pack == numpy pack of the
+    byte symbols, and decode(packed) == decode(bytes) == oracle, on aligned and unaligned rows."""
+    torch = torch_cuda
+    rng = np.random.default_rng(bits + 7 * frames)
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    noisy = bsc(rng, port.encode_batch(7, K7, msgs), 0.06, junk_upper_bits=True)
+    want = port.decode_batch(7, K7, noisy, T)
+    d_noisy = dev(torch, noisy)
+    pb = (T + 3) // 4
+    packed = ctx.pack_symbols(d_noisy, T)
+    ctx.sync()
+    assert np.array_equal(packed.cpu().numpy(), np_pack(noisy, T))
+    stride = pb + stride_pad
+    flat = torch.full((frames * stride + offset + 64,), 0xFF, dtype=torch.uint8, device="cuda")
+    view = flat[offset:offset + frames * stride].view(frames, stride)
+    view[:, :pb] = packed
+    out = ctx.decode_batch_packed(ced.K7_DEFAULT, view, bits)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_packed_host_pipeline(torch_cuda, ctx, port):
+    torch = torch_cuda
+    rng = np.random.default_rng(33)
+    frames, bits = 40000, 256
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    noisy = bsc(rng, port.encode_batch(7, K7, msgs), 0.04)
+    packed = np.zeros((frames, 80), dtype=np.uint8)
+    packed[:, :(T + 3) // 4] = np_pack(noisy, T)
+    out = torch.empty((frames, bits // 8), dtype=torch.uint8).pin_memory()
+    ctx.decode_batch_packed_host(ced.K7_DEFAULT, torch.from_numpy(packed).pin_memory(), bits, out)
+    sample = rng.choice(frames, 300, replace=False)
+    assert np.array_equal(out.numpy()[sample], port.decode_batch(7, K7, noisy[sample], T))
+
+
 # ------------------------------------------------------------------ batch encode
 @pytest.mark.parametrize("nbytes,frames,stride_pad", [(1, 1, 0), (2, 5, 0), (3, 40, 3), (32, 100, 10), (256, 257, 10),
                                                       (512, 300, 10), (512, 64, 0), (2048, 7, 10)])
