@@ -86,6 +86,8 @@ def load_abi():
     lib.ced_decode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_packed_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_pack_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_slice_soft_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_encode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_decode_scratch_bytes.argtypes = [i, i]
@@ -190,6 +192,28 @@ class Context:
         _check(self.lib, self.lib.ced_pack_symbols(self.h, segs.data_ptr(), segs.stride(0), nf, segs_per_frame,
                                                    out.data_ptr(), out.stride(0), _stream_handle(stream)),
                "ced_pack_symbols")
+        return out
+
+    def slice_soft_symbols(self, soft, segs_per_frame, out=None, stream=None, packed_stride=None):
+        """soft: int8 CUDA tensor [frames, >= 2*segs_per_frame] -> packed hard symbols."""
+        import torch
+        nf = soft.shape[0]
+        if out is None:
+            out = torch.zeros((nf, packed_stride or (segs_per_frame + 3) // 4), dtype=torch.uint8, device=soft.device)
+        _check(self.lib, self.lib.ced_slice_soft_symbols(self.h, soft.data_ptr(), soft.stride(0), nf, segs_per_frame,
+                                                         out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_slice_soft_symbols")
+        return out
+
+    def encode_batch_packed(self, code, msgs, out=None, stream=None, packed_stride=None):
+        import torch
+        nf, nb = msgs.shape
+        pb = (8 * nb + code.S + 3) // 4
+        if out is None:
+            out = torch.zeros((nf, packed_stride or pb), dtype=torch.uint8, device=msgs.device)
+        _check(self.lib, self.lib.ced_encode_batch_packed(self.h, C.byref(code._c), msgs.data_ptr(), msgs.stride(0),
+                                                          nf, nb, out.data_ptr(), out.stride(0),
+                                                          _stream_handle(stream)), "ced_encode_batch_packed")
         return out
 
     def encode_batch(self, code, msgs, out=None, stream=None, seg_stride=None):

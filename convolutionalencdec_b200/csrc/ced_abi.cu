@@ -487,7 +487,8 @@ int ced_probe_int_peak(ced_ctx *c, int mode, double *laneOpsPerSecond)
 }
 
 static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
-                        int frameBytes, uint8_t *dSegs, size_t segStride, int tailSegs, uint32_t hist, cudaStream_t s)
+                        int frameBytes, uint8_t *dSegs, size_t segStride, int tailSegs, uint32_t hist, cudaStream_t s,
+                        bool packed = false)
 {
     ced::EncTaps taps;
     for (int i = 0; i < 8; i++)
@@ -496,6 +497,19 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
     if (T == 0)
         return CED_OK;
     const int blocks = (nFrames + ced::kEncFramesPerBlock - 1) / ced::kEncFramesPerBlock;
+    if (packed) {
+        const int aligned4 = ((reinterpret_cast<uintptr_t>(dSegs) & 3u) == 0 && (segStride & 3u) == 0) ? 1 : 0;
+        if (code->constraintLen == 7)
+            ced::encodeBatchKernel<7, 2, true><<<blocks, ced::kEncThreads, 0, s>>>(
+                dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned4);
+        else
+            ced::encodeBatchKernel<0, 2, true><<<blocks, ced::kEncThreads, 0, s>>>(
+                dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, code->constraintLen, 2, taps, hist,
+                aligned4);
+        c->launches += 1;
+        CED_CUDA(cudaGetLastError());
+        return CED_OK;
+    }
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
     if (code->constraintLen == 7 && code->codedBits == 2)
         ced::encodeBatchKernel<7, 2><<<blocks, ced::kEncThreads, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs,
@@ -530,6 +544,53 @@ int ced_encode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, si
     CED_CUDA(cudaSetDevice(c->device));
     return launchEncode(c, code, dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, code->constraintLen - 1, 0u,
                         stream ? (cudaStream_t)stream : c->stream);
+}
+
+int ced_encode_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
+                            int frameBytes, uint8_t *dPacked, size_t packedStride, void *stream)
+{
+    if (!c || !code || nFrames < 0 || frameBytes <= 0 || (nFrames > 0 && (!dMsg || !dPacked))) {
+        setError("ced_encode_batch_packed: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (code->constraintLen < 2 || code->constraintLen > 9 || code->codedBits != 2) {
+        setError("ced_encode_batch_packed: the packed format is defined for n = 2 (K 2..9)");
+        return CED_ERR_UNSUPPORTED;
+    }
+    if (msgStride < (size_t)frameBytes ||
+        packedStride < (size_t)(8 * frameBytes + code->constraintLen - 1 + 3) / 4) {
+        setError("ced_encode_batch_packed: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    return launchEncode(c, code, dMsg, msgStride, nFrames, frameBytes, dPacked, packedStride, code->constraintLen - 1,
+                        0u, stream ? (cudaStream_t)stream : c->stream, true);
+}
+
+int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
+                           uint8_t *dPacked, size_t packedStride, void *stream)
+{
+    if (!c || nFrames < 0 || segsPerFrame <= 0 || (nFrames > 0 && (!dSoft || !dPacked)) ||
+        softStride < (size_t)2 * segsPerFrame || packedStride < (size_t)(segsPerFrame + 3) / 4) {
+        setError("ced_slice_soft_symbols: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int aligned = ((reinterpret_cast<uintptr_t>(dSoft) & 15u) == 0 && (softStride & 15u) == 0 &&
+                         (reinterpret_cast<uintptr_t>(dPacked) & 3u) == 0 && (packedStride & 3u) == 0) ? 1 : 0;
+    ced::sliceSoftSymbolsKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
+        dSoft, softStride, nFrames, segsPerFrame, dPacked, packedStride, aligned);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
 }
 
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */

@@ -151,6 +151,51 @@ packSymbolsKernel(const uint8_t *__restrict__ segs, size_t segStride, int nFrame
     }
 }
 
+/* Soft symbols -> packed hard symbols.  Soft format: two int8 per segment (soft value of coded bit 0,
+ * then of coded bit 1), BPSK convention bit 0 -> +, bit 1 -> - ; the hard decision is the sign bit
+ * (value 0 slices to bit 0).  The reference decodes hard decisions only, so soft input is defined by
+ * this slicing (SURVEY 8c "paths with no oracle").  One thread slices 16 segments (32 bytes). */
+__global__ void __launch_bounds__(256)
+sliceSoftSymbolsKernel(const int8_t *__restrict__ soft, size_t softStride, int nFrames, int segsPerFrame,
+                       uint8_t *__restrict__ packed, size_t packedStride, int aligned)
+{
+    const int chunksPerFrame = (segsPerFrame + 15) / 16;
+    const long long total = (long long)nFrames * chunksPerFrame;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long f = i / chunksPerFrame;
+        const int c = (int)(i - f * chunksPerFrame);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(soft) + (size_t)f * softStride + 32 * (size_t)c;
+        const int cnt = min(16, segsPerFrame - 16 * c);
+        uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (aligned && (size_t)(32 * c + 32) <= softStride) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(src));
+            const uint4 b = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+            for (int b2 = 0; b2 < 2 * cnt; b2++)
+                w[b2 >> 2] |= (uint32_t)src[b2] << (8 * (b2 & 3));
+        }
+        uint32_t out = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {   /* one word = 2 segments -> 4 bits */
+            const uint32_t m = (w[q] >> 7) & 0x01010101u;
+            out |= ((m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xFu) << (4 * q);
+        }
+        if (cnt < 16)
+            out &= (1u << (2 * cnt)) - 1u;
+        uint8_t *dst = packed + (size_t)f * packedStride + 4 * (size_t)c;
+        const int bytes = (cnt + 3) / 4;
+        if (aligned && bytes == 4) {
+            *reinterpret_cast<uint32_t *>(dst) = out;
+        } else {
+            for (int b2 = 0; b2 < bytes; b2++)
+                dst[b2] = (uint8_t)(out >> (8 * b2));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 randomBytesKernel(uint8_t *msg, size_t msgStride, int nFrames, int frameBytes, uint64_t seed, uint64_t firstFrame)
 {

@@ -51,12 +51,38 @@ __device__ __forceinline__ uint4 encode16(uint32_t win, const EncTaps &taps, int
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+/* n = 2 only: the same 16 segments as 4 packed bytes (segment s in bits 2s, 2s+1). */
+__device__ __forceinline__ uint32_t spreadBits16(uint32_t x)
+{
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+template <int KK>
+__device__ __forceinline__ uint32_t encode16Packed(uint32_t win, const EncTaps &taps, int K)
+{
+    const int kk = KK ? KK : K;
+    uint32_t c[2] = {0u, 0u};
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+#pragma unroll
+        for (int d = 0; d < (KK ? KK : 9); d++)
+            if (d < kk)
+                c[g] ^= (0u - ((taps.tap[g] >> d) & 1u)) & (win << d);
+        c[g] >>= 8;
+    }
+    return spreadBits16(c[0]) | (spreadBits16(c[1]) << 1);
+}
+
 /*
  * A CTA encodes kEncFramesPerBlock consecutive frames; its threads stride over the 16-segment
  * chunks of those frames (32-bit index math only).  KK/NN != 0 fix the constraint length and the
  * number of generators at compile time (the K=7 n=2 production code), 0 = run-time values.
  */
-template <int KK, int NN>
+template <int KK, int NN, bool PACKED = false>
 __global__ void __launch_bounds__(kEncThreads)
 encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
                   uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
@@ -80,6 +106,19 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
         const uint32_t b2 = (i0 + 2 < frameBytes) ? __ldg(m + i0 + 2) : 0u;
         /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, src/convEncode.c:91) */
         const uint32_t win = __brev(((b0 << 16) | (b1 << 8) | b2) << 8);
+        if (PACKED) { /* segStride / aligned16 then describe the packed rows (4-byte alignment suffices) */
+            const uint32_t pk = encode16Packed<KK>(win, taps, K);
+            uint8_t *dstp = segs + (size_t)f * segStride + 4 * (size_t)c;
+            const int cnt = min(16, T - 16 * c);
+            if (aligned16 && cnt == 16) {
+                *reinterpret_cast<uint32_t *>(dstp) = pk;
+            } else {
+                const uint32_t keep = cnt == 16 ? pk : (pk & ((1u << (2 * cnt)) - 1u));
+                for (int b2 = 0; b2 < (cnt + 3) / 4; b2++)
+                    dstp[b2] = (uint8_t)(keep >> (8 * b2));
+            }
+            continue;
+        }
         const uint4 v = encode16<KK, NN>(win, taps, K, n);
         uint8_t *dst = segs + (size_t)f * segStride + 16 * (size_t)c;
         if (aligned16 && 16 * c + 16 <= T) {

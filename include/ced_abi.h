@@ -108,6 +108,14 @@ int ced_decode_batch_packed_host(ced_ctx *ctx, const ced_code_t *code, const uin
                                  int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
 int ced_pack_symbols(ced_ctx *ctx, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
                      uint8_t *dPacked, size_t packedStride, void *stream);
+/* Encoder writing the packed format directly (n = 2 codes). */
+int ced_encode_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride,
+                            int nFrames, int frameBytes, uint8_t *dPacked, size_t packedStride, void *stream);
+/* Soft symbols (two int8 per segment: coded bit 0 then coded bit 1; BPSK bit 0 -> +, bit 1 -> -) are
+ * hard-sliced (sign bit; 0 slices to bit 0) into the packed format; decode with ced_decode_batch_packed.
+ * The reference is hard-decision only, so this slicing IS the definition of soft input here. */
+int ced_slice_soft_symbols(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
+                           uint8_t *dPacked, size_t packedStride, void *stream);
 
 /* Same operations on HOST buffers: pinned staging, chunked H2D / kernel / D2H
  * pipelined on two streams.  Synchronous: returns when hOut / hSegs is complete. */

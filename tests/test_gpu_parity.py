@@ -133,6 +133,46 @@ def test_packed_format_pack_and_decode(torch_cuda, ctx, port, bits, frames, stri
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("nbytes,frames,pad", [(1, 3, 0), (5, 40, 1), (32, 129, 2), (512, 200, 14), (2048, 5, 0)])
+def test_packed_encoder_output(torch_cuda, ctx, port, nbytes, frames, pad):
+    torch = torch_cuda
+    rng = np.random.default_rng(nbytes * 3 + frames)
+    msgs = rng.integers(0, 256, (frames, nbytes), dtype=np.uint8)
+    T = 8 * nbytes + 6
+    pb = (T + 3) // 4
+    out = torch.full((frames, pb + pad), 0xEE, dtype=torch.uint8, device="cuda")
+    ctx.encode_batch_packed(ced.K7_DEFAULT, dev(torch, msgs), out=out)
+    ctx.sync()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[:, :pb], np_pack(port.encode_batch(7, K7, msgs), T))
+    assert (got[:, pb:] == 0xEE).all()
+    k3 = ctx.encode_batch_packed(ced.Code(3, (0b111, 0b110)), dev(torch, msgs))
+    ctx.sync()
+    assert np.array_equal(k3.cpu().numpy(), np_pack(port.encode_batch(3, (0b111, 0b110), msgs), 8 * nbytes + 2))
+
+
+@pytest.mark.parametrize("bits,frames,pad", [(8, 2, 0), (40, 33, 3), (256, 129, 4), (4096, 100, 28)])
+def test_soft_symbols_are_hard_sliced(torch_cuda, ctx, port, bits, frames, pad):
+    """Soft input has no reference oracle; it is pinned by 'hard-slicing the soft symbols must reproduce
+    the hard path bit-exactly' (SURVEY 8c): sign = coded bit, any magnitude (0 slices to bit 0)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(bits + frames)
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    noisy = bsc(rng, port.encode_batch(7, K7, msgs), 0.07)
+    mag = rng.integers(0, 128, (frames, T, 2), dtype=np.int16)
+    bit = np.stack([noisy & 1, (noisy >> 1) & 1], axis=-1).astype(np.int16)
+    soft = np.where(bit == 1, -np.maximum(mag, 1), mag).astype(np.int8)       # bit 1 -> negative, bit 0 -> >= 0
+    buf = np.zeros((frames, 2 * T + pad), dtype=np.int8)
+    buf[:, :2 * T] = soft.reshape(frames, 2 * T)
+    packed = ctx.slice_soft_symbols(dev(torch, buf), T)
+    ctx.sync()
+    assert np.array_equal(packed.cpu().numpy(), np_pack(noisy, T))
+    out = ctx.decode_batch_packed(ced.K7_DEFAULT, packed, bits)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy(), port.decode_batch(7, K7, noisy, T))
+
+
 def test_packed_host_pipeline(torch_cuda, ctx, port):
     torch = torch_cuda
     rng = np.random.default_rng(33)
