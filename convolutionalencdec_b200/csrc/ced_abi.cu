@@ -136,9 +136,12 @@ struct ced_ctx {
         DeviceBuf<uint4> scratch;    /* survivor words of the wave in flight */
         DeviceBuf<uint4> schedState; /* FwdSched.state */
         DeviceBuf<int> schedFlags;   /* [0] unit counter, [1 + g] FwdSched.done */
+        cudaEvent_t idle = nullptr;  /* recorded after the last kernel that used this working set */
+        cudaStream_t lastStream = nullptr;
     } work[1 + kPipeDepth];
     cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
-    int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel */
+    int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
+    int sms = 0, fwdResident = 0;
     size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
     DeviceBuf<uint8_t> hostIn[kPipeDepth], hostOut[kPipeDepth];
     /* streaming path */
@@ -204,6 +207,8 @@ int ced_ctx_create(int device, ced_ctx **out)
     for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
         for (int e = 0; e < 3; e++)
             CED_CUDA(cudaEventCreate(&c->prof[w][e]));
+    for (auto &w : c->work)
+        CED_CUDA(cudaEventCreateWithFlags(&w.idle, cudaEventDisableTiming));
     {
         /* persistent forward grid: CED_FWD_BLOCKS_PER_SM CTAs of 4 warps per SM (default 4 = 4 warps per
          * sub-partition), never more than the kernel's resident capacity */
@@ -214,9 +219,9 @@ int ced_ctx_create(int device, ced_ctx **out)
         CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &resident, ced::k7ForwardKernel<Code0113, ced::PackedSymbols>, ced::kFwdThreads, 0));
         const char *env = getenv("CED_FWD_BLOCKS_PER_SM");
-        int perSm = env ? atoi(env) : 3; /* 3 warps per sub-partition measured best */
-        perSm = std::max(1, std::min(perSm, std::max(1, resident)));
-        c->fwdBlocks = sms * perSm;
+        c->sms = sms;
+        c->fwdResident = std::max(1, resident);
+        c->fwdBlocks = env ? sms * std::max(1, std::min(atoi(env), c->fwdResident)) : 0;
     }
     *out = c;
     return CED_OK;
@@ -229,6 +234,8 @@ void ced_ctx_destroy(ced_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &w : c->work) {
+        if (w.idle)
+            cudaEventDestroy(w.idle);
         w.scratch.release();
         w.schedState.release();
         w.schedFlags.release();
@@ -341,6 +348,10 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (rc != CED_OK)
             return rc;
     }
+    /* the working set is shared by all calls on this context: a call on another stream first waits for
+     * the previous one (use one context per stream to keep several decodes in flight) */
+    if (wk.lastStream && wk.lastStream != s)
+        CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
     c->profWaves = 0;
     for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
@@ -348,8 +359,13 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         const int pw = c->profWaves;
         const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
         const int groups = (wave + 31) / 32;
-        /* more persistent warps than groups would only spin */
-        const int blocks = std::max(1, std::min(c->fwdBlocks, (groups + 3) / 4));
+        /* persistent grid: as many 4-warp CTAs per SM as there are 32-frame groups per sub-partition,
+         * between 3 (2^16 frames: 3.46 groups per SMSP; a 4th warp would mostly spin) and 5 (measured:
+         * 2^18 frames 177.8 / 184.7 / 185.8 Gbit/s at 3 / 4 / 5), never more warps than groups */
+        int gridBlocks = c->fwdBlocks;
+        if (gridBlocks == 0)
+            gridBlocks = c->sms * std::max(3, std::min({5, c->fwdResident, groups / (4 * c->sms)}));
+        const int blocks = std::max(1, std::min(gridBlocks, (groups + 3) / 4));
         const uint8_t *in = dSegs + f0 * segStride;
         uint8_t *out = dOut + f0 * outStride;
         ced::FwdSched sched;
@@ -382,6 +398,8 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         }
         c->launches += 2;
     }
+    CED_CUDA(cudaEventRecord(wk.idle, s));
+    wk.lastStream = s;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
 }

@@ -145,8 +145,6 @@ CED_HD uint32_t signMask(uint32_t x) { return prmt(x, 0u, 0xba98u); }
 CED_HD uint32_t sel(uint32_t mask, uint32_t a, uint32_t b) { return (a & mask) | (b & ~mask); }
 
 constexpr uint32_t kGuard = 0x80808080u;
-/* byte-wise minimum of two words whose lanes are all < 128 */
-CED_HD uint32_t byteMinFwd(uint32_t a, uint32_t b) { return sel(signMask(b + kGuard - a), a, b); }
 constexpr uint32_t kInitMetricWord = 0x41414141u; /* NUM_STATES+1 = 65 in every lane (:59-67) */
 
 CED_HD void initMetrics(uint32_t (&R)[16])
@@ -233,100 +231,6 @@ CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], const uint32_t (&
     }
     T0 = t0;
     T1 = t1;
-}
-
-/*
- * Two threads per frame ("split" layout).  Thread h (0/1) of a frame owns the 32 positions with
- * position bit 5 = h in 8 registers; everything else (rotating labels, lane phases, survivor bit
- * layout: word = h, bit 8*(p&3) + ((p>>2)&7)) is as above.  Position bit 5 is the pair bit in
- * phase 0 only, where the partner metrics P[r] come from the other thread (one __shfl_xor_sync per
- * register) and each thread computes only its own half of every butterfly:
- *     thread 0 (state j):     new = min(self + d, partner + (2-d)), tie -> self,  decision = !FF
- *     thread 1 (state j+32):  new = min(self + d, partner + (2-d)), tie -> partner, decision = FF
- * exactly the lane-phase formulation with the lane swap replaced by a shuffle.  In phases 1..5
- * position bit 5 is an ordinary state bit that contributes to the branch-metric class, so the
- * caller passes per-thread tables: Xh[k] = X[k ^ (h ? cls(32, ph) : 0)], Eh[k] = Xh[k^3] - Xh[k] +
- * guard, with guard = 0x80.. / 0x7F.. for thread 0 / 1 in phase 0 and guardWord(ph) otherwise.
- * upperMask = h ? 0xFFFFFFFF : 0 flips the decision polarity of thread 1 in phase 0.
- */
-template <class Code, int PH>
-CED_HD void acsStepSplit(uint32_t (&R)[8], const uint32_t (&P)[8], const uint32_t (&X)[4], const uint32_t (&E)[4],
-                         uint32_t minusOne, uint32_t upperMask, uint32_t &Tw)
-{
-    constexpr int q = 5 - PH;
-    uint32_t t = 0;
-    if constexpr (q == 5) {
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint32_t k = Code::regCls(r, PH);
-            const uint32_t self = R[r] + X[k];
-            const uint32_t cross = P[r] + X[k ^ 3u];
-            const uint32_t m = signMask(subOnFma(P[r], R[r], minusOne) + E[k]);
-            R[r] = sel(m, self, cross);
-            t |= ~m & (0x01010101u << r);
-        }
-        t ^= upperMask;
-    } else if constexpr (q >= 2) {
-        constexpr int rb = q - 2;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            if ((r >> rb) & 1)
-                continue;
-            const int rh = r | (1 << rb);
-            const uint32_t k = Code::regCls(r, PH);
-            const uint32_t d = X[k], dc = X[k ^ 3u];
-            const uint32_t lo = R[r], hi = R[rh];
-            const uint32_t a0 = lo + d, a1 = hi + dc;
-            const uint32_t b0 = lo + dc, b1 = hi + d;
-            const uint32_t delta = subOnFma(hi, lo, minusOne);
-            const uint32_t ma = signMask(delta + E[k]);
-            const uint32_t mb = signMask(delta + E[k ^ 3u]);
-            R[r] = sel(ma, a0, a1);
-            R[rh] = sel(mb, b0, b1);
-            t |= ~ma & (0x01010101u << r);
-            t |= ~mb & (0x01010101u << rh);
-        }
-    } else {
-        constexpr uint32_t swapSel = (q == 1) ? 0x1032u : 0x2301u;
-        constexpr uint32_t upper = (q == 1) ? 0xFFFF0000u : 0xFF00FF00u;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const uint32_t k = Code::regCls(r, PH);
-            const uint32_t self = R[r] + X[k];
-            const uint32_t swapped = prmt(R[r], 0u, swapSel);
-            const uint32_t cross = swapped + X[k ^ 3u];
-            const uint32_t m = signMask(subOnFma(swapped, R[r], minusOne) + E[k]);
-            R[r] = sel(m, self, cross);
-            t |= ~m & (0x01010101u << r);
-        }
-        t ^= upper;
-    }
-    Tw = t;
-}
-
-/* branch-metric class contributed by position bit 5 (the thread bit of the split layout) */
-template <class Code>
-CED_HDC uint32_t threadBitCls(int ph)
-{
-    return Code::cls(32u, ph);
-}
-CED_HDC uint32_t splitGuardWord(int ph, int h)
-{
-    return ph == 0 ? (h ? 0x7F7F7F7Fu : 0x80808080u) : guardWord(ph);
-}
-template <class Code>
-CED_HDC uint32_t splitBmWord(int h, int ph, uint32_t rx, uint32_t k)
-{
-    return Code::bmWord(ph, rx, k ^ (h ? threadBitCls<Code>(ph) : 0u));
-}
-
-CED_HD uint32_t localMin8(const uint32_t (&R)[8])
-{
-    uint32_t v = byteMinFwd(byteMinFwd(byteMinFwd(R[0], R[4]), byteMinFwd(R[1], R[5])),
-                            byteMinFwd(byteMinFwd(R[2], R[6]), byteMinFwd(R[3], R[7])));
-    v = byteMinFwd(v, prmt(v, 0u, 0x1032u));
-    v = byteMinFwd(v, prmt(v, 0u, 0x2301u));
-    return v;
 }
 
 /* Subtract the minimum of the 64 metrics from all of them.  Decisions do not

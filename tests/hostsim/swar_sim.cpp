@@ -59,73 +59,6 @@ extern "C" int swar_sim_decode(const uint8_t *segs, int T, uint8_t *out, uint32_
     return (L + 7) / 8;
 }
 
-// ---- the two-threads-per-frame layout (acsStepSplit), both threads simulated in lock step ----
-template <int PH>
-static void stepSplit(uint32_t (&R)[2][8], uint32_t rx, uint32_t (&t)[2])
-{
-    uint32_t P[2][8];
-    for (int h = 0; h < 2; h++)
-        for (int r = 0; r < 8; r++)
-            P[h][r] = R[1 - h][r];           // what __shfl_xor_sync(.., 1) would deliver
-    for (int h = 0; h < 2; h++) {
-        uint32_t X[4], E[4];
-        for (uint32_t k = 0; k < 4; k++)
-            X[k] = ced::splitBmWord<Code>(h, PH, rx, k);
-        for (uint32_t k = 0; k < 4; k++)
-            E[k] = X[k ^ 3u] - X[k] + ced::splitGuardWord(PH, h);
-        ced::acsStepSplit<Code, PH>(R[h], P[h], X, E, 0xFFFFFFFFu, h ? 0xFFFFFFFFu : 0u, t[h]);
-    }
-}
-
-extern "C" int swar_sim_decode_split(const uint8_t *segs, int T, uint8_t *out, uint32_t *survOut, uint8_t *maxMetric,
-                                     int renormPeriod)
-{
-    uint32_t R[2][8];
-    for (int h = 0; h < 2; h++)
-        for (int r = 0; r < 8; r++)
-            R[h][r] = ced::kInitMetricWord;
-    R[0][0] = ced::kInitMetricWord & 0xFFFFFF00u;
-    std::vector<uint32_t> surv(2 * (size_t)T);
-    uint8_t mx = 0;
-    for (int t = 0; t < T; t++) {
-        uint32_t tw[2] = {0, 0}, rx = segs[t];
-        switch (t % 6) {
-        case 0: stepSplit<0>(R, rx, tw); break;
-        case 1: stepSplit<1>(R, rx, tw); break;
-        case 2: stepSplit<2>(R, rx, tw); break;
-        case 3: stepSplit<3>(R, rx, tw); break;
-        case 4: stepSplit<4>(R, rx, tw); break;
-        default: stepSplit<5>(R, rx, tw); break;
-        }
-        surv[2 * t] = tw[0];
-        surv[2 * t + 1] = tw[1];
-        for (int h = 0; h < 2; h++)
-            for (int r = 0; r < 8; r++)
-                for (int l = 0; l < 4; l++) {
-                    uint8_t v = (R[h][r] >> (8 * l)) & 0xFF;
-                    if (v > mx) mx = v;
-                }
-        if ((t + 1) % renormPeriod == 0) {
-            uint32_t v = ced::byteMinFwd(ced::localMin8(R[0]), ced::localMin8(R[1]));
-            for (int h = 0; h < 2; h++)
-                for (int r = 0; r < 8; r++)
-                    R[h][r] -= v;
-        }
-    }
-    if (maxMetric) *maxMetric = mx;
-    if (survOut)
-        for (size_t i = 0; i < surv.size(); i++) survOut[i] = surv[i];
-    const int L = T - 6;
-    uint32_t b = 0;
-    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
-    for (int t = T - 1; t >= 0; t--) {
-        uint32_t bit = ced::tracebackStep(b, surv[2 * t], surv[2 * t + 1], t % 6);
-        if (t < L)
-            out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
-    }
-    return (L + 7) / 8;
-}
-
 // decision of state s after step t from the packed words (for comparing with the oracle's survivors)
 extern "C" int swar_sim_decision(const uint32_t *surv, int t, int s)
 {

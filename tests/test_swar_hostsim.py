@@ -22,18 +22,17 @@ def sim():
     lib = C.CDLL(path)
     lib.swar_sim_decode.argtypes = [u8p, C.c_int, u8p, u32p, u8p, C.c_int]
     lib.swar_sim_decision.argtypes = [u32p, C.c_int, C.c_int]
-    lib.swar_sim_decode_split.argtypes = [u8p, C.c_int, u8p, u32p, u8p, C.c_int]
     return lib
 
 
-def run(sim, row, period=96, split=False):
+def run(sim, row, period=96):
     T = row.size
     out = np.zeros((T - 6) // 8, dtype=np.uint8)
     surv = np.zeros(2 * T, dtype=np.uint32)
     mx = C.c_uint8(0)
     row = np.ascontiguousarray(row)
-    fn = sim.swar_sim_decode_split if split else sim.swar_sim_decode
-    fn(row.ctypes.data_as(u8p), T, out.ctypes.data_as(u8p), surv.ctypes.data_as(u32p), C.byref(mx), period)
+    sim.swar_sim_decode(row.ctypes.data_as(u8p), T, out.ctypes.data_as(u8p), surv.ctypes.data_as(u32p), C.byref(mx),
+                        period)
     return out, surv, mx.value
 
 
@@ -73,19 +72,3 @@ def test_renorm_period_does_not_change_decisions(sim, port):
         got, _, mx = run(sim, row, period)
         assert np.array_equal(got, base) and mx < 126
 
-
-def test_split_layout_is_identical_to_single_thread_layout(sim, port):
-    """Two threads per frame (acsStepSplit): same decoded bytes AND the very same survivor words as the
-    one-thread-per-frame layout, hence the same traceback."""
-    rng = np.random.default_rng(99)
-    for bits in (8, 24, 96, 1024):
-        msgs = rng.integers(0, 256, (4, bits // 8), dtype=np.uint8)
-        segs = port.encode_batch(7, oracle.K7_G, msgs)
-        for p in (0.0, 0.08, 0.5):
-            noisy = bsc(rng, segs, p, junk_upper_bits=True)
-            want = port.decode_batch(7, oracle.K7_G, noisy, bits + 6)
-            for f in range(noisy.shape[0]):
-                a, sa, _ = run(sim, noisy[f])
-                b, sb, mx = run(sim, noisy[f], split=True)
-                assert np.array_equal(b, want[f]) and np.array_equal(a, b)
-                assert np.array_equal(sa, sb) and mx < 126
