@@ -154,7 +154,7 @@ packSymbolsKernel(const uint8_t *__restrict__ segs, size_t segStride, int nFrame
 /* Soft symbols -> packed hard symbols.  Soft format: two int8 per segment (soft value of coded bit 0,
  * then of coded bit 1), BPSK convention bit 0 -> +, bit 1 -> - ; the hard decision is the sign bit
  * (value 0 slices to bit 0).  The reference decodes hard decisions only, so soft input is defined by
- * this slicing (SURVEY 8c "paths with no oracle").  One thread slices 16 segments (32 bytes). */
+ * this slicing (no reference behaviour to match).  One thread slices 16 segments (32 bytes). */
 __global__ void __launch_bounds__(256)
 sliceSoftSymbolsKernel(const int8_t *__restrict__ soft, size_t softStride, int nFrames, int segsPerFrame,
                        uint8_t *__restrict__ packed, size_t packedStride, int aligned)
