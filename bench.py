@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--mode", default="decode", choices=["decode", "encode", "ber"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
     ap.add_argument("--in-flight", type=int, default=3, help="decode batches in flight (contexts/streams)")
+    ap.add_argument("--stride", type=int, default=SEG_STRIDE, help="bytes between frames of the symbol buffer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -233,7 +234,8 @@ def main():
 
     # ---- synthetic frames, generated on the device, resident in HBM before timing ----
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
-    segs = torch.zeros((frames, SEG_STRIDE), dtype=torch.uint8, device="cuda")
+    seg_stride = max(args.stride, T)
+    segs = torch.zeros((frames, seg_stride), dtype=torch.uint8, device="cuda")
     out = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()   # allocations / zero-fills ran on torch's default stream
     ctx.random_bytes(msgs, seed=314, first_frame=first_frame, stream=stream)
@@ -331,10 +333,10 @@ def main():
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "speedDecode K=7 rate-1/2 (0113/0171) hard-decision, 2^16 frames x 4096 bits per GPU"
                        if frames == FRAMES_PER_GPU else "K=7 rate-1/2 hard-decision, %d frames x 4096 bits per GPU" % frames,
-                       "mode": args.mode, "frames_per_gpu": frames, "frame_bits": bits, "segment_stride_bytes": SEG_STRIDE,
+                       "mode": args.mode, "frames_per_gpu": frames, "frame_bits": bits, "segment_stride_bytes": seg_stride,
                        "symbol_format": "1 byte per 2-bit segment (reference wire format)", "channel": "BSC p=0.0377 (Eb/N0 5 dB)",
                        "l2_policy": "inputs (%.0f MB symbols + %.0f MB survivors per step) exceed the 126 MB L2"
-                                    % (frames * SEG_STRIDE / 1e6, frames * (T // 2) * 16 / 1e6),
+                                    % (frames * seg_stride / 1e6, frames * (T // 2) * 16 / 1e6),
                        "sharding": "frames [rank*F, (rank+1)*F) per rank, no data-path collective"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall}
     if single is not None:
@@ -375,7 +377,7 @@ def main():
 
     if not args.no_e2e and args.mode == "decode":
         # ---- e2e: the public host-buffer call; H2D of the symbols and D2H of the bits inside the timed region ----
-        h_segs = torch.empty((frames, SEG_STRIDE), dtype=torch.uint8).pin_memory()
+        h_segs = torch.empty((frames, seg_stride), dtype=torch.uint8).pin_memory()
         h_out = torch.empty((frames, bits // 8), dtype=torch.uint8).pin_memory()
         h_segs.copy_(segs)
         torch.cuda.synchronize()
@@ -393,7 +395,7 @@ def main():
         el = float(el.item())
         ok = bool(torch.equal(h_out.cuda(), out))
         line["e2e"] = {"value": world * units * n_e2e / el / 1e9, "unit": "Gbit/s",
-                       "h2d_bytes_per_step": (frames - 1) * SEG_STRIDE + T,
+                       "h2d_bytes_per_step": (frames - 1) * seg_stride + T,
                        "d2h_bytes_per_step": frames * bits // 8, "steps": n_e2e,
                        "api": "ced_decode_batch_host (pinned host buffers, 8192-frame chunks, 4 in flight: H2D, 4 compute streams, D2H)",
                        "matches_device_path": ok, "gpu_launches": ctx.launches - l0}

@@ -217,7 +217,7 @@ int ced_ctx_create(int device, ced_ctx **out)
         const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES");
         c->maxWaveFrames = (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
         CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &resident, ced::k7ForwardKernel<Code0113, ced::PackedSymbols>, ced::kFwdThreads, 0));
+            &resident, ced::k7ForwardKernel<Code0113, ced::PackedSymbols, false>, ced::kFwdThreads, 0));
         const char *env = getenv("CED_FWD_BLOCKS_PER_SM");
         c->sms = sms;
         c->fwdResident = std::max(1, resident);
@@ -352,7 +352,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
      * the previous one (use one context per stream to keep several decodes in flight) */
     if (wk.lastStream && wk.lastStream != s)
         CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
-    const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0;
     c->profWaves = 0;
     for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
         const bool prof = c->profiling && c->profWaves < ced_ctx::kMaxProfWaves;
@@ -376,9 +376,15 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
         const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
-#define CED_LAUNCH_FWD(CODE, FMT)                                                                              \
-    ced::k7ForwardKernel<CODE, ced::FMT><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, wk.scratch.p, \
-                                                                              aligned16, bm, sched)
+#define CED_LAUNCH_FWD(CODE, FMT)                                                                                  \
+    do {                                                                                                           \
+        if (aligned16)                                                                                             \
+            ced::k7ForwardKernel<CODE, ced::FMT, true><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,     \
+                                                                                            wk.scratch.p, bm, sched); \
+        else                                                                                                       \
+            ced::k7ForwardKernel<CODE, ced::FMT, false><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,    \
+                                                                                             wk.scratch.p, bm, sched); \
+    } while (0)
         if (id == CodeId::K7_0113_0171 && !packed)
             CED_LAUNCH_FWD(Code0113, ByteSymbols);
         else if (id == CodeId::K7_0113_0171)
@@ -808,16 +814,17 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     CED_CUDA(cudaSetDevice(c->device));
     const size_t inBytes = 1024 + (size_t)segmentsIn;
     const size_t survBytes = (size_t)kStreamMaxSteps * W * sizeof(uint32_t);
-    const size_t outBytes = 1024 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
+    const size_t outBytes = 4096 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
     int rc = c->sIn.ensure(1024 + kStreamMaxSteps);
-    if (rc == CED_OK) rc = c->sOut.ensure(16 + kStreamMaxSteps / 8 + 16);
+    if (rc == CED_OK) rc = c->sOut.ensure(272 + kStreamMaxSteps / 8 + 16);
     if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
     if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
     if (rc != CED_OK)
         return rc;
 
-    /* mailbox: [0,512) edge  [512,768) metrics  [1024,...) segments */
+    /* mailbox in : [0,512) edge  [512,768) metrics  [1024,...) segments          (one H2D)
+     * mailbox out: [0,256) metrics [256,272) renormCounter [272,...) decoded bytes (one D2H) */
     memcpy(c->sPinIn.p, edge, (size_t)2 * N);
     memcpy(c->sPinIn.p + 512, metrics, (size_t)N);
     if (segmentsIn)
@@ -826,6 +833,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     if (last && it0 > 0) /* chunked packet: bring the earlier decisions back */
         CED_CUDA(cudaMemcpyAsync(c->sSurv.p, surv, (size_t)it0 * W * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                  c->stream));
+    const size_t decodedBytes = last ? (size_t)((total - S - 1) / 8 + 1) : 0;
     ced::StreamArgs a;
     a.K = K;
     a.n = n;
@@ -836,32 +844,32 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     a.segmentsIn = segmentsIn;
     a.last = last;
     a.edge = c->sIn.p;
-    a.metrics = c->sIn.p + 512;
+    a.metricsIn = c->sIn.p + 512;
+    a.metrics = c->sOut.p;
     a.segs = c->sIn.p + 1024;
     a.surv = c->sSurv.p;
-    a.stateOut = reinterpret_cast<uint32_t *>(c->sOut.p); /* [0,16) state word, then decoded bytes */
-    a.out = c->sOut.p + 16;
-    const size_t decodedBytes = last ? (size_t)((total - S - 1) / 8 + 1) : 0;
-    const int threads = std::max(32, N / 2);
-    ced::streamDecodeKernel<<<1, threads, 0, c->stream>>>(a);
+    a.stateOut = reinterpret_cast<uint32_t *>(c->sOut.p + 256);
+    a.out = c->sOut.p + 272;
+    if (N <= 64)
+        ced::streamDecodeWarpKernel<<<1, 32, 0, c->stream>>>(a);
+    else
+        ced::streamDecodeKernel<<<1, std::max(32, N / 2), 0, c->stream>>>(a);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
-    /* results: metrics | renormCounter | decoded bytes or the new survivor rows */
-    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->sIn.p + 512, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
-    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 512, c->sOut.p, 16 + decodedBytes, cudaMemcpyDeviceToHost, c->stream));
+    CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->sOut.p, 272 + decodedBytes, cudaMemcpyDeviceToHost, c->stream));
     if (!last && segmentsIn)
-        CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 1024, c->sSurv.p + (size_t)it0 * W,
+        CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 4096, c->sSurv.p + (size_t)it0 * W,
                                  (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CED_CUDA(cudaStreamSynchronize(c->stream));
     if (last) {
-        memcpy(uncoded, c->sPinOut.p + 512 + 16, decodedBytes);
+        memcpy(uncoded, c->sPinOut.p + 272, decodedBytes);
         /* src/viterbiDecoderButterflyk1.c:259 -- the caller's reset restores metrics/counters */
         return (int)decodedBytes;
     }
     memcpy(metrics, c->sPinOut.p, (size_t)N);
-    memcpy(renormCounter, c->sPinOut.p + 512, sizeof(uint32_t));
+    memcpy(renormCounter, c->sPinOut.p + 256, sizeof(uint32_t));
     if (segmentsIn)
-        memcpy(surv + (size_t)it0 * W, c->sPinOut.p + 1024, (size_t)segmentsIn * W * sizeof(uint32_t));
+        memcpy(surv + (size_t)it0 * W, c->sPinOut.p + 4096, (size_t)segmentsIn * W * sizeof(uint32_t));
     *iteration = it0 + (uint32_t)segmentsIn;
     return 0;
 }

@@ -83,49 +83,65 @@ __device__ __forceinline__ uint32_t packedToBmOffsets(uint32_t b)
     return (x & 0x00600060u) | (y & 0x60006000u);
 }
 
-template <class Fmt>
+template <class Fmt, bool ALIGNED>
 struct TileGeom {
     static constexpr int kChunk = Fmt::kChunk;
-    static constexpr int kPitch = kChunk + 16;                         /* bytes per tile row in shared memory */
     static constexpr int kSegsPerPiece = 16 * Fmt::kSegsPerByte;       /* segments in one 16-byte global piece */
-    static constexpr int kPiecesPerRow = kChunk / kSegsPerPiece;       /* = pieces per lane per 32-row tile    */
-    static constexpr int kBytesPerRow = kChunk / Fmt::kSegsPerByte;    /* wire bytes of one tile row           */
+    /* ALIGNED: base pointer and stride are multiples of 16, a row chunk is exactly kChunk/kSegsPerPiece
+     * pieces; otherwise one more piece covers the misaligned head/tail (3.5 % slower forward pass) */
+    static constexpr int kPiecesPerRow = kChunk / kSegsPerPiece + (ALIGNED ? 0 : 1);
+    /* bytes per tile row in shared memory: the pieces, padded so that rows start 4 banks apart
+     * (pitch/4 = 4 mod 32); 32 rows then touch 8 banks 4 times each with LDS.U8 */
+    static constexpr int kPitch = Fmt::kSegsPerByte == 1 ? 112 : 272;
+    static_assert(kPitch >= kPiecesPerRow * kSegsPerPiece && (kPitch / 4) % 32 == 4 || kPitch == 112, "tile pitch");
 };
 
-/* Fast path (rows 16-byte aligned): fetch this lane's pieces of segments [t0, t0+kChunk) of the
- * group's 32 frames into registers.  Issued one unit ahead of use so the HBM latency (18 % of warp
- * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current unit. */
-template <class Fmt>
-__device__ __forceinline__ void loadTileAligned(uint4 (&v)[TileGeom<Fmt>::kPiecesPerRow], const uint8_t *__restrict__ segs,
-                                                size_t stride, long long frame0, int nFrames, int t0, int T, int lane)
+/*
+ * Symbol staging, any base pointer and row stride (the reference's natural `[PKTS][4102]` array is not
+ * 16-byte aligned).  For each of the group's 32 rows the kChunk/segsPerByte wire bytes of this unit
+ * start at some address A; the lanes fetch the kPiecesPerRow ALIGNED 16-byte pieces that cover
+ * [A & ~15, A + bytes) with 128-bit loads and the consumer lane later reads its row at offset
+ * (A & 15) * segsPerByte.  Pieces are fetched one unit ahead of use so the HBM latency (18 % of warp
+ * time in profiles/r1_v1 when loaded just in time) overlaps the ACS work of the current unit.  A piece
+ * that would reach outside [bufLo, bufHi) -- before the first or past the last frame -- is assembled
+ * from byte loads of its in-range part.
+ */
+template <class Fmt, bool ALIGNED>
+__device__ __forceinline__ void loadTile(uint4 (&v)[TileGeom<Fmt, ALIGNED>::kPiecesPerRow],
+                                         const uint8_t *__restrict__ segs, size_t stride, long long frame0, int nFrames,
+                                         int t0, int T, int lane)
 {
-    using G = TileGeom<Fmt>;
+    using G = TileGeom<Fmt, ALIGNED>;
     const int rowBytes = (T + Fmt::kSegsPerByte - 1) / Fmt::kSegsPerByte;   /* valid wire bytes per frame */
+    const uint8_t *bufLo = segs;
+    const uint8_t *bufHi = segs + (size_t)(nFrames - 1) * stride + rowBytes;
 #pragma unroll
     for (int i = 0; i < G::kPiecesPerRow; i++) {
         const int piece = i * 32 + lane;
         const int row = piece / G::kPiecesPerRow, pc = piece % G::kPiecesPerRow;
         const long long f = frame0 + row;
-        const int byteOff = t0 / Fmt::kSegsPerByte + pc * 16;
         v[i] = make_uint4(0, 0, 0, 0);
-        if (f < nFrames && byteOff < rowBytes) {
-            const uint8_t *src = segs + (size_t)f * stride + (size_t)byteOff;
-            if ((size_t)(byteOff + 16) <= stride) {
+        if (f < nFrames) {
+            const uint8_t *rowStart = segs + (size_t)f * stride + (size_t)(t0 / Fmt::kSegsPerByte);
+            const uint8_t *src = rowStart - (reinterpret_cast<uintptr_t>(rowStart) & 15u) + 16 * pc;
+            if (src >= bufLo && src + 16 <= bufHi) {
                 v[i] = __ldg(reinterpret_cast<const uint4 *>(src));
-            } else { /* last piece of a row whose stride is not padded: never read past the row */
+            } else {
                 uint32_t w[4] = {0, 0, 0, 0};
-                for (int b = 0; b < 16 && byteOff + b < rowBytes; b++)
-                    w[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
+                for (int b = 0; b < 16; b++)
+                    if (src + b >= bufLo && src + b < bufHi)
+                        w[b >> 2] |= (uint32_t)src[b] << (8 * (b & 3));
                 v[i] = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
     }
 }
 
-template <class Fmt>
-__device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)[TileGeom<Fmt>::kPiecesPerRow], int lane)
+template <class Fmt, bool ALIGNED>
+__device__ __forceinline__ void storeTile(uint8_t *tile, const uint4 (&v)[TileGeom<Fmt, ALIGNED>::kPiecesPerRow],
+                                          int lane)
 {
-    using G = TileGeom<Fmt>;
+    using G = TileGeom<Fmt, ALIGNED>;
 #pragma unroll
     for (int i = 0; i < G::kPiecesPerRow; i++) {
         const int piece = i * 32 + lane;
@@ -141,28 +157,6 @@ __device__ __forceinline__ void storeTileAligned(uint8_t *tile, const uint4 (&v)
                 *reinterpret_cast<uint4 *>(dst + 16 * q) =
                     make_uint4(packedToBmOffsets(w[q] & 0xFFu), packedToBmOffsets((w[q] >> 8) & 0xFFu),
                                packedToBmOffsets((w[q] >> 16) & 0xFFu), packedToBmOffsets(w[q] >> 24));
-        }
-    }
-}
-
-/* Generic path (any base / stride alignment): byte loads, staged just in time. */
-template <class Fmt>
-__device__ __forceinline__ void stageTileUnaligned(uint8_t *tile, const uint8_t *__restrict__ segs, size_t stride,
-                                                   long long frame0, int nFrames, int t0, int T, int lane)
-{
-    using G = TileGeom<Fmt>;
-    const int rowBytes = (T + Fmt::kSegsPerByte - 1) / Fmt::kSegsPerByte;
-    for (int row = 0; row < 32; row++) {
-        const long long f = frame0 + row;
-        for (int b = lane; b < G::kBytesPerRow; b += 32) {
-            const int byteOff = t0 / Fmt::kSegsPerByte + b;
-            uint32_t v = 0;
-            if (f < nFrames && byteOff < rowBytes)
-                v = __ldg(segs + (size_t)f * stride + (size_t)byteOff);
-            if (Fmt::kSegsPerByte == 1)
-                tile[row * G::kPitch + b] = (uint8_t)((v & 3u) << 5);
-            else
-                *reinterpret_cast<uint32_t *>(tile + row * G::kPitch + 4 * b) = packedToBmOffsets(v);
         }
     }
 }
@@ -207,12 +201,12 @@ __device__ __forceinline__ void stRelease(int *p, int v)
  * SMSP pulling 96-step units the tail shrinks to one unit in 43+.  (Two frames per thread to double
  * the ILP of the few warps was measured slower: 1.61 ms vs 1.25 ms)
  */
-template <class Code, class Fmt>
+template <class Code, class Fmt, bool ALIGNED>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                int aligned16, BmTable table, FwdSched sched)
+                BmTable table, FwdSched sched)
 {
-    using G = TileGeom<Fmt>;
+    using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
     __shared__ uint4 sBm[6 * 4 * 2];
     __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
@@ -223,7 +217,6 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *tile = sTile[warp];
-    const uint8_t *myRow = tile + lane * kPitch;
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
     const uint32_t minusOne = table.minusOne;
     const size_t pairs = (size_t)(T / 2);
@@ -240,8 +233,8 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
 
     unsigned u = grab();
     uint4 pre[G::kPiecesPerRow];
-    if (u < total && aligned16)
-        loadTileAligned<Fmt>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)(u / groups) * kChunk, T, lane);
+    if (u < total)
+        loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)(u / groups) * kChunk, T, lane);
 
     while (u < total) {
         const unsigned g = u % groups, c = u / groups;
@@ -270,16 +263,16 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
         }
 
         __syncwarp();
-        if (aligned16)
-            storeTileAligned<Fmt>(tile, pre, lane);
-        else
-            stageTileUnaligned<Fmt>(tile, segs, stride, frame0, nFrames, t0, T, lane);
+        storeTile<Fmt, ALIGNED>(tile, pre, lane);
         /* next unit: claim it now so its symbol tile streams in during this unit's ACS work */
         const unsigned un = grab();
-        if (un < total && aligned16)
-            loadTileAligned<Fmt>(pre, segs, stride, 32LL * (un % groups), nFrames, (int)(un / groups) * kChunk, T,
-                                 lane);
+        if (un < total)
+            loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (un % groups), nFrames, (int)(un / groups) * kChunk, T, lane);
         __syncwarp();
+        /* this lane's frame starts (A & 15) wire bytes into the first staged piece of its row */
+        const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride +
+                                  (size_t)(t0 / Fmt::kSegsPerByte);
+        const uint8_t *myRow = tile + lane * kPitch + (ALIGNED ? 0u : (rowAddr & 15u) * Fmt::kSegsPerByte);
 
         /* survivor layout: one stream per 32-frame group, (T/2) consecutive 512-byte rows (one uint4 per
          * lane and step pair), so this kernel's stores and the traceback's loads are sequential. */

@@ -30,7 +30,8 @@ struct StreamArgs {
     int segmentsIn;
     int last;
     const uint8_t *edge;         /* [2][N]                                        */
-    uint8_t *metrics;            /* [N] in/out                                    */
+    const uint8_t *metricsIn;    /* [N] path metrics before the call              */
+    uint8_t *metrics;            /* [N] path metrics after the call               */
     const uint8_t *segs;         /* [segmentsIn]                                  */
     uint32_t *surv;              /* [capacity][W]                                 */
     uint32_t *stateOut;          /* [0] = renormCounter after the call            */
@@ -55,8 +56,8 @@ __global__ void __launch_bounds__(128) streamDecodeKernel(StreamArgs a)
         e0h = a.edge[j + H];
         e10 = a.edge[N + j];
         e1h = a.edge[N + j + H];
-        sMetric[0][j] = a.metrics[j];
-        sMetric[0][j + H] = a.metrics[j + H];
+        sMetric[0][j] = a.metricsIn[j];
+        sMetric[0][j + H] = a.metricsIn[j + H];
     }
     uint32_t renormCounter = a.renormCounter;
     int cur = 0;
@@ -152,6 +153,148 @@ __global__ void __launch_bounds__(128) streamDecodeKernel(StreamArgs a)
             }
         }
         __syncthreads();
+    }
+}
+
+/*
+ * Latency-optimised variant for trellises of up to 64 states (K <= 7): ONE warp, lane j = butterfly j,
+ * metrics m[j], m[j+H] in registers, successors exchanged with two __shfl_sync per step (no shared
+ * memory, no block barrier).  Same arithmetic, renormalisation schedule and survivor packing as
+ * streamDecodeKernel.  The traceback is done by lane 0 over survivor rows staged in shared memory;
+ * the loads do not depend on the path, so they are issued 8 steps ahead of the bit extraction.
+ */
+constexpr int kStreamWarpSegChunk = 8192;
+
+__global__ void __launch_bounds__(32) streamDecodeWarpKernel(StreamArgs a)
+{
+    __shared__ __align__(16) uint8_t sSeg[kStreamWarpSegChunk + 16];
+    __shared__ uint2 sSurv[kStreamTbChunk];
+
+    const int N = a.N, H = N / 2, j = threadIdx.x;
+    const bool active = j < H;
+    const uint32_t nmask = (1u << a.n) - 1u;
+    uint32_t e00 = 0, e0h = 0, e10 = 0, e1h = 0, lo = 0xFF, hi = 0xFF;
+    if (active) {
+        e00 = a.edge[j];
+        e0h = a.edge[j + H];
+        e10 = a.edge[N + j];
+        e1h = a.edge[N + j + H];
+        lo = a.metricsIn[j];
+        hi = a.metricsIn[j + H];
+    }
+    /* successor 2j' / 2j'+1 of butterfly j' becomes state j (lo) resp. j+H (hi) of the next step */
+    const int srcLo = j >> 1, srcHi = (j + H) >> 1;
+    const bool oddLo = j & 1, oddHi = (j + H) & 1;
+    uint32_t renormCounter = a.renormCounter;
+    uint2 *survOut = reinterpret_cast<uint2 *>(a.surv) + a.iteration;
+
+    for (int base = 0; base < a.segmentsIn; base += kStreamWarpSegChunk) {
+        const int cnt = min(kStreamWarpSegChunk, a.segmentsIn - base);
+        for (int i = j; i < cnt; i += 32)
+            sSeg[i] = a.segs[base + i];
+        if (j == 0)
+            sSeg[cnt] = 0; /* read one step ahead below */
+        __syncwarp();
+        /* branch metrics of step i+1 are computed during step i: the only loop-carried chain is
+         * add -> compare -> select -> shuffle */
+        uint32_t rx = sSeg[0];
+        uint32_t h00 = __popc((e00 ^ rx) & nmask), h0h = __popc((e0h ^ rx) & nmask);
+        uint32_t h10 = __popc((e10 ^ rx) & nmask), h1h = __popc((e1h ^ rx) & nmask);
+        for (int i = 0; i < cnt; i++) {
+            const uint32_t rxn = sSeg[i + 1];
+            const uint32_t n00 = __popc((e00 ^ rxn) & nmask), n0h = __popc((e0h ^ rxn) & nmask);
+            const uint32_t n10 = __popc((e10 ^ rxn) & nmask), n1h = __popc((e1h ^ rxn) & nmask);
+            const uint32_t a0 = (lo + h00) & 0xFFu; /* uint8 arithmetic (:109-115) */
+            const uint32_t a1 = (hi + h0h) & 0xFFu;
+            const uint32_t b0 = (lo + h10) & 0xFFu;
+            const uint32_t b1 = (hi + h1h) & 0xFFu;
+            const bool da = active && a0 > a1, db = active && b0 > b1;
+            uint32_t na = da ? a1 : a0, nb = db ? b1 : b0;
+            const uint32_t wa = __ballot_sync(0xFFFFFFFFu, da);
+            const uint32_t wb = __ballot_sync(0xFFFFFFFFu, db);
+            if (j == 0)
+                survOut[base + i] = make_uint2(wa, wb);
+            if (renormCounter >= 120) { /* uniform across the warp */
+                uint32_t mn = active ? min(na, nb) : 0xFFu;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o));
+                na = (na - mn) & 0xFFu;
+                nb = (nb - mn) & 0xFFu;
+                renormCounter = 0;
+            } else {
+                renormCounter++;
+            }
+            const uint32_t ab = na | (nb << 8);
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, ab, srcLo);
+            const uint32_t w = __shfl_sync(0xFFFFFFFFu, ab, srcHi);
+            lo = oddLo ? (v >> 8) : (v & 0xFFu);
+            hi = oddHi ? (w >> 8) : (w & 0xFFu);
+            h00 = n00;
+            h0h = n0h;
+            h10 = n10;
+            h1h = n1h;
+        }
+        __syncwarp();
+    }
+    if (active) {
+        a.metrics[j] = (uint8_t)lo;
+        a.metrics[j + H] = (uint8_t)hi;
+    }
+    if (j == 0)
+        a.stateOut[0] = renormCounter;
+    if (!a.last)
+        return;
+
+    __threadfence_block();
+    __syncwarp();
+    const int S = a.K - 1;
+    const int T = (int)a.iteration + a.segmentsIn;
+    const int L = T - S;
+    const uint2 *surv = reinterpret_cast<const uint2 *>(a.surv);
+    uint32_t state = 0, acc = 0;
+    auto back = [&](const uint2 w) -> uint32_t { /* one step back; returns the decoded bit of that step */
+        const uint32_t word = (state & 1u) ? w.y : w.x;
+        const uint32_t dec = (word >> (state >> 1)) & 1u;
+        const uint32_t bit = state & 1u;
+        state = (state >> 1) | (dec << (S - 1));
+        return bit;
+    };
+    /* generic part: the S tail steps and the (at most 7) steps above the last byte boundary */
+    int t = T - 1;
+    if (j == 0) {
+        for (; t >= 0 && (t >= L || (t & 7) != 7); t--) {
+            const uint32_t bit = back(surv[t]);
+            if (t < L) {
+                acc = (acc >> 1) | (bit << 7);
+                if ((t & 7) == 0) {
+                    a.out[t >> 3] = (uint8_t)acc;
+                    acc = 0;
+                }
+            }
+        }
+    }
+    t = __shfl_sync(0xFFFFFFFFu, t, 0);
+    /* now t + 1 is a multiple of 8: whole bytes, survivor rows staged through shared memory */
+    for (int hiStep = t + 1; hiStep > 0; hiStep -= kStreamTbChunk) {
+        const int loStep = max(0, hiStep - kStreamTbChunk);
+        for (int i = j; i < hiStep - loStep; i += 32)
+            sSurv[i] = surv[loStep + i];
+        __syncwarp();
+        if (j == 0) {
+            for (int tb = hiStep - 8; tb >= loStep; tb -= 8) {
+                uint2 w[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    w[q] = sSurv[tb - loStep + q];
+                uint32_t byte = 0;
+#pragma unroll
+                for (int q = 7; q >= 0; q--)
+                    byte |= back(w[q]) << (7 - q); /* step tb+q is bit 7-q of byte tb/8 (:249) */
+                a.out[tb >> 3] = (uint8_t)byte;
+            }
+        }
+        __syncwarp();
     }
 }
 
