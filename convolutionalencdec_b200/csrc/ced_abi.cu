@@ -309,6 +309,89 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
     return groups * 32 * perFrame + groups * 4 * 32 * sizeof(uint4) + (groups + 1) * sizeof(int);
 }
 
+/* Any k=1 code with K <= 9, n <= 8: one warp / CTA per frame (genericBatchDecodeKernel). */
+static int decodeBatchGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                              int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
+{
+    if (!code || code->constraintLen < 2 || code->constraintLen > 9 || code->codedBits < 1 ||
+        code->codedBits > CED_MAX_N) {
+        setError("ced_decode_batch: K must be 2..9 and n 1..8");
+        return CED_ERR_UNSUPPORTED;
+    }
+    const int K = code->constraintLen, n = code->codedBits, N = 1 << (K - 1), W = ced_stream_surv_words(N);
+    const int T = frameBits + K - 1;
+    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    ced_ctx::Work &wk = c->work[slot];
+    /* trellis labels and start metrics (table building, as viterbiInit does on the host) */
+    uint8_t table[1024];
+    uint32_t taps[CED_MAX_N];
+    for (int i = 0; i < n; i++)
+        taps[i] = reverseBits(code->gen[i], K);
+    for (int b = 0; b < 2; b++)
+        for (int st = 0; st < N; st++) {
+            const uint32_t reg = (((uint32_t)st << 1) | (uint32_t)b) & ((1u << K) - 1u);
+            uint8_t seg = 0;
+            for (int i = 0; i < n; i++)
+                seg |= (uint8_t)((__builtin_popcount(reg & taps[i]) & 1) << i);
+            table[b * N + st] = seg;
+        }
+    for (int st = 0; st < N; st++)
+        table[512 + st] = st == 0 ? 0 : (uint8_t)(N + 1);
+    const size_t perFrame = (size_t)T * W * sizeof(uint32_t);
+    size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(1, kMaxScratchBytes / perFrame));
+    const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
+    const int gridMax = c->sms * 16;
+    const size_t sinkBytes = 1024 + (size_t)gridMax * (256 + 4);
+    if (wk.scratch.bytes < firstWave * perFrame || wk.schedState.bytes < sinkBytes) {
+        CED_CUDA(cudaDeviceSynchronize());
+        int rc = wk.scratch.ensure(firstWave * perFrame);
+        if (rc == CED_OK) rc = wk.schedState.ensure(sinkBytes);
+        if (rc != CED_OK)
+            return rc;
+    }
+    if (wk.lastStream && wk.lastStream != s)
+        CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
+    uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p);
+    CED_CUDA(cudaMemcpyAsync(dTable, table, 1024, cudaMemcpyHostToDevice, s)); /* pageable source: staged by the driver */
+    for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
+        const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
+        ced::GenericBatchArgs g;
+        g.K = K;
+        g.n = n;
+        g.N = N;
+        g.W = W;
+        g.nFrames = wave;
+        g.T = T;
+        g.edge = dTable;
+        g.initMetrics = dTable + 512;
+        g.segs = dSegs + f0 * segStride;
+        g.segStride = segStride;
+        g.surv = reinterpret_cast<uint32_t *>(wk.scratch.p);
+        g.out = dOut + f0 * outStride;
+        g.outStride = outStride;
+        g.metricsSink = dTable + 1024;
+        g.stateSink = reinterpret_cast<uint32_t *>(dTable + 1024 + (size_t)gridMax * 256);
+        const int blocks = std::min(wave, gridMax);
+        if (N <= 64)
+            ced::genericBatchDecodeKernel<true><<<blocks, 32, 0, s>>>(g);
+        else
+            ced::genericBatchDecodeKernel<false><<<blocks, N / 2, 0, s>>>(g);
+        c->launches += 1;
+    }
+    CED_CUDA(cudaEventRecord(wk.idle, s));
+    wk.lastStream = s;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
 static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
                            int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0)
 {
@@ -324,8 +407,11 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     }
     const CodeId id = classify(code);
     if (id == CodeId::Unsupported) {
-        setError("ced_decode_batch: only K=7 n=2 g={0113,0171} or {0133,0171} is built");
-        return CED_ERR_UNSUPPORTED;
+        if (packed) {
+            setError("ced_decode_batch_packed: built for K=7 n=2 g={0113,0171} or {0133,0171} only");
+            return CED_ERR_UNSUPPORTED;
+        }
+        return decodeBatchGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
     }
     if (nFrames == 0)
         return CED_OK;

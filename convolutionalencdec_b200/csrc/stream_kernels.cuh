@@ -38,7 +38,7 @@ struct StreamArgs {
     uint8_t *out;                /* decoded bytes (last only)                     */
 };
 
-__global__ void __launch_bounds__(128) streamDecodeKernel(StreamArgs a)
+__device__ __forceinline__ void streamDecodeBlockBody(const StreamArgs &a)
 {
     __shared__ uint8_t sMetric[2][256];
     __shared__ uint8_t sSeg[kStreamSegChunk];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(128) streamDecodeKernel(StreamArgs a)
  */
 constexpr int kStreamWarpSegChunk = 8192;
 
-__global__ void __launch_bounds__(32) streamDecodeWarpKernel(StreamArgs a)
+__device__ __forceinline__ void streamDecodeWarpBody(const StreamArgs &a)
 {
     __shared__ __align__(16) uint8_t sSeg[kStreamWarpSegChunk + 16];
     __shared__ uint2 sSurv[kStreamTbChunk];
@@ -295,6 +295,63 @@ __global__ void __launch_bounds__(32) streamDecodeWarpKernel(StreamArgs a)
             }
         }
         __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) streamDecodeKernel(StreamArgs a)
+{
+    streamDecodeBlockBody(a);
+}
+__global__ void __launch_bounds__(32) streamDecodeWarpKernel(StreamArgs a)
+{
+    streamDecodeWarpBody(a);
+}
+
+/*
+ * Batch decoding for code parameters the SWAR kernel is not built for (K = 3, 5, 9, other
+ * generators, n up to 8): every CTA takes whole frames (grid-stride) through the same bodies as the
+ * per-frame API -- one warp per frame for <= 64 states, N/2 threads above.  Decisions do not depend on
+ * the renormalisation schedule, so the reference's schedule is simply kept.
+ */
+struct GenericBatchArgs {
+    int K, n, N, W;
+    int nFrames, T;
+    const uint8_t *edge;         /* [2][N] */
+    const uint8_t *initMetrics;  /* [N]: 0 for state 0, N+1 elsewhere (:59-67) */
+    const uint8_t *segs;
+    size_t segStride;
+    uint32_t *surv;              /* [nFrames][T][W] */
+    uint8_t *out;
+    size_t outStride;
+    uint8_t *metricsSink;        /* [gridDim.x][256] final metrics, unused */
+    uint32_t *stateSink;         /* [gridDim.x] */
+};
+
+template <bool WARP>
+__global__ void __launch_bounds__(128) genericBatchDecodeKernel(GenericBatchArgs g)
+{
+    for (long long f = blockIdx.x; f < g.nFrames; f += gridDim.x) {
+        StreamArgs a;
+        a.K = g.K;
+        a.n = g.n;
+        a.N = g.N;
+        a.W = g.W;
+        a.iteration = 0;
+        a.renormCounter = 0;
+        a.segmentsIn = g.T;
+        a.last = 1;
+        a.edge = g.edge;
+        a.metricsIn = g.initMetrics;
+        a.metrics = g.metricsSink + (size_t)blockIdx.x * 256;
+        a.segs = g.segs + (size_t)f * g.segStride;
+        a.surv = g.surv + (size_t)f * (size_t)g.T * g.W;
+        a.stateOut = g.stateSink + blockIdx.x;
+        a.out = g.out + (size_t)f * g.outStride;
+        if constexpr (WARP)
+            streamDecodeWarpBody(a);
+        else
+            streamDecodeBlockBody(a);
+        __syncthreads(); /* shared staging buffers are reused by the next frame */
     }
 }
 

@@ -83,11 +83,43 @@ def test_decode_batch_textbook_generators(torch_cuda, ctx, port):
     assert np.array_equal(out.cpu().numpy(), port.decode_batch(7, g, noisy, 518))
 
 
+@pytest.mark.parametrize("K,g,bits,frames", [
+    (3, (0b111, 0b110), 8, 5), (3, (0b111, 0b110), 256, 300), (3, (0b111, 0b101), 1000 // 8 * 8, 40),
+    (5, (0o23, 0o35), 512, 200), (7, (0o117, 0o155), 2048, 150), (7, (0o133, 0o145, 0o175), 256, 100),
+    (9, (0o561, 0o753), 512, 150), (9, (0o557, 0o663, 0o711), 4096, 33), (2, (0b11, 0b10), 64, 17),
+])
+def test_decode_batch_other_code_parameters(torch_cuda, ctx, port, K, g, bits, frames):
+    """any k=1 code with K <= 9 decodes through ced_decode_batch (generic one-warp/CTA-per-frame
+    kernel), incl. the hand-traced K=3 code whose generators lack the symmetry the reference's butterfly
+    needs; oracle = general butterflies (generic decoder's ACS, src/viterbiDecoder.c:95-128)."""
+    torch = torch_cuda
+    rng = np.random.default_rng(K * 1000 + bits)
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    clean = port.encode_batch(K, g, msgs)
+    n = len(g)
+    T = bits + K - 1
+    for p in (0.0, 0.03, 0.3):
+        flips = rng.random(clean.shape + (n,)) < p
+        noisy = clean.copy()
+        for j in range(n):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        want = port.decode_batch(K, g, noisy, T, symmetric=False)
+        view = torch.full((frames, T + 5), 0xFF, dtype=torch.uint8, device="cuda")
+        view[:, :T] = dev(torch, noisy)
+        out = ctx.decode_batch(ced.Code(K, g), view, bits)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), want), (K, g, p)
+        if p == 0.0:
+            assert np.array_equal(want, msgs)
+
+
 def test_decode_batch_rejects_what_it_cannot_do(torch_cuda, ctx):
     torch = torch_cuda
     segs = torch.zeros((4, 70), dtype=torch.uint8, device="cuda")
     with pytest.raises(ced.CedError):
-        ctx.decode_batch(ced.Code(7, (0o117, 0o155)), segs, 64)      # generators not built
+        ctx.decode_batch(ced.Code(10, (0o1167, 0o1545)), segs, 56)   # K > 9
+    with pytest.raises(ced.CedError):
+        ctx.decode_batch_packed(ced.Code(5, (0o23, 0o35)), segs, 64)  # packed format: K=7 codes only
     with pytest.raises(ced.CedError):
         ctx.decode_batch(ced.K7_DEFAULT, segs, 60)                    # not a multiple of 8
     with pytest.raises(ced.CedError):
