@@ -399,12 +399,6 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
     }
-    const int T = frameBits + ced::kTailSteps;
-    const size_t rowBytes = packed ? (size_t)(T + 3) / 4 : (size_t)T;
-    if (segStride < rowBytes || outStride < (size_t)(frameBits / 8)) {
-        setError("ced_decode_batch: stride shorter than a frame");
-        return CED_ERR_ARG;
-    }
     const CodeId id = classify(code);
     if (id == CodeId::Unsupported) {
         if (packed) {
@@ -412,6 +406,12 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             return CED_ERR_UNSUPPORTED;
         }
         return decodeBatchGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
+    }
+    const int T = frameBits + ced::kTailSteps;
+    const size_t rowBytes = packed ? (size_t)(T + 3) / 4 : (size_t)T;
+    if (segStride < rowBytes || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
     }
     if (nFrames == 0)
         return CED_OK;
