@@ -375,6 +375,14 @@ def main():
                                     "frac": units * ALGO_BYTES_PER_BIT / ((fwd_ms + tb_ms) * 1e-3) / 1e9 / hbm_peak,
                                     "note": "algorithmic symbol-in + bits-out bytes; not the binding roofline"}}
 
+    if args.mode == "encode":
+        # the encoder is HBM-bound: message bytes in + one byte per coded segment out
+        enc_bytes = frames * (bits // 8 + T)
+        achieved = enc_bytes / (ms_per_step * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "encodeBatchKernel", "achieved": achieved, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
+                            "algorithmic_bytes_per_launch": enc_bytes, "kernel_ms": ms_per_step, "traffic": None}
+
     if not args.no_e2e and args.mode == "decode":
         # ---- e2e: the public host-buffer call; H2D of the symbols and D2H of the bits inside the timed region ----
         h_segs = torch.empty((frames, seg_stride), dtype=torch.uint8).pin_memory()

@@ -609,7 +609,10 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
     const int blocks = (nFrames + ced::kEncFramesPerBlock - 1) / ced::kEncFramesPerBlock;
     if (packed) {
         const int aligned4 = ((reinterpret_cast<uintptr_t>(dSegs) & 3u) == 0 && (segStride & 3u) == 0) ? 1 : 0;
-        if (code->constraintLen == 7)
+        if (code->constraintLen == 7 && taps.tap[0] == ced::kFixedTap0 && taps.tap[1] == ced::kFixedTap1)
+            ced::encodeBatchKernel<7, 2, true, true><<<blocks, ced::kEncThreads, 0, s>>>(
+                dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned4);
+        else if (code->constraintLen == 7)
             ced::encodeBatchKernel<7, 2, true><<<blocks, ced::kEncThreads, 0, s>>>(
                 dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned4);
         else
@@ -621,7 +624,11 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
         return CED_OK;
     }
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
-    if (code->constraintLen == 7 && code->codedBits == 2)
+    if (code->constraintLen == 7 && code->codedBits == 2 && taps.tap[0] == ced::kFixedTap0 &&
+        taps.tap[1] == ced::kFixedTap1)
+        ced::encodeBatchKernel<7, 2, false, true><<<blocks, ced::kEncThreads, 0, s>>>(
+            dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned16);
+    else if (code->constraintLen == 7 && code->codedBits == 2)
         ced::encodeBatchKernel<7, 2><<<blocks, ced::kEncThreads, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs,
                                                                          segStride, tailSegs, 7, 2, taps, hist, aligned16);
     else

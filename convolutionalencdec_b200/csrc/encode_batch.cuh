@@ -26,7 +26,11 @@ constexpr int kEncThreads = 256;
 constexpr int kEncFramesPerBlock = 4;
 
 /* 16 coded segments (one uint4) from the 24-bit window `win` (bit i = input bit u[16c - 8 + i]). */
-template <int KK, int NN>
+/* FIXED = the production code K=7 n=2 g={0113,0171}: taps 0x69 / 0x4F are compile-time constants, so the
+ * tap loop folds to 3-4 shift/XORs per generator (src/convEncode.c:13-17 derives them at run time). */
+constexpr uint32_t kFixedTap0 = 0x69u, kFixedTap1 = 0x4Fu;
+
+template <int KK, int NN, bool FIXED = false>
 __device__ __forceinline__ uint4 encode16(uint32_t win, const EncTaps &taps, int K, int n)
 {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
@@ -35,7 +39,7 @@ __device__ __forceinline__ uint4 encode16(uint32_t win, const EncTaps &taps, int
     for (int g = 0; g < (NN ? NN : 8); g++) {
         if (g >= nn)
             break;
-        const uint32_t tap = taps.tap[g];
+        const uint32_t tap = FIXED ? (g == 0 ? kFixedTap0 : kFixedTap1) : taps.tap[g];
         uint32_t c16 = 0;
 #pragma unroll
         for (int d = 0; d < (KK ? KK : 9); d++)
@@ -61,17 +65,18 @@ __device__ __forceinline__ uint32_t spreadBits16(uint32_t x)
     x = (x | (x << 1)) & 0x55555555u;
     return x;
 }
-template <int KK>
+template <int KK, bool FIXED = false>
 __device__ __forceinline__ uint32_t encode16Packed(uint32_t win, const EncTaps &taps, int K)
 {
     const int kk = KK ? KK : K;
     uint32_t c[2] = {0u, 0u};
 #pragma unroll
     for (int g = 0; g < 2; g++) {
+        const uint32_t tap = FIXED ? (g == 0 ? kFixedTap0 : kFixedTap1) : taps.tap[g];
 #pragma unroll
         for (int d = 0; d < (KK ? KK : 9); d++)
             if (d < kk)
-                c[g] ^= (0u - ((taps.tap[g] >> d) & 1u)) & (win << d);
+                c[g] ^= (0u - ((tap >> d) & 1u)) & (win << d);
         c[g] >>= 8;
     }
     return spreadBits16(c[0]) | (spreadBits16(c[1]) << 1);
@@ -82,7 +87,7 @@ __device__ __forceinline__ uint32_t encode16Packed(uint32_t win, const EncTaps &
  * chunks of those frames (32-bit index math only).  KK/NN != 0 fix the constraint length and the
  * number of generators at compile time (the K=7 n=2 production code), 0 = run-time values.
  */
-template <int KK, int NN, bool PACKED = false>
+template <int KK, int NN, bool PACKED = false, bool FIXED = false>
 __global__ void __launch_bounds__(kEncThreads)
 encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
                   uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
@@ -107,7 +112,7 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
         /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, src/convEncode.c:91) */
         const uint32_t win = __brev(((b0 << 16) | (b1 << 8) | b2) << 8);
         if (PACKED) { /* segStride / aligned16 then describe the packed rows (4-byte alignment suffices) */
-            const uint32_t pk = encode16Packed<KK>(win, taps, K);
+            const uint32_t pk = encode16Packed<KK, FIXED>(win, taps, K);
             uint8_t *dstp = segs + (size_t)f * segStride + 4 * (size_t)c;
             const int cnt = min(16, T - 16 * c);
             if (aligned16 && cnt == 16) {
@@ -119,7 +124,7 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
             }
             continue;
         }
-        const uint4 v = encode16<KK, NN>(win, taps, K, n);
+        const uint4 v = encode16<KK, NN, FIXED>(win, taps, K, n);
         uint8_t *dst = segs + (size_t)f * segStride + 16 * (size_t)c;
         if (aligned16 && 16 * c + 16 <= T) {
             *reinterpret_cast<uint4 *>(dst) = v;

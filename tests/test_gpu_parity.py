@@ -426,6 +426,15 @@ def test_multi_wave_batches(torch_cuda, port):
     assert np.array_equal(outs[0][0], port.decode_batch(7, K7, outs[0][1][:, :262], 262))
 
 
+def test_exactly_sized_buffers_and_awkward_shapes():
+    """tools/sanitize_cases.py: every kernel on buffers with no slack behind them, misaligned bases, generic
+    codes, soft input, chunked per-frame calls (the script a memcheck run would use; compute-sanitizer is
+    closed on this pool, so it runs bare here)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_cases.py")], capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------ the reference's own drivers, unchanged
 def _driver(name):
     path = os.path.join(ROOT, "drivers", "_bin", name)
