@@ -719,7 +719,8 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
 {
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
-    const int chunk = std::min(nFrames, kHostChunkFrames);
+    static const int envChunk = getenv("CED_HOST_CHUNK_FRAMES") ? atoi(getenv("CED_HOST_CHUNK_FRAMES")) : 0;
+    const int chunk = std::min(nFrames, envChunk >= 32 ? envChunk : kHostChunkFrames);
     for (int b = 0; b < kPipeDepth; b++) {
         int rc = c->hostIn[b].ensure((size_t)chunk * inStride + 16);
         if (rc == CED_OK)

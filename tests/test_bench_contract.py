@@ -1,0 +1,51 @@
+"""bench.py prints exactly one JSON line with the keys the driver reads."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"]
+
+
+def _run(args, timeout):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                       timeout=timeout, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[-2000:]           # ONE line, nothing else on stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0"], 300)
+    for k in BASE_KEYS + ["impl", "cpu_baseline"]:
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "Gbit/s" and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"] and d["vs_baseline"] is None
+    assert 0.001 < d["value"] < 100.0
+
+
+@pytest.mark.gpu
+def test_our_arm_line():
+    d = _run(["--frames", "8192", "--steps", "4", "--warmup", "3"], 900)
+    for k in BASE_KEYS + ["roofline", "cpu_baseline", "clocks", "single_stream", "check"]:
+        assert k in d, k
+    assert d["dtype"] == "u8" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["vs_baseline"] is None
+    rf = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in rf, k
+    assert rf["bound"] == "int_alu" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 8192 * 4102 - 1 and e["d2h_bytes_per_step"] == 8192 * 512 and e["value"] > 0
+    assert e["matches_device_path"] is True and d["packed_format"]["matches_byte_format"] is True
+    assert d["gpu_launches"] >= 2 * 4 and d["clocks"]["sm_mhz"]
+    assert d["check"]["decoded_bits"] == 8192 * 4096 and 1e-4 < d["check"]["ber"] < 2e-3
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
