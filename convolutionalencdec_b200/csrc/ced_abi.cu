@@ -448,7 +448,8 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         /* persistent grid: as many 4-warp CTAs per SM as there are 32-frame groups per sub-partition,
          * between 3 (2^16 frames: 3.46 groups per SMSP; a 4th warp would mostly spin) and 5 (measured:
          * 2^18 frames 177.8 / 184.7 / 185.8 Gbit/s at 3 / 4 / 5), never more warps than groups */
-        int gridBlocks = c->fwdBlocks;
+        static const int envGrid = getenv("CED_FWD_GRID") ? atoi(getenv("CED_FWD_GRID")) : 0; /* experiments */
+        int gridBlocks = envGrid > 0 ? envGrid : c->fwdBlocks;
         if (gridBlocks == 0)
             gridBlocks = c->sms * std::max(3, std::min({5, c->fwdResident, groups / (4 * c->sms)}));
         const int blocks = std::max(1, std::min(gridBlocks, (groups + 3) / 4));
