@@ -625,8 +625,15 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
         return CED_OK;
     }
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
+    const int msgAligned16 = ((reinterpret_cast<uintptr_t>(dMsg) & 15u) == 0 && (msgStride & 15u) == 0) ? 1 : 0;
+    const size_t smemBytes = (size_t)ced::kEncSmemFrames * ((size_t)(frameBytes + 47) / 16 * 16);
     if (code->constraintLen == 7 && code->codedBits == 2 && taps.tap[0] == ced::kFixedTap0 &&
-        taps.tap[1] == ced::kFixedTap1)
+        taps.tap[1] == ced::kFixedTap1 && aligned16 && hist == 0u && smemBytes <= 40 * 1024) {
+        const int blocksS = (nFrames + ced::kEncSmemFrames - 1) / ced::kEncSmemFrames;
+        ced::encodeBatchSmemKernel<<<blocksS, ced::kEncThreads, smemBytes, s>>>(dMsg, msgStride, nFrames, frameBytes,
+                                                                                dSegs, segStride, tailSegs, msgAligned16);
+    } else if (code->constraintLen == 7 && code->codedBits == 2 && taps.tap[0] == ced::kFixedTap0 &&
+               taps.tap[1] == ced::kFixedTap1)
         ced::encodeBatchKernel<7, 2, false, true><<<blocks, ced::kEncThreads, 0, s>>>(
             dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned16);
     else if (code->constraintLen == 7 && code->codedBits == 2)

@@ -136,4 +136,83 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
     }
 }
 
+/*
+ * Fast path for the production code (K=7, g={0113,0171}, byte-per-segment output, 16-byte aligned
+ * segment rows).  ncu on the kernel above showed 82 % issue-slot utilisation at 31 % DRAM throughput
+ * (profiles/r1_v9_ncu_full_summary.txt) and each thread's load -> compute -> store chain was exposed
+ * once per item.  Here a CTA first stages the messages of kEncSmemFrames frames in shared memory
+ * (one global latency per CTA), then every warp emits whole 512-segment spans: lane l produces
+ * segments [512*span + 16*l, +16) from three staged bytes and the warp's STG.128 covers 512
+ * contiguous bytes.  Index math is a couple of adds per item.
+ */
+constexpr int kEncSmemFrames = 8;
+
+__device__ __forceinline__ uint4 encode16Fixed(uint32_t win)
+{
+    /* taps 0x69 = bits 0,3,5,6 and 0x4F = bits 0,1,2,3,6 (src/convEncode.c:13-17 on 0113 / 0171) */
+    const uint32_t s3 = win << 3, s6 = win << 6;
+    const uint32_t c0 = (win ^ s3 ^ (win << 5) ^ s6) >> 8;
+    const uint32_t c1 = (win ^ (win << 1) ^ (win << 2) ^ s3 ^ s6) >> 8;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t n0 = (c0 >> (4 * q)) & 0xFu, n1 = (c1 >> (4 * q)) & 0xFu;
+        w[q] = ((n0 * 0x00204081u) & 0x01010101u) + 2u * ((n1 * 0x00204081u) & 0x01010101u);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(kEncThreads)
+encodeBatchSmemKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
+                      uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int msgAligned16)
+{
+    extern __shared__ __align__(16) uint8_t sMsg[];   /* [frames][16 zero bytes | message | >= 16 zero bytes] */
+    const int rowPitch = (frameBytes + 47) / 16 * 16; /* 16 in front + message + tail padding */
+    const int T = 8 * frameBytes + tailSegs;
+    const int spans = (T + 511) / 512;
+    const long long frameBase = (long long)blockIdx.x * kEncSmemFrames;
+    const int framesHere = (int)min((long long)kEncSmemFrames, (long long)nFrames - frameBase);
+
+    /* stage: zero fill, then the messages */
+    for (int i = threadIdx.x; i < framesHere * rowPitch / 16; i += kEncThreads)
+        reinterpret_cast<uint4 *>(sMsg)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (msgAligned16 && (frameBytes & 15) == 0) {
+        const int vecPerRow = frameBytes / 16;
+        for (int i = threadIdx.x; i < framesHere * vecPerRow; i += kEncThreads) {
+            const int fl = i / vecPerRow, v = i - fl * vecPerRow;
+            reinterpret_cast<uint4 *>(sMsg + fl * rowPitch + 16)[v] =
+                __ldg(reinterpret_cast<const uint4 *>(msg + (size_t)(frameBase + fl) * msgStride) + v);
+        }
+    } else {
+        for (int i = threadIdx.x; i < framesHere * frameBytes; i += kEncThreads) {
+            const int fl = i / frameBytes, b = i - fl * frameBytes;
+            sMsg[fl * rowPitch + 16 + b] = __ldg(msg + (size_t)(frameBase + fl) * msgStride + b);
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int unit = warp; unit < framesHere * spans; unit += kEncThreads / 32) {
+        const int fl = unit / spans, span = unit - fl * spans;
+        const int seg0 = 512 * span + 16 * lane;
+        if (seg0 >= T)
+            continue;
+        /* message bytes 2c-1, 2c, 2c+1 with c = seg0/16; byte -1 and bytes past the end are zero */
+        const uint8_t *p = sMsg + fl * rowPitch + 16 + 64 * span + 2 * lane;
+        const uint32_t b0 = p[-1];
+        const uint32_t b12 = *reinterpret_cast<const uint16_t *>(p);   /* b1 | b2 << 8 */
+        const uint32_t win = __brev((b0 << 24) | ((b12 & 0xFFu) << 16) | ((b12 >> 8) << 8));
+        const uint4 v = encode16Fixed(win);
+        uint8_t *dst = segs + (size_t)(frameBase + fl) * segStride + seg0;
+        if (seg0 + 16 <= T) {
+            *reinterpret_cast<uint4 *>(dst) = v;
+        } else {
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            for (int s2 = 0; s2 < T - seg0; s2++)
+                dst[s2] = (uint8_t)(w[s2 >> 2] >> (8 * (s2 & 3)));
+        }
+    }
+}
+
 } // namespace ced
