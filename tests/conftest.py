@@ -11,6 +11,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # Built artefacts are git-ignored: build whatever is missing (nvcc cross-compiles without a GPU).
+    import shutil
+    import subprocess
+    needed = {"cuda": "convolutionalencdec_b200/libced_cuda.so", "host": "convolutionalencdec_b200/libconvencdec_k7.so",
+              "oracle": "oracle/libced_oracle.so", "hostsim": "tests/hostsim/libswar_sim.so"}
+    missing = [t for t, path in needed.items() if not os.path.exists(os.path.join(ROOT, path))]
+    if missing and shutil.which("make") and (shutil.which("nvcc") or "cuda" not in missing):
+        subprocess.run(["make", "-C", ROOT] + missing, check=False, stdout=subprocess.DEVNULL)
 
 
 def bsc(rng, segs, p, junk_upper_bits=False):
