@@ -16,7 +16,7 @@ CFLAGS := -O2 -g -std=gnu11 -fPIC -Wall -Iinclude
 HOST_SRCS := $(CSRC)/host/convEncode.c $(CSRC)/host/convHelpers.c $(CSRC)/host/viterbiDecoder.c $(CSRC)/host/ced_introspect.c
 CUDA_HDRS := $(wildcard $(CSRC)/*.cuh) include/ced_abi.h
 
-all: cuda host oracle hostsim drivers
+all: cuda host oracle hostsim drivers examples
 
 cuda: $(PKG)/libced_cuda.so
 $(PKG)/libced_cuda.so: $(CSRC)/ced_abi.cu $(CUDA_HDRS)
@@ -29,6 +29,11 @@ $(PKG)/libconvencdec_k7.so: $(HOST_SRCS) $(CSRC)/host/params/default/convCodePar
 $(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)
 	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
 	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
+
+examples: examples/_bin/batch_roundtrip
+examples/_bin/batch_roundtrip: examples/batch_roundtrip.c include/ced_abi.h $(PKG)/libced_cuda.so
+	mkdir -p examples/_bin
+	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude -o $@ $< -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 
 oracle:
 	$(MAKE) -C oracle CED_REF=$(CED_REF) all
@@ -63,7 +68,7 @@ endif
 
 clean:
 	rm -f $(PKG)/*.so tests/hostsim/*.so
-	rm -rf $(DRV)
+	rm -rf $(DRV) examples/_bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all cuda host oracle hostsim drivers clean
+.PHONY: all cuda host oracle hostsim drivers examples clean

@@ -188,13 +188,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="decode", choices=["decode", "encode", "ber"])
-    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="frames per GPU (default 2^16; 2^20 in encode mode = BASELINE config 3)")
     ap.add_argument("--in-flight", type=int, default=3, help="decode batches in flight (contexts/streams)")
     ap.add_argument("--stride", type=int, default=SEG_STRIDE, help="bytes between frames of the symbol buffer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.frames <= 0:
+        args.frames = (1 << 20) if args.mode == "encode" else FRAMES_PER_GPU
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -331,8 +334,11 @@ def main():
             "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "speedDecode K=7 rate-1/2 (0113/0171) hard-decision, 2^16 frames x 4096 bits per GPU"
-                       if frames == FRAMES_PER_GPU else "K=7 rate-1/2 hard-decision, %d frames x 4096 bits per GPU" % frames,
+            "config": {"workload": ("speedEncode K=7 rate-1/2 (0113/0171), %d frames x 4096 bits per GPU" % frames)
+                       if args.mode == "encode" else
+                       ("speedDecode K=7 rate-1/2 (0113/0171) hard-decision, 2^16 frames x 4096 bits per GPU"
+                        if frames == FRAMES_PER_GPU else
+                        "K=7 rate-1/2 hard-decision, %d frames x 4096 bits per GPU" % frames),
                        "mode": args.mode, "frames_per_gpu": frames, "frame_bits": bits, "segment_stride_bytes": seg_stride,
                        "symbol_format": "1 byte per 2-bit segment (reference wire format)", "channel": "BSC p=0.0377 (Eb/N0 5 dB)",
                        "l2_policy": "inputs (%.0f MB symbols + %.0f MB survivors per step) exceed the 126 MB L2"

@@ -435,6 +435,16 @@ def test_exactly_sized_buffers_and_awkward_shapes():
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_plain_c_user_of_the_batch_abi():
+    """examples/batch_roundtrip.c: a C program (no CUDA headers) encodes, corrupts and decodes 20000 frames
+    through ced_encode_batch_host / ced_decode_batch_host."""
+    path = os.path.join(ROOT, "examples", "_bin", "batch_roundtrip")
+    if not os.path.exists(path):
+        pytest.skip("examples/_bin/batch_roundtrip not built")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and " 0 wrong bytes" in r.stdout, r.stdout + r.stderr
+
+
 # ------------------------------------------------------------------ the reference's own drivers, unchanged
 def _driver(name):
     path = os.path.join(ROOT, "drivers", "_bin", name)
