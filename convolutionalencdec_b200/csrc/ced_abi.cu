@@ -463,14 +463,16 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
         const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
+        static const int envCpu = getenv("CED_FWD_CHUNKS_PER_UNIT") ? atoi(getenv("CED_FWD_CHUNKS_PER_UNIT")) : 0;
+        const int cpu = envCpu > 0 ? envCpu : 2; /* chunks a warp runs before handing its group on: 1 / 2 / 4 / 8 -> 1.249 / 1.217 / 1.225 / 1.262 ms */
 #define CED_LAUNCH_FWD(CODE, FMT)                                                                                  \
     do {                                                                                                           \
         if (aligned16)                                                                                             \
             ced::k7ForwardKernel<CODE, ced::FMT, true><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,     \
-                                                                                            wk.scratch.p, bm, sched); \
+                                                                                            wk.scratch.p, bm, sched, cpu); \
         else                                                                                                       \
             ced::k7ForwardKernel<CODE, ced::FMT, false><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,    \
-                                                                                             wk.scratch.p, bm, sched); \
+                                                                                             wk.scratch.p, bm, sched, cpu); \
     } while (0)
         if (id == CodeId::K7_0113_0171 && !packed)
             CED_LAUNCH_FWD(Code0113, ByteSymbols);

@@ -204,7 +204,7 @@ __device__ __forceinline__ void stRelease(int *p, int v)
 template <class Code, class Fmt, bool ALIGNED>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                BmTable table, FwdSched sched)
+                BmTable table, FwdSched sched, int chunksPerUnit)
 {
     using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
@@ -222,7 +222,12 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     const size_t pairs = (size_t)(T / 2);
     const unsigned groups = (unsigned)((nFrames + 31) / 32);
     const unsigned chunks = (unsigned)((T + kChunk - 1) / kChunk);
-    const unsigned total = groups * chunks;
+    /* a unit = chunksPerUnit consecutive chunks of one group, run by one warp without hand-off: the
+     * claim atomic, the state round trip through L2 and the release fence (which waits for all of the
+     * warp's outstanding survivor stores) cost ~20 % of warp time at one chunk per unit (ncu v9:
+     * membar 0.30, long_scoreboard 0.42, sleeping 0.10 stall cycles per issue) */
+    const unsigned unitsPerGroup = (chunks + chunksPerUnit - 1) / chunksPerUnit;
+    const unsigned total = groups * unitsPerGroup;
 
     auto grab = [&]() -> unsigned {
         unsigned v = 0;
@@ -234,21 +239,22 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     unsigned u = grab();
     uint4 pre[G::kPiecesPerRow];
     if (u < total)
-        loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)(u / groups) * kChunk, T, lane);
+        loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames,
+                               (int)((u / groups) * chunksPerUnit) * kChunk, T, lane);
 
     while (u < total) {
-        const unsigned g = u % groups, c = u / groups;
+        const unsigned g = u % groups, su = u / groups;
+        const unsigned cFirst = su * chunksPerUnit, cEnd = min(chunks, cFirst + chunksPerUnit);
         const long long frame0 = 32LL * g;
-        const int t0 = (int)c * kChunk;
         const bool live = frame0 + lane < nFrames;
         uint4 *stateSlot = sched.state + ((size_t)g * 4) * 32 + lane;
 
         uint32_t R[16];
-        if (c == 0) {
+        if (su == 0) {
             initMetrics(R);
         } else {
             if (lane == 0)
-                while (ldAcquire(sched.done + g) < (int)c)
+                while (ldAcquire(sched.done + g) < (int)su)
                     __nanosleep(200);
             __syncwarp();
             __threadfence();
@@ -261,13 +267,21 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
                 R[4 * i + 3] = v.w;
             }
         }
-
+        unsigned un = total;
+      for (unsigned c = cFirst; c < cEnd; c++) {
+        const int t0 = (int)c * kChunk;
         __syncwarp();
         storeTile<Fmt, ALIGNED>(tile, pre, lane);
-        /* next unit: claim it now so its symbol tile streams in during this unit's ACS work */
-        const unsigned un = grab();
-        if (un < total)
-            loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (un % groups), nFrames, (int)(un / groups) * kChunk, T, lane);
+        /* prefetch the next tile: the following chunk of this unit, or the first chunk of the next
+         * unit, which is claimed now so that its symbols stream in during this chunk's ACS work */
+        if (c + 1 < cEnd) {
+            loadTile<Fmt, ALIGNED>(pre, segs, stride, frame0, nFrames, t0 + kChunk, T, lane);
+        } else {
+            un = grab();
+            if (un < total)
+                loadTile<Fmt, ALIGNED>(pre, segs, stride, 32LL * (un % groups), nFrames,
+                                       (int)((un / groups) * chunksPerUnit) * kChunk, T, lane);
+        }
         __syncwarp();
         /* this lane's frame starts (A & 15) wire bytes into the first staged piece of its row */
         const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride +
@@ -314,14 +328,15 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
             if (done < steps || c + 1 < chunks)
                 renorm(R); /* every kRenormPeriod = 96 steps, see DESIGN.md 4.3 */
         }
-        if (c + 1 < chunks) {
+      } /* chunks of this unit */
+        if (cEnd < chunks) {
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 __stcg(stateSlot + i * 32, make_uint4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]));
             __threadfence();
             __syncwarp();
             if (lane == 0)
-                stRelease(sched.done + g, (int)c + 1);
+                stRelease(sched.done + g, (int)su + 1);
         }
         u = un;
     }
