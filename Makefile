@@ -19,8 +19,8 @@ CUDA_HDRS := $(wildcard $(CSRC)/*.cuh) include/ced_abi.h
 all: cuda host oracle hostsim drivers examples
 
 cuda: $(PKG)/libced_cuda.so
-$(PKG)/libced_cuda.so: $(CSRC)/ced_abi.cu $(CUDA_HDRS)
-	$(NVCC) $(NVFLAGS) -shared -o $@ $<
+$(PKG)/libced_cuda.so: $(CSRC)/ced_abi.cu $(CSRC)/host_pack.cpp $(CUDA_HDRS)
+	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared -o $@ $(CSRC)/ced_abi.cu $(CSRC)/host_pack.cpp
 
 host: $(PKG)/libconvencdec_k7.so $(PKG)/libconvencdec_k3.so
 $(PKG)/libconvencdec_k7.so: $(HOST_SRCS) $(CSRC)/host/params/default/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)

@@ -17,6 +17,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+
+namespace ced_host {
+struct Packer;
+Packer *packerCreate(int threads);
+void packerDestroy(Packer *p);
+int packerThreads(const Packer *p);
+void packerRun(Packer *p, const uint8_t *in, size_t inStride, int nRows, int segs, uint8_t *out, size_t outStride);
+} // namespace ced_host
 
 namespace {
 
@@ -140,6 +149,10 @@ struct ced_ctx {
         cudaStream_t lastStream = nullptr;
     } work[1 + kPipeDepth];
     cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
+    /* host-side transfer compression (host_pack.cpp): pinned packed staging + worker threads */
+    ced_host::Packer *packer = nullptr;
+    PinnedBuf packStage[kPipeDepth];
+    cudaEvent_t stageFree[kPipeDepth] = {};
     int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
     int sms = 0, fwdResident = 0;
     size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
@@ -209,6 +222,8 @@ int ced_ctx_create(int device, ced_ctx **out)
             CED_CUDA(cudaEventCreate(&c->prof[w][e]));
     for (auto &w : c->work)
         CED_CUDA(cudaEventCreateWithFlags(&w.idle, cudaEventDisableTiming));
+    for (int i = 0; i < kPipeDepth; i++)
+        CED_CUDA(cudaEventCreateWithFlags(&c->stageFree[i], cudaEventDisableTiming));
     {
         /* persistent forward grid: CED_FWD_BLOCKS_PER_SM CTAs of 4 warps per SM (default 4 = 4 warps per
          * sub-partition), never more than the kernel's resident capacity */
@@ -240,9 +255,15 @@ void ced_ctx_destroy(ced_ctx *c)
         w.schedState.release();
         w.schedFlags.release();
     }
-    for (int i = 0; i < kPipeDepth; i++)
+    for (int i = 0; i < kPipeDepth; i++) {
         if (c->pipe[i])
             cudaStreamDestroy(c->pipe[i]);
+        if (c->stageFree[i])
+            cudaEventDestroy(c->stageFree[i]);
+        c->packStage[i].release();
+    }
+    if (c->packer)
+        ced_host::packerDestroy(c->packer);
     for (int i = 0; i < kPipeDepth; i++) {
         c->hostIn[i].release();
         c->hostOut[i].release();
@@ -721,7 +742,7 @@ int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, i
 }
 
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
-enum class HostOp { Encode, Decode, DecodePacked };
+enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack };
 
 static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
@@ -729,8 +750,14 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
 {
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
+    const size_t packStride = op == HostOp::DecodeViaPack ? (((size_t)frameParam + 6 + 3) / 4 + 15) / 16 * 16 : 0;
     static const int envChunk = getenv("CED_HOST_CHUNK_FRAMES") ? atoi(getenv("CED_HOST_CHUNK_FRAMES")) : 0;
     const int chunk = std::min(nFrames, envChunk >= 32 ? envChunk : kHostChunkFrames);
+    for (int b = 0; b < kPipeDepth && op == HostOp::DecodeViaPack; b++) {
+        int rc = c->packStage[b].ensure((size_t)chunk * packStride + 16);
+        if (rc != CED_OK)
+            return rc;
+    }
     for (int b = 0; b < kPipeDepth; b++) {
         int rc = c->hostIn[b].ensure((size_t)chunk * inStride + 16);
         if (rc == CED_OK)
@@ -748,6 +775,18 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         const size_t outBytes = (size_t)(cnt - 1) * outStride + outRowBytes;
         if (idx >= kPipeDepth)
             CED_CUDA(cudaStreamWaitEvent(c->h2d, c->inFree[b], 0));
+        if (op == HostOp::DecodeViaPack) {
+            /* pack this chunk on the host (4 segments per byte) into pinned staging, then copy a quarter
+             * of the bytes; the staging slot is reused once its previous H2D has completed */
+            const int T = frameParam + 6;
+            const size_t pStride = packStride;
+            if (idx >= kPipeDepth)
+                CED_CUDA(cudaEventSynchronize(c->stageFree[b]));
+            ced_host::packerRun(c->packer, hIn + (size_t)f0 * inStride, inStride, cnt, T, c->packStage[b].p, pStride);
+            CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, c->packStage[b].p, (size_t)cnt * pStride, cudaMemcpyHostToDevice,
+                                     c->h2d));
+            CED_CUDA(cudaEventRecord(c->stageFree[b], c->h2d));
+        } else
         CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, hIn + (size_t)f0 * inStride, inBytes, cudaMemcpyHostToDevice, c->h2d));
         CED_CUDA(cudaEventRecord(c->inReady[b], c->h2d));
         CED_CUDA(cudaStreamWaitEvent(cs, c->inReady[b], 0));
@@ -756,6 +795,9 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         int rc;
         if (op == HostOp::Encode)
             rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride, cs);
+        else if (op == HostOp::DecodeViaPack)
+            rc = decodeBatchImpl(c, code, true, c->hostIn[b].p, packStride, cnt, frameParam, c->hostOut[b].p, outStride,
+                                 cs, 1 + b);
         else
             rc = decodeBatchImpl(c, code, op == HostOp::DecodePacked, c->hostIn[b].p, inStride, cnt, frameParam,
                                  c->hostOut[b].p, outStride, cs, 1 + b);
@@ -783,7 +825,27 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     }
     if (nFrames == 0)
         return CED_OK;
-    return hostPipeline(c, code, HostOp::Decode, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
+    /* Optional transfer compression (CED_HOST_PACK=1): pack the symbols to 2 bits on the host and copy a
+     * quarter of the bytes.  OFF by default: on the bench box the host reads memory at about the same
+     * ~55 GB/s as the PCIe copy itself (e2e 48.5 vs 47.2 Gbit/s with 8 threads, slower with 16), so it
+     * only pays on hosts with more memory bandwidth per GPU.  CED_HOST_THREADS sets the pool size
+     * (default: host cores / visible GPUs, at most 16). */
+    HostOp op = HostOp::Decode;
+    if (classify(code) != CodeId::Unsupported && getenv("CED_HOST_PACK")) {
+        std::lock_guard<std::recursive_mutex> lock(c->mu);
+        if (!c->packer) {
+            int nDev = 1;
+            cudaGetDeviceCount(&nDev);
+            const char *envT = getenv("CED_HOST_THREADS");
+            int threads = envT ? atoi(envT) : (int)std::thread::hardware_concurrency() / std::max(1, nDev);
+            c->packer = ced_host::packerCreate(std::max(1, std::min(threads, 16)));
+        }
+        const char *envP = getenv("CED_HOST_PACK");
+        const bool usePack = envP && atoi(envP) != 0;
+        if (usePack)
+            op = HostOp::DecodeViaPack;
+    }
+    return hostPipeline(c, code, op, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
                         frameBits, hOut, outStride, (size_t)frameBits / 8);
 }
 

@@ -108,6 +108,12 @@ int ced_decode_batch_packed_host(ced_ctx *ctx, const ced_code_t *code, const uin
                                  int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
 int ced_pack_symbols(ced_ctx *ctx, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
                      uint8_t *dPacked, size_t packedStride, void *stream);
+/* The same packing on the HOST (no GPU involved; `threads` worker threads, AVX2 when available), e.g. for a
+ * receiver that wants to hand ced_decode_batch_packed_host a quarter of the bytes.  ced_decode_batch_host can
+ * use it internally as transfer compression (CED_HOST_PACK=1); off by default because on the bench box the
+ * host's memory bandwidth, not PCIe, is then the limit. */
+int ced_host_pack_symbols(const uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame, uint8_t *packed,
+                          size_t packedStride, int threads);
 /* Encoder writing the packed format directly (n = 2 codes). */
 int ced_encode_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride,
                             int nFrames, int frameBytes, uint8_t *dPacked, size_t packedStride, void *stream);

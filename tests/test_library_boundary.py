@@ -114,3 +114,25 @@ def test_sharding_covers_every_frame_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_host_side_symbol_packing_matches_the_format_definition():
+    """ced_host_pack_symbols (the transfer compression inside ced_decode_batch_host): segment t -> bits
+    2*(t%4).. of byte t/4, low two bits of each byte only; any length, stride and thread count."""
+    import ctypes as C
+    lib = ced.load_abi()
+    rng = np.random.default_rng(12)
+    for segs, frames, pad, threads in ((1, 3, 0, 1), (7, 5, 2, 2), (31, 9, 1, 3), (32, 4, 0, 4), (70, 33, 5, 8),
+                                       (4102, 64, 10, 16), (4102, 7, 0, 5), (262, 1000, 0, 7)):
+        raw = rng.integers(0, 256, (frames, segs + pad), dtype=np.uint8)
+        pb = (segs + 3) // 4
+        out = np.full((frames, pb + 3), 0xEE, dtype=np.uint8)
+        rc = lib.ced_host_pack_symbols(raw.ctypes.data, raw.strides[0], frames, segs, out.ctypes.data, out.strides[0],
+                                       threads)
+        assert rc == 0
+        padded = np.zeros((frames, pb * 4), dtype=np.uint8)
+        padded[:, :segs] = raw[:, :segs] & 3
+        q = padded.reshape(frames, pb, 4)
+        want = q[..., 0] | (q[..., 1] << 2) | (q[..., 2] << 4) | (q[..., 3] << 6)
+        assert np.array_equal(out[:, :pb], want), (segs, frames)
+        assert (out[:, pb:] == 0xEE).all()
