@@ -388,6 +388,36 @@ def test_bertest_first_packets_through_the_dropin_api(golden):
     assert errs == int(counts[2])
 
 
+def test_batches_in_flight_on_separate_contexts(torch_cuda, port):
+    """What bench.py does for `value`: several decodes in flight, one ced_ctx + CUDA stream each, plus two
+    calls on ONE context from different streams (serialised by the context's event).  Every output must
+    still equal the oracle's."""
+    torch = torch_cuda
+    rng = np.random.default_rng(5)
+    bits, frames = 2048, 3000
+    T = bits + 6
+    ctxs = [ced.Context(0) for _ in range(3)]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    inputs, outs = [], []
+    for i in range(4):
+        msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+        noisy = bsc(rng, port.encode_batch(7, K7, msgs), 0.05)
+        inputs.append(noisy)
+    d_in = [dev(torch, x) for x in inputs]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        outs = []
+        for i in range(4):
+            c = ctxs[min(i, 2)]                      # lanes 2 and 3 share a context on different streams
+            outs.append(c.decode_batch(ced.K7_DEFAULT, d_in[i], bits, stream=streams[i]))
+        torch.cuda.synchronize()
+        sample = rng.choice(frames, 64, replace=False)
+        for i in range(4):
+            assert np.array_equal(outs[i].cpu().numpy()[sample], port.decode_batch(7, K7, inputs[i][sample], T)), (rep, i)
+    for c in ctxs:
+        c.close()
+
+
 def test_ber_sweep_subset_identical_to_reference_decoder(torch_cuda):
     """BASELINE config 4 in miniature: per Eb/N0 point the GPU's decoded bytes equal the reference
     decoder's on the same hard symbols, so the BER curves are identical."""
