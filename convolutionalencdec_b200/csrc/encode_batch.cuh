@@ -139,7 +139,7 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
 /*
  * Fast path for the production code (K=7, g={0113,0171}, byte-per-segment output, 16-byte aligned
  * segment rows).  ncu on the kernel above showed 82 % issue-slot utilisation at 31 % DRAM throughput
- * (profiles/r1_v9_ncu_full_summary.txt) and each thread's load -> compute -> store chain was exposed
+ * (profiles/r1_final_ncu_full_summary.txt) and each thread's load -> compute -> store chain was exposed
  * once per item.  Here a CTA first stages the messages of kEncSmemFrames frames in shared memory
  * (one global latency per CTA), then every warp emits whole 512-segment spans: lane l produces
  * segments [512*span + 16*l, +16) from three staged bytes and the warp's STG.128 covers 512
