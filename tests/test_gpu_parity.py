@@ -388,6 +388,29 @@ def test_bertest_first_packets_through_the_dropin_api(golden):
     assert errs == int(counts[2])
 
 
+def test_bertestk7_golden_integers_through_the_batch_path(torch_cuda, ctx, port):
+    """berTestK7's three configurations (berTestK7/berTestK7.c:95-165, srand(9865)): the very packets the
+    reference driver generates (same rand() stream, reproduced by the oracle's driver restatement) decoded
+    10000 at a time by ced_decode_batch must give the integers the reference binary prints:
+    92418 / 9655 / 655 decoded bit errors of 20,480,000."""
+    torch = torch_cuda
+    golden = [(2296339, 92418), (1525431, 9655), (928843, 655)]
+    port.lib.orc_srand(9865)
+    for (flips, errors), p in zip(golden, (5.585640e-02, 3.716174e-02, 2.262231e-02)):
+        counts, noisy, msgs = port.bertest(7, K7, 10000, 256, p, want_data=True)
+        assert counts.tolist() == [flips, 41080000, errors, 20480000]
+        d_noisy, d_msgs = dev(torch, noisy), dev(torch, msgs)
+        dec = ctx.decode_batch(ced.K7_DEFAULT, d_noisy, 2048)
+        cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ctx.ber_count(dec, d_msgs, cnt)
+        ctx.sync()
+        assert cnt.tolist() == [errors, 20480000]
+        packed = ctx.pack_symbols(d_noisy, 2054)
+        dec_p = ctx.decode_batch_packed(ced.K7_DEFAULT, packed, 2048)
+        ctx.sync()
+        assert torch.equal(dec, dec_p)
+
+
 def test_batches_in_flight_on_separate_contexts(torch_cuda, port):
     """What bench.py does for `value`: several decodes in flight, one ced_ctx + CUDA stream each, plus two
     calls on ONE context from different streams (serialised by the context's event).  Every output must
