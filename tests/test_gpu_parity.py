@@ -441,6 +441,56 @@ def test_batches_in_flight_on_separate_contexts(torch_cuda, port):
         c.close()
 
 
+def test_concurrent_host_threads(torch_cuda, port):
+    """The reference library is re-entrant per state struct (SURVEY 8b 'Threading'); here every call funnels
+    into one GPU context, so calls from several host threads are serialised by the context's lock and must
+    still each get their own answer: per-frame calls on private state structs next to batch calls."""
+    import threading
+    torch = torch_cuda
+    rng = np.random.default_rng(17)
+    api = ced.RefApi("k7")
+    ctx = ced.Context(0)
+    frames = [bsc(rng, port.encode_batch(7, K7, rng.integers(0, 256, (1, 64), dtype=np.uint8)), 0.05)[0]
+              for _ in range(6)]
+    want = [port.decode_batch(7, K7, f[None, :], 518)[0] for f in frames]
+    batch_in = bsc(rng, port.encode_batch(7, K7, rng.integers(0, 256, (500, 64), dtype=np.uint8)), 0.05)
+    batch_want = port.decode_batch(7, K7, batch_in, 518)
+    errors = []
+
+    def per_frame(i):
+        try:
+            dec = api.decoder()
+            dec.VITERBI_RESET()
+            dec.VITERBI_INIT()
+            for rep in range(25):
+                a = dec.VITERBI_DECODER_HARD(frames[i][:200], False)
+                b = dec.VITERBI_DECODER_HARD(frames[i][200:], True)
+                if a.size or not np.array_equal(b, want[i]):
+                    errors.append(("frame", i, rep))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    def batch():
+        try:
+            torch.cuda.set_device(0)
+            d_in = torch.from_numpy(batch_in).cuda()
+            for rep in range(25):
+                out = ctx.decode_batch(ced.K7_DEFAULT, d_in, 512)
+                ctx.sync()
+                if not np.array_equal(out.cpu().numpy(), batch_want):
+                    errors.append(("batch", rep))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=per_frame, args=(i,)) for i in range(6)] + [threading.Thread(target=batch)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ctx.close()
+    assert not errors, errors[:5]
+
+
 def test_ber_sweep_subset_identical_to_reference_decoder(torch_cuda):
     """BASELINE config 4 in miniature: per Eb/N0 point the GPU's decoded bytes equal the reference
     decoder's on the same hard symbols, so the BER curves are identical."""
