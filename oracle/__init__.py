@@ -198,6 +198,8 @@ class Ref:
         lib.refh_encode_chunked.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
         lib.refh_decode_batch.restype = C.c_int
         lib.refh_decode_batch.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, _u8p, C.c_size_t]
+        lib.refh_decode_batch_mt.restype = C.c_int
+        lib.refh_decode_batch_mt.argtypes = [_u8p, C.c_size_t, C.c_int, C.c_int, _u8p, C.c_size_t, C.c_int]
         lib.refh_decode_chunked.restype = C.c_int
         lib.refh_decode_chunked.argtypes = [_u8p, C.c_int, C.c_int, _u8p, _u8p]
         lib.refh_bertest.restype = C.c_int
@@ -236,6 +238,15 @@ class Ref:
         nbytes = (T - 7) // 8 + 1
         out = np.zeros((nf, nbytes), dtype=np.uint8)
         self.lib.refh_decode_batch(_p(segs), stride, nf, T, _p(out), nbytes)
+        return out
+
+    def decode_batch_mt(self, segs, T, threads=None):
+        """Every frame through the reference decoder, frames split over host threads."""
+        segs = np.ascontiguousarray(segs, dtype=np.uint8)
+        nf, stride = segs.shape
+        nbytes = (T - 7) // 8 + 1
+        out = np.zeros((nf, nbytes), dtype=np.uint8)
+        self.lib.refh_decode_batch_mt(_p(segs), stride, nf, T, _p(out), nbytes, threads or (os.cpu_count() or 1))
         return out
 
     def decode_chunked(self, segs, chunk):

@@ -256,3 +256,41 @@ int64_t refh_speed_encode(const uint8_t *msgs, int nFrames, int frameBytes, int 
     free(args);
     return bits;
 }
+
+/* whole-batch decode on several threads (full-size parity test: every frame of a 2^16-frame batch) */
+typedef struct {
+    const uint8_t *segs;
+    size_t stride, outStride;
+    int first, count, segsPerFrame;
+    uint8_t *out;
+} refh_mt_arg_t;
+
+static void *refh_mt_thread(void *p)
+{
+    refh_mt_arg_t *a = (refh_mt_arg_t *)p;
+    viterbiHardState_t *st = refh_new_decoder();
+    for (int f = a->first; f < a->first + a->count; f++)
+        VITERBI_DECODER_HARD(st, (uint8_t *)a->segs + (size_t)f * a->stride, a->out + (size_t)f * a->outStride,
+                             a->segsPerFrame, true);
+    free(st);
+    return NULL;
+}
+
+int refh_decode_batch_mt(const uint8_t *segs, size_t stride, int nFrames, int segsPerFrame, uint8_t *out,
+                         size_t outStride, int nThreads)
+{
+    if (nThreads < 1)
+        nThreads = 1;
+    pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nThreads);
+    refh_mt_arg_t *args = calloc((size_t)nThreads, sizeof(refh_mt_arg_t));
+    for (int i = 0; i < nThreads; i++) {
+        const int lo = (int)((long long)nFrames * i / nThreads), hi = (int)((long long)nFrames * (i + 1) / nThreads);
+        args[i] = (refh_mt_arg_t){segs, stride, outStride, lo, hi - lo, segsPerFrame, out};
+        pthread_create(&th[i], NULL, refh_mt_thread, &args[i]);
+    }
+    for (int i = 0; i < nThreads; i++)
+        pthread_join(th[i], NULL);
+    free(th);
+    free(args);
+    return 0;
+}

@@ -296,6 +296,12 @@ def test_full_size_roundtrip_and_sampled_parity(torch_cuda, ctx, port):
     noisy = segs[torch.from_numpy(sample).cuda()].cpu().numpy()[:, :bits + 6]
     assert np.array_equal(dec[torch.from_numpy(sample).cuda()].cpu().numpy(),
                           port.decode_batch(7, K7, noisy, bits + 6))
+    # and EVERY one of the 65,536 frames against the unmodified reference decoder, when it was built
+    R = oracle.ref()
+    if R is not None:
+        want = R.decode_batch_mt(segs.cpu().numpy(), bits + 6)
+        got = dec.cpu().numpy()
+        assert np.array_equal(got, want), "frames differing from the reference: %d" % int((got != want).any(axis=1).sum())
 
 
 def test_channel_is_independent_of_sharding(torch_cuda, ctx):
