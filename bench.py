@@ -369,7 +369,16 @@ def main():
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("k7ForwardKernel_dram_bytes_per_launch")
+        # instruction-level view: the 6-step loop body of k7ForwardKernel is 724 SASS instructions (cuobjdump -sass
+        # of the committed build) = 120.7 warp-instructions per 32 frame-steps; an SM sub-partition
+        # issues at most one warp-instruction per cycle and the kernel splits them ~50/50 over the ALU and FMA pipes
+        sm_mhz = (clocks.get("sm_mhz") or 1965.0)
+        warp_instr = frames * T * (724.0 / 6.0) / 32.0
+        ipc = warp_instr / (148 * 4 * fwd_ms * 1e-3 * sm_mhz * 1e6)
         line["roofline"] = {"bound": "int_alu", "kernel": "k7ForwardKernel", "achieved": achieved,
+                            "issue": {"instr_per_frame_step": 724.0 / 6.0, "ipc_per_sm_subpartition": ipc, "peak": 1.0,
+                                      "frac": ipc, "note": "SASS instruction count x frame-steps / (592 sub-partitions x "
+                                                            "kernel cycles at the sampled SM clock)"},
                             "peak": int_peak / 1e12, "unit": "Tiop/s", "frac": achieved / (int_peak / 1e12),
                             "peak_source": "measured live: dependent-free LOP3 stream (ced_probe_int_peak mode 0)",
                             "peak_with_imad_coissue": int_peak_dual / 1e12,

@@ -43,6 +43,7 @@ def test_our_arm_line():
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in rf, k
     assert rf["bound"] == "int_alu" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert 0.0 < rf["issue"]["ipc_per_sm_subpartition"] <= 1.0
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] > 8192 * 4102 - 1 and e["d2h_bytes_per_step"] == 8192 * 512 and e["value"] > 0
     assert e["matches_device_path"] is True and d["packed_format"]["matches_byte_format"] is True
