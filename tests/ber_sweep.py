@@ -92,6 +92,8 @@ def main(argv=None):
             checker, kind = (lambda noisy, T: P.decode_batch(7, oracle.K7_G, noisy, T)), "port (oracle/ced_oracle.c)"
     ctx = ced.Context(local_rank)
     code = ced.K7_DEFAULT
+    from convolutionalencdec_b200 import ber_theory
+    spectrum = ber_theory.distance_spectrum(7, [0o113, 0o171], 20)
     rows = []
     for i, db in enumerate(float(x) for x in args.points.split(",")):
         p = bsc_probability(db)
@@ -102,7 +104,8 @@ def main(argv=None):
         c = [int(x) for x in counters.cpu().tolist()]
         rows.append({"ebn0_db": db, "bsc_p": p, "channel_flips": c[0], "coded_bits": c[1], "decoded_errors": c[2],
                      "decoded_bits": c[3], "channel_ber": c[0] / c[1], "decoded_ber": c[2] / c[3],
-                     "subset_check": check})
+                     "union_bound_hard": ber_theory.hard_decision_ber(p, spectrum),
+                     "uncoded_bpsk_ber": ber_theory.bpsk_ber(db), "subset_check": check})
         if rank == 0:
             print("Eb/N0 %4.1f dB  p=%.5f  channel BER %.5e  decoded BER %.5e  (%d errors / %d bits)%s"
                   % (db, p, c[0] / c[1], c[2] / c[3], c[2], c[3],
@@ -110,6 +113,7 @@ def main(argv=None):
                      % (check["frames"], check["reference_decoded_errors"], check["gpu_decoded_errors"],
                         check["bytes_identical"])), file=sys.stderr)
     result = {"config": "K=7 r=1/2 g=(0113,0171), %d-bit packets, hard-decision BSC from BPSK+AWGN" % PKT_BITS,
+              "distance_spectrum": {"dfree": spectrum.dfree, "weight": spectrum.weight, "event": spectrum.event},
               "n_gpus": world, "frames_per_gpu": args.frames_per_gpu, "checker": kind, "points": rows}
     if rank == 0:
         text = json.dumps(result, indent=1)
