@@ -532,6 +532,140 @@ int ced_decode_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     return decodeBatchImpl(c, code, true, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
 }
 
+/* ------------------------------------------------ continuous streams, windowed traceback */
+
+static inline size_t windowCarryGroupBytes(int depth)
+{
+    /* per 32-stream group: 4 rows of metrics (uint4 x 32), 32 start positions, depth/2 survivor rows */
+    return 4 * 32 * sizeof(uint4) + 32 * sizeof(uint32_t) + (size_t)(depth / 2) * 32 * sizeof(uint4);
+}
+
+size_t ced_window_carry_bytes(int nStreams, int depth)
+{
+    if (nStreams <= 0 || depth < 24 || depth % 24)
+        return 0;
+    return (size_t)((nStreams + 31) / 32) * windowCarryGroupBytes(depth);
+}
+
+int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nStreams,
+                            int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
+                            size_t outStride, void *stream)
+{
+    if (!c || nStreams < 0 || nSegments < 0 || depth < 24 || depth % 24 || depth > 8184 || streamPos % 96 ||
+        (nStreams > 0 && (!dSegs || !dOut || !dCarry)) || (reinterpret_cast<uintptr_t>(dCarry) & 15u)) {
+        setError("ced_decode_window_batch: bad argument (depth and streamPos must be multiples of 24 / 96)");
+        return CED_ERR_ARG;
+    }
+    const CodeId id = classify(code);
+    if (id == CodeId::Unsupported) {
+        setError("ced_decode_window_batch: built for K=7 n=2 g={0113,0171} or {0133,0171} only");
+        return CED_ERR_UNSUPPORTED;
+    }
+    if (last ? (nSegments < ced::kTailSteps || (streamPos + (uint64_t)nSegments - ced::kTailSteps) % 8 != 0)
+             : (nSegments == 0 || nSegments % 96 != 0)) {
+        setError("ced_decode_window_batch: a slice must be a positive multiple of 96 segments; the last one must "
+                 "end the stream on a byte boundary plus K-1 tail segments");
+        return CED_ERR_ARG;
+    }
+    if (nSegments > kStreamMaxSteps * 4) {
+        setError("ced_decode_window_batch: slice too long");
+        return CED_ERR_ARG;
+    }
+    /* local step index l = absolute step - (streamPos - depth): rows [0, depth) are the carried decisions */
+    const int emitLo = (int)std::max<int64_t>(0, (int64_t)depth - (int64_t)streamPos);
+    const int Tl = depth + nSegments;
+    const int emitHi = last ? Tl - ced::kTailSteps : nSegments;
+    const int bytesOut = emitHi > emitLo ? (emitHi - emitLo) / 8 : 0;
+    if (segStride < (size_t)nSegments || outStride < (size_t)bytesOut) {
+        setError("ced_decode_window_batch: stride shorter than a slice");
+        return CED_ERR_ARG;
+    }
+    if (nStreams == 0)
+        return bytesOut;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const size_t perFrame = (size_t)(Tl / 2) * sizeof(uint4);
+    size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
+    waveMax = waveMax / 64 * 64;
+    const size_t firstWave = std::min<size_t>((size_t)nStreams, waveMax);
+    const size_t firstGroups = (firstWave + 31) / 32;
+    ced_ctx::Work &wk = c->work[0];
+    if (wk.scratch.bytes < firstGroups * 32 * perFrame || wk.schedState.bytes < firstGroups * 4 * 32 * sizeof(uint4) ||
+        wk.schedFlags.bytes < (firstGroups + 1) * sizeof(int)) {
+        CED_CUDA(cudaDeviceSynchronize());
+        int rc = wk.scratch.ensure(firstGroups * 32 * perFrame);
+        if (rc == CED_OK) rc = wk.schedState.ensure(firstGroups * 4 * 32 * sizeof(uint4));
+        if (rc == CED_OK) rc = wk.schedFlags.ensure((firstGroups + 1) * sizeof(int));
+        if (rc != CED_OK)
+            return rc;
+    }
+    if (wk.lastStream && wk.lastStream != s)
+        CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0;
+    const size_t allGroups = (size_t)(nStreams + 31) / 32;
+    uint8_t *carry = static_cast<uint8_t *>(dCarry);
+    uint4 *carryMetrics = reinterpret_cast<uint4 *>(carry);
+    uint32_t *carryStart = reinterpret_cast<uint32_t *>(carry + allGroups * 4 * 32 * sizeof(uint4));
+    uint8_t *carrySurv = carry + allGroups * (4 * 32 * sizeof(uint4) + 32 * sizeof(uint32_t));
+    const size_t tailBytes = (size_t)(depth / 2) * 32 * sizeof(uint4);   /* per group */
+    const size_t rowBytes = (size_t)(Tl / 2) * 32 * sizeof(uint4);       /* per group in the scratch */
+    for (size_t f0 = 0; f0 < (size_t)nStreams; f0 += waveMax) {
+        const int wave = (int)std::min<size_t>(waveMax, (size_t)nStreams - f0);
+        const int groups = (wave + 31) / 32;
+        const size_t g0 = f0 / 32;
+        if (streamPos > 0)
+            CED_CUDA(cudaMemcpy2DAsync(wk.scratch.p, rowBytes, carrySurv + g0 * tailBytes, tailBytes, tailBytes,
+                                       (size_t)groups, cudaMemcpyDeviceToDevice, s));
+        int gridBlocks = c->fwdBlocks;
+        if (gridBlocks == 0)
+            gridBlocks = c->sms * std::max(3, std::min({5, c->fwdResident, groups / (4 * c->sms)}));
+        const int blocks = std::max(1, std::min(gridBlocks, (groups + 3) / 4));
+        ced::FwdSched sched;
+        sched.counter = reinterpret_cast<unsigned int *>(wk.schedFlags.p);
+        sched.done = wk.schedFlags.p + 1;
+        sched.state = wk.schedState.p;
+        CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
+        ced::FwdWindow win;
+        win.metricsIn = streamPos > 0 ? carryMetrics + g0 * 4 * 32 : nullptr;
+        win.metricsOut = last ? nullptr : carryMetrics + g0 * 4 * 32;
+        win.startPos = carryStart + g0 * 32;
+        win.survPairs = Tl / 2;
+        win.pairOffset = depth / 2;
+        const uint8_t *in = dSegs + f0 * segStride;
+        const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
+#define CED_LAUNCH_WIN(CODE)                                                                                       \
+    do {                                                                                                           \
+        if (aligned16)                                                                                             \
+            ced::k7ForwardKernel<CODE, ced::ByteSymbols, true, true><<<blocks, ced::kFwdThreads, 0, s>>>(          \
+                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win);                                  \
+        else                                                                                                       \
+            ced::k7ForwardKernel<CODE, ced::ByteSymbols, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(         \
+                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win);                                  \
+    } while (0)
+        if (id == CodeId::K7_0113_0171)
+            CED_LAUNCH_WIN(Code0113);
+        else
+            CED_LAUNCH_WIN(Code0133);
+#undef CED_LAUNCH_WIN
+        c->launches += 1;
+        if (bytesOut > 0) {
+            ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+                wk.scratch.p, wave, Tl, dOut + f0 * outStride, outStride, last ? nullptr : win.startPos,
+                last ? ced::kTailSteps : depth, emitLo);
+            c->launches += 1;
+        }
+        if (!last)
+            CED_CUDA(cudaMemcpy2DAsync(carrySurv + g0 * tailBytes, tailBytes,
+                                       reinterpret_cast<uint8_t *>(wk.scratch.p) + (size_t)(nSegments / 2) * 32 * sizeof(uint4),
+                                       rowBytes, tailBytes, (size_t)groups, cudaMemcpyDeviceToDevice, s));
+    }
+    CED_CUDA(cudaEventRecord(wk.idle, s));
+    wk.lastStream = s;
+    CED_CUDA(cudaGetLastError());
+    return bytesOut;
+}
+
 int ced_pack_symbols(ced_ctx *c, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
                      uint8_t *dPacked, size_t packedStride, void *stream)
 {

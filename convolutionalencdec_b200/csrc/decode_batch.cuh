@@ -201,10 +201,23 @@ __device__ __forceinline__ void stRelease(int *p, int v)
  * SMSP pulling 96-step units the tail shrinks to one unit in 43+.  (Two frames per thread to double
  * the ILP of the few warps was measured slower: 1.61 ms vs 1.25 ms)
  */
-template <class Code, class Fmt, bool ALIGNED>
+/*
+ * Continuous streams (ced_decode_window_batch): the T steps of this launch continue a stream whose metrics
+ * come from / go back to a caller-owned carry block, and the survivor rows of this launch are appended
+ * behind the `pairOffset` rows kept from the previous call (the traceback depth).
+ */
+struct FwdWindow {
+    const uint4 *metricsIn;  /* [groups][4][32] or NULL = start of the stream (state 0)             */
+    uint4 *metricsOut;       /* [groups][4][32] renormalised metrics after the last step, or NULL    */
+    uint32_t *startPos;      /* [groups][32] best-metric position after the last step (traceback b)  */
+    int survPairs;           /* survivor rows (step pairs) per group in `surv`                       */
+    int pairOffset;          /* rows in front of this launch's first step                            */
+};
+
+template <class Code, class Fmt, bool ALIGNED, bool CARRY = false>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                BmTable table, FwdSched sched, int chunksPerUnit)
+                BmTable table, FwdSched sched, int chunksPerUnit, FwdWindow win = FwdWindow())
 {
     using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
@@ -219,7 +232,8 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     uint8_t *tile = sTile[warp];
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
     const uint32_t minusOne = table.minusOne;
-    const size_t pairs = (size_t)(T / 2);
+    const size_t pairs = CARRY ? (size_t)win.survPairs : (size_t)(T / 2);
+    const size_t pairOffset = CARRY ? (size_t)win.pairOffset : 0;
     const unsigned groups = (unsigned)((nFrames + 31) / 32);
     const unsigned chunks = (unsigned)((T + kChunk - 1) / kChunk);
     /* a unit = chunksPerUnit consecutive chunks of one group, run by one warp without hand-off: the
@@ -252,6 +266,18 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
         uint32_t R[16];
         if (su == 0) {
             initMetrics(R);
+            if constexpr (CARRY) {
+                if (win.metricsIn) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint4 v = __ldcg(win.metricsIn + ((size_t)g * 4 + i) * 32 + lane);
+                        R[4 * i] = v.x;
+                        R[4 * i + 1] = v.y;
+                        R[4 * i + 2] = v.z;
+                        R[4 * i + 3] = v.w;
+                    }
+                }
+            }
         } else {
             if (lane == 0)
                 while (ldAcquire(sched.done + g) < (int)su)
@@ -290,7 +316,7 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
 
         /* survivor layout: one stream per 32-frame group, (T/2) consecutive 512-byte rows (one uint4 per
          * lane and step pair), so this kernel's stores and the traceback's loads are sequential. */
-        uint4 *o = surv + ((size_t)g * pairs + (size_t)(t0 / 2)) * 32 + lane;
+        uint4 *o = surv + ((size_t)g * pairs + pairOffset + (size_t)(t0 / 2)) * 32 + lane;
         const int steps = min(kChunk, T - t0);
         const uint8_t *p = myRow;
         for (int done = 0; done < steps;) {
@@ -337,6 +363,26 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
             __syncwarp();
             if (lane == 0)
                 stRelease(sched.done + g, (int)su + 1);
+        } else if constexpr (CARRY) {
+            if (win.metricsOut) {
+                /* T is a multiple of 96 here, so the next step has phase 0: position == state */
+                renorm(R);
+                uint32_t best = 0;
+#pragma unroll
+                for (int r = 15; r >= 0; r--) {
+                    /* zero-byte finder, exact for bytes < 128; the lowest flagged lane is always a true zero */
+                    const uint32_t z = (R[r] - 0x01010101u) & ~R[r] & 0x80808080u;
+                    if (z)
+                        best = 4u * r + ((__ffs((int)z) - 1) >> 3);
+                }
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        __stcg(win.metricsOut + ((size_t)g * 4 + i) * 32 + lane,
+                               make_uint4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]));
+                    win.startPos[(size_t)g * 32 + lane] = 32u * (best >> 5) + 8u * (best & 3u) + ((best >> 2) & 7u);
+                }
+            }
         }
         u = un;
     }
@@ -387,8 +433,12 @@ __device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
  * slots while the current block is walked -- 192..384 bytes in flight per thread.
  * Steps [24*floor(L/24), T) -- the S tail steps plus at most two bytes -- take the generic path.
  */
+/* Window form (continuous streams): start at the position startPos[frame] instead of state 0, drop the top
+ * `skip` steps instead of the S tail steps, and stop above step `emitLo` (a multiple of 24), whose bit is
+ * the first one of the output row. */
 __global__ void __launch_bounds__(kTbThreads)
-k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride)
+k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride,
+                  const uint32_t *__restrict__ startPos = nullptr, int skip = kTailSteps, int emitLo = 0)
 {
     __shared__ uint4 sW[2][12][kTbThreads];
     const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,8 +447,9 @@ k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *_
     const size_t pairs = (size_t)(T / 2);
     const uint4 *s = surv + ((size_t)(frame / 32) * pairs) * 32 + (frame & 31);   /* warp-major, see k7ForwardKernel */
     uint8_t *dst = out + (size_t)frame * outStride;
-    const int L = T - kTailSteps;
+    const int L = T - skip;
     const int blocks24 = L / 24;
+    const int loBlock = emitLo / 24;
     const int tid = threadIdx.x;
 
     auto prefetch = [&](int blk, int buf) {
@@ -408,10 +459,10 @@ k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *_
             cpAsync16(&sW[buf][i][tid], p + (size_t)(11 - i) * 32);   /* slot 0 = highest pair of the block */
         asm volatile("cp.async.commit_group;");
     };
-    if (blocks24 > 0)
+    if (blocks24 > loBlock)
         prefetch(blocks24 - 1, 0);
 
-    uint32_t b = 0;                 /* state 0 sits at position 0 in every phase */
+    uint32_t b = startPos ? startPos[frame] : 0u;   /* state 0 sits at position 0 in every phase */
     int ph = (T - 1) % 6;           /* phase of step 2m+1                        */
     uint32_t acc = 0;
     for (int m = T / 2 - 1; m >= blocks24 * 12; m--) {
@@ -421,17 +472,18 @@ k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *_
         ph = ph ? ph - 1 : 5;
         const uint32_t b0 = tracebackStep(b, w.x, w.y, ph);
         ph = ph ? ph - 1 : 5;
-        if (t < L) {                /* the S = 6 tail steps carry no output (:208-223) */
+        if (t < L && t >= emitLo) { /* the S = 6 tail steps carry no output (:208-223) */
             acc = (acc >> 2) | (b1 << 6) | (b0 << 7);   /* first visited (t%8 == 7) ends as the LSb (:249) */
             if ((t & 7) == 0) {
-                dst[t >> 3] = (uint8_t)acc;
+                dst[(t - emitLo) >> 3] = (uint8_t)acc;
                 acc = 0;
             }
         }
     }
+    dst -= 3 * loBlock;
     int buf = 0;
-    for (int blk = blocks24 - 1; blk >= 0; blk--, buf ^= 1) {
-        if (blk > 0) {
+    for (int blk = blocks24 - 1; blk >= loBlock; blk--, buf ^= 1) {
+        if (blk > loBlock) {
             prefetch(blk - 1, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {

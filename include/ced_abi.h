@@ -135,6 +135,28 @@ int ced_encode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *h
  * batch of this shape (grown on demand, reused across calls). */
 size_t ced_decode_scratch_bytes(int nFrames, int frameBits);
 
+/*
+ * Continuous streams with windowed traceback (bounded survivor memory for streams longer than the
+ * reference's MAX_PKT_LEN_SEGMENTS; TRACEBACK_LEN src/viterbiDecoder.h:19 and vitdec(..., tblen, ...) in
+ * scripts/matlab/viterbiBEREstimate.m:99 are the models, the reference's own windowed decoder does not
+ * run at HEAD).  nStreams independent K=7 streams that started in state 0 are decoded a slice at a time:
+ * every call consumes the next nSegments segments of each stream (row i of dSegs) and writes the bits
+ * that became final -- each decided by a traceback of at least `depth` steps from the best-metric state --
+ * at the start of row i of dOut, MSb-first.  The caller concatenates the rows of successive calls.
+ *   streamPos  segments of each stream consumed by earlier calls (0 on the first call)
+ *   depth      traceback depth in steps, a multiple of 24 (48 covers the usual 5*K = 35)
+ *   last       the stream ends with this slice, terminated by K-1 zero bits: traceback starts in state 0
+ *              and everything left is flushed (total length - (K-1) must be a multiple of 8)
+ *   dCarry     ced_window_carry_bytes(nStreams, depth) bytes of device memory, 16-byte aligned, owned by
+ *              the caller and passed unchanged from call to call (metrics + the last `depth` decisions)
+ * nSegments and streamPos must be multiples of 96 except nSegments of the last call.
+ * Returns the number of decoded BYTES written per stream by this call (>= 0), or a negative CED_ERR_*.
+ */
+size_t ced_window_carry_bytes(int nStreams, int depth);
+int ced_decode_window_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
+                            int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
+                            uint8_t *dOut, size_t outStride, void *stream);
+
 /* dCounters[0] += popcount(dA ^ dB) over nFrames x bytesPerFrame; dCounters[1] +=
  * bits compared.  Device-side uint64 counters, so a BER sweep can all-reduce
  * them (NCCL sum) without a host round trip. */

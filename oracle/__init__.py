@@ -63,6 +63,8 @@ class Port:
         lib.orc_decode_batch.restype = C.c_int
         lib.orc_decode_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_int, _u8p, C.c_size_t, C.c_int, C.c_int,
                                          _u8p, C.c_size_t]
+        lib.orc_decode_window.restype = C.c_int
+        lib.orc_decode_window.argtypes = [C.c_int, C.c_int, _u64p, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
         lib.orc_encode_batch.restype = C.c_int
         lib.orc_encode_batch.argtypes = [C.c_int, C.c_int, _u64p, _u8p, C.c_size_t, C.c_int, C.c_int, _u8p,
                                          C.c_size_t]
@@ -109,6 +111,15 @@ class Port:
         rc = self.lib.orc_decode_batch(K, len(g), self._g(g), int(symmetric), _p(segs), stride, nf, T, _p(out),
                                        nbytes)
         assert rc == 0
+        return out
+
+    def decode_window(self, K, g, segs, call_segs, depth):
+        """One terminated stream decoded with windowed traceback (orc_decode_window: semantics defined there)."""
+        segs = np.ascontiguousarray(segs, dtype=np.uint8)
+        T = segs.size
+        out = np.zeros((T - (K - 1) + 7) // 8, dtype=np.uint8)
+        rc = self.lib.orc_decode_window(K, len(g), self._g(g), _p(segs), T, int(call_segs), int(depth), _p(out))
+        assert rc == T - (K - 1), rc
         return out
 
     def decoder(self, K, g, symmetric=True, max_segments=16390):

@@ -259,6 +259,58 @@ int orc_dec_step(orc_decoder_t *d, const uint8_t *segs, int segmentsIn, uint8_t 
     return bytesOut;
 }
 
+/*
+ * Windowed traceback over a long (continuous) terminated stream, SURVEY 8(f)4.  PARITY UNPINNED against the
+ * reference: its only sliding-window decoder (TRACEBACK_LEN = 5K, src/viterbiDecoder.h:19, generic
+ * viterbiDecoderHard src/viterbiDecoder.c:32-258) aborts at HEAD and no test reaches it; the behavioural
+ * model is MATLAB's vitdec(..., tblen, ..., 'hard') (scripts/matlab/viterbiBEREstimate.m:17,99).  This
+ * function DEFINES the semantics the CUDA window path is tested against:
+ *   - the forward recursion is the reference's (orc_dec_step, bit-exact decisions);
+ *   - the stream arrives in calls of `callSegs` segments (the last call takes the rest);
+ *   - after a call that ends at step P (not the last) the decoder starts in the state with the smallest
+ *     metric (lowest state index on ties), walks the survivors back and emits the bits of the steps
+ *     below P - depth that were not emitted before -- every bit is decided by a traceback of at
+ *     least `depth` steps;
+ *   - the last call starts in state 0 (terminated stream, :205-223), drops the S tail steps and emits
+ *     everything left.
+ * Output bit t is bit 0 of the survivor state after step t, MSb-first (:244-249).  Returns the number
+ * of bits written (total - S) or -1.
+ */
+int orc_decode_window(int K, int n, const uint64_t *g, const uint8_t *segs, int totalSegs, int callSegs,
+                      int depth, uint8_t *out)
+{
+    if (callSegs <= 0 || depth < 0 || totalSegs <= K - 1)
+        return -1;
+    orc_decoder_t *d = orc_dec_new(K, n, g, 1, totalSegs);
+    if (!d)
+        return -1;
+    const int N = d->N, S = d->S;
+    memset(out, 0, (size_t)(totalSegs - S + 7) / 8);
+    int emitted = 0; /* bits of steps [0, emitted) are final */
+    for (int P0 = 0; P0 < totalSegs;) {
+        const int P = (totalSegs - P0 <= callSegs) ? totalSegs : P0 + callSegs;
+        const int lastCall = P == totalSegs;
+        orc_dec_step(d, segs + P0, P - P0, NULL, 0);
+        uint32_t state = 0;
+        if (!lastCall)
+            for (int s2 = 1; s2 < N; s2++)
+                if (d->metric[s2] < d->metric[state])
+                    state = (uint32_t)s2;
+        const int hi = lastCall ? totalSegs - S : P - depth; /* emit steps [emitted, hi) */
+        for (int t = P - 1; t >= emitted; t--) {
+            const uint32_t dec = d->surv[(size_t)t * (size_t)N + state];
+            if (t < hi && (state & 1u))
+                out[t / 8] |= (uint8_t)(0x80u >> (t % 8));
+            state = (state >> 1) | (dec << (S - 1));
+        }
+        if (hi > emitted)
+            emitted = hi;
+        P0 = P;
+    }
+    orc_dec_free(d);
+    return emitted;
+}
+
 /* whole frames, one-shot (speedDecode.c:79 call shape) */
 int orc_decode_batch(int K, int n, const uint64_t *g, int symmetric, const uint8_t *segs,
                      size_t segStride, int nFrames, int segsPerFrame, uint8_t *out, size_t outStride)

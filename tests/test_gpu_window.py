@@ -1,0 +1,108 @@
+"""Continuous streams with windowed traceback through the C ABI, against the oracle's definition
+(oracle/ced_oracle.c orc_decode_window).  PARITY UNPINNED against the reference -- its windowed decoder does not
+run at HEAD -- so two anchors tie it back to the pinned path: the forward recursion is shared with
+ced_decode_batch, and with a depth longer than the stream the output must equal the reference's full traceback."""
+import numpy as np
+import pytest
+
+import convolutionalencdec_b200 as ced
+import oracle
+from conftest import bsc
+
+pytestmark = pytest.mark.gpu
+K7 = oracle.K7_G
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    c = ced.Context(0)
+    yield c
+    c.close()
+
+
+def make_streams(port, rng, n_streams, total_segs, p):
+    bits = total_segs - 6
+    assert bits % 8 == 0
+    msgs = rng.integers(0, 256, (n_streams, bits // 8), dtype=np.uint8)
+    clean = port.encode_batch(7, K7, msgs)
+    return msgs, bsc(rng, clean, p)
+
+
+def run_window(ctx, noisy, call_segs, depth, offset=0):
+    import torch
+    n_streams, total = noisy.shape
+    stride = (total + 15) // 16 * 16 + 16
+    buf = torch.zeros(n_streams * stride + 16, dtype=torch.uint8, device="cuda")
+    d = buf[offset:offset + n_streams * stride].view(n_streams, stride)
+    d[:, :total] = torch.from_numpy(noisy).cuda()
+    dec = ctx.window_decoder(ced.K7_DEFAULT, n_streams, depth)
+    pieces, pos = [], 0
+    while pos < total:
+        n = total - pos if total - pos <= call_segs else call_segs
+        pieces.append(dec.push(d[:, pos:pos + n], last=(pos + n == total)).clone())
+        pos += n
+    ctx.sync()
+    return torch.cat(pieces, dim=1).cpu().numpy()
+
+
+@pytest.mark.parametrize("n_streams,total,call,depth,p,offset", [
+    (100, 4902, 960, 48, 0.04, 0),
+    (100, 4902, 960, 24, 0.08, 0),
+    (33, 96 * 30 + 6, 96, 192, 0.06, 0),      # depth longer than a slice: the first calls emit nothing
+    (64, 96 * 20 + 14, 192, 96, 0.05, 1),     # misaligned base pointer
+    (5, 96 * 12 + 38, 288, 48, 0.10, 0),
+    (1, 96 + 6, 96, 24, 0.02, 0),
+    (40, 1926, 96 * 40, 48, 0.05, 0),         # one call: first and last at once
+])
+def test_window_decode_matches_oracle_definition(ctx, port, n_streams, total, call, depth, p, offset):
+    rng = np.random.default_rng(total * 7 + depth)
+    msgs, noisy = make_streams(port, rng, n_streams, total, p)
+    got = run_window(ctx, noisy, call, depth, offset)
+    assert got.shape == msgs.shape
+    for i in range(n_streams):
+        want = port.decode_window(7, K7, noisy[i], call, depth)
+        assert np.array_equal(got[i], want), (i, int(np.bitwise_count(got[i] ^ want).sum()))
+
+
+def test_window_longer_than_stream_equals_full_traceback(ctx, port, ref):
+    """depth >= stream length: every bit is decided by the final traceback from state 0, i.e. the reference's
+    full-frame decoder (src/viterbiDecoderButterflyk1.c:200-260) on the same symbols."""
+    rng = np.random.default_rng(5)
+    total = 96 * 8 + 6
+    msgs, noisy = make_streams(port, rng, 70, total, 0.07)
+    got = run_window(ctx, noisy, 96 * 2, 96 * 9)
+    assert np.array_equal(got, ref.decode_batch(noisy, total))
+
+
+def test_window_long_stream_beyond_reference_packet_limit(ctx, port):
+    """A stream of 2^17 bits (8x the reference's MAX_PKT_LEN_UNCODED_BITS) with 12 KB of survivors per stream in
+    flight; noise-free symbols must give back the message, noisy ones stay within the full decoder's error count."""
+    import torch
+    rng = np.random.default_rng(11)
+    total = (1 << 17) + 6
+    assert (total - 6) % 96 != 0    # the last slice is ragged
+    msgs, noisy = make_streams(port, rng, 32, total, 0.0)
+    assert np.array_equal(run_window(ctx, noisy, 96 * 16, 48), msgs)
+    noisy = bsc(rng, noisy, 0.03)
+    got = run_window(ctx, noisy, 96 * 16, 48)
+    want = np.stack([port.decode_window(7, K7, noisy[i], 96 * 16, 48) for i in range(4)])
+    assert np.array_equal(got[:4], want)
+    errs = int(np.bitwise_count(got ^ msgs).sum())
+    assert errs < 1e-3 * msgs.size * 8, errs
+
+
+def test_window_argument_checks(ctx):
+    import torch
+    segs = torch.zeros((4, 192), dtype=torch.uint8, device="cuda")
+    with pytest.raises(ValueError):
+        ctx.window_decoder(ced.K7_DEFAULT, 4, 35)          # depth must be a multiple of 24
+    dec = ctx.window_decoder(ced.K7_DEFAULT, 4, 48)
+    with pytest.raises(ced.CedError):
+        dec.push(segs[:, :100])                            # slices are multiples of 96
+    with pytest.raises(ced.CedError):
+        dec.push(segs[:, :96 + 7], last=True)              # stream must end on a byte boundary + tail
+    k3 = ced.Code(3, [7, 6])
+    with pytest.raises(ced.CedError):
+        ctx.window_decoder(k3, 4, 48).push(segs[:, :96])   # SWAR codes only
