@@ -367,20 +367,13 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
             if (win.metricsOut) {
                 /* T is a multiple of 96 here, so the next step has phase 0: position == state */
                 renorm(R);
-                uint32_t best = 0;
-#pragma unroll
-                for (int r = 15; r >= 0; r--) {
-                    /* zero-byte finder, exact for bytes < 128; the lowest flagged lane is always a true zero */
-                    const uint32_t z = (R[r] - 0x01010101u) & ~R[r] & 0x80808080u;
-                    if (z)
-                        best = 4u * r + ((__ffs((int)z) - 1) >> 3);
-                }
+                const uint32_t best = bestPositionB(R);
                 if (live) {
 #pragma unroll
                     for (int i = 0; i < 4; i++)
                         __stcg(win.metricsOut + ((size_t)g * 4 + i) * 32 + lane,
                                make_uint4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]));
-                    win.startPos[(size_t)g * 32 + lane] = 32u * (best >> 5) + 8u * (best & 3u) + ((best >> 2) & 7u);
+                    win.startPos[(size_t)g * 32 + lane] = best;
                 }
             }
         }

@@ -268,6 +268,27 @@ CED_HDC int pairBitInB(int ph)
     return (int)((0x340125u >> (4 * ph)) & 7u);
 }
 
+/* Windowed traceback start (continuous streams): after renorm() the smallest metric is 0; returns, in b form, the
+ * lowest position holding it.  Called between slices, where the next phase is 0 and position == state, so ties go
+ * to the lowest state.  The zero-byte finder is exact for bytes < 128 up to and including the lowest zero lane. */
+CED_HD uint32_t bestPositionB(const uint32_t (&R)[16])
+{
+    uint32_t best = 0;
+#pragma unroll
+    for (int r = 15; r >= 0; r--) {
+        const uint32_t z = (R[r] - 0x01010101u) & ~R[r] & 0x80808080u;
+        if (z) {
+#ifdef __CUDA_ARCH__
+            const int first = __ffs((int)z) - 1;
+#else
+            const int first = __builtin_ffs((int)z) - 1;
+#endif
+            best = 4u * (uint32_t)r + (uint32_t)(first >> 3);
+        }
+    }
+    return 32u * (best >> 5) + 8u * (best & 3u) + ((best >> 2) & 7u);
+}
+
 /* One backward step through trellis step t (phase ph).  On entry b locates the
  * survivor state after step t; returns that state's newest bit (the decoded bit
  * of step t, src/viterbiDecoderButterflyk1.c:244-249) and moves b to the

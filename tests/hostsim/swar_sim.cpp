@@ -59,6 +59,48 @@ extern "C" int swar_sim_decode(const uint8_t *segs, int T, uint8_t *out, uint32_
     return (L + 7) / 8;
 }
 
+// The windowed procedure of ced_decode_window_batch for one stream (slices of callSegs, a multiple of 96;
+// traceback from the best-metric position after every slice, from state 0 after the last one).
+extern "C" int swar_sim_window(const uint8_t *segs, int T, int callSegs, int depth, uint8_t *out)
+{
+    uint32_t R[16];
+    ced::initMetrics(R);
+    std::vector<uint32_t> surv(2 * (size_t)T);
+    const int L = T - 6;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
+    int emitted = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t t0 = 0, t1 = 0, rx = segs[t];
+        switch (t % 6) {
+        case 0: stepPhase<0>(R, rx, t0, t1); break;
+        case 1: stepPhase<1>(R, rx, t0, t1); break;
+        case 2: stepPhase<2>(R, rx, t0, t1); break;
+        case 3: stepPhase<3>(R, rx, t0, t1); break;
+        case 4: stepPhase<4>(R, rx, t0, t1); break;
+        default: stepPhase<5>(R, rx, t0, t1); break;
+        }
+        surv[2 * t] = t0;
+        surv[2 * t + 1] = t1;
+        const int P = t + 1;
+        const bool lastCall = P == T;
+        if (P % 96 == 0 && !lastCall)
+            ced::renorm(R);
+        if (!lastCall && !(P % callSegs == 0 && T - P > 0))
+            continue;
+        if (!lastCall && T - (P - callSegs) <= callSegs)
+            continue; /* the remainder belongs to the last call */
+        uint32_t b = lastCall ? 0u : ced::bestPositionB(R);
+        const int hi = lastCall ? L : P - depth;
+        for (int u = P - 1; u >= emitted; u--) {
+            uint32_t bit = ced::tracebackStep(b, surv[2 * u], surv[2 * u + 1], u % 6);
+            if (u < hi)
+                out[u / 8] |= (uint8_t)(bit << (7 - (u % 8)));
+        }
+        if (hi > emitted) emitted = hi;
+    }
+    return emitted;
+}
+
 // decision of state s after step t from the packed words (for comparing with the oracle's survivors)
 extern "C" int swar_sim_decision(const uint32_t *surv, int t, int s)
 {

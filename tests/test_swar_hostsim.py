@@ -72,3 +72,20 @@ def test_renorm_period_does_not_change_decisions(sim, port):
         got, _, mx = run(sim, row, period)
         assert np.array_equal(got, base) and mx < 126
 
+
+
+@pytest.mark.parametrize("total,call,depth,p", [(96 * 20 + 6, 96, 24, 0.08), (96 * 20 + 14, 192, 48, 0.06),
+                                                (96 * 9 + 38, 288, 96, 0.10), (96 * 12 + 6, 96, 192, 0.12),
+                                                (96 * 3 + 6, 96 * 8, 48, 0.05)])
+def test_window_procedure_matches_oracle_definition(sim, port, total, call, depth, p):
+    """Best-position start (bestPositionB), survivor-bit-index traceback and the slice bookkeeping of the windowed
+    decoder, on the host, against orc_decode_window -- incl. high noise so that metric ties occur."""
+    sim.swar_sim_window.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p]
+    rng = np.random.default_rng(total + depth)
+    for _ in range(6):
+        msg = rng.integers(0, 256, (1, (total - 6) // 8), dtype=np.uint8)
+        noisy = np.ascontiguousarray(bsc(rng, port.encode_batch(7, oracle.K7_G, msg), p)[0])
+        out = np.zeros((total - 6) // 8, dtype=np.uint8)
+        rc = sim.swar_sim_window(noisy.ctypes.data_as(u8p), total, call, depth, out.ctypes.data_as(u8p))
+        assert rc == total - 6
+        assert np.array_equal(out, port.decode_window(7, oracle.K7_G, noisy, call, depth))
