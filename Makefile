@@ -13,7 +13,8 @@ PKG := convolutionalencdec_b200
 CSRC := $(PKG)/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
 CFLAGS := -O2 -g -std=gnu11 -fPIC -Wall -Iinclude
-HOST_SRCS := $(CSRC)/host/convEncode.c $(CSRC)/host/convHelpers.c $(CSRC)/host/viterbiDecoder.c $(CSRC)/host/ced_introspect.c
+HOST_SRCS := $(CSRC)/host/convEncode.c $(CSRC)/host/convHelpers.c $(CSRC)/host/viterbiDecoder.c $(CSRC)/host/ced_introspect.c \
+             $(CSRC)/host/viterbiDecoderQueue.c
 CUDA_HDRS := $(wildcard $(CSRC)/*.cuh) include/ced_abi.h
 
 all: cuda host oracle hostsim drivers examples
@@ -30,7 +31,11 @@ $(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCode
 	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
 	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
 
-examples: examples/_bin/batch_roundtrip
+examples: examples/_bin/batch_roundtrip examples/_bin/speed_decode_queued
+examples/_bin/speed_decode_queued: examples/speed_decode_queued.c $(wildcard include/*.h) $(PKG)/libconvencdec_k7.so
+	mkdir -p examples/_bin
+	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude/params/default -Iinclude -o $@ $< -L$(PKG) -lconvencdec_k7 -lced_cuda -pthread \
+	    -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 examples/_bin/batch_roundtrip: examples/batch_roundtrip.c include/ced_abi.h $(PKG)/libced_cuda.so
 	mkdir -p examples/_bin
 	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude -o $@ $< -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN/../../$(PKG)'

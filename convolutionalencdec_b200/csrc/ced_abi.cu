@@ -318,6 +318,30 @@ uint64_t ced_launch_count(const ced_ctx *c)
     return c ? c->launches : 0;
 }
 
+int ced_host_alloc(size_t bytes, void **out)
+{
+    if (!out || bytes == 0) {
+        setError("ced_host_alloc: bad argument");
+        return CED_ERR_ARG;
+    }
+    ced_ctx *c = ced_default_ctx();   /* makes sure a device is selected */
+    if (!c)
+        return CED_ERR_CUDA;
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) {
+        setError("cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return CED_ERR_NOMEM;
+    }
+    return CED_OK;
+}
+
+void ced_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
 size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
 {
     if (nFrames <= 0 || frameBits <= 0)

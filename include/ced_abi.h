@@ -131,6 +131,10 @@ int ced_decode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *h
 int ced_encode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride,
                           int nFrames, int frameBytes, uint8_t *hSegs, size_t segStride);
 
+/* Page-locked host memory for the *_host calls (pageable buffers work too, at a fraction of the PCIe rate). */
+int ced_host_alloc(size_t bytes, void **out);
+void ced_host_free(void *p);
+
 /* Bytes of survivor scratch ced_decode_batch keeps inside the context for a
  * batch of this shape (grown on demand, reused across calls). */
 size_t ced_decode_scratch_bytes(int nFrames, int frameBits);
