@@ -31,8 +31,8 @@ $(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCode
 	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
 	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
 
-examples: examples/_bin/batch_roundtrip examples/_bin/speed_decode_queued
-examples/_bin/speed_decode_queued: examples/speed_decode_queued.c $(wildcard include/*.h) $(PKG)/libconvencdec_k7.so
+examples: examples/_bin/batch_roundtrip examples/_bin/speed_queued
+examples/_bin/speed_queued: examples/speed_queued.c $(wildcard include/*.h) $(PKG)/libconvencdec_k7.so
 	mkdir -p examples/_bin
 	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude/params/default -Iinclude -o $@ $< -L$(PKG) -lconvencdec_k7 -lced_cuda -pthread \
 	    -Wl,-rpath,'$$ORIGIN/../../$(PKG)'

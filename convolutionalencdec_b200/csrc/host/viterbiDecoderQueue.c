@@ -1,6 +1,7 @@
 /*
- * include/viterbiDecoderQueue.h: collects whole packets into page-locked batches and decodes a batch with one
- * ced_decode_batch_host call on a worker thread while the caller fills the other batch.
+ * include/viterbiDecoderQueue.h: collects whole packets into page-locked batches and decodes (or encodes) a batch
+ * with one ced_decode_batch_host / ced_encode_batch_host call on a worker thread while the caller fills the other
+ * batch.
  */
 #include "viterbiDecoderQueue.h"
 #include "ced_abi.h"
@@ -19,7 +20,8 @@ typedef struct {
 } queueBatch_t;
 
 struct viterbiQueue {
-    int segments, outBytes, maxPackets;
+    int encode;         /* 0: segments in, bytes out; 1: bytes in, segments out */
+    int segments, outBytes, maxPackets;   /* outBytes = information bytes per packet */
     size_t stride;
     queueBatch_t batch[2];
     int fill;           /* batch the producer writes into */
@@ -49,11 +51,19 @@ static void *queueWorker(void *arg)
             break;
         queueBatch_t *b = &q->batch[next];
         pthread_mutex_unlock(&q->mu);
-        if (ced_decode_batch_host(q->ctx, &q->code, b->segs, q->stride, b->count, 8 * q->outBytes, b->bytes,
-                                  (size_t)q->outBytes) != CED_OK)
-            queueFail("decode");
-        for (int i = 0; i < b->count; i++)
-            memcpy(b->dest[i], b->bytes + (size_t)i * q->outBytes, (size_t)q->outBytes);
+        if (q->encode) {
+            if (ced_encode_batch_host(q->ctx, &q->code, b->bytes, (size_t)q->outBytes, b->count, q->outBytes, b->segs,
+                                      q->stride) != CED_OK)
+                queueFail("encode");
+            for (int i = 0; i < b->count; i++)
+                memcpy(b->dest[i], b->segs + (size_t)i * q->stride, (size_t)q->segments);
+        } else {
+            if (ced_decode_batch_host(q->ctx, &q->code, b->segs, q->stride, b->count, 8 * q->outBytes, b->bytes,
+                                      (size_t)q->outBytes) != CED_OK)
+                queueFail("decode");
+            for (int i = 0; i < b->count; i++)
+                memcpy(b->dest[i], b->bytes + (size_t)i * q->outBytes, (size_t)q->outBytes);
+        }
         pthread_mutex_lock(&q->mu);
         q->delivered += b->count;
         b->count = 0;
@@ -65,7 +75,7 @@ static void *queueWorker(void *arg)
     return NULL;
 }
 
-viterbiQueue_t *viterbiQueueCreate(int segmentsPerPacket, int maxPackets)
+static viterbiQueue_t *queueCreate(int segmentsPerPacket, int maxPackets, int encode)
 {
     const int bits = (segmentsPerPacket - S) * k;
     if (segmentsPerPacket <= S || bits % 8 != 0 || maxPackets <= 0) {
@@ -75,6 +85,7 @@ viterbiQueue_t *viterbiQueueCreate(int segmentsPerPacket, int maxPackets)
     viterbiQueue_t *q = (viterbiQueue_t *)calloc(1, sizeof(*q));
     if (!q)
         return NULL;
+    q->encode = encode;
     q->segments = segmentsPerPacket;
     q->outBytes = bits / 8;
     q->maxPackets = maxPackets;
@@ -104,6 +115,20 @@ viterbiQueue_t *viterbiQueueCreate(int segmentsPerPacket, int maxPackets)
     return q;
 }
 
+viterbiQueue_t *viterbiQueueCreate(int segmentsPerPacket, int maxPackets)
+{
+    return queueCreate(segmentsPerPacket, maxPackets, 0);
+}
+
+convEncQueue_t *convEncQueueCreate(int bytesPerPacket, int maxPackets)
+{
+    if (bytesPerPacket <= 0) {
+        printf("convEncQueue: packets must have at least one byte\n");
+        exit(1);
+    }
+    return queueCreate(8 * bytesPerPacket / k + S, maxPackets, 1);
+}
+
 /* hand the filling batch to the worker and continue in the other one once it is free */
 static void queueHandOver(viterbiQueue_t *q)
 {
@@ -124,6 +149,26 @@ int viterbiQueueSubmit(viterbiQueue_t *q, const uint8_t *codedSegments, uint8_t 
     if (++b->count == q->maxPackets)
         queueHandOver(q);
     return q->outBytes;
+}
+
+int convEncQueueSubmit(convEncQueue_t *q, const uint8_t *uncoded, uint8_t *codedSegments)
+{
+    queueBatch_t *b = &q->batch[q->fill];
+    memcpy(b->bytes + (size_t)b->count * q->outBytes, uncoded, (size_t)q->outBytes);
+    b->dest[b->count] = codedSegments;
+    if (++b->count == q->maxPackets)
+        queueHandOver(q);
+    return q->segments;
+}
+
+long convEncQueueFlush(convEncQueue_t *q)
+{
+    return viterbiQueueFlush(q);
+}
+
+void convEncQueueDestroy(convEncQueue_t *q)
+{
+    viterbiQueueDestroy(q);
 }
 
 long viterbiQueueFlush(viterbiQueue_t *q)

@@ -1,11 +1,12 @@
 /*
- * The reference's decode-speed loop (speedDecode/speedDecode.c:72-110: pre-encoded 2048-bit packets, decode them
- * over and over, report information Mbps) with the two-line change of include/viterbiDecoderQueue.h: packets are
- * submitted one by one exactly as before, the library decodes them on the GPU a batch at a time.
- * Every decoded packet is compared with its message at the end.
+ * The reference's speed loops (speedEncode/speedEncode.c:55-90 and speedDecode/speedDecode.c:72-110: 2048-bit
+ * packets, encode / decode them over and over, report information Mbps) with the two-line change of
+ * include/viterbiDecoderQueue.h: packets are submitted one by one exactly as before, the library runs them on the
+ * GPU a batch at a time.  The first packets are checked against the synchronous convEnc, every decoded packet
+ * against its message.
  *
- *   gcc -O2 -std=gnu11 -Iinclude/params/default -Iinclude -o examples/_bin/speed_decode_queued \
- *       examples/speed_decode_queued.c -Lconvolutionalencdec_b200 -lconvencdec_k7 -lced_cuda -pthread
+ *   gcc -O2 -std=gnu11 -Iinclude/params/default -Iinclude -o examples/_bin/speed_queued \
+ *       examples/speed_queued.c -Lconvolutionalencdec_b200 -lconvencdec_k7 -lced_cuda -pthread
  */
 #include "convEncode.h"
 #include "viterbiDecoder.h"
@@ -38,14 +39,33 @@ int main(int argc, char **argv)
     resetConvEncoder(&enc);
     initConvEncoder(&enc);
     srand(314);
-    for (int i = 0; i < PKTS; i++) {
+    for (int i = 0; i < PKTS; i++)
         for (int j = 0; j < PKT_BYTES; j++)
             msg[i][j] = (uint8_t)rand();
-        if (convEnc(&enc, msg[i], coded[i], PKT_BYTES, true) != PKT_SEGS)
+
+    convEncQueue_t *eq = convEncQueueCreate(PKT_BYTES, perBatch);
+    long encoded = 0;
+    const double e0 = now();
+    double e1 = e0;
+    do {
+        for (int i = 0; i < PKTS; i++)
+            convEncQueueSubmit(eq, msg[i], coded[i]);      /* was: convEnc(&enc, msg[i], coded[i], PKT_BYTES, true) */
+        encoded += convEncQueueFlush(eq);
+        e1 = now();
+    } while (e1 - e0 < seconds);
+    convEncQueueDestroy(eq);
+    long encWrong = 0;
+    for (int i = 0; i < 64; i++) {
+        uint8_t want[PKT_SEGS];
+        if (convEnc(&enc, msg[i], want, PKT_BYTES, true) != PKT_SEGS)
             return 1;
+        encWrong += memcmp(want, coded[i], PKT_SEGS) != 0;
+    }
+    printf("Encode rate: %f Mbps (%ld packets)\n", (double)encoded * 8.0 * PKT_BYTES / (e1 - e0) / 1e6, encoded);
+
+    for (int i = 0; i < PKTS; i++)
         for (int j = 7 + i % 5; j < PKT_SEGS; j += 61) /* a correctable sprinkle of channel errors */
             coded[i][j] ^= (uint8_t)(1 + (j & 1));
-    }
 
     viterbiQueue_t *q = viterbiQueueCreate(PKT_SEGS, perBatch);
     for (int i = 0; i < PKTS; i++)  /* warm-up pass */
@@ -68,6 +88,6 @@ int main(int argc, char **argv)
         wrong += memcmp(decoded[i], msg[i], PKT_BYTES) != 0;
     printf("Packets: %ld, Packet bits: %d, Batch: %d\n", packets, 8 * PKT_BYTES, perBatch);
     printf("Rate: %f Mbps\n", (double)packets * 8.0 * PKT_BYTES / (t1 - t0) / 1e6);
-    printf("%s\n", wrong ? "Failed: decoded packets differ from the messages" : "Success!");
-    return wrong ? 1 : 0;
+    printf("%s\n", (wrong || encWrong) ? "Failed: results differ from the synchronous API / the messages" : "Success!");
+    return (wrong || encWrong) ? 1 : 0;
 }

@@ -27,4 +27,12 @@ int viterbiQueueSubmit(viterbiQueue_t *q, const uint8_t *codedSegments, uint8_t 
 long viterbiQueueFlush(viterbiQueue_t *q);
 void viterbiQueueDestroy(viterbiQueue_t *q);
 
+/* The same for the encoder loop (speedEncode/speedEncode.c:65-67, one convEnc(..., last=true) per packet):
+ * `codedSegments` receives 8*bytesPerPacket/k + S segments some time before the next Flush returns. */
+typedef struct viterbiQueue convEncQueue_t;
+convEncQueue_t *convEncQueueCreate(int bytesPerPacket, int maxPackets);
+int convEncQueueSubmit(convEncQueue_t *q, const uint8_t *uncoded, uint8_t *codedSegments);
+long convEncQueueFlush(convEncQueue_t *q);
+void convEncQueueDestroy(convEncQueue_t *q);
+
 #endif
