@@ -18,6 +18,7 @@
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <vector>
 
 namespace ced_host {
 struct Packer;
@@ -111,7 +112,7 @@ struct PinnedBuf {
     }
 };
 
-enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171 };
+enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171, K7_Runtime };
 
 CodeId classify(const ced_code_t *c)
 {
@@ -121,6 +122,11 @@ CodeId classify(const ced_code_t *c)
         return CodeId::K7_0113_0171;
     if (c->gen[0] == 0133 && c->gen[1] == 0171)
         return CodeId::K7_0133_0171;
+    /* any other pair whose generators tap the newest and the oldest bit (the butterfly symmetry the
+     * reference itself requires, src/viterbiDecoder.c:20-24): SWAR kernel driven by a step table */
+    auto bothEnds = [](uint64_t g) { return g < 128 && (g & 1u) && ((g >> 6) & 1u); };
+    if (bothEnds(c->gen[0]) && bothEnds(c->gen[1]))
+        return CodeId::K7_Runtime;
     return CodeId::Unsupported;
 }
 
@@ -164,6 +170,12 @@ struct ced_ctx {
     std::recursive_mutex mu;
     uint64_t launches = 0;
     ced::BmTable bm0113, bm0133;
+    /* step tables of run-time K=7 codes (ced::buildStepTable), built on first use and kept */
+    struct StepTable {
+        uint64_t g0, g1;
+        uint2 *dev;
+    };
+    std::vector<StepTable> stepTables;
     /* optional kernel timing (ced_ctx_set_profiling) */
     bool profiling = false;
     static constexpr int kMaxProfWaves = 64;
@@ -272,6 +284,9 @@ void ced_ctx_destroy(ced_ctx *c)
         cudaEventDestroy(c->outReady[i]);
         cudaEventDestroy(c->outFree[i]);
     }
+    for (auto &t : c->stepTables)
+        cudaFree(t.dev);
+    c->stepTables.clear();
     c->sIn.release();
     c->sOut.release();
     c->sSurv.release();
@@ -352,6 +367,24 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
     wave = std::min<size_t>((size_t)nFrames, wave / 32 * 32);
     const size_t groups = (wave + 63) / 64 * 2;
     return groups * 32 * perFrame + groups * 4 * 32 * sizeof(uint4) + (groups + 1) * sizeof(int);
+}
+
+/* device copy of the step table of a run-time K=7 code (caller holds c->mu, device is current) */
+static int stepTableFor(ced_ctx *c, const ced_code_t *code, const uint2 **out)
+{
+    for (const auto &t : c->stepTables)
+        if (t.g0 == code->gen[0] && t.g1 == code->gen[1]) {
+            *out = t.dev;
+            return CED_OK;
+        }
+    std::vector<ced::Word2> host(ced::kStepTableEntries);
+    ced::buildStepTable(ced::makeK7Taps((uint32_t)code->gen[0], (uint32_t)code->gen[1]), host.data());
+    uint2 *dev = nullptr;
+    CED_CUDA(cudaMalloc(&dev, host.size() * sizeof(ced::Word2)));
+    CED_CUDA(cudaMemcpy(dev, host.data(), host.size() * sizeof(ced::Word2), cudaMemcpyHostToDevice));
+    c->stepTables.push_back({code->gen[0], code->gen[1], dev});
+    *out = dev;
+    return CED_OK;
 }
 
 /* Any k=1 code with K <= 9, n <= 8: one warp / CTA per frame (genericBatchDecodeKernel). */
@@ -447,7 +480,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     const CodeId id = classify(code);
     if (id == CodeId::Unsupported) {
         if (packed) {
-            setError("ced_decode_batch_packed: built for K=7 n=2 g={0113,0171} or {0133,0171} only");
+            setError("ced_decode_batch_packed: K=7 n=2 codes whose generators tap the newest and the oldest bit only");
             return CED_ERR_UNSUPPORTED;
         }
         return decodeBatchGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
@@ -463,6 +496,12 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const uint2 *stepTable = nullptr;
+    if (id == CodeId::K7_Runtime) {
+        int rc = stepTableFor(c, code, &stepTable);
+        if (rc != CED_OK)
+            return rc;
+    }
     const size_t perFrame = (size_t)(T / 2) * sizeof(uint4);
     size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
     waveMax = waveMax / 64 * 64;
@@ -513,13 +552,17 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
 #define CED_LAUNCH_FWD(CODE, FMT)                                                                                  \
     do {                                                                                                           \
         if (aligned16)                                                                                             \
-            ced::k7ForwardKernel<CODE, ced::FMT, true><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,     \
-                                                                                            wk.scratch.p, bm, sched, cpu); \
+            ced::k7ForwardKernel<CODE, ced::FMT, true><<<blocks, ced::kFwdThreads, 0, s>>>(                         \
+                in, segStride, wave, T, wk.scratch.p, bm, sched, cpu, ced::FwdWindow(), stepTable);                \
         else                                                                                                       \
-            ced::k7ForwardKernel<CODE, ced::FMT, false><<<blocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T,    \
-                                                                                             wk.scratch.p, bm, sched, cpu); \
+            ced::k7ForwardKernel<CODE, ced::FMT, false><<<blocks, ced::kFwdThreads, 0, s>>>(                        \
+                in, segStride, wave, T, wk.scratch.p, bm, sched, cpu, ced::FwdWindow(), stepTable);                \
     } while (0)
-        if (id == CodeId::K7_0113_0171 && !packed)
+        if (id == CodeId::K7_Runtime && !packed)
+            CED_LAUNCH_FWD(ced::RuntimeK7, ByteSymbols);
+        else if (id == CodeId::K7_Runtime)
+            CED_LAUNCH_FWD(ced::RuntimeK7, PackedSymbols);
+        else if (id == CodeId::K7_0113_0171 && !packed)
             CED_LAUNCH_FWD(Code0113, ByteSymbols);
         else if (id == CodeId::K7_0113_0171)
             CED_LAUNCH_FWD(Code0113, PackedSymbols);
@@ -582,7 +625,7 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     }
     const CodeId id = classify(code);
     if (id == CodeId::Unsupported) {
-        setError("ced_decode_window_batch: built for K=7 n=2 g={0113,0171} or {0133,0171} only");
+        setError("ced_decode_window_batch: K=7 n=2 codes whose generators tap the newest and the oldest bit only");
         return CED_ERR_UNSUPPORTED;
     }
     if (last ? (nSegments < ced::kTailSteps || (streamPos + (uint64_t)nSegments - ced::kTailSteps) % 8 != 0)
@@ -609,6 +652,12 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const uint2 *stepTable = nullptr;
+    if (id == CodeId::K7_Runtime) {
+        int rc = stepTableFor(c, code, &stepTable);
+        if (rc != CED_OK)
+            return rc;
+    }
     const size_t perFrame = (size_t)(Tl / 2) * sizeof(uint4);
     size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
     waveMax = waveMax / 64 * 64;
@@ -662,12 +711,14 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     do {                                                                                                           \
         if (aligned16)                                                                                             \
             ced::k7ForwardKernel<CODE, ced::ByteSymbols, true, true><<<blocks, ced::kFwdThreads, 0, s>>>(          \
-                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win);                                  \
+                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
         else                                                                                                       \
             ced::k7ForwardKernel<CODE, ced::ByteSymbols, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(         \
-                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win);                                  \
+                in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
     } while (0)
-        if (id == CodeId::K7_0113_0171)
+        if (id == CodeId::K7_Runtime)
+            CED_LAUNCH_WIN(ced::RuntimeK7);
+        else if (id == CodeId::K7_0113_0171)
             CED_LAUNCH_WIN(Code0113);
         else
             CED_LAUNCH_WIN(Code0133);

@@ -166,11 +166,16 @@ __device__ __forceinline__ void fwdStep(uint32_t (&R)[16], const uint8_t *bmBase
                                         uint32_t minusOne, uint32_t &t0, uint32_t &t1)
 {
     const uint32_t off = symPtr[PH];
-    const uint4 x = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + off);
-    const uint4 xg = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + 16 + off);
-    const uint32_t X[4] = {x.x, x.y, x.z, x.w};
-    const uint32_t E[4] = {xg.x, xg.y, xg.z, xg.w};
-    acsStep<Code, PH>(R, X, E, minusOne, t0, t1);
+    if constexpr (Code::kRuntime) {
+        /* step table [phase][entry][rx] of 8-byte entries; off = rx * 32 */
+        acsStepTable<PH>(R, reinterpret_cast<const uint2 *>(bmBase + PH * 512 + (off >> 2)), minusOne, t0, t1);
+    } else {
+        const uint4 x = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + off);
+        const uint4 xg = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + 16 + off);
+        const uint32_t X[4] = {x.x, x.y, x.z, x.w};
+        const uint32_t E[4] = {xg.x, xg.y, xg.z, xg.w};
+        acsStep<Code, PH>(R, X, E, minusOne, t0, t1);
+    }
 }
 
 /* Work distribution of the forward kernel.  A unit is (group of 32 frames, chunk of kChunk steps);
@@ -217,15 +222,21 @@ struct FwdWindow {
 template <class Code, class Fmt, bool ALIGNED, bool CARRY = false>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                BmTable table, FwdSched sched, int chunksPerUnit, FwdWindow win = FwdWindow())
+                BmTable table, FwdSched sched, int chunksPerUnit, FwdWindow win = FwdWindow(),
+                const uint2 *__restrict__ stepTable = nullptr)
 {
     using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
-    __shared__ uint4 sBm[6 * 4 * 2];
+    __shared__ uint4 sBm[Code::kRuntime ? kStepTableEntries / 2 : 6 * 4 * 2];
     __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
 
-    if (threadIdx.x < 48)
-        sBm[threadIdx.x] = table.x[threadIdx.x];
+    if constexpr (Code::kRuntime) {
+        for (int i = threadIdx.x; i < kStepTableEntries; i += kFwdThreads)
+            reinterpret_cast<uint2 *>(sBm)[i] = stepTable[i];
+    } else {
+        if (threadIdx.x < 48)
+            sBm[threadIdx.x] = table.x[threadIdx.x];
+    }
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -101,6 +101,46 @@ extern "C" int swar_sim_window(const uint8_t *segs, int T, int callSegs, int dep
     return emitted;
 }
 
+// Same frame decode through the run-time table path (acsStepTable + buildStepTable) for any symmetric K=7 n=2 code.
+template <int PH>
+static void stepTable(uint32_t (&R)[16], const ced::Word2 *table, uint32_t rx, uint32_t &t0, uint32_t &t1)
+{
+    ced::acsStepTable<PH>(R, table + PH * 64 + (int)(rx & 3u), 0xFFFFFFFFu, t0, t1);
+}
+
+extern "C" int swar_sim_decode_rt(uint32_t g0, uint32_t g1, const uint8_t *segs, int T, uint8_t *out)
+{
+    std::vector<ced::Word2> table(ced::kStepTableEntries);
+    ced::buildStepTable(ced::makeK7Taps(g0, g1), table.data());
+    uint32_t R[16];
+    ced::initMetrics(R);
+    std::vector<uint32_t> surv(2 * (size_t)T);
+    for (int t = 0; t < T; t++) {
+        uint32_t t0 = 0, t1 = 0, rx = segs[t];
+        switch (t % 6) {
+        case 0: stepTable<0>(R, table.data(), rx, t0, t1); break;
+        case 1: stepTable<1>(R, table.data(), rx, t0, t1); break;
+        case 2: stepTable<2>(R, table.data(), rx, t0, t1); break;
+        case 3: stepTable<3>(R, table.data(), rx, t0, t1); break;
+        case 4: stepTable<4>(R, table.data(), rx, t0, t1); break;
+        default: stepTable<5>(R, table.data(), rx, t0, t1); break;
+        }
+        surv[2 * t] = t0;
+        surv[2 * t + 1] = t1;
+        if ((t + 1) % 96 == 0)
+            ced::renorm(R);
+    }
+    const int L = T - 6;
+    uint32_t b = 0;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        uint32_t bit = ced::tracebackStep(b, surv[2 * t], surv[2 * t + 1], t % 6);
+        if (t < L)
+            out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
+    }
+    return (L + 7) / 8;
+}
+
 // decision of state s after step t from the packed words (for comparing with the oracle's survivors)
 extern "C" int swar_sim_decision(const uint32_t *surv, int t, int s)
 {

@@ -113,6 +113,40 @@ def test_decode_batch_other_code_parameters(torch_cuda, ctx, port, K, g, bits, f
             assert np.array_equal(want, msgs)
 
 
+@pytest.mark.parametrize("g", [(0o171, 0o133), (0o117, 0o155), (0o135, 0o163), (0o145, 0o175), (0o101, 0o177)])
+def test_decode_batch_any_symmetric_k7_code_runs_the_swar_kernel(torch_cuda, ctx, port, g):
+    """K=7 n=2 generators known only at run time -- the SWAR forward kernel driven by a step table
+    (RuntimeK7) -- byte and packed symbols, aligned and misaligned rows, and the windowed decoder."""
+    torch = torch_cuda
+    rng = np.random.default_rng(g[0] * 1000 + g[1])
+    code = ced.Code(7, g)
+    frames, bits = 333, 4096
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    enc = ctx.encode_batch(code, dev(torch, msgs))
+    ctx.sync()
+    clean = port.encode_batch(7, list(g), msgs)
+    assert np.array_equal(enc.cpu().numpy()[:, :T], clean)
+    for p in (0.0, 0.05, 0.5):
+        noisy = bsc(rng, clean, p)
+        want = port.decode_batch(7, list(g), noisy, T)
+        aligned = torch.zeros((frames, 4112), dtype=torch.uint8, device="cuda")
+        aligned[:, :T] = dev(torch, noisy)
+        ragged = dev(torch, noisy)                       # stride 4102: the alignment-agnostic staging
+        out_a = ctx.decode_batch(code, aligned, bits)
+        out_r = ctx.decode_batch(code, ragged, bits)
+        out_p = ctx.decode_batch_packed(code, ctx.pack_symbols(aligned, T), bits)
+        ctx.sync()
+        for out in (out_a, out_r, out_p):
+            assert np.array_equal(out.cpu().numpy(), want), (g, p)
+    wd = ctx.window_decoder(code, frames, depth=48)
+    pieces = [wd.push(aligned[:, a:min(a + 960, T)], last=a + 960 >= T).clone() for a in range(0, T, 960)]
+    ctx.sync()
+    got = torch.cat(pieces, dim=1).cpu().numpy()
+    for i in range(0, frames, 37):
+        assert np.array_equal(got[i], port.decode_window(7, list(g), noisy[i], 960, 48))
+
+
 def test_decode_batch_rejects_what_it_cannot_do(torch_cuda, ctx):
     torch = torch_cuda
     segs = torch.zeros((4, 70), dtype=torch.uint8, device="cuda")

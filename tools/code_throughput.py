@@ -1,0 +1,34 @@
+"""Decode throughput per code: the two compile-time K=7 codes, run-time K=7 generators through the
+step-table SWAR kernel, and other K / n through the generic one-warp-per-frame kernel."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import convolutionalencdec_b200 as ced  # noqa: E402
+
+ctx = ced.Context(0)
+bits = 4096
+for K, g, frames in ((7, (0o113, 0o171), 1 << 16), (7, (0o133, 0o171), 1 << 16), (7, (0o171, 0o133), 1 << 16),
+                     (7, (0o117, 0o155), 1 << 16), (7, (0o133, 0o170), 1 << 14), (3, (7, 6), 1 << 14),
+                     (9, (0o561, 0o753), 1 << 14), (7, (0o133, 0o145, 0o175), 1 << 14)):
+    code = ced.Code(K, g)
+    T = bits + K - 1
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=3)
+    segs = ctx.encode_batch(code, msgs, seg_stride=(T + 15) // 16 * 16)
+    ctx.bsc_channel(segs, T, len(g), 0.03, seed=4)
+    out = torch.empty_like(msgs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(3):
+        if rep == 1:
+            e0.record()
+        ctx.decode_batch(code, segs, bits, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    errs = int((out != msgs).sum())
+    print("K=%d g=%s frames=%d: %8.1f Gbit/s (%.3f ms), %d wrong bytes" % (
+        K, [oct(x) for x in g], frames, frames * bits / ms / 1e6, ms, errs))
+ctx.close()
