@@ -112,19 +112,23 @@ struct PinnedBuf {
     }
 };
 
-enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171, K7_Runtime };
+enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171, K7_Runtime, K7_RuntimeN3 };
 
 CodeId classify(const ced_code_t *c)
 {
+    /* generators that tap the newest and the oldest bit (the butterfly symmetry the reference itself
+     * requires, src/viterbiDecoder.c:20-24) */
+    auto bothEnds = [](uint64_t g) { return g < 128 && (g & 1u) && ((g >> 6) & 1u); };
+    if (c && c->constraintLen == 7 && c->codedBits == 3 && bothEnds(c->gen[0]) && bothEnds(c->gen[1]) &&
+        bothEnds(c->gen[2]))
+        return CodeId::K7_RuntimeN3;
     if (!c || c->constraintLen != 7 || c->codedBits != 2)
         return CodeId::Unsupported;
     if (c->gen[0] == 0113 && c->gen[1] == 0171)
         return CodeId::K7_0113_0171;
     if (c->gen[0] == 0133 && c->gen[1] == 0171)
         return CodeId::K7_0133_0171;
-    /* any other pair whose generators tap the newest and the oldest bit (the butterfly symmetry the
-     * reference itself requires, src/viterbiDecoder.c:20-24): SWAR kernel driven by a step table */
-    auto bothEnds = [](uint64_t g) { return g < 128 && (g & 1u) && ((g >> 6) & 1u); };
+    /* any other symmetric pair: SWAR kernel driven by a step table */
     if (bothEnds(c->gen[0]) && bothEnds(c->gen[1]))
         return CodeId::K7_Runtime;
     return CodeId::Unsupported;
@@ -172,7 +176,8 @@ struct ced_ctx {
     ced::BmTable bm0113, bm0133;
     /* step tables of run-time K=7 codes (ced::buildStepTable), built on first use and kept */
     struct StepTable {
-        uint64_t g0, g1;
+        int n;
+        uint64_t g[3];
         uint2 *dev;
     };
     std::vector<StepTable> stepTables;
@@ -372,17 +377,20 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
 /* device copy of the step table of a run-time K=7 code (caller holds c->mu, device is current) */
 static int stepTableFor(ced_ctx *c, const ced_code_t *code, const uint2 **out)
 {
+    const int n = code->codedBits;
+    const uint64_t g2 = n > 2 ? code->gen[2] : 0;
     for (const auto &t : c->stepTables)
-        if (t.g0 == code->gen[0] && t.g1 == code->gen[1]) {
+        if (t.n == n && t.g[0] == code->gen[0] && t.g[1] == code->gen[1] && t.g[2] == g2) {
             *out = t.dev;
             return CED_OK;
         }
-    std::vector<ced::Word2> host(ced::kStepTableEntries);
-    ced::buildStepTable(ced::makeK7Taps((uint32_t)code->gen[0], (uint32_t)code->gen[1]), host.data());
+    const uint32_t gens[3] = {(uint32_t)code->gen[0], (uint32_t)code->gen[1], (uint32_t)g2};
+    std::vector<ced::Word2> host((size_t)6 * 16 * (1u << n));
+    ced::buildStepTable(ced::makeK7Taps(n, gens), host.data());
     uint2 *dev = nullptr;
     CED_CUDA(cudaMalloc(&dev, host.size() * sizeof(ced::Word2)));
     CED_CUDA(cudaMemcpy(dev, host.data(), host.size() * sizeof(ced::Word2), cudaMemcpyHostToDevice));
-    c->stepTables.push_back({code->gen[0], code->gen[1], dev});
+    c->stepTables.push_back({n, {code->gen[0], code->gen[1], g2}, dev});
     *out = dev;
     return CED_OK;
 }
@@ -478,9 +486,9 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         return CED_ERR_ARG;
     }
     const CodeId id = classify(code);
-    if (id == CodeId::Unsupported) {
+    if (id == CodeId::Unsupported || (packed && id == CodeId::K7_RuntimeN3)) {
         if (packed) {
-            setError("ced_decode_batch_packed: K=7 n=2 codes whose generators tap the newest and the oldest bit only");
+            setError("ced_decode_batch_packed: 2-bit packing is for K=7 n=2 codes whose generators tap both ends");
             return CED_ERR_UNSUPPORTED;
         }
         return decodeBatchGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
@@ -497,7 +505,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     const uint2 *stepTable = nullptr;
-    if (id == CodeId::K7_Runtime) {
+    if (id == CodeId::K7_Runtime || id == CodeId::K7_RuntimeN3) {
         int rc = stepTableFor(c, code, &stepTable);
         if (rc != CED_OK)
             return rc;
@@ -558,10 +566,12 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             ced::k7ForwardKernel<CODE, ced::FMT, false><<<blocks, ced::kFwdThreads, 0, s>>>(                        \
                 in, segStride, wave, T, wk.scratch.p, bm, sched, cpu, ced::FwdWindow(), stepTable);                \
     } while (0)
-        if (id == CodeId::K7_Runtime && !packed)
-            CED_LAUNCH_FWD(ced::RuntimeK7, ByteSymbols);
+        if (id == CodeId::K7_RuntimeN3)
+            CED_LAUNCH_FWD(ced::RuntimeK7<3>, ByteSymbols);
+        else if (id == CodeId::K7_Runtime && !packed)
+            CED_LAUNCH_FWD(ced::RuntimeK7<2>, ByteSymbols);
         else if (id == CodeId::K7_Runtime)
-            CED_LAUNCH_FWD(ced::RuntimeK7, PackedSymbols);
+            CED_LAUNCH_FWD(ced::RuntimeK7<2>, PackedSymbols);
         else if (id == CodeId::K7_0113_0171 && !packed)
             CED_LAUNCH_FWD(Code0113, ByteSymbols);
         else if (id == CodeId::K7_0113_0171)
@@ -625,7 +635,7 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     }
     const CodeId id = classify(code);
     if (id == CodeId::Unsupported) {
-        setError("ced_decode_window_batch: K=7 n=2 codes whose generators tap the newest and the oldest bit only");
+        setError("ced_decode_window_batch: K=7 codes with 2 or 3 generators that tap the newest and the oldest bit only");
         return CED_ERR_UNSUPPORTED;
     }
     if (last ? (nSegments < ced::kTailSteps || (streamPos + (uint64_t)nSegments - ced::kTailSteps) % 8 != 0)
@@ -653,7 +663,7 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     const uint2 *stepTable = nullptr;
-    if (id == CodeId::K7_Runtime) {
+    if (id == CodeId::K7_Runtime || id == CodeId::K7_RuntimeN3) {
         int rc = stepTableFor(c, code, &stepTable);
         if (rc != CED_OK)
             return rc;
@@ -716,8 +726,10 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
             ced::k7ForwardKernel<CODE, ced::ByteSymbols, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(         \
                 in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
     } while (0)
-        if (id == CodeId::K7_Runtime)
-            CED_LAUNCH_WIN(ced::RuntimeK7);
+        if (id == CodeId::K7_RuntimeN3)
+            CED_LAUNCH_WIN(ced::RuntimeK7<3>);
+        else if (id == CodeId::K7_Runtime)
+            CED_LAUNCH_WIN(ced::RuntimeK7<2>);
         else if (id == CodeId::K7_0113_0171)
             CED_LAUNCH_WIN(Code0113);
         else

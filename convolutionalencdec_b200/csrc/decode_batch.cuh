@@ -69,9 +69,9 @@ inline BmTable makeBmTable()
 
 /* four byte-format segments per word -> four table offsets: keep the n=2 low bits
  * (calcHammingDist(..., n), src/viterbiDecoder.c:279-283) and scale by the 32-byte table entry */
-__device__ __forceinline__ uint32_t toBmOffset(uint32_t w)
+__device__ __forceinline__ uint32_t toBmOffset(uint32_t w, uint32_t symMask)
 {
-    return (w & 0x03030303u) << 5;
+    return (w & symMask) << 5;
 }
 /* one packed byte b = [s3 s2 s1 s0] -> four table offsets (s_j * 32 in byte j).  The even and the odd
  * segments are spread by separate multiplies so that the shifted copies never overlap (a single
@@ -139,7 +139,7 @@ __device__ __forceinline__ void loadTile(uint4 (&v)[TileGeom<Fmt, ALIGNED>::kPie
 
 template <class Fmt, bool ALIGNED>
 __device__ __forceinline__ void storeTile(uint8_t *tile, const uint4 (&v)[TileGeom<Fmt, ALIGNED>::kPiecesPerRow],
-                                          int lane)
+                                          int lane, uint32_t symMask)
 {
     using G = TileGeom<Fmt, ALIGNED>;
 #pragma unroll
@@ -150,7 +150,8 @@ __device__ __forceinline__ void storeTile(uint8_t *tile, const uint4 (&v)[TileGe
         const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
         if (Fmt::kSegsPerByte == 1) {
             *reinterpret_cast<uint4 *>(dst) =
-                make_uint4(toBmOffset(w[0]), toBmOffset(w[1]), toBmOffset(w[2]), toBmOffset(w[3]));
+                make_uint4(toBmOffset(w[0], symMask), toBmOffset(w[1], symMask), toBmOffset(w[2], symMask),
+                           toBmOffset(w[3], symMask));
         } else {
 #pragma unroll
             for (int q = 0; q < 4; q++) /* each word: 4 packed bytes = 16 segments = one uint4 of offsets */
@@ -168,7 +169,8 @@ __device__ __forceinline__ void fwdStep(uint32_t (&R)[16], const uint8_t *bmBase
     const uint32_t off = symPtr[PH];
     if constexpr (Code::kRuntime) {
         /* step table [phase][entry][rx] of 8-byte entries; off = rx * 32 */
-        acsStepTable<PH>(R, reinterpret_cast<const uint2 *>(bmBase + PH * 512 + (off >> 2)), minusOne, t0, t1);
+        acsStepTable<PH, Code::kCodedBits>(
+            R, reinterpret_cast<const uint2 *>(bmBase + PH * (128 * Code::kVariants) + (off >> 2)), minusOne, t0, t1);
     } else {
         const uint4 x = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + off);
         const uint4 xg = *reinterpret_cast<const uint4 *>(bmBase + PH * 128 + 16 + off);
@@ -211,6 +213,17 @@ __device__ __forceinline__ void stRelease(int *p, int v)
  * come from / go back to a caller-owned carry block, and the survivor rows of this launch are appended
  * behind the `pairOffset` rows kept from the previous call (the traceback depth).
  */
+/* uint4 slots of shared memory for the branch-metric operands: the 768-byte class table of a compile-time
+ * code, or the step table of a run-time one */
+template <class Code, bool RT = Code::kRuntime>
+struct StepTableUint4 {
+    static constexpr int value = 6 * 4 * 2;
+};
+template <class Code>
+struct StepTableUint4<Code, true> {
+    static constexpr int value = Code::kTableEntries / 2;
+};
+
 struct FwdWindow {
     const uint4 *metricsIn;  /* [groups][4][32] or NULL = start of the stream (state 0)             */
     uint4 *metricsOut;       /* [groups][4][32] renormalised metrics after the last step, or NULL    */
@@ -227,11 +240,11 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
 {
     using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
-    __shared__ uint4 sBm[Code::kRuntime ? kStepTableEntries / 2 : 6 * 4 * 2];
+    __shared__ uint4 sBm[StepTableUint4<Code>::value];
     __shared__ __align__(16) uint8_t sTile[kFwdThreads / 32][32 * kPitch];
 
     if constexpr (Code::kRuntime) {
-        for (int i = threadIdx.x; i < kStepTableEntries; i += kFwdThreads)
+        for (int i = threadIdx.x; i < 2 * StepTableUint4<Code>::value; i += kFwdThreads)
             reinterpret_cast<uint2 *>(sBm)[i] = stepTable[i];
     } else {
         if (threadIdx.x < 48)
@@ -308,7 +321,7 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
       for (unsigned c = cFirst; c < cEnd; c++) {
         const int t0 = (int)c * kChunk;
         __syncwarp();
-        storeTile<Fmt, ALIGNED>(tile, pre, lane);
+        storeTile<Fmt, ALIGNED>(tile, pre, lane, Code::kSymMask);
         /* prefetch the next tile: the following chunk of this unit, or the first chunk of the next
          * unit, which is claimed now so that its symbols stream in during this chunk's ACS work */
         if (c + 1 < cEnd) {
@@ -331,7 +344,7 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
         const int steps = min(kChunk, T - t0);
         const uint8_t *p = myRow;
         for (int done = 0; done < steps;) {
-            const int n = min(kRenormPeriod, steps - done);
+            const int n = min(Code::kRenormPeriod, steps - done);
             const int full = n / 6;
             for (int it = 0; it < full; it++) {
                 uint4 s;
@@ -363,7 +376,7 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
             }
             done += n;
             if (done < steps || c + 1 < chunks)
-                renorm(R); /* every kRenormPeriod = 96 steps, see DESIGN.md 4.3 */
+                renorm(R); /* every Code::kRenormPeriod (96) steps, see DESIGN.md 4.3 */
         }
       } /* chunks of this unit */
         if (cEnd < chunks) {

@@ -74,6 +74,9 @@ template <uint32_t G0, uint32_t G1>
 struct K7Code {
     static constexpr int K = 7;
     static constexpr bool kRuntime = false;
+    static constexpr int kCodedBits = 2;
+    static constexpr int kRenormPeriod = 96;            /* DESIGN.md 4.3 */
+    static constexpr uint32_t kSymMask = 0x03030303u;   /* calcHammingDist(..., n): only the low n bits count */
     static constexpr uint32_t g0 = G0, g1 = G1;
     /* src/convEncode.c:163-175: bit-reverse so bit 0 taps the newest input */
     static CED_HDC uint32_t rev7(uint32_t g)
@@ -240,47 +243,69 @@ CED_HD void acsStep(uint32_t (&R)[16], const uint32_t (&X)[4], const uint32_t (&
  * builds once per code and the kernel keeps in shared memory: for every (phase, received symbol) sixteen
  * 8-byte entries, one per butterfly (register-pair phases: 8 used) or per register (lane phases), holding
  * { X[k], E[k] } for the class k acsStep would have picked; the complements follow arithmetically,
- *   X[k^3] = 0x02020202 - X[k]        E[k^3] = 2 * guardWord - E[k]     (mod 2^32, exact)
+ *   X[k^full] = n * 0x01010101 - X[k]        E[k^full] = 2 * guardWord - E[k]     (mod 2^32, exact)
  * The lanes of a warp are different frames with different symbols, so one load touches up to four entries
  * (rx = 0..3): they are stored next to each other, [phase][entry][rx], 32 contiguous bytes = 8 banks, which
  * makes the load conflict-free.  (Measured on the way: [phase][rx][entry] puts the four on the same banks --
  * 4-way conflicts, shared-memory pipe 95 % busy, 87 Gbit/s; 16-byte entries holding all four operands:
  * 52.7 Gbit/s.) */
 struct Word2 { uint32_t x, y; }; /* layout of a uint2, usable in host code without CUDA headers */
-constexpr int kStepTableEntries = 6 * 4 * 16;
-constexpr uint32_t kTwoPerLane = 0x02020202u; /* n = 2: X[k] + X[k^3] in every lane */
-struct RuntimeK7 { /* tag: "the code is whatever the step table in shared memory says" */
+
+/* tag: "the code is whatever the step table in shared memory says"; N = coded bits per segment (2 or 3).
+ * With N = 3 a branch costs up to 3, so the metrics are renormalised every 24 steps: spread <= 3 * 6 = 18 after
+ * a renorm, + 3 * 24 growth + 3 for the candidate = 93 < 128 (same argument as DESIGN.md 4.3). */
+template <int N>
+struct RuntimeK7 {
+    static_assert(N == 2 || N == 3, "step tables are built for 2 or 3 coded bits");
     static constexpr bool kRuntime = true;
+    static constexpr int kCodedBits = N;
+    static constexpr int kVariants = 1 << N;                 /* received symbols */
+    static constexpr int kTableEntries = 6 * 16 * kVariants; /* Word2 each */
+    static constexpr int kRenormPeriod = N == 2 ? 96 : 24;
+    static constexpr uint32_t kSymMask = 0x01010101u * (uint32_t)(kVariants - 1);
 };
 
 struct K7Taps {
-    uint32_t tap0, tap1; /* generators bit-reversed onto the shift register (src/convEncode.c:163-175) */
-    CED_HD uint32_t segment(uint32_t reg) const { return parity32(reg & tap0) | (parity32(reg & tap1) << 1); }
+    uint32_t tap[3]; /* generators bit-reversed onto the shift register (src/convEncode.c:163-175) */
+    int n;
+    CED_HD uint32_t segment(uint32_t reg) const
+    {
+        uint32_t v = 0;
+        for (int i = 0; i < n; i++)
+            v |= parity32(reg & tap[i]) << i;
+        return v;
+    }
     CED_HD uint32_t cls(uint32_t p, int ph) const { return segment(((rotl6(p, ph) & 31u) << 1) & 127u); }
     CED_HD uint32_t bmWord(int ph, uint32_t rx, uint32_t k) const
     {
         uint32_t w = 0;
-        for (uint32_t l = 0; l < 4; l++)
-            w |= hd2(rx & 3u, k ^ cls(l, ph)) << (8 * l);
+        for (uint32_t l = 0; l < 4; l++) {
+            uint32_t diff = (rx ^ k ^ cls(l, ph)) & ((1u << n) - 1u), hd = 0;
+            for (; diff; diff >>= 1)
+                hd += diff & 1u;
+            w |= hd << (8 * l);
+        }
         return w;
     }
 };
 
-CED_HD K7Taps makeK7Taps(uint32_t g0, uint32_t g1)
+CED_HD K7Taps makeK7Taps(int n, const uint32_t *gens)
 {
-    K7Taps t = {0u, 0u};
-    for (int i = 0; i < 7; i++) {
-        t.tap0 |= ((g0 >> i) & 1u) << (6 - i);
-        t.tap1 |= ((g1 >> i) & 1u) << (6 - i);
-    }
+    K7Taps t = {{0u, 0u, 0u}, n};
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < 7; i++)
+            t.tap[j] |= ((gens[j] >> i) & 1u) << (6 - i);
     return t;
 }
 
-inline void buildStepTable(const K7Taps &c, Word2 *out /* [kStepTableEntries] */)
+/* out[6 * 16 * 2^n]: entry idx of (phase, rx) at out[(phase * 16 + idx) * 2^n + rx] */
+inline void buildStepTable(const K7Taps &c, Word2 *out)
 {
+    const int variants = 1 << c.n;
+    const uint32_t full = (uint32_t)variants - 1u;
     for (int ph = 0; ph < 6; ph++)
-        for (uint32_t rx = 0; rx < 4; rx++) {
-            Word2 *e = out + ph * 64 + (int)rx; /* entry idx of this (ph, rx) at e[4 * idx] */
+        for (uint32_t rx = 0; rx < (uint32_t)variants; rx++) {
+            Word2 *e = out + ph * 16 * variants + (int)rx;
             const uint32_t gw = guardWord(ph);
             const int q = 5 - ph;
             int idx = 0;
@@ -288,22 +313,24 @@ inline void buildStepTable(const K7Taps &c, Word2 *out /* [kStepTableEntries] */
                 if (q >= 2 && ((r >> (q - 2)) & 1))
                     continue;
                 const uint32_t k = c.cls((uint32_t)r << 2, ph);
-                const uint32_t d = c.bmWord(ph, rx, k), dc = c.bmWord(ph, rx, k ^ 3u);
-                e[4 * idx].x = d;
-                e[4 * idx].y = dc - d + gw;
+                const uint32_t d = c.bmWord(ph, rx, k), dc = c.bmWord(ph, rx, k ^ full);
+                e[variants * idx].x = d;
+                e[variants * idx].y = dc - d + gw;
                 idx++;
             }
             for (; idx < 16; idx++)
-                e[4 * idx].x = e[4 * idx].y = 0u;
+                e[variants * idx].x = e[variants * idx].y = 0u;
         }
 }
 
 /* acsStep with the operands taken from the table entries of (PH, rx) -- tab points at entry 0 of that pair,
- * entry i sits at tab[4 * i] -- same arithmetic, same decisions */
-template <int PH, class Entry>
+ * entry i sits at tab[2^N * i] -- same arithmetic, same decisions */
+template <int PH, int N, class Entry>
 CED_HD void acsStepTable(uint32_t (&R)[16], const Entry *tab, uint32_t minusOne, uint32_t &T0, uint32_t &T1)
 {
     constexpr int q = 5 - PH;
+    constexpr int stride = 1 << N;
+    constexpr uint32_t kBitsPerLane = 0x01010101u * (uint32_t)N; /* X[k] + X[k ^ full] in every lane */
     uint32_t t0 = 0, t1 = 0;
     if constexpr (q >= 2) {
         constexpr int rb = q - 2;
@@ -313,8 +340,8 @@ CED_HD void acsStepTable(uint32_t (&R)[16], const Entry *tab, uint32_t minusOne,
             if ((r >> rb) & 1)
                 continue;
             const int rh = r | (1 << rb);
-            const Entry e = tab[4 * idx++];
-            const uint32_t d = e.x, dc = subOnFma(kTwoPerLane, d, minusOne);
+            const Entry e = tab[stride * idx++];
+            const uint32_t d = e.x, dc = subOnFma(kBitsPerLane, d, minusOne);
             const uint32_t lo = R[r], hi = R[rh];
             const uint32_t a0 = lo + d, a1 = hi + dc;
             const uint32_t b0 = lo + dc, b1 = hi + d;
@@ -332,10 +359,10 @@ CED_HD void acsStepTable(uint32_t (&R)[16], const Entry *tab, uint32_t minusOne,
         constexpr uint32_t upper = (q == 1) ? 0xFFFF0000u : 0xFF00FF00u;
 #pragma unroll
         for (int r = 0; r < 16; r++) {
-            const Entry e = tab[4 * r];
+            const Entry e = tab[stride * r];
             const uint32_t self = R[r] + e.x;
             const uint32_t swapped = prmt(R[r], 0u, swapSel);
-            const uint32_t cross = swapped + (kTwoPerLane - e.x);
+            const uint32_t cross = swapped + (kBitsPerLane - e.x);
             const uint32_t m = signMask(subOnFma(swapped, R[r], minusOne) + e.y);
             R[r] = sel(m, self, cross);
             const uint32_t c = 0x01010101u << (r & 7);

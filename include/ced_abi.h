@@ -91,10 +91,10 @@ int ced_probe_int_peak(ced_ctx *ctx, int mode, double *laneOpsPerSecond);
  * launch there.  Calls are asynchronous with respect to the host.
  * Fastest when base pointers and strides are multiples of 16 bytes; any
  * alignment is accepted.
- * Codes: any k=1 code with constraintLen 2..9 and 1..8 coded bits.  K=7 n=2 codes
- * whose generators tap the newest and the oldest bit (src/viterbiDecoder.c:20-24)
+ * Codes: any k=1 code with constraintLen 2..9 and 1..8 coded bits.  K=7 codes with
+ * 2 or 3 generators that all tap the newest and the oldest bit (src/viterbiDecoder.c:20-24)
  * run on the SIMD-in-word kernel -- 0113/0171 and 0133/0171 compiled in, any other
- * pair through a table built on first use; everything else on a generic kernel.
+ * set through a table built on first use; everything else on a generic kernel.
  */
 int ced_decode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
                      int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream);

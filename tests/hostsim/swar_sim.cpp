@@ -101,33 +101,41 @@ extern "C" int swar_sim_window(const uint8_t *segs, int T, int callSegs, int dep
     return emitted;
 }
 
-// Same frame decode through the run-time table path (acsStepTable + buildStepTable) for any symmetric K=7 n=2 code.
-template <int PH>
+// Same frame decode through the run-time table path (acsStepTable + buildStepTable) for any symmetric K=7 code
+// with n = 2 or 3 generators.
+template <int PH, int N>
 static void stepTable(uint32_t (&R)[16], const ced::Word2 *table, uint32_t rx, uint32_t &t0, uint32_t &t1)
 {
-    ced::acsStepTable<PH>(R, table + PH * 64 + (int)(rx & 3u), 0xFFFFFFFFu, t0, t1);
+    ced::acsStepTable<PH, N>(R, table + PH * 16 * (1 << N) + (int)(rx & ((1u << N) - 1u)), 0xFFFFFFFFu, t0, t1);
 }
 
-extern "C" int swar_sim_decode_rt(uint32_t g0, uint32_t g1, const uint8_t *segs, int T, uint8_t *out)
+template <int N>
+static int decodeRuntime(const uint32_t *gens, const uint8_t *segs, int T, uint8_t *out)
 {
-    std::vector<ced::Word2> table(ced::kStepTableEntries);
-    ced::buildStepTable(ced::makeK7Taps(g0, g1), table.data());
+    std::vector<ced::Word2> table((size_t)ced::RuntimeK7<N>::kTableEntries);
+    ced::buildStepTable(ced::makeK7Taps(N, gens), table.data());
     uint32_t R[16];
     ced::initMetrics(R);
     std::vector<uint32_t> surv(2 * (size_t)T);
+    uint8_t mx = 0;
     for (int t = 0; t < T; t++) {
         uint32_t t0 = 0, t1 = 0, rx = segs[t];
         switch (t % 6) {
-        case 0: stepTable<0>(R, table.data(), rx, t0, t1); break;
-        case 1: stepTable<1>(R, table.data(), rx, t0, t1); break;
-        case 2: stepTable<2>(R, table.data(), rx, t0, t1); break;
-        case 3: stepTable<3>(R, table.data(), rx, t0, t1); break;
-        case 4: stepTable<4>(R, table.data(), rx, t0, t1); break;
-        default: stepTable<5>(R, table.data(), rx, t0, t1); break;
+        case 0: stepTable<0, N>(R, table.data(), rx, t0, t1); break;
+        case 1: stepTable<1, N>(R, table.data(), rx, t0, t1); break;
+        case 2: stepTable<2, N>(R, table.data(), rx, t0, t1); break;
+        case 3: stepTable<3, N>(R, table.data(), rx, t0, t1); break;
+        case 4: stepTable<4, N>(R, table.data(), rx, t0, t1); break;
+        default: stepTable<5, N>(R, table.data(), rx, t0, t1); break;
         }
         surv[2 * t] = t0;
         surv[2 * t + 1] = t1;
-        if ((t + 1) % 96 == 0)
+        for (int r = 0; r < 16; r++)
+            for (int l = 0; l < 4; l++) {
+                uint8_t v = (R[r] >> (8 * l)) & 0xFF;
+                if (v > mx) mx = v;
+            }
+        if ((t + 1) % ced::RuntimeK7<N>::kRenormPeriod == 0)
             ced::renorm(R);
     }
     const int L = T - 6;
@@ -138,7 +146,12 @@ extern "C" int swar_sim_decode_rt(uint32_t g0, uint32_t g1, const uint8_t *segs,
         if (t < L)
             out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
     }
-    return (L + 7) / 8;
+    return mx; /* largest metric seen: must stay below 128 - n for the guard-bit compare */
+}
+
+extern "C" int swar_sim_decode_rt(int n, const uint32_t *gens, const uint8_t *segs, int T, uint8_t *out)
+{
+    return n == 3 ? decodeRuntime<3>(gens, segs, T, out) : decodeRuntime<2>(gens, segs, T, out);
 }
 
 // decision of state s after step t from the packed words (for comparing with the oracle's survivors)

@@ -113,10 +113,11 @@ def test_decode_batch_other_code_parameters(torch_cuda, ctx, port, K, g, bits, f
             assert np.array_equal(want, msgs)
 
 
-@pytest.mark.parametrize("g", [(0o171, 0o133), (0o117, 0o155), (0o135, 0o163), (0o145, 0o175), (0o101, 0o177)])
+@pytest.mark.parametrize("g", [(0o171, 0o133), (0o117, 0o155), (0o135, 0o163), (0o145, 0o175), (0o101, 0o177),
+                               (0o133, 0o171, 0o165), (0o133, 0o145, 0o175), (0o175, 0o133, 0o171)])
 def test_decode_batch_any_symmetric_k7_code_runs_the_swar_kernel(torch_cuda, ctx, port, g):
-    """K=7 n=2 generators known only at run time -- the SWAR forward kernel driven by a step table
-    (RuntimeK7) -- byte and packed symbols, aligned and misaligned rows, and the windowed decoder."""
+    """K=7 generators (n = 2 or 3) known only at run time -- the SWAR forward kernel driven by a step
+    table (RuntimeK7<n>) -- byte and packed symbols, aligned and misaligned rows, and the windowed decoder."""
     torch = torch_cuda
     rng = np.random.default_rng(g[0] * 1000 + g[1])
     code = ced.Code(7, g)
@@ -128,16 +129,20 @@ def test_decode_batch_any_symmetric_k7_code_runs_the_swar_kernel(torch_cuda, ctx
     clean = port.encode_batch(7, list(g), msgs)
     assert np.array_equal(enc.cpu().numpy()[:, :T], clean)
     for p in (0.0, 0.05, 0.5):
-        noisy = bsc(rng, clean, p)
+        noisy = clean.copy()
+        flips = rng.random(clean.shape + (len(g),)) < p
+        for j in range(len(g)):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        noisy |= (rng.integers(0, 2, clean.shape, dtype=np.uint8) << len(g))   # junk above the n coded bits
         want = port.decode_batch(7, list(g), noisy, T)
         aligned = torch.zeros((frames, 4112), dtype=torch.uint8, device="cuda")
         aligned[:, :T] = dev(torch, noisy)
         ragged = dev(torch, noisy)                       # stride 4102: the alignment-agnostic staging
-        out_a = ctx.decode_batch(code, aligned, bits)
-        out_r = ctx.decode_batch(code, ragged, bits)
-        out_p = ctx.decode_batch_packed(code, ctx.pack_symbols(aligned, T), bits)
+        outs = [ctx.decode_batch(code, aligned, bits), ctx.decode_batch(code, ragged, bits)]
+        if len(g) == 2:
+            outs.append(ctx.decode_batch_packed(code, ctx.pack_symbols(aligned, T), bits))
         ctx.sync()
-        for out in (out_a, out_r, out_p):
+        for out in outs:
             assert np.array_equal(out.cpu().numpy(), want), (g, p)
     wd = ctx.window_decoder(code, frames, depth=48)
     pieces = [wd.push(aligned[:, a:min(a + 960, T)], last=a + 960 >= T).clone() for a in range(0, T, 960)]

@@ -92,14 +92,25 @@ def test_window_procedure_matches_oracle_definition(sim, port, total, call, dept
 
 
 @pytest.mark.parametrize("g", [(0o113, 0o171), (0o133, 0o171), (0o171, 0o133), (0o117, 0o155), (0o135, 0o163),
-                               (0o101, 0o177), (0o145, 0o175)])
+                               (0o101, 0o177), (0o145, 0o175), (0o133, 0o171, 0o165), (0o133, 0o145, 0o175),
+                               (0o175, 0o133, 0o171), (0o101, 0o101, 0o177)])
 def test_runtime_table_path_matches_oracle(sim, port, g):
-    """acsStepTable + buildStepTable (generators known only at run time) against the oracle, per code."""
-    sim.swar_sim_decode_rt.argtypes = [C.c_uint32, C.c_uint32, u8p, C.c_int, u8p]
-    rng = np.random.default_rng(g[0] * 512 + g[1])
-    for bits, p in ((48, 0.0), (512, 0.03), (2048, 0.07), (1024, 0.5)):
+    """acsStepTable + buildStepTable (generators known only at run time, n = 2 or 3) against the oracle, per code;
+    the largest metric must leave the guard bit free (renorm every 96 / 24 steps)."""
+    sim.swar_sim_decode_rt.argtypes = [C.c_int, u32p, u8p, C.c_int, u8p]
+    rng = np.random.default_rng(sum(g))
+    n = len(g)
+    gens = np.array(g, dtype=np.uint32)
+    for bits, p in ((48, 0.0), (512, 0.03), (2048, 0.07), (1024, 0.5), (4096, 0.5)):
         msg = rng.integers(0, 256, (1, bits // 8), dtype=np.uint8)
-        noisy = np.ascontiguousarray(bsc(rng, port.encode_batch(7, list(g), msg), p)[0])
+        clean = port.encode_batch(7, list(g), msg)
+        flips = rng.random(clean.shape + (n,)) < p
+        noisy = clean.copy()
+        for j in range(n):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        noisy = np.ascontiguousarray(noisy[0])
         out = np.zeros(bits // 8, dtype=np.uint8)
-        sim.swar_sim_decode_rt(g[0], g[1], noisy.ctypes.data_as(u8p), bits + 6, out.ctypes.data_as(u8p))
+        mx = sim.swar_sim_decode_rt(n, gens.ctypes.data_as(u32p), noisy.ctypes.data_as(u8p), bits + 6,
+                                    out.ctypes.data_as(u8p))
+        assert mx < 128 - n, (g, bits, p, mx)
         assert np.array_equal(out, port.decode_batch(7, list(g), noisy[None, :], bits + 6)[0]), (g, bits, p)

@@ -12,7 +12,7 @@ ctx = ced.Context(0)
 bits = 4096
 for K, g, frames in ((7, (0o113, 0o171), 1 << 16), (7, (0o133, 0o171), 1 << 16), (7, (0o171, 0o133), 1 << 16),
                      (7, (0o117, 0o155), 1 << 16), (7, (0o133, 0o170), 1 << 14), (3, (7, 6), 1 << 14),
-                     (9, (0o561, 0o753), 1 << 14), (7, (0o133, 0o145, 0o175), 1 << 14)):
+                     (9, (0o561, 0o753), 1 << 14), (7, (0o133, 0o171, 0o165), 1 << 16), (7, (0o133, 0o145, 0o174), 1 << 14)):
     code = ced.Code(K, g)
     T = bits + K - 1
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
