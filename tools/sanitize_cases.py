@@ -45,6 +45,23 @@ for K, g in ((3, (7, 6)), (9, (0o561, 0o753))):
     ctx.sync()
     ok &= bool(torch.equal(dec, msgs))
     print("K=%d generic round trip:" % K, bool(torch.equal(dec, msgs)))
+# run-time generators on the SWAR kernel (n = 2 and 3) and the windowed decoder, exactly sized buffers
+for g in ((0o171, 0o133), (0o133, 0o171, 0o165)):
+    c3 = ced.Code(7, g)
+    frames, bits = 45, 96 * 5 + 90
+    T = bits + 6
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=sum(g))
+    flat = torch.zeros(frames * T + 3, dtype=torch.uint8, device="cuda")
+    segs = flat[3:].view(frames, T)
+    ctx.encode_batch(c3, msgs, out=segs)
+    dec = ctx.decode_batch(c3, segs, bits)
+    wd = ctx.window_decoder(c3, frames, depth=24)
+    parts = [wd.push(segs[:, a:min(a + 192, T)], last=a + 192 >= T).clone() for a in range(0, T, 192)]
+    ctx.sync()
+    good = bool(torch.equal(dec, msgs)) and bool(torch.equal(torch.cat(parts, dim=1), msgs))
+    ok &= good
+    print("run-time code %s batch + windowed round trip:" % (g,), good)
 # soft symbols
 soft = torch.randint(-128, 128, (20, 2 * 262 + 4), dtype=torch.int8, device="cuda")
 pk = ctx.slice_soft_symbols(soft, 262)
