@@ -48,7 +48,7 @@ for K, g in ((3, (7, 6)), (9, (0o561, 0o753))):
 # run-time generators on the SWAR kernel (n = 2 and 3) and the windowed decoder, exactly sized buffers
 for g in ((0o171, 0o133), (0o133, 0o171, 0o165)):
     c3 = ced.Code(7, g)
-    frames, bits = 45, 96 * 5 + 90
+    frames, bits = 45, 96 * 5 + 88
     T = bits + 6
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
     ctx.random_bytes(msgs, seed=sum(g))
