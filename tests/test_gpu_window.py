@@ -106,3 +106,49 @@ def test_window_argument_checks(ctx):
     k3 = ced.Code(3, [7, 6])
     with pytest.raises(ced.CedError):
         ctx.window_decoder(k3, 4, 48).push(segs[:, :96])   # SWAR codes only
+
+
+def test_outputs_stay_inside_their_rows(ctx, port):
+    """compute-sanitizer is not available on the GPU pool: canary bytes around and between the output rows of the
+    batch decoder, the encoder and the windowed decoder (and around its carry block) must survive."""
+    import torch
+    rng = np.random.default_rng(3)
+    frames, bits = 77, 96 * 6 + 88
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    d_msgs = torch.from_numpy(msgs).cuda()
+
+    def guarded(rows, row_bytes, stride):
+        flat = torch.full((rows * stride + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        return flat, flat[32:32 + rows * stride].view(rows, stride)
+
+    def intact(flat, view, row_bytes):
+        v = view.clone()
+        v[:, :row_bytes] = 0xA5
+        return bool((flat[:32] == 0xA5).all() and (flat[-32:] == 0xA5).all() and (v == 0xA5).all())
+
+    for code in (ced.K7_DEFAULT, ced.Code(7, (0o171, 0o133)), ced.Code(7, (0o133, 0o171, 0o165)), ced.Code(3, (7, 6))):
+        Tc = bits + code.S
+        sflat, segs = guarded(frames, Tc, Tc + 9)
+        ctx.encode_batch(code, d_msgs, out=segs)
+        oflat, out = guarded(frames, bits // 8, bits // 8 + 5)
+        ctx.decode_batch(code, segs, bits, out=out)
+        ctx.sync()
+        assert intact(sflat, segs, Tc) and intact(oflat, out, bits // 8), code.g
+        assert torch.equal(out[:, :bits // 8], d_msgs)
+    segs = ctx.encode_batch(ced.K7_DEFAULT, d_msgs)
+    wd = ctx.window_decoder(ced.K7_DEFAULT, frames, depth=48)
+    carry_bytes = wd.carry.numel()
+    cflat = torch.full((carry_bytes + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+    wd.carry = cflat[32:32 + carry_bytes]
+    got = []
+    for a in range(0, T, 192):
+        n, last = min(192, T - a), a + 192 >= T
+        rows = (n + 48) // 8
+        oflat, out = guarded(frames, rows, rows + 3)
+        piece = wd.push(segs[:, a:a + n], last=last, out=out)
+        ctx.sync()
+        assert intact(oflat, out, piece.shape[1])
+        got.append(piece.clone())
+    assert bool((cflat[:32] == 0xA5).all() and (cflat[-32:] == 0xA5).all())
+    assert torch.equal(torch.cat(got, dim=1), d_msgs)
