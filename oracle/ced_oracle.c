@@ -12,6 +12,9 @@
  *   - the K=7 KATs of SURVEY 8(c) (poly 0x69/0x4f, edge table, 38-segment vector)
  *   - the berTestK7 golden counts (berTestK7/berTestK7.c with srand(9865))
  *   - the unmodified reference objects in oracle/_ref (random frames, bit-exact)
+ * Exception -- PARITY UNPINNED: orc_decode_window() (windowed traceback for continuous streams) has no
+ * runnable counterpart in the reference; it defines the semantics of ced_decode_window_batch and says
+ * so in its own comment.
  *
  * Each function cites the reference lines it restates.  The reference fixes the
  * code at compile time (src/defaultParams/convCodeParams.h:8-17); here K, n and
