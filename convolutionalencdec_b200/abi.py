@@ -93,6 +93,8 @@ def load_abi():
     lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_decode_scratch_bytes.argtypes = [i, i]
     lib.ced_decode_scratch_bytes.restype = sz
+    lib.ced_host_register.argtypes = [vp, sz]
+    lib.ced_host_unregister.argtypes = [vp]
     lib.ced_window_carry_bytes.argtypes = [i, i]
     lib.ced_window_carry_bytes.restype = sz
     lib.ced_decode_window_batch.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
@@ -214,6 +216,13 @@ class Context:
                                                           out.stride(0), _stream_handle(stream)),
                "ced_decode_batch_packed")
         return out
+
+    def host_register(self, array):
+        """Page-lock a numpy array the caller keeps passing to the *_host calls."""
+        _check(self.lib, self.lib.ced_host_register(array.ctypes.data, array.nbytes), "ced_host_register")
+
+    def host_unregister(self, array):
+        _check(self.lib, self.lib.ced_host_unregister(array.ctypes.data), "ced_host_unregister")
 
     def window_decoder(self, code, n_streams, depth=48):
         """Continuous streams with windowed traceback (ced_decode_window_batch)."""

@@ -162,6 +162,7 @@ struct ced_ctx {
     /* host-side transfer compression (host_pack.cpp): pinned packed staging + worker threads */
     ced_host::Packer *packer = nullptr;
     PinnedBuf packStage[kPipeDepth];
+    PinnedBuf outStage[kPipeDepth];  /* results on their way to a pageable caller buffer */
     cudaEvent_t stageFree[kPipeDepth] = {};
     int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
     int sms = 0, fwdResident = 0;
@@ -278,6 +279,7 @@ void ced_ctx_destroy(ced_ctx *c)
         if (c->stageFree[i])
             cudaEventDestroy(c->stageFree[i]);
         c->packStage[i].release();
+        c->outStage[i].release();
     }
     if (c->packer)
         ced_host::packerDestroy(c->packer);
@@ -360,6 +362,28 @@ void ced_host_free(void *p)
 {
     if (p)
         cudaFreeHost(p);
+}
+
+int ced_host_register(void *p, size_t bytes)
+{
+    if (!p || bytes == 0) {
+        setError("ced_host_register: bad argument");
+        return CED_ERR_ARG;
+    }
+    ced_ctx *c = ced_default_ctx();
+    if (!c)
+        return CED_ERR_CUDA;
+    CED_CUDA(cudaSetDevice(c->device));
+    CED_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return CED_OK;
+}
+
+int ced_host_unregister(void *p)
+{
+    if (!p)
+        return CED_ERR_ARG;
+    CED_CUDA(cudaHostUnregister(p));
+    return CED_OK;
 }
 
 size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
@@ -965,6 +989,29 @@ int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, i
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
 enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack };
 
+/* ordinary malloc'ed / stack memory, i.e. neither page-locked by CUDA nor registered */
+static bool isPageable(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int ensurePacker(ced_ctx *c)
+{
+    if (!c->packer) {
+        int nDev = 1;
+        cudaGetDeviceCount(&nDev);
+        const char *envT = getenv("CED_HOST_THREADS");
+        int threads = envT ? atoi(envT) : (int)std::thread::hardware_concurrency() / std::max(1, nDev);
+        c->packer = ced_host::packerCreate(std::max(1, std::min(threads, 16)));
+    }
+    return c->packer ? CED_OK : CED_ERR_NOMEM;
+}
+
 static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
                         size_t outRowBytes)
@@ -986,6 +1033,27 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         if (rc != CED_OK)
             return rc;
     }
+    /* A D2H copy into pageable memory stalls the calling thread until the chunk's kernels are done, which would
+     * serialise the pipeline: such results go to page-locked staging first and are moved by the host one
+     * pipeline round later. */
+    const bool stageOut = isPageable(hOut);
+    struct Pending {
+        uint8_t *dst;
+        size_t bytes;
+    } pending[kPipeDepth] = {};
+    for (int b = 0; b < kPipeDepth && stageOut; b++) {
+        int rc = c->outStage[b].ensure((size_t)chunk * outStride + 16);
+        if (rc != CED_OK)
+            return rc;
+    }
+    auto deliver = [&](int b) -> int {
+        if (pending[b].bytes) {
+            CED_CUDA(cudaEventSynchronize(c->outFree[b]));
+            memcpy(pending[b].dst, c->outStage[b].p, pending[b].bytes);
+            pending[b].bytes = 0;
+        }
+        return CED_OK;
+    };
     int idx = 0;
     for (int f0 = 0; f0 < nFrames; f0 += chunk, idx++) {
         const int b = idx % kPipeDepth;
@@ -1027,9 +1095,23 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         CED_CUDA(cudaEventRecord(c->inFree[b], cs));
         CED_CUDA(cudaEventRecord(c->outReady[b], cs));
         CED_CUDA(cudaStreamWaitEvent(c->d2h, c->outReady[b], 0));
-        CED_CUDA(cudaMemcpyAsync(hOut + (size_t)f0 * outStride, c->hostOut[b].p, outBytes, cudaMemcpyDeviceToHost,
-                                 c->d2h));
+        if (stageOut) {
+            int drc = deliver(b);   /* the slot's previous result leaves the staging buffer first */
+            if (drc != CED_OK)
+                return drc;
+            CED_CUDA(cudaMemcpyAsync(c->outStage[b].p, c->hostOut[b].p, outBytes, cudaMemcpyDeviceToHost, c->d2h));
+            pending[b].dst = hOut + (size_t)f0 * outStride;
+            pending[b].bytes = outBytes;
+        } else {
+            CED_CUDA(cudaMemcpyAsync(hOut + (size_t)f0 * outStride, c->hostOut[b].p, outBytes, cudaMemcpyDeviceToHost,
+                                     c->d2h));
+        }
         CED_CUDA(cudaEventRecord(c->outFree[b], c->d2h));
+    }
+    for (int b = 0; b < kPipeDepth; b++) {
+        int drc = deliver(b);
+        if (drc != CED_OK)
+            return drc;
     }
     CED_CUDA(cudaStreamSynchronize(c->d2h));
     for (int i = 0; i < kPipeDepth; i++)
@@ -1046,25 +1128,27 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     }
     if (nFrames == 0)
         return CED_OK;
-    /* Optional transfer compression (CED_HOST_PACK=1): pack the symbols to 2 bits on the host and copy a
-     * quarter of the bytes.  OFF by default: on the bench box the host reads memory at about the same
-     * ~55 GB/s as the PCIe copy itself (e2e 48.5 vs 47.2 Gbit/s with 8 threads, slower with 16), so it
-     * only pays on hosts with more memory bandwidth per GPU.  CED_HOST_THREADS sets the pool size
-     * (default: host cores / visible GPUs, at most 16). */
+    /* Transfer compression: worker threads pack the symbols to 2 bits into page-locked staging and a quarter of
+     * the bytes crosses PCIe.
+     *  - page-locked caller buffers: OFF by default (CED_HOST_PACK=1 turns it on): on the bench box the host
+     *    reads memory at about the same ~55 GB/s as the PCIe copy itself (e2e 48.5 vs 47.2 Gbit/s with 8 threads,
+     *    slower with 16), so it only pays on hosts with more memory bandwidth per GPU;
+     *  - pageable caller buffers (what a program written against the reference owns): ON (CED_HOST_PACK=0 turns
+     *    it off) -- a direct copy from pageable memory runs at ~10 GB/s, the packing threads read it at several
+     *    times that.
+     * CED_HOST_THREADS sets the pool size (default: host cores / visible GPUs, at most 16). */
     HostOp op = HostOp::Decode;
-    if (classify(code) != CodeId::Unsupported && getenv("CED_HOST_PACK")) {
-        std::lock_guard<std::recursive_mutex> lock(c->mu);
-        if (!c->packer) {
-            int nDev = 1;
-            cudaGetDeviceCount(&nDev);
-            const char *envT = getenv("CED_HOST_THREADS");
-            int threads = envT ? atoi(envT) : (int)std::thread::hardware_concurrency() / std::max(1, nDev);
-            c->packer = ced_host::packerCreate(std::max(1, std::min(threads, 16)));
-        }
+    const CodeId id = classify(code);
+    if (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171 || id == CodeId::K7_Runtime) {
         const char *envP = getenv("CED_HOST_PACK");
-        const bool usePack = envP && atoi(envP) != 0;
-        if (usePack)
+        const bool usePack = envP ? atoi(envP) != 0 : isPageable(hSegs);
+        if (usePack) {
+            std::lock_guard<std::recursive_mutex> lock(c->mu);
+            int rc = ensurePacker(c);
+            if (rc != CED_OK)
+                return rc;
             op = HostOp::DecodeViaPack;
+        }
     }
     return hostPipeline(c, code, op, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
                         frameBits, hOut, outStride, (size_t)frameBits / 8);

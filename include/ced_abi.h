@@ -138,6 +138,10 @@ int ced_encode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *h
 /* Page-locked host memory for the *_host calls (pageable buffers work too, at a fraction of the PCIe rate). */
 int ced_host_alloc(size_t bytes, void **out);
 void ced_host_free(void *p);
+/* Page-lock memory the caller already owns (malloc'ed arrays it will pass to the *_host calls many times);
+ * takes about as long as one copy of the buffer, so it pays from the second call on. */
+int ced_host_register(void *p, size_t bytes);
+int ced_host_unregister(void *p);
 
 /* Bytes of survivor scratch ced_decode_batch keeps inside the context for a
  * batch of this shape (grown on demand, reused across calls). */
