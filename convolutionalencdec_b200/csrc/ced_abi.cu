@@ -458,7 +458,7 @@ static int decodeBatchGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
     const size_t perFrame = (size_t)T * W * sizeof(uint32_t);
     size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(1, kMaxScratchBytes / perFrame));
     const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
-    const int gridMax = c->sms * 16;
+    const int gridMax = c->sms * (N <= 64 ? 32 : 16);   /* one-warp CTAs: 32 per SM (6 KB of shared memory each) */
     const size_t sinkBytes = 1024 + (size_t)gridMax * (256 + 4);
     if (wk.scratch.bytes < firstWave * perFrame || wk.schedState.bytes < sinkBytes) {
         CED_CUDA(cudaDeviceSynchronize());

@@ -163,7 +163,7 @@ __device__ __forceinline__ void streamDecodeBlockBody(const StreamArgs &a)
  * streamDecodeKernel.  The traceback is done by lane 0 over survivor rows staged in shared memory;
  * the loads do not depend on the path, so they are issued 8 steps ahead of the bit extraction.
  */
-constexpr int kStreamWarpSegChunk = 8192;
+constexpr int kStreamWarpSegChunk = 2048;
 
 __device__ __forceinline__ void streamDecodeWarpBody(const StreamArgs &a)
 {
