@@ -42,6 +42,11 @@ def test_dropin_exports_reference_symbols(params):
     exported = {line.split()[-1] for line in out.stdout.splitlines() if line.strip()}
     missing = [s for s in REFERENCE_SYMBOLS if s not in exported]
     assert not missing, missing
+    # the extension header of the same library (include/viterbiDecoderQueue.h)
+    with open(os.path.join(ROOT, "include", "viterbiDecoderQueue.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b((?:viterbiQueue|convEncQueue)[A-Za-z]+)\s*\(", text))
+    assert len(declared) == 8 and declared <= exported, declared - exported
 
 
 def test_host_tables_match_reference_values(golden):
