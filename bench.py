@@ -442,7 +442,8 @@ def main():
                        "h2d_bytes_per_step": (frames - 1) * seg_stride + T,
                        "d2h_bytes_per_step": frames * bits // 8, "steps": n_e2e,
                        "api": "ced_decode_batch_host (pinned host buffers, 8192-frame chunks, 4 in flight: H2D, 4 compute "
-                              "streams, D2H); %d host threads, one context each, keep calls in flight" % n_host,
+                              "streams, D2H; host worker threads pack to 2 bits the chunks the copy engine is not ready "
+                              "for); %d host threads, one context each, keep calls in flight" % n_host,
                        "one_call_at_a_time": world * units * n_e2e / el1 / 1e9,
                        "matches_device_path": ok, "gpu_launches": sum(c_.launches for c_ in host_ctx) - l0}
 

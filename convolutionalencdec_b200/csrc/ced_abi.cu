@@ -987,7 +987,7 @@ int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, i
 }
 
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
-enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack };
+enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack, DecodeAdaptive };
 
 /* ordinary malloc'ed / stack memory, i.e. neither page-locked by CUDA nor registered */
 static bool isPageable(const void *p)
@@ -1007,7 +1007,7 @@ static int ensurePacker(ced_ctx *c)
         cudaGetDeviceCount(&nDev);
         const char *envT = getenv("CED_HOST_THREADS");
         int threads = envT ? atoi(envT) : (int)std::thread::hardware_concurrency() / std::max(1, nDev);
-        c->packer = ced_host::packerCreate(std::max(1, std::min(threads, 16)));
+        c->packer = ced_host::packerCreate(std::max(1, std::min(threads, envT ? 64 : 8)));
     }
     return c->packer ? CED_OK : CED_ERR_NOMEM;
 }
@@ -1018,10 +1018,16 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
 {
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
-    const size_t packStride = op == HostOp::DecodeViaPack ? (((size_t)frameParam + 6 + 3) / 4 + 15) / 16 * 16 : 0;
+    const bool mayPack = op == HostOp::DecodeViaPack || op == HostOp::DecodeAdaptive;
+    const size_t packStride = mayPack ? (((size_t)frameParam + 6 + 3) / 4 + 15) / 16 * 16 : 0;
+    /* DecodeAdaptive: a chunk is packed by the host threads only while the copy engine still has `lookback`
+     * earlier chunks queued, i.e. while packing costs the link nothing (CED_HOST_PACK_LOOKBACK, 1..kPipeDepth-1;
+     * measured 1 / 2 / 3 chunks: 73.5 / 79.2 / 72.8 Gbit/s with two callers, tools/host_pack_modes.py) */
+    const int envLook = getenv("CED_HOST_PACK_LOOKBACK") ? atoi(getenv("CED_HOST_PACK_LOOKBACK")) : 0;
+    const int lookback = std::max(1, std::min(envLook > 0 ? envLook : 2, kPipeDepth - 1));
     static const int envChunk = getenv("CED_HOST_CHUNK_FRAMES") ? atoi(getenv("CED_HOST_CHUNK_FRAMES")) : 0;
     const int chunk = std::min(nFrames, envChunk >= 32 ? envChunk : kHostChunkFrames);
-    for (int b = 0; b < kPipeDepth && op == HostOp::DecodeViaPack; b++) {
+    for (int b = 0; b < kPipeDepth && mayPack; b++) {
         int rc = c->packStage[b].ensure((size_t)chunk * packStride + 16);
         if (rc != CED_OK)
             return rc;
@@ -1054,7 +1060,7 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         }
         return CED_OK;
     };
-    int idx = 0;
+    int idx = 0, nPackedChunks = 0;
     for (int f0 = 0; f0 < nFrames; f0 += chunk, idx++) {
         const int b = idx % kPipeDepth;
         cudaStream_t cs = c->pipe[b]; /* consecutive chunks run on different compute streams, so their
@@ -1064,7 +1070,13 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         const size_t outBytes = (size_t)(cnt - 1) * outStride + outRowBytes;
         if (idx >= kPipeDepth)
             CED_CUDA(cudaStreamWaitEvent(c->h2d, c->inFree[b], 0));
-        if (op == HostOp::DecodeViaPack) {
+        bool packThis = op == HostOp::DecodeViaPack;
+        if (op == HostOp::DecodeAdaptive && idx >= lookback) {
+            packThis = cudaEventQuery(c->inReady[(idx - lookback) % kPipeDepth]) == cudaErrorNotReady;
+            cudaGetLastError();
+        }
+        nPackedChunks += packThis ? 1 : 0;
+        if (packThis) {
             /* pack this chunk on the host (4 segments per byte) into pinned staging, then copy a quarter
              * of the bytes; the staging slot is reused once its previous H2D has completed */
             const int T = frameParam + 6;
@@ -1084,7 +1096,7 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
         int rc;
         if (op == HostOp::Encode)
             rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride, cs);
-        else if (op == HostOp::DecodeViaPack)
+        else if (packThis)
             rc = decodeBatchImpl(c, code, true, c->hostIn[b].p, packStride, cnt, frameParam, c->hostOut[b].p, outStride,
                                  cs, 1 + b);
         else
@@ -1116,6 +1128,9 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
     CED_CUDA(cudaStreamSynchronize(c->d2h));
     for (int i = 0; i < kPipeDepth; i++)
         CED_CUDA(cudaStreamSynchronize(c->pipe[i]));
+    static const bool trace = getenv("CED_HOST_PACK_TRACE") != nullptr;
+    if (trace && mayPack)
+        fprintf(stderr, "ced host pipeline: %d of %d chunks packed on the host\n", nPackedChunks, idx);
     return CED_OK;
 }
 
@@ -1129,25 +1144,26 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     if (nFrames == 0)
         return CED_OK;
     /* Transfer compression: worker threads pack the symbols to 2 bits into page-locked staging and a quarter of
-     * the bytes crosses PCIe.
-     *  - page-locked caller buffers: OFF by default (CED_HOST_PACK=1 turns it on): on the bench box the host
-     *    reads memory at about the same ~55 GB/s as the PCIe copy itself (e2e 48.5 vs 47.2 Gbit/s with 8 threads,
-     *    slower with 16), so it only pays on hosts with more memory bandwidth per GPU;
-     *  - pageable caller buffers (what a program written against the reference owns): ON (CED_HOST_PACK=0 turns
-     *    it off) -- a direct copy from pageable memory runs at ~10 GB/s, the packing threads read it at several
-     *    times that.
-     * CED_HOST_THREADS sets the pool size (default: host cores / visible GPUs, at most 16). */
+     * the bytes crosses PCIe.  CED_HOST_PACK selects 0 = never, 1 = every chunk, 2 = adaptive; the default is
+     *  - page-locked caller buffers: adaptive.  The copy engine moves raw chunks at the PCIe rate (~54 GB/s) while
+     *    the host threads pack the chunks it is not ready for, so both read the caller's buffer at once: 53.6 ->
+     *    79 Gbit/s with two callers, 47 -> 56-63 with one, close to the ~93 GB/s at which this host reads its own
+     *    memory at all (packing every chunk: 48.7 / 66.8 -- the host alone is slower than the link);
+     *  - pageable caller buffers (what a program written against the reference owns): every chunk -- a direct
+     *    copy from pageable memory runs at ~10 GB/s, the packing threads read it at several times that.
+     * CED_HOST_THREADS sets the pool size (default: host cores / visible GPUs, at most 8). */
     HostOp op = HostOp::Decode;
     const CodeId id = classify(code);
     if (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171 || id == CodeId::K7_Runtime) {
         const char *envP = getenv("CED_HOST_PACK");
-        const bool usePack = envP ? atoi(envP) != 0 : isPageable(hSegs);
-        if (usePack) {
+        const int mode = envP ? atoi(envP) : (isPageable(hSegs) ? 1 : 2);
+        if (mode != 0) {
             std::lock_guard<std::recursive_mutex> lock(c->mu);
             int rc = ensurePacker(c);
             if (rc != CED_OK)
                 return rc;
-            op = HostOp::DecodeViaPack;
+            /* 2: pack only the chunks the copy engine is not ready for (page-locked buffers) */
+            op = mode == 2 && !isPageable(hSegs) ? HostOp::DecodeAdaptive : HostOp::DecodeViaPack;
         }
     }
     return hostPipeline(c, code, op, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,

@@ -113,9 +113,10 @@ int ced_decode_batch_packed_host(ced_ctx *ctx, const ced_code_t *code, const uin
 int ced_pack_symbols(ced_ctx *ctx, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,
                      uint8_t *dPacked, size_t packedStride, void *stream);
 /* The same packing on the HOST (no GPU involved; `threads` worker threads, AVX2 when available), e.g. for a
- * receiver that wants to hand ced_decode_batch_packed_host a quarter of the bytes.  ced_decode_batch_host can
- * use it internally as transfer compression (CED_HOST_PACK=1); off by default because on the bench box the
- * host's memory bandwidth, not PCIe, is then the limit. */
+ * receiver that wants to hand ced_decode_batch_packed_host a quarter of the bytes.  ced_decode_batch_host
+ * uses it internally as transfer compression: for page-locked buffers only on the chunks the copy engine is not
+ * ready for, for pageable buffers on every chunk (CED_HOST_PACK = 0 / 1 / 2 forces never / always / adaptive;
+ * DESIGN.md 6). */
 int ced_host_pack_symbols(const uint8_t *segs, size_t segStride, int nFrames, int segsPerFrame, uint8_t *packed,
                           size_t packedStride, int threads);
 /* Encoder writing the packed format directly (n = 2 codes). */
@@ -127,8 +128,9 @@ int ced_encode_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t 
 int ced_slice_soft_symbols(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
                            uint8_t *dPacked, size_t packedStride, void *stream);
 
-/* Same operations on HOST buffers: pinned staging, chunked H2D / kernel / D2H
- * pipelined on two streams.  Synchronous: returns when hOut / hSegs is complete. */
+/* Same operations on HOST buffers: chunked H2D / kernel / D2H pipelined on a copy-in stream, four compute
+ * streams and a copy-out stream; host worker threads pack part of the symbol chunks to 2 bits while the copy
+ * engine moves the others.  Synchronous: returns when hOut / hSegs is complete. */
 int ced_decode_batch_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hSegs, size_t segStride,
                           int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
 

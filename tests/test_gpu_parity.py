@@ -307,6 +307,44 @@ def test_host_buffer_pipeline_roundtrip(torch_cuda, ctx, port):
     assert np.array_equal(out[sample], port.decode_batch(7, K7, noisy[sample, :T], T))
 
 
+def test_host_transfer_compression_modes_agree(torch_cuda, ctx, port, monkeypatch):
+    """ced_decode_batch_host on page-locked buffers: raw copies, every chunk packed by the host threads, and the
+    adaptive mix (the default) must return the same bytes, equal to the oracle's on a sample."""
+    torch = torch_cuda
+    rng = np.random.default_rng(77)
+    frames, bits = 70000, 512      # 9 pipeline chunks of 8192 frames, ragged last one
+    T = bits + 6
+    msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+    noisy = np.full((frames, T + 7), 0xEC, dtype=np.uint8)     # rows not 16-byte aligned, upper bits set
+    noisy[:, :T] = bsc(rng, port.encode_batch(7, K7, msgs), 0.05) | 0xA0
+    h_in = torch.from_numpy(noisy).pin_memory()
+    sample = rng.choice(frames, 200, replace=False)
+    want = port.decode_batch(7, K7, noisy[sample, :T] & 3, T)
+    outs = []
+    for mode, look in (("0", "1"), ("1", "1"), ("2", "1"), ("2", "3"), (None, None)):
+        if mode is None:
+            monkeypatch.delenv("CED_HOST_PACK", raising=False)
+            monkeypatch.delenv("CED_HOST_PACK_LOOKBACK", raising=False)
+        else:
+            monkeypatch.setenv("CED_HOST_PACK", mode)
+            monkeypatch.setenv("CED_HOST_PACK_LOOKBACK", look)
+        out = torch.zeros((frames, bits // 8), dtype=torch.uint8).pin_memory()
+        ctx.decode_batch_host(ced.K7_DEFAULT, h_in, bits, out)
+        assert np.array_equal(out.numpy()[sample], want), mode
+        outs.append(out.numpy().copy())
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    # a run-time K=7 code takes the same route
+    code = ced.Code(7, (0o117, 0o155))
+    noisy2 = bsc(rng, port.encode_batch(7, (0o117, 0o155), msgs[:20000]), 0.03)
+    h2 = torch.from_numpy(noisy2).pin_memory()
+    out2 = torch.zeros((20000, bits // 8), dtype=torch.uint8).pin_memory()
+    monkeypatch.setenv("CED_HOST_PACK", "2")
+    monkeypatch.setenv("CED_HOST_PACK_LOOKBACK", "1")
+    ctx.decode_batch_host(code, h2, bits, out2)
+    assert np.array_equal(out2.numpy()[:100], port.decode_batch(7, (0o117, 0o155), noisy2[:100], T))
+
+
 # ------------------------------------------------------------------ full-size properties
 def test_full_size_roundtrip_and_sampled_parity(torch_cuda, ctx, port):
     """BASELINE config 2 shape: 2^16 frames x 4096 bits.  encode -> decode must be the identity;
