@@ -394,9 +394,14 @@ def main():
         # the encoder is HBM-bound: message bytes in + one byte per coded segment out
         enc_bytes = frames * (bits // 8 + T)
         achieved = enc_bytes / (ms_per_step * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "encodeBatchKernel", "achieved": achieved, "peak": hbm_peak,
+        enc_traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath) and frames == 1 << 20:
+            with open(tpath) as f:
+                enc_traffic = json.load(f).get("encodeBatchLutKernel_dram_bytes_per_launch_2p20_frames")
+        line["roofline"] = {"bound": "hbm", "kernel": "encodeBatchLutKernel", "achieved": achieved, "peak": hbm_peak,
                             "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src,
-                            "algorithmic_bytes_per_launch": enc_bytes, "kernel_ms": ms_per_step, "traffic": None}
+                            "algorithmic_bytes_per_launch": enc_bytes, "kernel_ms": ms_per_step, "traffic": enc_traffic}
 
     def host_calls_in_flight(call, n_calls, n_threads):
         """n_calls synchronous host-buffer calls issued from n_threads host threads (one ced_ctx and one set of

@@ -137,80 +137,120 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
 }
 
 /*
- * Fast path for the production code (K=7, g={0113,0171}, byte-per-segment output, 16-byte aligned
- * segment rows).  ncu on the kernel above showed 82 % issue-slot utilisation at 31 % DRAM throughput
- * (profiles/r1_final_ncu_full_summary.txt) and each thread's load -> compute -> store chain was exposed
- * once per item.  Here a CTA first stages the messages of kEncSmemFrames frames in shared memory
- * (one global latency per CTA), then every warp emits whole 512-segment spans: lane l produces
- * segments [512*span + 16*l, +16) from three staged bytes and the warp's STG.128 covers 512
- * contiguous bytes.  Index math is a couple of adds per item.
+ * Table-spread encoder for n = 2 codes with byte-per-segment output and 16-byte aligned segment rows.
+ *
+ * ncu on the kernel above: ~100 instructions per STG.128, issue-bound at 3.9 TB/s.  Two changes cut that to ~40:
+ *   - a warp owns whole frames (no division per item) and lane l of iteration k encodes the 16 segments of chunk
+ *     32k + l, so one STG.128 of the warp covers 512 contiguous bytes -- full 32-byte sectors.  tools/write_probe.cu:
+ *     this HBM takes 7.1 TB/s of full-sector writes, but a store instruction that leaves sectors half written (e.g. 32
+ *     contiguous bytes per lane as two STG.128) halves the rate, because the L2 fetches a sector on a partial write;
+ *   - the 1-bit -> 1-byte spread (shift, mask, multiply, mask per nibble and generator) becomes a table lookup: the
+ *     nibbles of the two coded-bit words are interleaved with two LOP3 (index = c0 nibble | c1 nibble << 4) and a
+ *     256-entry shared-memory table returns the four output bytes of four segments.
+ * Message bytes come straight from global memory through L1 (two 2-byte loads per chunk, four chunks' loads in
+ * flight per lane before the first use; the 128-byte line is shared by the whole warp).  The ragged end of a row is
+ * written with at most four stores.
  */
-constexpr int kEncSmemFrames = 8;
+constexpr int kEncLutThreads = 256;
 
-__device__ __forceinline__ uint4 encode16Fixed(uint32_t win)
+/* 16 coded segments of chunk c from the window x = byte(2c-1) << 24 | byte(2c) << 16 | byte(2c+1) << 8 (low byte: don't
+ * care), spread to one byte per segment through the table */
+template <bool FIXED>
+__device__ __forceinline__ uint4 encodeChunkLut(uint32_t x, uint32_t tap0, uint32_t tap1, const uint32_t *lut)
 {
-    /* taps 0x69 = bits 0,3,5,6 and 0x4F = bits 0,1,2,3,6 (src/convEncode.c:13-17 on 0113 / 0171) */
-    const uint32_t s3 = win << 3, s6 = win << 6;
-    const uint32_t c0 = (win ^ s3 ^ (win << 5) ^ s6) >> 8;
-    const uint32_t c1 = (win ^ (win << 1) ^ (win << 2) ^ s3 ^ s6) >> 8;
-    uint32_t w[4];
+    /* window bit i = input bit u[16c - 8 + i]  (bytes are sent MSb first, src/convEncode.c:91) */
+    const uint32_t win = __brev(x);
+    uint32_t c0, c1;
+    if (FIXED) { /* taps 0x69 = {0,3,5,6}, 0x4F = {0,1,2,3,6}  (src/convEncode.c:13-17 on 0113 / 0171) */
+        const uint32_t s3 = win << 3, s6 = win << 6;
+        c0 = (win ^ s3 ^ (win << 5) ^ s6) >> 8;
+        c1 = (win ^ (win << 1) ^ (win << 2) ^ s3 ^ s6) >> 8;
+    } else {
+        c0 = c1 = 0u;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        const uint32_t n0 = (c0 >> (4 * q)) & 0xFu, n1 = (c1 >> (4 * q)) & 0xFu;
-        w[q] = ((n0 * 0x00204081u) & 0x01010101u) + 2u * ((n1 * 0x00204081u) & 0x01010101u);
+        for (int d = 0; d <= 8; d++) {
+            c0 ^= (0u - ((tap0 >> d) & 1u)) & (win << d);
+            c1 ^= (0u - ((tap1 >> d) & 1u)) & (win << d);
+        }
+        c0 >>= 8;
+        c1 >>= 8;
     }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    const uint32_t ze = (c0 & 0x0F0Fu) | ((c1 << 4) & 0xF0F0u); /* segments 8k .. 8k+3   in byte k */
+    const uint32_t zo = ((c0 >> 4) & 0x0F0Fu) | (c1 & 0xF0F0u); /* segments 8k+4 .. 8k+7 in byte k */
+    return make_uint4(lut[ze & 0xFFu], lut[zo & 0xFFu], lut[ze >> 8], lut[zo >> 8]);
 }
 
-__global__ void __launch_bounds__(kEncThreads)
-encodeBatchSmemKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
-                      uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int msgAligned16)
+template <bool FIXED>
+__global__ void __launch_bounds__(kEncLutThreads)
+encodeBatchLutKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
+                     uint8_t *__restrict__ segs, size_t segStride, int tailSegs, uint32_t tap0, uint32_t tap1)
 {
-    extern __shared__ __align__(16) uint8_t sMsg[];   /* [frames][16 zero bytes | message | >= 16 zero bytes] */
-    const int rowPitch = (frameBytes + 47) / 16 * 16; /* 16 in front + message + tail padding */
-    const int T = 8 * frameBytes + tailSegs;
-    const int spans = (T + 511) / 512;
-    const long long frameBase = (long long)blockIdx.x * kEncSmemFrames;
-    const int framesHere = (int)min((long long)kEncSmemFrames, (long long)nFrames - frameBase);
-
-    /* stage: zero fill, then the messages */
-    for (int i = threadIdx.x; i < framesHere * rowPitch / 16; i += kEncThreads)
-        reinterpret_cast<uint4 *>(sMsg)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-    if (msgAligned16 && (frameBytes & 15) == 0) {
-        const int vecPerRow = frameBytes / 16;
-        for (int i = threadIdx.x; i < framesHere * vecPerRow; i += kEncThreads) {
-            const int fl = i / vecPerRow, v = i - fl * vecPerRow;
-            reinterpret_cast<uint4 *>(sMsg + fl * rowPitch + 16)[v] =
-                __ldg(reinterpret_cast<const uint4 *>(msg + (size_t)(frameBase + fl) * msgStride) + v);
-        }
-    } else {
-        for (int i = threadIdx.x; i < framesHere * frameBytes; i += kEncThreads) {
-            const int fl = i / frameBytes, b = i - fl * frameBytes;
-            sMsg[fl * rowPitch + 16 + b] = __ldg(msg + (size_t)(frameBase + fl) * msgStride + b);
-        }
+    __shared__ uint32_t lut[256];
+    {
+        const uint32_t idx = threadIdx.x;
+        uint32_t e = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            e |= (((idx >> i) & 1u) | (((idx >> (4 + i)) & 1u) << 1)) << (8 * i); /* generator i in bit i */
+        lut[idx] = e;
     }
     __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int unit = warp; unit < framesHere * spans; unit += kEncThreads / 32) {
-        const int fl = unit / spans, span = unit - fl * spans;
-        const int seg0 = 512 * span + 16 * lane;
-        if (seg0 >= T)
-            continue;
-        /* message bytes 2c-1, 2c, 2c+1 with c = seg0/16; byte -1 and bytes past the end are zero */
-        const uint8_t *p = sMsg + fl * rowPitch + 16 + 64 * span + 2 * lane;
-        const uint32_t b0 = p[-1];
-        const uint32_t b12 = *reinterpret_cast<const uint16_t *>(p);   /* b1 | b2 << 8 */
-        const uint32_t win = __brev((b0 << 24) | ((b12 & 0xFFu) << 16) | ((b12 >> 8) << 8));
-        const uint4 v = encode16Fixed(win);
-        uint8_t *dst = segs + (size_t)(frameBase + fl) * segStride + seg0;
-        if (seg0 + 16 <= T) {
-            *reinterpret_cast<uint4 *>(dst) = v;
-        } else {
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-            for (int s2 = 0; s2 < T - seg0; s2++)
-                dst[s2] = (uint8_t)(w[s2 >> 2] >> (8 * (s2 & 3)));
+    const int T = 8 * frameBytes + tailSegs;
+    const int chunks = (T + 15) / 16;
+    /* chunks whose three message bytes 2c-1 .. 2c+1 all exist (c = 0 apart): whole warp iterations of them run
+     * without bounds checks; frameBytes is even on this path */
+    const int interiorIters = (frameBytes / 2) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long warps = (long long)gridDim.x * (kEncLutThreads / 32);
+    for (long long f = (long long)blockIdx.x * (kEncLutThreads / 32) + (threadIdx.x >> 5); f < nFrames; f += warps) {
+        const uint8_t *m = msg + (size_t)f * msgStride;
+        uint8_t *out = segs + (size_t)f * segStride;
+        const uint16_t *m16 = reinterpret_cast<const uint16_t *>(m);
+        uint4 *out16 = reinterpret_cast<uint4 *>(out);
+        int k = 0;
+        for (; k + 4 <= interiorIters; k += 4) {
+            uint32_t a[4], h[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c = 32 * (k + u) + lane;
+                a[u] = __ldg(m16 + max(c - 1, 0)); /* bytes 2c-2, 2c-1 */
+                h[u] = __ldg(m16 + c);             /* bytes 2c, 2c+1   */
+            }
+            if (k == 0 && lane == 0)
+                a[0] = 0u; /* nothing precedes the first byte: the register starts at STARTING_STATE 0 */
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                out16[32 * (k + u) + lane] = encodeChunkLut<FIXED>(__byte_perm(a[u], h[u], 0x1450), tap0, tap1, lut);
+        }
+        /* the remaining chunks: ragged message end, zero tail (src/convEncode.c:108-119), ragged row end */
+        for (int c = 32 * k + lane; c < chunks; c += 32) {
+            const int i1 = 2 * c;
+            const uint32_t b0 = (c > 0 && i1 - 1 < frameBytes) ? __ldg(m + i1 - 1) : 0u;
+            const uint32_t b1 = (i1 < frameBytes) ? __ldg(m + i1) : 0u;
+            const uint32_t b2 = (i1 + 1 < frameBytes) ? __ldg(m + i1 + 1) : 0u;
+            const uint4 v = encodeChunkLut<FIXED>((b0 << 24) | (b1 << 16) | (b2 << 8), tap0, tap1, lut);
+            uint8_t *dst = out + 16 * c;
+            const int cnt = T - 16 * c;
+            if (cnt >= 16) {
+                *reinterpret_cast<uint4 *>(dst) = v;
+            } else { /* ragged end: 8 + 4 + 2 + 1 bytes as needed (dst is 16-byte aligned) */
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                int b = 0;
+                if (cnt & 8) {
+                    *reinterpret_cast<uint2 *>(dst) = make_uint2(v.x, v.y);
+                    b = 8;
+                }
+                if (cnt & 4) {
+                    *reinterpret_cast<uint32_t *>(dst + b) = w[b >> 2];
+                    b += 4;
+                }
+                if (cnt & 2) {
+                    *reinterpret_cast<uint16_t *>(dst + b) = (uint16_t)(w[b >> 2] >> (8 * (b & 3)));
+                    b += 2;
+                }
+                if (cnt & 1)
+                    dst[b] = (uint8_t)(w[b >> 2] >> (8 * (b & 3)));
+            }
         }
     }
 }

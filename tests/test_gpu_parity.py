@@ -275,6 +275,35 @@ def test_encode_batch_vs_oracle(torch_cuda, ctx, port, golden, nbytes, frames, s
     assert (got[:, T:] == 0xEE).all()  # padding untouched
 
 
+@pytest.mark.parametrize("K,g", [(7, (0o113, 0o171)), (7, (0o133, 0o171)), (9, (0o561, 0o753)), (3, (0b111, 0b110)),
+                                 (5, (0o23, 0o35))])
+def test_encode_batch_table_kernel(torch_cuda, ctx, port, K, g):
+    """16-byte aligned segment rows, n = 2: encodeBatchLutKernel (a warp per frame, 512 bytes per warp store, table
+    spread).  Frame lengths around the 64-byte iteration boundaries, many frames per warp, canaries."""
+    torch = torch_cuda
+    code = ced.Code(K, g)
+    rng = np.random.default_rng(K)
+    for nbytes, frames in ((1, 5), (3, 40), (4, 3), (8, 1000), (33, 50), (62, 9), (64, 70), (66, 9), (124, 33), (128, 70),
+                           (132, 9), (512, 2500), (1000, 17), (2048, 5)):
+        msgs = rng.integers(0, 256, (frames, nbytes), dtype=np.uint8)
+        msgs[0] = 0xFF
+        T = 8 * nbytes + K - 1
+        stride = (T + 15) // 16 * 16 + 16
+        out = torch.full((frames, stride), 0xEE, dtype=torch.uint8, device="cuda")
+        ctx.encode_batch(code, dev(torch, msgs), out=out)
+        ctx.sync()
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:, :T], port.encode_batch(K, g, msgs)), (K, g, nbytes)
+        assert (got[:, T:] == 0xEE).all(), (K, g, nbytes)
+    # message rows embedded in a wider, 4-byte aligned array
+    wide = rng.integers(0, 256, (300, 72), dtype=np.uint8)
+    d_wide = dev(torch, wide)
+    out = torch.full((300, 8 * 64 + 16), 0xEE, dtype=torch.uint8, device="cuda")
+    ctx.encode_batch(code, d_wide[:, 4:68], out=out)
+    ctx.sync()
+    assert np.array_equal(out.cpu().numpy()[:, :8 * 64 + K - 1], port.encode_batch(K, g, wide[:, 4:68]))
+
+
 def test_encode_batch_matches_reference_fixtures_and_other_codes(torch_cuda, ctx, port, golden):
     torch = torch_cuda
     for bits in (8, 64, 256, 2048, 4096):
