@@ -12,6 +12,7 @@
 #include "stream_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -164,6 +165,7 @@ struct ced_ctx {
     PinnedBuf packStage[kPipeDepth];
     PinnedBuf outStage[kPipeDepth];  /* results on their way to a pageable caller buffer */
     cudaEvent_t stageFree[kPipeDepth] = {};
+    int packHoldoff = 0, packPenalty = 1; /* adaptive transfer compression: back-off after the link ran dry */
     int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
     int sms = 0, fwdResident = 0;
     size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
@@ -1020,6 +1022,68 @@ static int ensurePacker(ced_ctx *c)
     return c->packer ? CED_OK : CED_ERR_NOMEM;
 }
 
+/*
+ * Whether packing chunks on the host pays depends on the machine: on a box with 16 cores per GPU the PCIe link is
+ * the bottleneck and the mix gains 45 % (53.6 -> 77 Gbit/s); on the 8-GPU box (32 cores, 4 per GPU, all links
+ * sharing the host memory) raw copies already run at a third of the link rate and packing loses 9 % (156 -> 142
+ * Gbit/s in total; with every rank calibrating at once the measurement below is also too noisy there: 3 of 8 ranks
+ * chose packing, 146 Gbit/s).  So (1) hosts with fewer than 8 cores per visible GPU always copy raw, and (2) elsewhere
+ * every process measures it once per device: the first 16 eligible calls alternate four raw,
+ * four adaptive (the first of each four is a transition and not counted), then the faster mode is kept -- adaptive
+ * only if it is at least 5 % faster -- and re-measured after 512 calls.  CED_HOST_PACK = 0 / 1 / 2 bypasses this.
+ */
+struct PackTuner {
+    std::mutex mu;
+    int calls = 0;          /* eligible calls since the last (re)start of the calibration */
+    double rate[2] = {0, 0};
+    int n[2] = {0, 0};
+    int decided = -1;       /* -1 calibrating, 0 raw copies, 1 adaptive packing */
+    int sinceDecision = 0;
+};
+static PackTuner gPackTuner[32];
+constexpr int kTunerPhaseCalls = 4, kTunerCalibrationCalls = 16, kTunerRedoAfter = 512;
+
+/* returns the mode for this call (0 raw, 1 adaptive) and its ticket (>= 0 while calibrating, else -1) */
+static int packTunerBegin(int device, int *ticket)
+{
+    PackTuner &t = gPackTuner[device & 31];
+    std::lock_guard<std::mutex> lock(t.mu);
+    if (t.decided >= 0) {
+        *ticket = -1;
+        const int mode = t.decided;
+        if (++t.sinceDecision > kTunerRedoAfter) { /* measure again: other processes may have come or gone */
+            t.calls = t.n[0] = t.n[1] = 0;
+            t.rate[0] = t.rate[1] = 0;
+            t.decided = -1;
+        }
+        return mode;
+    }
+    *ticket = t.calls++;
+    return (*ticket / kTunerPhaseCalls) % 2;
+}
+
+static void packTunerEnd(int device, int ticket, int mode, double bytesPerSecond)
+{
+    if (ticket < 0)
+        return;
+    PackTuner &t = gPackTuner[device & 31];
+    std::lock_guard<std::mutex> lock(t.mu);
+    if (t.decided >= 0)
+        return;
+    if (ticket % kTunerPhaseCalls != 0) {
+        t.rate[mode] += bytesPerSecond;
+        t.n[mode]++;
+    }
+    if (t.n[0] + t.n[1] >= kTunerCalibrationCalls - kTunerCalibrationCalls / kTunerPhaseCalls && t.n[0] && t.n[1]) {
+        const double raw = t.rate[0] / t.n[0], mix = t.rate[1] / t.n[1];
+        t.decided = mix > 1.05 * raw ? 1 : 0;
+        t.sinceDecision = 0;
+        if (getenv("CED_HOST_PACK_TRACE"))
+            fprintf(stderr, "ced host pipeline: device %d raw %.1f GB/s, adaptive packing %.1f GB/s per call -> %s\n",
+                    device, raw / 1e9, mix / 1e9, t.decided ? "adaptive" : "raw copies");
+    }
+}
+
 static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
                         size_t outRowBytes)
@@ -1080,8 +1144,12 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
             CED_CUDA(cudaStreamWaitEvent(c->h2d, c->inFree[b], 0));
         bool packThis = op == HostOp::DecodeViaPack;
         if (op == HostOp::DecodeAdaptive && idx >= lookback) {
-            packThis = cudaEventQuery(c->inReady[(idx - lookback) % kPipeDepth]) == cudaErrorNotReady;
-            cudaGetLastError();
+            if (c->packHoldoff > 0) {
+                c->packHoldoff--;
+            } else {
+                packThis = cudaEventQuery(c->inReady[(idx - lookback) % kPipeDepth]) == cudaErrorNotReady;
+                cudaGetLastError();
+            }
         }
         nPackedChunks += packThis ? 1 : 0;
         if (packThis) {
@@ -1095,6 +1163,18 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
             CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, c->packStage[b].p, (size_t)cnt * pStride, cudaMemcpyHostToDevice,
                                      c->h2d));
             CED_CUDA(cudaEventRecord(c->stageFree[b], c->h2d));
+            if (op == HostOp::DecodeAdaptive) {
+                /* did the copy engine run out of work while the host was packing (slow or oversubscribed host
+                 * cores)?  Then the next chunks go raw, twice as many after every repeat. */
+                const bool ranDry = cudaEventQuery(c->inReady[(idx - 1) % kPipeDepth]) == cudaSuccess;
+                cudaGetLastError();
+                if (ranDry) {
+                    c->packHoldoff = c->packPenalty;
+                    c->packPenalty = std::min(2 * c->packPenalty, 16);
+                } else {
+                    c->packPenalty = std::max(1, c->packPenalty / 2);
+                }
+            }
         } else
         CED_CUDA(cudaMemcpyAsync(c->hostIn[b].p, hIn + (size_t)f0 * inStride, inBytes, cudaMemcpyHostToDevice, c->h2d));
         CED_CUDA(cudaEventRecord(c->inReady[b], c->h2d));
@@ -1152,30 +1232,56 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     if (nFrames == 0)
         return CED_OK;
     /* Transfer compression: worker threads pack the symbols to 2 bits into page-locked staging and a quarter of
-     * the bytes crosses PCIe.  CED_HOST_PACK selects 0 = never, 1 = every chunk, 2 = adaptive; the default is
-     *  - page-locked caller buffers: adaptive.  The copy engine moves raw chunks at the PCIe rate (~54 GB/s) while
-     *    the host threads pack the chunks it is not ready for, so both read the caller's buffer at once: 53.6 ->
-     *    79 Gbit/s with two callers, 47 -> 56-63 with one, close to the ~93 GB/s at which this host reads its own
-     *    memory at all (packing every chunk: 48.7 / 66.8 -- the host alone is slower than the link);
+     * the bytes crosses PCIe.  CED_HOST_PACK forces 0 = never, 1 = every chunk, 2 = adaptive; the default is
+     *  - page-locked caller buffers: adaptive, if this machine gains from it (PackTuner above measures that during
+     *    the first 16 calls of at least four chunks; shorter calls copy raw).  The copy engine moves raw chunks at
+     *    the PCIe rate (~54 GB/s) while the host threads pack the chunks it is not ready for, so both read the
+     *    caller's buffer at once: 53.6 -> 77 Gbit/s with two callers, 47 -> 56-63 with one, close to the ~93 GB/s
+     *    at which that host reads its own memory at all (packing every chunk: 48.7 / 66.8 -- the host alone is
+     *    slower than the link);
      *  - pageable caller buffers (what a program written against the reference owns): every chunk -- a direct
      *    copy from pageable memory runs at ~10 GB/s, the packing threads read it at several times that.
      * CED_HOST_THREADS sets the pool size (default: host cores / visible GPUs, at most 8). */
     HostOp op = HostOp::Decode;
+    bool tuned = false;
+    int ticket = -1, tunedMode = 0;
     const CodeId id = classify(code);
     if (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171 || id == CodeId::K7_Runtime) {
         const char *envP = getenv("CED_HOST_PACK");
-        const int mode = envP ? atoi(envP) : (isPageable(hSegs) ? 1 : 2);
+        const bool pageable = isPageable(hSegs);
+        int mode = envP ? atoi(envP) : (pageable ? 1 : 2);
+        if (!envP && !pageable) {
+            /* page-locked buffers: adaptive packing only where this machine gains from it (PackTuner) */
+            static const int coresPerGpu = [] {
+                int nDev = 1;
+                cudaGetDeviceCount(&nDev);
+                return (int)std::thread::hardware_concurrency() / std::max(1, nDev);
+            }();
+            if (nFrames >= 4 * kHostChunkFrames && coresPerGpu >= 8)
+                tuned = true;
+            else
+                mode = 0;
+        }
+        if (tuned)
+            mode = packTunerBegin(c->device, &ticket) ? 2 : 0;
+        tunedMode = mode == 2 ? 1 : 0;
         if (mode != 0) {
             std::lock_guard<std::recursive_mutex> lock(c->mu);
             int rc = ensurePacker(c);
             if (rc != CED_OK)
                 return rc;
             /* 2: pack only the chunks the copy engine is not ready for (page-locked buffers) */
-            op = mode == 2 && !isPageable(hSegs) ? HostOp::DecodeAdaptive : HostOp::DecodeViaPack;
+            op = mode == 2 && !pageable ? HostOp::DecodeAdaptive : HostOp::DecodeViaPack;
         }
     }
-    return hostPipeline(c, code, op, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
-                        frameBits, hOut, outStride, (size_t)frameBits / 8);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = hostPipeline(c, code, op, hSegs, segStride, (size_t)frameBits + code->constraintLen - 1, nFrames,
+                                frameBits, hOut, outStride, (size_t)frameBits / 8);
+    if (tuned && rc == CED_OK) {
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        packTunerEnd(c->device, ticket, tunedMode, (double)nFrames * (double)(frameBits + 6) / std::max(sec, 1e-9));
+    }
+    return rc;
 }
 
 int ced_decode_batch_packed_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hPacked, size_t packedStride,
