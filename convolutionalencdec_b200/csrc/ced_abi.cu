@@ -904,13 +904,22 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
          * grid): 8 / 16 per SM measured 4213 / 4399 Gbit/s at 2^20 frames */
         static const int envPerSm = getenv("CED_ENC_CTAS_PER_SM") ? atoi(getenv("CED_ENC_CTAS_PER_SM")) : 0;
         const long long perSm = envPerSm > 0 ? envPerSm : 16;
-        const int blocksL = (int)std::min<long long>(((long long)nFrames + 7) / 8, (long long)(c->sms > 0 ? c->sms : 148) * perSm);
-        if (fixedTaps)
-            ced::encodeBatchLutKernel<true><<<blocksL, ced::kEncLutThreads, 0, s>>>(
-                dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, taps.tap[0], taps.tap[1]);
+        const int chunksL = (T + 15) / 16;
+        const int fpw = chunksL > 16 ? 1 : chunksL > 8 ? 2 : chunksL > 4 ? 4 : chunksL > 2 ? 8 : chunksL > 1 ? 16 : 32; /* frames per warp */
+        const int blocksL = (int)std::min<long long>(((long long)nFrames + 8 * fpw - 1) / (8 * fpw),
+                                                     (long long)(c->sms > 0 ? c->sms : 148) * perSm);
+        auto launchLut = [&](auto kernel) {
+            kernel<<<blocksL, ced::kEncLutThreads, 0, s>>>(dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs,
+                                                          taps.tap[0], taps.tap[1]);
+        };
+        if (fixedTaps && fpw > 1)
+            launchLut(ced::encodeBatchLutKernel<true, true>);
+        else if (fixedTaps)
+            launchLut(ced::encodeBatchLutKernel<true, false>);
+        else if (fpw > 1)
+            launchLut(ced::encodeBatchLutKernel<false, true>);
         else
-            ced::encodeBatchLutKernel<false><<<blocksL, ced::kEncLutThreads, 0, s>>>(
-                dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, taps.tap[0], taps.tap[1]);
+            launchLut(ced::encodeBatchLutKernel<false, false>);
     } else if (fixedTaps)
         ced::encodeBatchKernel<7, 2, false, true><<<blocks, ced::kEncThreads, 0, s>>>(
             dMsg, msgStride, nFrames, frameBytes, dSegs, segStride, tailSegs, 7, 2, taps, hist, aligned16);

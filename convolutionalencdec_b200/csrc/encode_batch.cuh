@@ -180,7 +180,7 @@ __device__ __forceinline__ uint4 encodeChunkLut(uint32_t x, uint32_t tap0, uint3
     return make_uint4(lut[ze & 0xFFu], lut[zo & 0xFFu], lut[ze >> 8], lut[zo >> 8]);
 }
 
-template <bool FIXED>
+template <bool FIXED, bool SHORT>
 __global__ void __launch_bounds__(kEncLutThreads)
 encodeBatchLutKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
                      uint8_t *__restrict__ segs, size_t segStride, int tailSegs, uint32_t tap0, uint32_t tap1)
@@ -201,8 +201,13 @@ encodeBatchLutKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFra
      * without bounds checks; frameBytes is even on this path */
     const int interiorIters = (frameBytes / 2) / 32;
     const int lane = threadIdx.x & 31;
+    /* SHORT frames (at most 16 chunks): a warp encodes 32 / cp2 frames side by side, cp2 lanes each; a separate
+     * instantiation because per-lane frame pointers cost the long-frame loop 5 % */
+    const int cp2 = !SHORT ? 32 : chunks > 8 ? 16 : chunks > 4 ? 8 : chunks > 2 ? 4 : chunks > 1 ? 2 : 1;
+    const int framesPerWarp = 32 / cp2, cl = lane & (cp2 - 1);
     const long long warps = (long long)gridDim.x * (kEncLutThreads / 32);
-    for (long long f = (long long)blockIdx.x * (kEncLutThreads / 32) + (threadIdx.x >> 5); f < nFrames; f += warps) {
+    for (long long f = ((long long)blockIdx.x * (kEncLutThreads / 32) + (threadIdx.x >> 5)) * framesPerWarp + lane / cp2;
+         f < nFrames; f += warps * framesPerWarp) {
         const uint8_t *m = msg + (size_t)f * msgStride;
         uint8_t *out = segs + (size_t)f * segStride;
         const uint16_t *m16 = reinterpret_cast<const uint16_t *>(m);
@@ -212,7 +217,7 @@ encodeBatchLutKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFra
             uint32_t a[4], h[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int c = 32 * (k + u) + lane;
+                const int c = 32 * (k + u) + lane; /* whole-warp iterations exist only when cp2 == 32 */
                 a[u] = __ldg(m16 + max(c - 1, 0)); /* bytes 2c-2, 2c-1 */
                 h[u] = __ldg(m16 + c);             /* bytes 2c, 2c+1   */
             }
@@ -222,8 +227,16 @@ encodeBatchLutKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFra
             for (int u = 0; u < 4; u++)
                 out16[32 * (k + u) + lane] = encodeChunkLut<FIXED>(__byte_perm(a[u], h[u], 0x1450), tap0, tap1, lut);
         }
+        for (; k < interiorIters; k++) { /* whole-warp iterations left over by the unrolled loop */
+            const int c = 32 * k + lane;
+            uint32_t a = __ldg(m16 + max(c - 1, 0));
+            const uint32_t h = __ldg(m16 + c);
+            if (c == 0)
+                a = 0u;
+            out16[c] = encodeChunkLut<FIXED>(__byte_perm(a, h, 0x1450), tap0, tap1, lut);
+        }
         /* the remaining chunks: ragged message end, zero tail (src/convEncode.c:108-119), ragged row end */
-        for (int c = 32 * k + lane; c < chunks; c += 32) {
+        for (int c = 32 * k + cl; c < chunks; c += cp2) {
             const int i1 = 2 * c;
             const uint32_t b0 = (c > 0 && i1 - 1 < frameBytes) ? __ldg(m + i1 - 1) : 0u;
             const uint32_t b1 = (i1 < frameBytes) ? __ldg(m + i1) : 0u;
