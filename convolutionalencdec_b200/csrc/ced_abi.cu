@@ -8,6 +8,7 @@
 #include "channel_kernels.cuh"
 #include "decode_batch.cuh"
 #include "encode_batch.cuh"
+#include "frame_parallel.cuh"
 #include "probe_kernels.cuh"
 #include "stream_kernels.cuh"
 
@@ -173,6 +174,7 @@ struct ced_ctx {
     /* streaming path */
     DeviceBuf<uint8_t> sIn, sOut;
     DeviceBuf<uint32_t> sSurv;
+    DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
     PinnedBuf sPinIn, sPinOut;
     std::recursive_mutex mu;
     uint64_t launches = 0;
@@ -299,6 +301,7 @@ void ced_ctx_destroy(ced_ctx *c)
     c->sIn.release();
     c->sOut.release();
     c->sSurv.release();
+    c->sParallel.release();
     c->sPinIn.release();
     c->sPinOut.release();
     for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
@@ -1399,6 +1402,16 @@ static int streamZeroCopyMask()
     return mask;
 }
 
+/* CED_STREAM_PARALLEL=0 sends one-shot K=7 packets through the single-warp kernel as well */
+static bool streamParallelEnabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("CED_STREAM_PARALLEL");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 int ced_stream_surv_words(int nStates)
 {
     const int H = nStates / 2;
@@ -1435,8 +1448,21 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     const size_t inBytes = 1024 + (size_t)segmentsIn;
     const size_t survBytes = (size_t)kStreamMaxSteps * W * sizeof(uint32_t);
     const size_t outBytes = 4096 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
-    int rc = c->sIn.ensure(1024 + kStreamMaxSteps);
+    /* A whole 64-state n = 2 packet in one call (what speedDecode.c:79 and berTestK7.c:157 issue): every
+     * block of 32 steps is worked on at once (frame_parallel.cuh).  The reference's uint8 metrics cannot
+     * wrap from reset-like starting values, which is what makes plain ints equivalent. */
+    bool parallel = K == 7 && n == 2 && last && it0 == 0 && *renormCounter == 0 && segmentsIn > 2 * S &&
+                    streamParallelEnabled();
+    for (int i = 0; parallel && i < N; i++)
+        parallel = metrics[i] <= N + 1;
+    int rc = c->sIn.ensure(1024 + kStreamMaxSteps + 64);
     if (rc == CED_OK) rc = c->sOut.ensure(272 + kStreamMaxSteps / 8 + 16);
+    if (rc == CED_OK && parallel && !c->sParallel.p) {
+        const ced::FpScratch lay = ced::fpScratchLayout(kStreamMaxSteps);
+        rc = c->sParallel.ensure(lay.total);
+        if (rc == CED_OK)
+            CED_CUDA(cudaMemsetAsync(c->sParallel.p + lay.tickets, 0, 16, c->stream));
+    }
     if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
     if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
@@ -1451,7 +1477,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         memcpy(c->sPinIn.p + 1024, segs, (size_t)segmentsIn);
     const int zc = streamZeroCopyMask();
     const bool zcIn = (zc & 2) != 0, zcOut = (zc & 4) != 0;
-    if (!zcIn)
+    if (!zcIn || parallel) /* the 64 passes over a block all read its segments: keep those reads on the device */
         CED_CUDA(cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream));
     if (last && it0 > 0) /* chunked packet: bring the earlier decisions back */
         CED_CUDA(cudaMemcpyAsync(c->sSurv.p, surv, (size_t)it0 * W * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -1466,7 +1492,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     a.renormCounter = *renormCounter;
     a.segmentsIn = segmentsIn;
     a.last = last;
-    uint8_t *mbIn = zcIn ? c->sPinIn.p : c->sIn.p, *mbOut = zcOut ? c->sPinOut.p : c->sOut.p;
+    uint8_t *mbIn = (zcIn && !parallel) ? c->sPinIn.p : c->sIn.p, *mbOut = zcOut ? c->sPinOut.p : c->sOut.p;
     a.edge = mbIn;
     a.metricsIn = mbIn + 512;
     a.metrics = mbOut;
@@ -1474,7 +1500,25 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     a.surv = c->sSurv.p;
     a.stateOut = reinterpret_cast<uint32_t *>(mbOut + 256);
     a.out = mbOut + 272;
-    if (N <= 64)
+    if (parallel) {
+        const ced::FpScratch lay = ced::fpScratchLayout(kStreamMaxSteps);
+        ced::FpArgs f;
+        f.T = segmentsIn;
+        f.nBlocks = (segmentsIn + ced::kFpBlock - 1) / ced::kFpBlock;
+        f.edge = a.edge;
+        f.metricsIn = a.metricsIn;
+        f.segs = a.segs;
+        f.cost = c->sParallel.p + lay.cost;
+        f.bits = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bits);
+        f.v = reinterpret_cast<int *>(c->sParallel.p + lay.v);
+        f.best = reinterpret_cast<uint2 *>(c->sParallel.p + lay.best);
+        f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
+        f.out = a.out;
+        const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
+        ced::fpBlockKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+        ced::fpSelectKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+        c->launches += 1;
+    } else if (N <= 64)
         ced::streamDecodeWarpKernel<<<1, 32, 0, c->stream>>>(a);
     else
         ced::streamDecodeKernel<<<1, std::max(32, N / 2), 0, c->stream>>>(a);

@@ -1,0 +1,280 @@
+/*
+ * frame_parallel.cuh -- ONE packet decoded by the whole GPU: the latency path behind a one-shot
+ * VITERBI_DECODER_HARD(.., last = true) call (src/viterbiDecoderButterflyk1.c:82-263) for the
+ * 64-state, n = 2 code, as issued per packet by speedDecode.c:79 and berTestK7.c:157.
+ *
+ * The add-compare-select recursion is sequential in time (2054 dependent steps for the reference's
+ * speedDecode packet), which a single warp cannot run faster than ~100 ns per step.  It is however a
+ * (min,+) matrix product chain, so the packet is cut into blocks of 32 steps:
+ *
+ *   fpBlockKernel   one warp per (block c, start state s): a forward pass over the block that starts
+ *                   with metric 0 in s only and carries the input bits of each survivor in a register
+ *                   (register exchange), giving cost_c[s][e] and bits_c[s][e] for all 64 end states e.
+ *                   The last CTA to finish then runs the short sequential part: v_{c+1}[e] =
+ *                   min_s v_c[s] + cost_c[s][e], 64 x 64 candidates per block on 256 threads.
+ *   fpSelectKernel  one warp per (c, e): which start state the survivor into e came from, the minimum of
+ *                   the key (v_c[s] + cost_c[s][e], bits_c[s][e], rev6(s)).  The last CTA walks the
+ *                   resulting table back from state 0 (:205) block by block and writes the packed bits.
+ *
+ * Exactness.  The reference keeps the path from the LOWER predecessor on equal metrics (strict `>`,
+ * :129-130); the predecessors j and j+32 differ in their oldest input bit, so every survivor is the
+ * minimum over paths of (cost, input bits read as a number with LATER bits more significant).  The key
+ * above is that order written per block: in-block bits first, then the six bits before the block
+ * (the start state, newest bit first = rev6).  Metrics are plain ints here; the reference's uint8
+ * metrics never wrap for this code, so decisions coincide.  tests/frame_parallel_model.py
+ * is the same procedure in numpy, compared on the CPU with the sequential decoder.
+ *
+ * Lane mapping of fpBlockKernel.  Position = (5 lane bits, 1 slot bit); a lane holds two states.  Before
+ * step t (phase r = t mod 5) the slot bit holds the newest state bit b0 and lane bit i holds state bit
+ * ((i + r) mod 5) + 1.  The oldest bit b5 (the one a butterfly pairs on) sits in lane bit q = 4 - r:
+ * one __shfl_xor_sync swaps it with the slot bit, the butterfly is then local to the lane (slot 0 = lower
+ * predecessor, slot 1 = upper), writes its successors 2j / 2j+1 back into slots 0 / 1, and the labelling
+ * has advanced to phase r + 1 without any further data movement.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ced {
+
+constexpr int kFpBlock = 32;        /* trellis steps per block (the survivor's input bits fill one register) */
+constexpr int kFpThreads = 256;     /* 8 warps per CTA */
+constexpr int kFpUnreach = 128;     /* starting metric of the 63 states a pass does not start in */
+constexpr int kFpBig = 1 << 20;     /* added to candidates that do not start in s (short last block) */
+constexpr int kFpChainBlocks = 80;  /* blocks of the survivor table staged per pass of the final walk */
+
+struct FpArgs {
+    int T;                     /* segments of the packet */
+    int nBlocks;               /* ceil(T / 32) */
+    const uint8_t *edge;       /* [2][64] edge labels, as StreamArgs.edge */
+    const uint8_t *metricsIn;  /* [64] path metrics before the packet */
+    const uint8_t *segs;       /* 16-byte aligned, readable up to nBlocks * 32 bytes */
+    uint8_t *cost;             /* [nBlocks][64 e][64 s] */
+    uint32_t *bits;            /* [nBlocks][64 e][64 s] */
+    int *v;                    /* [nBlocks + 1][64] */
+    uint2 *best;               /* [nBlocks][64 e] = {bits, start state} */
+    unsigned int *tickets;     /* [2], zero between calls */
+    uint8_t *out;              /* (T - 6 - 1) / 8 + 1 decoded bytes, MSb first (:249) */
+};
+
+/* state bit held by lane bit `b` in phase r, see above */
+__device__ __forceinline__ int fpLaneBitRole(int b, int r)
+{
+    return ((b + r) % 5) + 1;
+}
+
+template <int T0>
+__device__ __forceinline__ void fpStep(int lane, const uint32_t (&seg)[8], const uint32_t *dist, int &m0, int &m1,
+                                       uint32_t &p0, uint32_t &p1)
+{
+    constexpr int r = T0 % 5, q = 4 - r;
+    const bool up = (lane >> q) & 1;
+    const int keepM = up ? m1 : m0, sendM = up ? m0 : m1;
+    const uint32_t keepP = up ? p1 : p0, sendP = up ? p0 : p1;
+    const int recvM = __shfl_xor_sync(0xFFFFFFFFu, sendM, 1 << q);
+    const uint32_t recvP = __shfl_xor_sync(0xFFFFFFFFu, sendP, 1 << q);
+    const int lo = up ? recvM : keepM, hi = up ? keepM : recvM;
+    const uint32_t pLo = up ? recvP : keepP, pHi = up ? keepP : recvP;
+    const uint32_t rx = (seg[T0 >> 2] >> (8 * (T0 & 3))) & 3u; /* calcHammingDist(.., n = 2) looks at two bits */
+    const uint32_t d = dist[(r * 4 + rx) * 32];
+    const int a0 = lo + (int)(d & 0xFFu), a1 = hi + (int)((d >> 8) & 0xFFu);
+    const int b0 = lo + (int)((d >> 16) & 0xFFu), b1 = hi + (int)(d >> 24);
+    const bool da = a0 > a1, db = b0 > b1; /* tie -> lower predecessor (:129-130) */
+    m0 = da ? a1 : a0;
+    m1 = db ? b1 : b0;
+    p0 = da ? pHi : pLo;
+    p1 = (db ? pHi : pLo) | (1u << T0);
+}
+
+template <int T0>
+__device__ __forceinline__ void fpSteps(int steps, int lane, const uint32_t (&seg)[8], const uint32_t *dist, int &m0,
+                                        int &m1, uint32_t &p0, uint32_t &p1)
+{
+    if constexpr (T0 < kFpBlock) {
+        if (T0 >= steps) /* uniform across the warp */
+            return;
+        fpStep<T0>(lane, seg, dist, m0, m1, p0, p1);
+        fpSteps<T0 + 1>(steps, lane, seg, dist, m0, m1, p0, p1);
+    }
+}
+
+__global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
+{
+    __shared__ uint32_t sDist[5 * 4 * 32]; /* [phase][rx][lane] -> d00 | d0h << 8 | d10 << 16 | d1h << 24 */
+    __shared__ int sV[2][64];
+    __shared__ int sLast;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int i = tid; i < 5 * 4 * 32; i += kFpThreads) {
+        const int l = i & 31, r = i >> 7, q = 4 - r;
+        const uint32_t rx = (i >> 5) & 3;
+        int j = (l >> q) & 1; /* after the swap lane bit q holds b0 */
+        for (int b = 0; b < 5; b++)
+            if (b != q)
+                j |= ((l >> b) & 1) << fpLaneBitRole(b, r);
+        auto hd = [rx](uint32_t e) {
+            const uint32_t x = (e ^ rx) & 3u;
+            return x - (x >> 1);
+        };
+        sDist[i] = hd(a.edge[j]) | hd(a.edge[j + 32]) << 8 | hd(a.edge[64 + j]) << 16 | hd(a.edge[64 + j + 32]) << 24;
+    }
+    __syncthreads();
+
+    const int wid = blockIdx.x * (kFpThreads / 32) + warp;
+    const int c = wid >> 6, s = wid & 63;
+    if (c < a.nBlocks) {
+        const int steps = min(kFpBlock, a.T - c * kFpBlock);
+        const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
+        const uint4 s0 = sp[0], s1 = sp[1];
+        const uint32_t seg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        int m0 = (2 * lane == s) ? 0 : kFpUnreach, m1 = (2 * lane + 1 == s) ? 0 : kFpUnreach;
+        uint32_t p0 = 0, p1 = 0;
+        fpSteps<0>(steps, lane, seg, sDist + lane, m0, m1, p0, p1);
+        const int r = steps % 5;
+        int e = 0;
+        for (int b = 0; b < 5; b++)
+            e |= ((lane >> b) & 1) << fpLaneBitRole(b, r);
+        const size_t row = (size_t)c * 64;
+        a.cost[(row + e) * 64 + s] = (uint8_t)m0;
+        a.cost[(row + e + 1) * 64 + s] = (uint8_t)m1;
+        a.bits[(row + e) * 64 + s] = p0;
+        a.bits[(row + e + 1) * 64 + s] = p1;
+    }
+
+    /* the last CTA to get here runs the sequential part */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+        sLast = atomicAdd(&a.tickets[0], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!sLast)
+        return;
+    __threadfence();
+    if (tid < 64) {
+        const int x = a.metricsIn[tid];
+        sV[0][tid] = x;
+        a.v[tid] = x;
+    }
+    __syncthreads();
+    const int e = tid >> 2, g = tid & 3;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(a.cost) + e * 4 + g;
+    uint4 nxt = __ldcg(cp);
+    for (int c2 = 0; c2 < a.nBlocks; c2++) {
+        const uint4 cur = nxt;
+        if (c2 + 1 < a.nBlocks)
+            nxt = __ldcg(cp + (size_t)(c2 + 1) * 256);
+        const int *vs = sV[c2 & 1] + 16 * g;
+        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
+        const bool checked = c2 == a.nBlocks - 1; /* only a last block shorter than 6 steps has unreachable pairs */
+        int acc0 = 0x7FFFFFFF, acc1 = 0x7FFFFFFF;
+#pragma unroll
+        for (int k = 0; k < 16; k += 2) {
+            int x0 = (int)((w[k >> 2] >> (8 * (k & 3))) & 0xFFu), x1 = (int)((w[k >> 2] >> (8 * (k & 3) + 8)) & 0xFFu);
+            if (checked) {
+                x0 += x0 >= kFpUnreach ? kFpBig : 0;
+                x1 += x1 >= kFpUnreach ? kFpBig : 0;
+            }
+            acc0 = min(acc0, vs[k] + x0);
+            acc1 = min(acc1, vs[k + 1] + x1);
+        }
+        int acc = min(acc0, acc1);
+        acc = min(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 1));
+        acc = min(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 2));
+        if (g == 0) {
+            sV[(c2 + 1) & 1][e] = acc;
+            a.v[(c2 + 1) * 64 + e] = acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+        a.tickets[0] = 0;
+}
+
+__global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
+{
+    __shared__ uint2 sBest[kFpChainBlocks * 64];
+    __shared__ uint32_t sWord[kFpChainBlocks];
+    __shared__ int sState, sLast;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wid = blockIdx.x * (kFpThreads / 32) + warp;
+    const int c = wid >> 6, e = wid & 63;
+    if (c < a.nBlocks) {
+        const size_t row = ((size_t)c * 64 + e) * 64;
+        unsigned long long key = ~0ull;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = lane + 32 * h;
+            const int x = a.cost[row + s];
+            const unsigned long long tot = (unsigned long long)(a.v[c * 64 + s] + x + (x >= kFpUnreach ? kFpBig : 0));
+            const unsigned long long k2 = tot << 38 | (unsigned long long)a.bits[row + s] << 6 | (__brev(s) >> 26);
+            key = k2 < key ? k2 : key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = other < key ? other : key;
+        }
+        if (lane == 0)
+            a.best[c * 64 + e] = make_uint2((uint32_t)(key >> 6), __brev((uint32_t)key & 63u) >> 26);
+    }
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        sLast = atomicAdd(&a.tickets[1], 1u) == gridDim.x - 1;
+        sState = 0; /* the traceback starts in state 0 (:205) */
+    }
+    __syncthreads();
+    if (!sLast)
+        return;
+    __threadfence();
+    const int L = a.T - 6, outBytes = (L - 1) / 8 + 1;
+    for (int hi = a.nBlocks; hi > 0; hi -= kFpChainBlocks) {
+        const int lo = max(0, hi - kFpChainBlocks);
+        for (int i = tid; i < (hi - lo) * 64; i += kFpThreads)
+            sBest[i] = __ldcg(a.best + (size_t)lo * 64 + i);
+        __syncthreads();
+        if (tid == 0) {
+            int st = sState;
+            for (int cb = hi - 1; cb >= lo; cb--) {
+                const uint2 b = sBest[(cb - lo) * 64 + st];
+                sWord[cb - lo] = b.x;
+                st = (int)b.y;
+            }
+            sState = st;
+        }
+        __syncthreads();
+        for (int i = tid; i < (hi - lo) * 4; i += kFpThreads) {
+            const int idx = (lo + (i >> 2)) * 4 + (i & 3); /* output byte; input bit t of a block is bit t of its word */
+            if (idx < outBytes) {
+                uint32_t by = __brev((sWord[i >> 2] >> (8 * (i & 3))) & 0xFFu) >> 24; /* MSb first (:249) */
+                const int valid = L - idx * 8;
+                if (valid < 8)
+                    by &= (0xFF00u >> valid) & 0xFFu; /* last partial byte is zero-filled (:226-227) */
+                a.out[idx] = (uint8_t)by;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+        a.tickets[1] = 0;
+}
+
+/* bytes of device scratch for packets of up to maxSteps segments, and the carve-up */
+struct FpScratch {
+    size_t cost, bits, v, best, tickets, total;
+};
+inline FpScratch fpScratchLayout(int maxSteps)
+{
+    const size_t nb = (size_t)(maxSteps + kFpBlock - 1) / kFpBlock;
+    FpScratch s;
+    s.cost = 0;
+    s.bits = s.cost + nb * 4096;
+    s.v = s.bits + nb * 4096 * 4;
+    s.best = s.v + (nb + 1) * 64 * 4;
+    s.tickets = s.best + nb * 64 * 8;
+    s.total = s.tickets + 16;
+    return s;
+}
+
+} // namespace ced

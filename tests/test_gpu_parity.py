@@ -468,6 +468,40 @@ def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
     assert np.array_equal(dec.VITERBI_DECODER_HARD(big[:0], True, max_bytes=4096), want)
 
 
+@pytest.mark.parametrize("T", [13, 14, 33, 37, 38, 39, 70, 262, 1030, 2054, 2055, 4102, 16390])
+def test_one_shot_packets_take_the_frame_parallel_kernels(port, T):
+    """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs fpBlockKernel / fpSelectKernel
+    (csrc/frame_parallel.cuh): same bytes as the sequential decoder for clean, noisy, all-zero and
+    pure-noise packets, for lengths that leave a short last block or a partial last byte, and the decoder
+    is usable for chunked packets afterwards."""
+    api = ced.RefApi("k7")
+    dec = api.decoder()
+    dec.VITERBI_RESET()
+    dec.VITERBI_INIT()
+    rng = np.random.default_rng(T)
+    L = T - 6
+    lib = ced.load_abi()
+    count = lambda: int(lib.ced_launch_count(lib.ced_default_ctx()))
+    for rep, p in enumerate((0.0, 0.04, 0.12, 0.5, None, "zero")):
+        msg = rng.integers(0, 256, (1, (L + 7) // 8), dtype=np.uint8)
+        segs = port.encode_batch(7, K7, msg)[:, :T].copy()
+        if p is None:
+            segs[:] = rng.integers(0, 256, segs.shape)       # only the low two bits of a byte count
+        elif p == "zero":
+            segs[:] = 0
+        else:
+            segs = bsc(rng, segs, p)
+        want = port.decode_batch(7, K7, segs, T)[0][:(L - 1) // 8 + 1]
+        launches = count()
+        got = dec.VITERBI_DECODER_HARD(segs[0], True, max_bytes=4096)
+        assert count() - launches == 2, "expected the two frame-parallel kernels"
+        assert np.array_equal(got, want), (T, rep)
+        assert dec.nodeMetricsCur().tolist() == [0] + [65] * 63
+    # the same packet in two calls goes through the sequential kernel and gives the same bytes
+    assert dec.VITERBI_DECODER_HARD(segs[0, :7], False).size == 0
+    assert np.array_equal(dec.VITERBI_DECODER_HARD(segs[0, 7:], True, max_bytes=4096), want)
+
+
 def test_streaming_encoder_chunks_and_kat(golden, port):
     api = ced.RefApi("k7")
     enc = api.encoder()
