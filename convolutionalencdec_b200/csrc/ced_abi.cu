@@ -175,6 +175,8 @@ struct ced_ctx {
     DeviceBuf<uint8_t> sIn, sOut;
     DeviceBuf<uint32_t> sSurv;
     DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
+    cudaGraphExec_t fpGraph = nullptr; /* copy in + fpBlockKernel + fpSelectKernel for packets of fpGraphSegs segments */
+    int fpGraphSegs = 0;
     PinnedBuf sPinIn, sPinOut;
     std::recursive_mutex mu;
     uint64_t launches = 0;
@@ -302,6 +304,8 @@ void ced_ctx_destroy(ced_ctx *c)
     c->sOut.release();
     c->sSurv.release();
     c->sParallel.release();
+    if (c->fpGraph)
+        cudaGraphExecDestroy(c->fpGraph);
     c->sPinIn.release();
     c->sPinOut.release();
     for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
@@ -1403,6 +1407,16 @@ static int streamZeroCopyMask()
 }
 
 /* CED_STREAM_PARALLEL=0 sends one-shot K=7 packets through the single-warp kernel as well */
+/* CED_STREAM_GRAPH=0 issues the copy and the two kernels of that path one by one instead of as one graph launch */
+static bool streamGraphEnabled()
+{
+    static const bool on = [] {
+        const char *e = getenv("CED_STREAM_GRAPH");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
 static bool streamParallelEnabled()
 {
     static const bool on = [] {
@@ -1477,7 +1491,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         memcpy(c->sPinIn.p + 1024, segs, (size_t)segmentsIn);
     const int zc = streamZeroCopyMask();
     const bool zcIn = (zc & 2) != 0, zcOut = (zc & 4) != 0;
-    if (!zcIn || parallel) /* the 64 passes over a block all read its segments: keep those reads on the device */
+    if (!zcIn && !parallel)
         CED_CUDA(cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream));
     if (last && it0 > 0) /* chunked packet: bring the earlier decisions back */
         CED_CUDA(cudaMemcpyAsync(c->sSurv.p, surv, (size_t)it0 * W * sizeof(uint32_t), cudaMemcpyHostToDevice,
@@ -1515,8 +1529,38 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
         f.out = a.out;
         const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
-        ced::fpBlockKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
-        ced::fpSelectKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+        /* the 64 passes over a block all read its segments: those reads stay on the device (one small copy) */
+        auto issue = [&]() -> cudaError_t {
+            cudaError_t e = cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess)
+                return e;
+            ced::fpBlockKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+            ced::fpSelectKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+            if (!zcOut)
+                e = cudaMemcpyAsync(c->sPinOut.p, c->sOut.p, 272 + decodedBytes, cudaMemcpyDeviceToHost, c->stream);
+            return e != cudaSuccess ? e : cudaGetLastError();
+        };
+        if (streamGraphEnabled()) {
+            /* per-packet loops call with one packet length: the three submissions become one graph launch */
+            if (!c->fpGraph || c->fpGraphSegs != segmentsIn) {
+                if (c->fpGraph)
+                    cudaGraphExecDestroy(c->fpGraph);
+                c->fpGraph = nullptr;
+                cudaGraph_t g = nullptr;
+                CED_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                const cudaError_t e1 = issue();
+                const cudaError_t e2 = cudaStreamEndCapture(c->stream, &g);
+                CED_CUDA(e1);
+                CED_CUDA(e2);
+                const cudaError_t e3 = cudaGraphInstantiate(&c->fpGraph, g, 0);
+                cudaGraphDestroy(g);
+                CED_CUDA(e3);
+                c->fpGraphSegs = segmentsIn;
+            }
+            CED_CUDA(cudaGraphLaunch(c->fpGraph, c->stream));
+        } else {
+            CED_CUDA(issue());
+        }
         c->launches += 1;
     } else if (N <= 64)
         ced::streamDecodeWarpKernel<<<1, 32, 0, c->stream>>>(a);
@@ -1524,7 +1568,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         ced::streamDecodeKernel<<<1, std::max(32, N / 2), 0, c->stream>>>(a);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
-    if (!zcOut)
+    if (!zcOut && !parallel)
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->sOut.p, 272 + decodedBytes, cudaMemcpyDeviceToHost, c->stream));
     if (!last && segmentsIn)
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 4096, c->sSurv.p + (size_t)it0 * W,

@@ -41,6 +41,7 @@ constexpr int kFpBlock = 32;        /* trellis steps per block (the survivor's i
 constexpr int kFpThreads = 256;     /* 8 warps per CTA */
 constexpr int kFpUnreach = 128;     /* starting metric of the 63 states a pass does not start in */
 constexpr int kFpBig = 1 << 20;     /* added to candidates that do not start in s (short last block) */
+constexpr int kFpAhead = 8;        /* blocks of costs in flight ahead of the sequential min-plus chain */
 constexpr int kFpChainBlocks = 80;  /* blocks of the survivor table staged per pass of the final walk */
 
 struct FpArgs {
@@ -101,10 +102,23 @@ __device__ __forceinline__ void fpSteps(int steps, int lane, const uint32_t (&se
 __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 {
     __shared__ uint32_t sDist[5 * 4 * 32]; /* [phase][rx][lane] -> d00 | d0h << 8 | d10 << 16 | d1h << 24 */
-    __shared__ int sV[2][64];
+    __shared__ __align__(16) uint8_t sEdge[128];
+    __shared__ __align__(16) uint8_t sOutCost[64][kFpThreads / 32];  /* [e][s - s0] of this CTA's 8 passes */
+    __shared__ __align__(16) uint32_t sOutBits[64][kFpThreads / 32];
+    __shared__ __align__(16) uint32_t sV[2][32];                     /* v as u16x2 pairs (s = 2k, 2k + 1) */
+    __shared__ uint4 sCost[kFpAhead][kFpThreads];                    /* ring of the sequential part */
     __shared__ int sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kFpThreads / 32;
 
+    /* a CTA = 8 consecutive start states of ONE block c (64 % kWarps == 0) */
+    const int wid = blockIdx.x * kWarps + warp;
+    const int c = wid >> 6, s = wid & 63;
+    const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
+    const uint4 s0 = sp[0], s1 = sp[1]; /* in flight while the table is built */
+    if (tid < 32)
+        reinterpret_cast<uint32_t *>(sEdge)[tid] = reinterpret_cast<const uint32_t *>(a.edge)[tid];
+    __syncthreads();
     for (int i = tid; i < 5 * 4 * 32; i += kFpThreads) {
         const int l = i & 31, r = i >> 7, q = 4 - r;
         const uint32_t rx = (i >> 5) & 3;
@@ -116,16 +130,12 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
             const uint32_t x = (e ^ rx) & 3u;
             return x - (x >> 1);
         };
-        sDist[i] = hd(a.edge[j]) | hd(a.edge[j + 32]) << 8 | hd(a.edge[64 + j]) << 16 | hd(a.edge[64 + j + 32]) << 24;
+        sDist[i] = hd(sEdge[j]) | hd(sEdge[j + 32]) << 8 | hd(sEdge[64 + j]) << 16 | hd(sEdge[64 + j + 32]) << 24;
     }
     __syncthreads();
 
-    const int wid = blockIdx.x * (kFpThreads / 32) + warp;
-    const int c = wid >> 6, s = wid & 63;
-    if (c < a.nBlocks) {
+    {
         const int steps = min(kFpBlock, a.T - c * kFpBlock);
-        const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
-        const uint4 s0 = sp[0], s1 = sp[1];
         const uint32_t seg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         int m0 = (2 * lane == s) ? 0 : kFpUnreach, m1 = (2 * lane + 1 == s) ? 0 : kFpUnreach;
         uint32_t p0 = 0, p1 = 0;
@@ -134,11 +144,21 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
         int e = 0;
         for (int b = 0; b < 5; b++)
             e |= ((lane >> b) & 1) << fpLaneBitRole(b, r);
-        const size_t row = (size_t)c * 64;
-        a.cost[(row + e) * 64 + s] = (uint8_t)m0;
-        a.cost[(row + e + 1) * 64 + s] = (uint8_t)m1;
-        a.bits[(row + e) * 64 + s] = p0;
-        a.bits[(row + e + 1) * 64 + s] = p1;
+        sOutCost[e][warp] = (uint8_t)m0;
+        sOutCost[e + 1][warp] = (uint8_t)m1;
+        sOutBits[e][warp] = p0;
+        sOutBits[e + 1][warp] = p1;
+    }
+    __syncthreads();
+    { /* rows of 8 start states: one 8-byte and two 16-byte stores per end state instead of 16 scattered ones */
+        const size_t row = (size_t)c * 64, sBase = (size_t)(blockIdx.x * kWarps) & 63;
+        if (tid < 64)
+            *reinterpret_cast<uint2 *>(a.cost + (row + tid) * 64 + sBase) = *reinterpret_cast<const uint2 *>(sOutCost[tid]);
+        else if (tid < 192) {
+            const int e = (tid - 64) >> 1, h = (tid - 64) & 1;
+            *reinterpret_cast<uint4 *>(a.bits + (row + e) * 64 + sBase + 4 * h) =
+                *reinterpret_cast<const uint4 *>(&sOutBits[e][4 * h]);
+        }
     }
 
     /* the last CTA to get here runs the sequential part */
@@ -150,39 +170,60 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     if (!sLast)
         return;
     __threadfence();
+    /* 256 threads = 64 end states x 4 quarters of the start states.  The costs do not depend on v, so
+     * each thread streams its own 16 bytes per block through a private shared-memory ring kFpAhead blocks
+     * ahead (cp.async, no registers held).  v stays below 65 + 64 per block < 2^16 for any packet the API
+     * takes, so candidates are formed two at a time: VIADDMNMX.U16x2 = min(v + cost, acc) on both halves. */
+    const int e = tid >> 2, g = tid & 3;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(a.cost) + tid; /* e * 4 + g == tid */
+    const int nb = a.nBlocks;
+    auto fetch = [&](int c2) {
+        if (c2 < nb) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sCost[c2 % kFpAhead][tid]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(cp + (size_t)c2 * 256));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    for (int k = 0; k < kFpAhead; k++)
+        fetch(k);
     if (tid < 64) {
         const int x = a.metricsIn[tid];
-        sV[0][tid] = x;
+        reinterpret_cast<uint16_t *>(sV[0])[tid] = (uint16_t)x;
         a.v[tid] = x;
     }
     __syncthreads();
-    const int e = tid >> 2, g = tid & 3;
-    const uint4 *cp = reinterpret_cast<const uint4 *>(a.cost) + e * 4 + g;
-    uint4 nxt = __ldcg(cp);
-    for (int c2 = 0; c2 < a.nBlocks; c2++) {
-        const uint4 cur = nxt;
-        if (c2 + 1 < a.nBlocks)
-            nxt = __ldcg(cp + (size_t)(c2 + 1) * 256);
-        const int *vs = sV[c2 & 1] + 16 * g;
+    for (int c2 = 0; c2 < nb; c2++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kFpAhead - 1) : "memory");
+        const uint4 cur = sCost[c2 % kFpAhead][tid];
+        fetch(c2 + kFpAhead);
+        const uint4 va = *reinterpret_cast<const uint4 *>(&sV[c2 & 1][8 * g]);
+        const uint4 vb = *reinterpret_cast<const uint4 *>(&sV[c2 & 1][8 * g + 4]);
         const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        const bool checked = c2 == a.nBlocks - 1; /* only a last block shorter than 6 steps has unreachable pairs */
-        int acc0 = 0x7FFFFFFF, acc1 = 0x7FFFFFFF;
+        const uint32_t v2[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        uint32_t m;
+        if (c2 < nb - 1) {
+            uint32_t acc0 = 0xFFFFFFFFu, acc1 = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < 16; k += 2) {
-            int x0 = (int)((w[k >> 2] >> (8 * (k & 3))) & 0xFFu), x1 = (int)((w[k >> 2] >> (8 * (k & 3) + 8)) & 0xFFu);
-            if (checked) {
-                x0 += x0 >= kFpUnreach ? kFpBig : 0;
-                x1 += x1 >= kFpUnreach ? kFpBig : 0;
+            for (int i = 0; i < 4; i++) {
+                acc0 = __viaddmin_u16x2(v2[2 * i], __byte_perm(w[i], 0, 0x4140), acc0);
+                acc1 = __viaddmin_u16x2(v2[2 * i + 1], __byte_perm(w[i], 0, 0x4342), acc1);
             }
-            acc0 = min(acc0, vs[k] + x0);
-            acc1 = min(acc1, vs[k + 1] + x1);
+            const uint32_t acc = __vminu2(acc0, acc1);
+            m = min(acc & 0xFFFFu, acc >> 16);
+        } else { /* only a last block shorter than 6 steps has (s, e) pairs without a path */
+            m = 0x7FFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                x += x >= (uint32_t)kFpUnreach ? (uint32_t)kFpBig : 0u;
+                m = min(m, ((v2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) + x);
+            }
         }
-        int acc = min(acc0, acc1);
-        acc = min(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 1));
-        acc = min(acc, __shfl_xor_sync(0xFFFFFFFFu, acc, 2));
+        m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
         if (g == 0) {
-            sV[(c2 + 1) & 1][e] = acc;
-            a.v[(c2 + 1) * 64 + e] = acc;
+            reinterpret_cast<uint16_t *>(sV[(c2 + 1) & 1])[e] = (uint16_t)m;
+            a.v[(c2 + 1) * 64 + e] = (int)m;
         }
         __syncthreads();
     }
@@ -192,7 +233,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 
 __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
 {
-    __shared__ uint2 sBest[kFpChainBlocks * 64];
+    __shared__ __align__(16) uint2 sBest[kFpChainBlocks * 64];
     __shared__ uint32_t sWord[kFpChainBlocks];
     __shared__ int sState, sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -231,8 +272,22 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
     const int L = a.T - 6, outBytes = (L - 1) / 8 + 1;
     for (int hi = a.nBlocks; hi > 0; hi -= kFpChainBlocks) {
         const int lo = max(0, hi - kFpChainBlocks);
-        for (int i = tid; i < (hi - lo) * 64; i += kFpThreads)
-            sBest[i] = __ldcg(a.best + (size_t)lo * 64 + i);
+        { /* 32 entries (two per 16-byte load) per thread and round, all loads of a round in flight together */
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.best + (size_t)lo * 64);
+            uint4 *dst = reinterpret_cast<uint4 *>(sBest);
+            const int n4 = (hi - lo) * 32;
+            for (int base = 0; base < n4; base += 10 * kFpThreads) {
+                uint4 r[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++)
+                    if (base + k * kFpThreads + tid < n4)
+                        r[k] = __ldcg(src + base + k * kFpThreads + tid);
+#pragma unroll
+                for (int k = 0; k < 10; k++)
+                    if (base + k * kFpThreads + tid < n4)
+                        dst[base + k * kFpThreads + tid] = r[k];
+            }
+        }
         __syncthreads();
         if (tid == 0) {
             int st = sState;
