@@ -1417,6 +1417,20 @@ static bool streamGraphEnabled()
     return on;
 }
 
+/* CED_FP_STAMPS=1: the frame-parallel kernels record %globaltimer at their phase boundaries into host-visible
+ * memory and every call prints the intervals to stderr (a measurement aid) */
+static unsigned long long *fpStamps()
+{
+    static unsigned long long *p = [] {
+        const char *e = getenv("CED_FP_STAMPS");
+        unsigned long long *q = nullptr;
+        if (e && atoi(e) != 0 && cudaMallocHost(reinterpret_cast<void **>(&q), 16 * sizeof(unsigned long long)) != cudaSuccess)
+            q = nullptr;
+        return q;
+    }();
+    return p;
+}
+
 static bool streamParallelEnabled()
 {
     static const bool on = [] {
@@ -1528,6 +1542,12 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         f.best = reinterpret_cast<uint2 *>(c->sParallel.p + lay.best);
         f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
         f.out = a.out;
+        f.stamps = fpStamps();
+        f.stampAll = getenv("CED_FP_STAMPS") && atoi(getenv("CED_FP_STAMPS")) > 1;
+        if (f.stamps) { /* the device is idle here: every call ends with a synchronise */
+            f.stamps[0] = f.stamps[5] = ~0ull;
+            f.stamps[1] = f.stamps[6] = 0;
+        }
         const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
         /* the 64 passes over a block all read its segments: those reads stay on the device (one small copy) */
         auto issue = [&]() -> cudaError_t {
@@ -1574,6 +1594,12 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 4096, c->sSurv.p + (size_t)it0 * W,
                                  (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CED_CUDA(cudaStreamSynchronize(c->stream));
+    if (parallel && fpStamps()) {
+        const unsigned long long *st = fpStamps();
+        fprintf(stderr, "fp T=%d: passes %.1f  fence+ticket %.1f  prologue %.1f  chain %.1f | gap %.1f | select %.1f  fence+ticket %.1f  walk+write %.1f  (us)\n",
+                segmentsIn, (st[1] - st[0]) * 1e-3, (st[2] - st[1]) * 1e-3, (st[3] - st[2]) * 1e-3, (st[4] - st[3]) * 1e-3,
+                ((double)st[5] - (double)st[4]) * 1e-3, (st[6] - st[5]) * 1e-3, (st[7] - st[6]) * 1e-3, (st[8] - st[7]) * 1e-3);
+    }
     if (last) {
         memcpy(uncoded, c->sPinOut.p + 272, decodedBytes);
         /* src/viterbiDecoderButterflyk1.c:259 -- the caller's reset restores metrics/counters */

@@ -56,7 +56,27 @@ struct FpArgs {
     uint2 *best;               /* [nBlocks][64 e] = {bits, start state} */
     unsigned int *tickets;     /* [2], zero between calls */
     uint8_t *out;              /* (T - 6 - 1) / 8 + 1 decoded bytes, MSb first (:249) */
+    int stampAll;              /* also the grid-wide (atomic, slow over PCIe) stamps */
+    unsigned long long *stamps; /* optional: %globaltimer at the phase boundaries (CED_FP_STAMPS=1), else null */
 };
+
+__device__ __forceinline__ unsigned long long fpNow()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void fpStamp(const FpArgs &a, int slot, int mode)
+{
+    if (a.stamps && threadIdx.x == 0 && (mode == 0 || a.stampAll)) {
+        if (mode < 0)
+            atomicMin(a.stamps + slot, fpNow());
+        else if (mode > 0)
+            atomicMax(a.stamps + slot, fpNow());
+        else
+            a.stamps[slot] = fpNow();
+    }
+}
 
 /* state bit held by lane bit `b` in phase r, see above */
 __device__ __forceinline__ int fpLaneBitRole(int b, int r)
@@ -99,6 +119,86 @@ __device__ __forceinline__ void fpSteps(int steps, int lane, const uint32_t (&se
     }
 }
 
+
+/*
+ * The sequential part: v_{c+1}[e] = min_s v_c[s] + cost_c[s][e] on 64 * TPE threads (TPE threads share an
+ * end state e and split the 64 start states).  The costs do not depend on v, so each thread streams its
+ * own 64 / TPE bytes per block through a private shared-memory ring kFpAhead blocks ahead (cp.async, no
+ * registers held).  v stays below 65 + 64 per block < 2^16 for any packet the API takes, so candidates are
+ * formed two at a time: VIADDMNMX.U16x2 = min(v + cost, acc) on both halves of a register.
+ */
+template <int TPE, int AHEAD>
+__device__ __forceinline__ void fpChain(const FpArgs &a, uint32_t (&sV)[2][32], uint4 *ring, int tid)
+{
+    constexpr int kThreads = 64 * TPE, kPieces = 4 / TPE; /* 16-byte pieces of cost per thread and block */
+    if (tid >= kThreads)
+        return;
+    const int e = tid / TPE, h = tid % TPE;
+    const uint4 *cp = reinterpret_cast<const uint4 *>(a.cost) + e * 4 + h * kPieces;
+    const int nb = a.nBlocks;
+    auto fetch = [&](int c2) {
+        if (c2 < nb) {
+#pragma unroll
+            for (int p = 0; p < kPieces; p++) {
+                const uint32_t d = (uint32_t)__cvta_generic_to_shared(ring + (c2 % AHEAD) * 256 + p * kThreads + tid);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(cp + (size_t)c2 * 256 + p));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    for (int k = 0; k < AHEAD; k++)
+        fetch(k);
+    for (int c2 = 0; c2 < nb; c2++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
+        uint4 cur[kPieces];
+#pragma unroll
+        for (int p = 0; p < kPieces; p++)
+            cur[p] = ring[(c2 % AHEAD) * 256 + p * kThreads + tid];
+        fetch(c2 + AHEAD);
+        const uint32_t *vs = &sV[c2 & 1][h * (32 / TPE)];
+        uint32_t m;
+        if (c2 < nb - 1) {
+            uint32_t acc[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+#pragma unroll
+            for (int p = 0; p < kPieces; p++) {
+                const uint4 va = *reinterpret_cast<const uint4 *>(vs + 8 * p);
+                const uint4 vb = *reinterpret_cast<const uint4 *>(vs + 8 * p + 4);
+                acc[0] = __viaddmin_u16x2(va.x, __byte_perm(cur[p].x, 0, 0x4140), acc[0]);
+                acc[1] = __viaddmin_u16x2(va.y, __byte_perm(cur[p].x, 0, 0x4342), acc[1]);
+                acc[2] = __viaddmin_u16x2(va.z, __byte_perm(cur[p].y, 0, 0x4140), acc[2]);
+                acc[3] = __viaddmin_u16x2(va.w, __byte_perm(cur[p].y, 0, 0x4342), acc[3]);
+                acc[0] = __viaddmin_u16x2(vb.x, __byte_perm(cur[p].z, 0, 0x4140), acc[0]);
+                acc[1] = __viaddmin_u16x2(vb.y, __byte_perm(cur[p].z, 0, 0x4342), acc[1]);
+                acc[2] = __viaddmin_u16x2(vb.z, __byte_perm(cur[p].w, 0, 0x4140), acc[2]);
+                acc[3] = __viaddmin_u16x2(vb.w, __byte_perm(cur[p].w, 0, 0x4342), acc[3]);
+            }
+            const uint32_t x = __vminu2(__vminu2(acc[0], acc[1]), __vminu2(acc[2], acc[3]));
+            m = min(x & 0xFFFFu, x >> 16);
+        } else { /* only a last block shorter than 6 steps has (s, e) pairs without a path */
+            m = 0x7FFFFFFFu;
+#pragma unroll
+            for (int p = 0; p < kPieces; p++) {
+                const uint32_t w[4] = {cur[p].x, cur[p].y, cur[p].z, cur[p].w};
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    uint32_t x = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+                    x += x >= (uint32_t)kFpUnreach ? (uint32_t)kFpBig : 0u;
+                    m = min(m, ((vs[8 * p + (i >> 1)] >> (16 * (i & 1))) & 0xFFFFu) + x);
+                }
+            }
+        }
+        if (TPE >= 2)
+            m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
+        if (TPE >= 4)
+            m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
+        if (h == 0) {
+            reinterpret_cast<uint16_t *>(sV[(c2 + 1) & 1])[e] = (uint16_t)m;
+            a.v[(c2 + 1) * 64 + e] = (int)m;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    }
+}
+
 __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 {
     __shared__ uint32_t sDist[5 * 4 * 32]; /* [phase][rx][lane] -> d00 | d0h << 8 | d10 << 16 | d1h << 24 */
@@ -106,7 +206,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     __shared__ __align__(16) uint8_t sOutCost[64][kFpThreads / 32];  /* [e][s - s0] of this CTA's 8 passes */
     __shared__ __align__(16) uint32_t sOutBits[64][kFpThreads / 32];
     __shared__ __align__(16) uint32_t sV[2][32];                     /* v as u16x2 pairs (s = 2k, 2k + 1) */
-    __shared__ uint4 sCost[kFpAhead][kFpThreads];                    /* ring of the sequential part */
+    __shared__ uint4 sCost[kFpAhead][256];                           /* ring of the sequential part */
     __shared__ int sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kFpThreads / 32;
@@ -115,6 +215,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     const int wid = blockIdx.x * kWarps + warp;
     const int c = wid >> 6, s = wid & 63;
     const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
+    fpStamp(a, 0, -1);
     const uint4 s0 = sp[0], s1 = sp[1]; /* in flight while the table is built */
     if (tid < 32)
         reinterpret_cast<uint32_t *>(sEdge)[tid] = reinterpret_cast<const uint32_t *>(a.edge)[tid];
@@ -150,7 +251,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
         sOutBits[e + 1][warp] = p1;
     }
     __syncthreads();
-    { /* rows of 8 start states: one 8-byte and two 16-byte stores per end state instead of 16 scattered ones */
+    { /* rows of 8 start states: whole sectors: 512 contiguous bytes of costs, 32 bytes of bits per end state */
         const size_t row = (size_t)c * 64, sBase = (size_t)(blockIdx.x * kWarps) & 63;
         if (tid < 64)
             *reinterpret_cast<uint2 *>(a.cost + (row + tid) * 64 + sBase) = *reinterpret_cast<const uint2 *>(sOutCost[tid]);
@@ -162,6 +263,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     }
 
     /* the last CTA to get here runs the sequential part */
+    fpStamp(a, 1, 1);
     __threadfence();
     __syncthreads();
     if (tid == 0)
@@ -169,64 +271,18 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     __syncthreads();
     if (!sLast)
         return;
+    fpStamp(a, 2, 0);
     __threadfence();
-    /* 256 threads = 64 end states x 4 quarters of the start states.  The costs do not depend on v, so
-     * each thread streams its own 16 bytes per block through a private shared-memory ring kFpAhead blocks
-     * ahead (cp.async, no registers held).  v stays below 65 + 64 per block < 2^16 for any packet the API
-     * takes, so candidates are formed two at a time: VIADDMNMX.U16x2 = min(v + cost, acc) on both halves. */
-    const int e = tid >> 2, g = tid & 3;
-    const uint4 *cp = reinterpret_cast<const uint4 *>(a.cost) + tid; /* e * 4 + g == tid */
-    const int nb = a.nBlocks;
-    auto fetch = [&](int c2) {
-        if (c2 < nb) {
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sCost[c2 % kFpAhead][tid]);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(cp + (size_t)c2 * 256));
-        }
-        asm volatile("cp.async.commit_group;");
-    };
-    for (int k = 0; k < kFpAhead; k++)
-        fetch(k);
     if (tid < 64) {
         const int x = a.metricsIn[tid];
         reinterpret_cast<uint16_t *>(sV[0])[tid] = (uint16_t)x;
         a.v[tid] = x;
     }
     __syncthreads();
-    for (int c2 = 0; c2 < nb; c2++) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kFpAhead - 1) : "memory");
-        const uint4 cur = sCost[c2 % kFpAhead][tid];
-        fetch(c2 + kFpAhead);
-        const uint4 va = *reinterpret_cast<const uint4 *>(&sV[c2 & 1][8 * g]);
-        const uint4 vb = *reinterpret_cast<const uint4 *>(&sV[c2 & 1][8 * g + 4]);
-        const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
-        const uint32_t v2[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-        uint32_t m;
-        if (c2 < nb - 1) {
-            uint32_t acc0 = 0xFFFFFFFFu, acc1 = 0xFFFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                acc0 = __viaddmin_u16x2(v2[2 * i], __byte_perm(w[i], 0, 0x4140), acc0);
-                acc1 = __viaddmin_u16x2(v2[2 * i + 1], __byte_perm(w[i], 0, 0x4342), acc1);
-            }
-            const uint32_t acc = __vminu2(acc0, acc1);
-            m = min(acc & 0xFFFFu, acc >> 16);
-        } else { /* only a last block shorter than 6 steps has (s, e) pairs without a path */
-            m = 0x7FFFFFFFu;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t x = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                x += x >= (uint32_t)kFpUnreach ? (uint32_t)kFpBig : 0u;
-                m = min(m, ((v2[i >> 1] >> (16 * (i & 1))) & 0xFFFFu) + x);
-            }
-        }
-        m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 1));
-        m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, 2));
-        if (g == 0) {
-            reinterpret_cast<uint16_t *>(sV[(c2 + 1) & 1])[e] = (uint16_t)m;
-            a.v[(c2 + 1) * 64 + e] = (int)m;
-        }
-        __syncthreads();
-    }
+    fpStamp(a, 3, 0);
+    fpChain<4, kFpAhead>(a, sV, &sCost[0][0], tid);
+    __syncthreads();
+    fpStamp(a, 4, 0);
     if (tid == 0)
         a.tickets[0] = 0;
 }
@@ -235,10 +291,12 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
 {
     __shared__ __align__(16) uint2 sBest[kFpChainBlocks * 64];
     __shared__ uint32_t sWord[kFpChainBlocks];
+    __shared__ uint2 sOut[kFpThreads / 32];
     __shared__ int sState, sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wid = blockIdx.x * (kFpThreads / 32) + warp;
     const int c = wid >> 6, e = wid & 63;
+    fpStamp(a, 5, -1);
     if (c < a.nBlocks) {
         const size_t row = ((size_t)c * 64 + e) * 64;
         unsigned long long key = ~0ull;
@@ -256,9 +314,13 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
             key = other < key ? other : key;
         }
         if (lane == 0)
-            a.best[c * 64 + e] = make_uint2((uint32_t)(key >> 6), __brev((uint32_t)key & 63u) >> 26);
+            sOut[warp] = make_uint2((uint32_t)(key >> 6), __brev((uint32_t)key & 63u) >> 26);
     }
+    __syncthreads();
+    if (tid < kFpThreads / 32 && c < a.nBlocks) /* the CTA's 8 entries as whole sectors */
+        a.best[(size_t)blockIdx.x * (kFpThreads / 32) + tid] = sOut[tid];
 
+    fpStamp(a, 6, 1);
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -269,6 +331,7 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
     if (!sLast)
         return;
     __threadfence();
+    fpStamp(a, 7, 0);
     const int L = a.T - 6, outBytes = (L - 1) / 8 + 1;
     for (int hi = a.nBlocks; hi > 0; hi -= kFpChainBlocks) {
         const int lo = max(0, hi - kFpChainBlocks);
@@ -311,6 +374,7 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
         }
         __syncthreads();
     }
+    fpStamp(a, 8, 0);
     if (tid == 0)
         a.tickets[1] = 0;
 }
