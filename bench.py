@@ -156,6 +156,56 @@ def _cpu_reference_rate(seconds, threads=None, frames=None):
                       % (frames, FRAME_BITS, el, threads, how)}, bits, el
 
 
+def per_packet_rate(seconds, bits=2048):
+    """speedDecode's loop (16 packets, one synchronous last=true call each) through libconvencdec_k7.so."""
+    import ctypes
+    import numpy as np
+    import torch
+    import convolutionalencdec_b200 as ced
+    with c_stdout_to_stderr():
+        api = ced.RefApi("k7")
+        enc = api.encoder(); enc.resetConvEncoder(); enc.initConvEncoder()
+        dec = api.decoder(); dec.VITERBI_RESET(); dec.VITERBI_INIT()
+        rng = np.random.default_rng(314)
+        msgs = rng.integers(0, 256, (16, bits // 8), dtype=np.uint8)
+        segs = np.stack([enc.convEnc(m, True) for m in msgs])
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        out = np.zeros(bits // 8 + 8, dtype=np.uint8)
+        ptrs, outp, T = [segs[i].ctypes.data_as(u8p) for i in range(16)], out.ctypes.data_as(u8p), bits + 6
+        call = api.lib.viterbiDecoderHardButterflyk1
+        lib = ced.load_abi()
+        launches0 = int(lib.ced_launch_count(lib.ced_default_ctx()))
+        ok = True
+        for i in range(64):
+            call(dec.p, ptrs[i % 16], outp, T, True)
+            ok = ok and bool(np.array_equal(out[:bits // 8], msgs[i % 16]))
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            for i in range(16):
+                call(dec.p, ptrs[i], outp, T, True)
+            n += 16
+        dt = time.perf_counter() - t0
+        launches = int(lib.ced_launch_count(lib.ced_default_ctx())) - launches0
+    return {"value": n * bits / dt / 1e6, "unit": "Mbit/s", "us_per_call": dt / n * 1e6, "packet_bits": bits,
+            "calls": n, "gpu_launches": launches, "round_trip_ok": ok,
+            "api": "viterbiDecoderHardButterflyk1(last=true), one packet per synchronous call, host buffers "
+                   "(the call speedDecode.c:79 makes); whole packet decoded at once by fpBlockKernel + fpSelectKernel"}
+
+
+def per_packet_reference_rate(seconds, bits=2048):
+    """The same loop on the reference's own C decoder, one host core (oracle/_ref)."""
+    import numpy as np
+    import oracle
+    with c_stdout_to_stderr():
+        R = oracle.ref()
+        if R is None:
+            return None
+        rng = np.random.default_rng(314)
+        segs = R.encode_batch(rng.integers(0, 256, (16, bits // 8), dtype=np.uint8))
+        done, el = R.speed_decode(segs, bits + 6, 1, seconds)
+    return {"value": done / el / 1e6, "unit": "Mbit/s", "cores": 1, "kind": "reference"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -496,6 +546,10 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.mode == "decode":
         line["cpu_baseline"] = cpu_reference_rate(4.0)[0]
+        # the reference's own driver shape: ONE 2048-bit packet per synchronous VITERBI_DECODER_HARD call
+        # (speedDecode.c:18-23,79) through the drop-in host C library, next to the reference C on one core
+        line["per_packet"] = per_packet_rate(1.0)
+        line["cpu_baseline"]["one_core_2048_bit_packets"] = per_packet_reference_rate(1.0)
 
     if rank == 0:
         print(json.dumps(line), flush=True)

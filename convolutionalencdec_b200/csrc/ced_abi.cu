@@ -1595,10 +1595,17 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                                  (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CED_CUDA(cudaStreamSynchronize(c->stream));
     if (parallel && fpStamps()) {
+        static unsigned long long calls = 0;
         const unsigned long long *st = fpStamps();
-        fprintf(stderr, "fp T=%d: passes %.1f  fence+ticket %.1f  prologue %.1f  chain %.1f | gap %.1f | select %.1f  fence+ticket %.1f  walk+write %.1f  (us)\n",
-                segmentsIn, (st[1] - st[0]) * 1e-3, (st[2] - st[1]) * 1e-3, (st[3] - st[2]) * 1e-3, (st[4] - st[3]) * 1e-3,
-                ((double)st[5] - (double)st[4]) * 1e-3, (st[6] - st[5]) * 1e-3, (st[7] - st[6]) * 1e-3, (st[8] - st[7]) * 1e-3);
+        if (calls++ % 1000 == 2) { /* every 1000th call, so a tight loop stays tight */
+            fprintf(stderr, "fp T=%d: prologue %.1f  chain %.1f (SM clock %.0f MHz) | kernel gap %.1f | walk+write %.1f  us",
+                    segmentsIn, (st[3] - st[2]) * 1e-3, (st[4] - st[3]) * 1e-3,
+                    (double)(st[11] - st[10]) / (double)(st[4] - st[3]) * 1e3, ((double)st[5] - (double)st[4]) * 1e-3,
+                    (st[8] - st[7]) * 1e-3);
+            if (st[1]) /* CED_FP_STAMPS=2: grid-wide stamps (atomics on host memory, they slow the kernels down) */
+                fprintf(stderr, "  passes %.1f  select %.1f", (st[1] - st[0]) * 1e-3, (st[6] - st[5]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
     }
     if (last) {
         memcpy(uncoded, c->sPinOut.p + 272, decodedBytes);

@@ -280,8 +280,12 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     }
     __syncthreads();
     fpStamp(a, 3, 0);
+    if (a.stamps && tid == 0)
+        a.stamps[10] = (unsigned long long)clock64();
     fpChain<4, kFpAhead>(a, sV, &sCost[0][0], tid);
     __syncthreads();
+    if (a.stamps && tid == 0)
+        a.stamps[11] = (unsigned long long)clock64();
     fpStamp(a, 4, 0);
     if (tid == 0)
         a.tickets[0] = 0;
@@ -296,7 +300,10 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wid = blockIdx.x * (kFpThreads / 32) + warp;
     const int c = wid >> 6, e = wid & 63;
-    fpStamp(a, 5, -1);
+    if (a.stampAll)
+        fpStamp(a, 5, -1);
+    else if (blockIdx.x == 0)
+        fpStamp(a, 5, 0);
     if (c < a.nBlocks) {
         const size_t row = ((size_t)c * 64 + e) * 64;
         unsigned long long key = ~0ull;

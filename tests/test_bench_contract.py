@@ -50,3 +50,5 @@ def test_our_arm_line():
     assert d["gpu_launches"] >= 2 * 4 and d["clocks"]["sm_mhz"]
     assert d["check"]["decoded_bits"] == 8192 * 4096 and 1e-4 < d["check"]["ber"] < 2e-3
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    pp = d["per_packet"]                       # one 2048-bit packet per call: the two frame-parallel kernels each time
+    assert pp["round_trip_ok"] is True and pp["gpu_launches"] == 2 * (pp["calls"] + 64) and pp["value"] > 0
