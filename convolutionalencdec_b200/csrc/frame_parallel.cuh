@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
     fpStamp(a, 0, -1);
     const uint4 s0 = sp[0], s1 = sp[1]; /* in flight while the table is built */
+    const int metric0 = tid < 64 ? a.metricsIn[tid] : 0; /* only the CTA that runs the sequential part uses it */
     if (tid < 32)
         reinterpret_cast<uint32_t *>(sEdge)[tid] = reinterpret_cast<const uint32_t *>(a.edge)[tid];
     __syncthreads();
@@ -274,9 +275,8 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     fpStamp(a, 2, 0);
     __threadfence();
     if (tid < 64) {
-        const int x = a.metricsIn[tid];
-        reinterpret_cast<uint16_t *>(sV[0])[tid] = (uint16_t)x;
-        a.v[tid] = x;
+        reinterpret_cast<uint16_t *>(sV[0])[tid] = (uint16_t)metric0;
+        a.v[tid] = metric0;
     }
     __syncthreads();
     fpStamp(a, 3, 0);
