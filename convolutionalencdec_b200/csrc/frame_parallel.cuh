@@ -84,41 +84,67 @@ __device__ __forceinline__ int fpLaneBitRole(int b, int r)
     return ((b + r) % 5) + 1;
 }
 
+/*
+ * One trellis step of a pass.  M = m0 | m1 << 16 (the lane's two metrics), p0 / p1 the survivors' input bits.
+ * Both lanes of a pair send their whole M; one PRMT with a per-lane selector picks (lower, upper) predecessor
+ * = (own.lo, partner.lo) or (partner.hi, own.hi).  The two candidates of a successor then sit in the two halves
+ * of one register: one add forms both, VIMNMX.U16x2 against the half-swapped copy gives the minimum in both halves
+ * and the predicate a0 <= a1, i.e. the reference's tie rule (keep the lower predecessor unless strictly greater,
+ * :129-130).  21 instructions + 2 shuffles per step (the scalar form needed 35: the passes are ALU-pipe bound,
+ * profiles/r1_packet_kernels_ncu.txt).
+ */
 template <int T0>
-__device__ __forceinline__ void fpStep(int lane, const uint32_t (&seg)[8], const uint32_t *dist, int &m0, int &m1,
-                                       uint32_t &p0, uint32_t &p1)
+__device__ __forceinline__ void fpStep(const uint32_t (&seg)[kFpBlock / 4], const uint2 *dist, const uint32_t (&selLH)[5],
+                                       const uint32_t (&upMask)[5], uint32_t &M, uint32_t &p0, uint32_t &p1)
 {
     constexpr int r = T0 % 5, q = 4 - r;
-    const bool up = (lane >> q) & 1;
-    const int keepM = up ? m1 : m0, sendM = up ? m0 : m1;
-    const uint32_t keepP = up ? p1 : p0, sendP = up ? p0 : p1;
-    const int recvM = __shfl_xor_sync(0xFFFFFFFFu, sendM, 1 << q);
+    const uint32_t um = upMask[r];
+    const uint32_t sendP = (p0 & um) | (p1 & ~um);
+    const uint32_t recvM = __shfl_xor_sync(0xFFFFFFFFu, M, 1 << q);
     const uint32_t recvP = __shfl_xor_sync(0xFFFFFFFFu, sendP, 1 << q);
-    const int lo = up ? recvM : keepM, hi = up ? keepM : recvM;
-    const uint32_t pLo = up ? recvP : keepP, pHi = up ? keepP : recvP;
+    const uint32_t LH = __byte_perm(M, recvM, selLH[r]);
+    const uint32_t pLo = (recvP & um) | (p0 & ~um), pHi = (p1 & um) | (recvP & ~um);
     const uint32_t rx = (seg[T0 >> 2] >> (8 * (T0 & 3))) & 3u; /* calcHammingDist(.., n = 2) looks at two bits */
-    const uint32_t d = dist[(r * 4 + rx) * 32];
-    const int a0 = lo + (int)(d & 0xFFu), a1 = hi + (int)((d >> 8) & 0xFFu);
-    const int b0 = lo + (int)((d >> 16) & 0xFFu), b1 = hi + (int)(d >> 24);
-    const bool da = a0 > a1, db = b0 > b1; /* tie -> lower predecessor (:129-130) */
-    m0 = da ? a1 : a0;
-    m1 = db ? b1 : b0;
-    p0 = da ? pHi : pLo;
-    p1 = (db ? pHi : pLo) | (1u << T0);
+    const uint2 d = dist[(r * 4 + rx) * 32];
+    const uint32_t A = LH + d.x, B = LH + d.y;
+    bool aHi, aLo, bHi, bLo;
+    const uint32_t RA = __vibmin_u16x2(A, __byte_perm(A, 0, 0x1032), &aHi, &aLo);
+    const uint32_t RB = __vibmin_u16x2(B, __byte_perm(B, 0, 0x1032), &bHi, &bLo);
+    M = __byte_perm(RA, RB, 0x5410);
+    p0 = aLo ? pLo : pHi;
+    p1 = (bLo ? pLo : pHi) | (1u << T0);
 }
 
 template <int T0>
-__device__ __forceinline__ void fpSteps(int steps, int lane, const uint32_t (&seg)[8], const uint32_t *dist, int &m0,
-                                        int &m1, uint32_t &p0, uint32_t &p1)
+__device__ __forceinline__ void fpSteps(const uint32_t (&seg)[kFpBlock / 4], const uint2 *dist, const uint32_t (&selLH)[5],
+                                        const uint32_t (&upMask)[5], uint32_t &M, uint32_t &p0, uint32_t &p1)
 {
     if constexpr (T0 < kFpBlock) {
-        if (T0 >= steps) /* uniform across the warp */
-            return;
-        fpStep<T0>(lane, seg, dist, m0, m1, p0, p1);
-        fpSteps<T0 + 1>(steps, lane, seg, dist, m0, m1, p0, p1);
+        fpStep<T0>(seg, dist, selLH, upMask, M, p0, p1);
+        fpSteps<T0 + 1>(seg, dist, selLH, upMask, M, p0, p1);
     }
 }
 
+/* the same step with the step index at run time: the last, shorter block of a packet */
+__device__ __forceinline__ void fpStepDyn(int t, int lane, uint32_t rx, const uint2 *dist, uint32_t &M, uint32_t &p0,
+                                          uint32_t &p1)
+{
+    const int r = t % 5, q = 4 - r;
+    const bool up = (lane >> q) & 1;
+    const uint32_t sendP = up ? p0 : p1;
+    const uint32_t recvM = __shfl_xor_sync(0xFFFFFFFFu, M, 1 << q);
+    const uint32_t recvP = __shfl_xor_sync(0xFFFFFFFFu, sendP, 1 << q);
+    const uint32_t LH = __byte_perm(M, recvM, up ? 0x3276u : 0x5410u);
+    const uint32_t pLo = up ? recvP : p0, pHi = up ? p1 : recvP;
+    const uint2 d = dist[(r * 4 + (rx & 3u)) * 32];
+    const uint32_t A = LH + d.x, B = LH + d.y;
+    bool aHi, aLo, bHi, bLo;
+    const uint32_t RA = __vibmin_u16x2(A, __byte_perm(A, 0, 0x1032), &aHi, &aLo);
+    const uint32_t RB = __vibmin_u16x2(B, __byte_perm(B, 0, 0x1032), &bHi, &bLo);
+    M = __byte_perm(RA, RB, 0x5410);
+    p0 = aLo ? pLo : pHi;
+    p1 = (bLo ? pLo : pHi) | (1u << t);
+}
 
 /*
  * The sequential part: v_{c+1}[e] = min_s v_c[s] + cost_c[s][e] on 64 * TPE threads (TPE threads share an
@@ -201,7 +227,7 @@ __device__ __forceinline__ void fpChain(const FpArgs &a, uint32_t (&sV)[2][32], 
 
 __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 {
-    __shared__ uint32_t sDist[5 * 4 * 32]; /* [phase][rx][lane] -> d00 | d0h << 8 | d10 << 16 | d1h << 24 */
+    __shared__ uint2 sDist[5 * 4 * 32]; /* [phase][rx][lane] -> {d00 | d0h << 16, d10 | d1h << 16} */
     __shared__ __align__(16) uint8_t sEdge[128];
     __shared__ __align__(16) uint8_t sOutCost[64][kFpThreads / 32];  /* [e][s - s0] of this CTA's 8 passes */
     __shared__ __align__(16) uint32_t sOutBits[64][kFpThreads / 32];
@@ -232,16 +258,29 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
             const uint32_t x = (e ^ rx) & 3u;
             return x - (x >> 1);
         };
-        sDist[i] = hd(sEdge[j]) | hd(sEdge[j + 32]) << 8 | hd(sEdge[64 + j]) << 16 | hd(sEdge[64 + j + 32]) << 24;
+        sDist[i] = make_uint2(hd(sEdge[j]) | hd(sEdge[j + 32]) << 16, hd(sEdge[64 + j]) | hd(sEdge[64 + j + 32]) << 16);
     }
     __syncthreads();
 
     {
         const int steps = min(kFpBlock, a.T - c * kFpBlock);
         const uint32_t seg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        int m0 = (2 * lane == s) ? 0 : kFpUnreach, m1 = (2 * lane + 1 == s) ? 0 : kFpUnreach;
+        uint32_t M = ((2 * lane == s) ? 0u : (uint32_t)kFpUnreach) | ((2 * lane + 1 == s) ? 0u : (uint32_t)kFpUnreach) << 16;
         uint32_t p0 = 0, p1 = 0;
-        fpSteps<0>(steps, lane, seg, sDist + lane, m0, m1, p0, p1);
+        uint32_t selLH[5], upMask[5];
+#pragma unroll
+        for (int ph = 0; ph < 5; ph++) {
+            const bool up = (lane >> (4 - ph)) & 1;
+            selLH[ph] = up ? 0x3276u : 0x5410u;
+            upMask[ph] = up ? 0xFFFFFFFFu : 0u;
+        }
+        if (steps == kFpBlock) {
+            fpSteps<0>(seg, sDist + lane, selLH, upMask, M, p0, p1);
+        } else {
+            for (int t = 0; t < steps; t++) /* uniform trip count */
+                fpStepDyn(t, lane, a.segs[(size_t)c * kFpBlock + t], sDist + lane, M, p0, p1);
+        }
+        const uint32_t m0 = M & 0xFFFFu, m1 = M >> 16;
         const int r = steps % 5;
         int e = 0;
         for (int b = 0; b < 5; b++)
