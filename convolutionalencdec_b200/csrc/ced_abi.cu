@@ -1537,9 +1537,10 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         f.metricsIn = a.metricsIn;
         f.segs = a.segs;
         f.cost = c->sParallel.p + lay.cost;
-        f.bits = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bits);
+        f.bitsLo = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bitsLo);
+        f.bitsHi = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bitsHi);
         f.v = reinterpret_cast<int *>(c->sParallel.p + lay.v);
-        f.best = reinterpret_cast<uint2 *>(c->sParallel.p + lay.best);
+        f.best = reinterpret_cast<uint4 *>(c->sParallel.p + lay.best);
         f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
         f.out = a.out;
         f.stamps = fpStamps();

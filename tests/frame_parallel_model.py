@@ -15,7 +15,7 @@ rev6(s) compares the six input bits that precede the block, newest first.
 """
 import numpy as np
 
-BLOCK = 32
+BLOCK = 64
 INF = 1 << 20
 
 
