@@ -1477,7 +1477,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     const size_t survBytes = (size_t)kStreamMaxSteps * W * sizeof(uint32_t);
     const size_t outBytes = 4096 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
     /* A whole 64-state n = 2 packet in one call (what speedDecode.c:79 and berTestK7.c:157 issue): every
-     * block of 32 steps is worked on at once (frame_parallel.cuh).  The reference's uint8 metrics cannot
+     * block of 64 steps is worked on at once (frame_parallel.cuh).  The reference's uint8 metrics cannot
      * wrap from reset-like starting values, which is what makes plain ints equivalent. */
     bool parallel = K == 7 && n == 2 && last && it0 == 0 && *renormCounter == 0 && segmentsIn > 2 * S &&
                     streamParallelEnabled();

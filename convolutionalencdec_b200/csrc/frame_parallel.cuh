@@ -5,10 +5,10 @@
  *
  * The add-compare-select recursion is sequential in time (2054 dependent steps for the reference's
  * speedDecode packet), which a single warp cannot run faster than ~100 ns per step.  It is however a
- * (min,+) matrix product chain, so the packet is cut into blocks of 32 steps:
+ * (min,+) matrix product chain, so the packet is cut into blocks of 64 steps:
  *
  *   fpBlockKernel   one warp per (block c, start state s): a forward pass over the block that starts
- *                   with metric 0 in s only and carries the input bits of each survivor in a register
+ *                   with metric 0 in s only and carries the input bits of each survivor in two registers
  *                   (register exchange), giving cost_c[s][e] and bits_c[s][e] for all 64 end states e.
  *                   The last CTA to finish then runs the short sequential part: v_{c+1}[e] =
  *                   min_s v_c[s] + cost_c[s][e], 64 x 64 candidates per block on 256 threads.
@@ -91,7 +91,7 @@ __device__ __forceinline__ int fpLaneBitRole(int b, int r)
  * = (own.lo, partner.lo) or (partner.hi, own.hi).  The two candidates of a successor then sit in the two halves
  * of one register: one add forms both, VIMNMX.U16x2 against the half-swapped copy gives the minimum in both halves
  * and the predicate a0 <= a1, i.e. the reference's tie rule (keep the lower predecessor unless strictly greater,
- * :129-130).  21 instructions + 2 shuffles per step (the scalar form needed 35: the passes are ALU-pipe bound,
+ * :129-130).  21-27 instructions + 2-3 shuffles per step (the scalar form needed 35: the passes are ALU-pipe bound,
  * profiles/r1_packet_kernels_ncu.txt).
  */
 template <int T0>
