@@ -1477,13 +1477,13 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     const size_t survBytes = (size_t)kStreamMaxSteps * W * sizeof(uint32_t);
     const size_t outBytes = 4096 + std::max<size_t>(survBytes, kStreamMaxSteps / 8 + 8);
     /* A whole 64-state n = 2 packet in one call (what speedDecode.c:79 and berTestK7.c:157 issue): every
-     * block of 64 steps is worked on at once (frame_parallel.cuh).  The reference's uint8 metrics cannot
+     * block of 128 steps is worked on at once (frame_parallel.cuh).  The reference's uint8 metrics cannot
      * wrap from reset-like starting values, which is what makes plain ints equivalent. */
     bool parallel = K == 7 && n == 2 && last && it0 == 0 && *renormCounter == 0 && segmentsIn > 2 * S &&
                     streamParallelEnabled();
     for (int i = 0; parallel && i < N; i++)
         parallel = metrics[i] <= N + 1;
-    int rc = c->sIn.ensure(1024 + kStreamMaxSteps + 64);
+    int rc = c->sIn.ensure(1024 + kStreamMaxSteps + 2 * ced::kFpBlock);
     if (rc == CED_OK) rc = c->sOut.ensure(272 + kStreamMaxSteps / 8 + 16);
     if (rc == CED_OK && parallel && !c->sParallel.p) {
         const ced::FpScratch lay = ced::fpScratchLayout(kStreamMaxSteps);
@@ -1537,10 +1537,10 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         f.metricsIn = a.metricsIn;
         f.segs = a.segs;
         f.cost = c->sParallel.p + lay.cost;
-        f.bitsLo = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bitsLo);
-        f.bitsHi = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bitsHi);
+        for (int w = 0; w < ced::kFpWords; w++)
+            f.bits[w] = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bits[w]);
         f.v = reinterpret_cast<int *>(c->sParallel.p + lay.v);
-        f.best = reinterpret_cast<uint4 *>(c->sParallel.p + lay.best);
+        f.best = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.best);
         f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
         f.out = a.out;
         f.stamps = fpStamps();

@@ -5,10 +5,10 @@
  *
  * The add-compare-select recursion is sequential in time (2054 dependent steps for the reference's
  * speedDecode packet), which a single warp cannot run faster than ~100 ns per step.  It is however a
- * (min,+) matrix product chain, so the packet is cut into blocks of 64 steps:
+ * (min,+) matrix product chain, so the packet is cut into blocks of kFpBlock = 128 steps:
  *
  *   fpBlockKernel   one warp per (block c, start state s): a forward pass over the block that starts
- *                   with metric 0 in s only and carries the input bits of each survivor in two registers
+ *                   with metric 0 in s only and carries the input bits of each survivor in kFpWords registers
  *                   (register exchange), giving cost_c[s][e] and bits_c[s][e] for all 64 end states e.
  *                   The last CTA to finish then runs the short sequential part: v_{c+1}[e] =
  *                   min_s v_c[s] + cost_c[s][e], 64 x 64 candidates per block on 256 threads.
@@ -37,13 +37,17 @@
 
 namespace ced {
 
-constexpr int kFpBlock = 64;        /* trellis steps per block (the survivor's input bits fill two registers) */
+constexpr int kFpBlock = 128;       /* trellis steps per block */
+constexpr int kFpWords = kFpBlock / 32; /* registers holding the input bits of one survivor */
 constexpr int kFpThreads = 256;     /* 8 warps per CTA */
-constexpr int kFpUnreach = 120;     /* starting metric of the 63 states a pass does not start in: above any real
-                                     * in-block cost (<= 58 + 12: a free step costs at most 1), 120 + 2 * 64 < 256 */
+constexpr int kFpUnreach = 0x1000;  /* starting metric of the 63 states a pass does not start in (u16 lanes) */
+constexpr int kFpNoPath = 255;      /* stored cost of an (s, e) pair without a path; real in-block costs stay below
+                                     * (kFpBlock - 6) + 12: a free step costs at most 1 */
+static_assert(kFpBlock + 6 < kFpNoPath, "costs are stored as bytes");
 constexpr int kFpBig = 1 << 20;     /* added to candidates that do not start in s (short last block) */
 constexpr int kFpAhead = 8;        /* blocks of costs in flight ahead of the sequential min-plus chain */
-constexpr int kFpChainBlocks = 40;  /* blocks of the survivor table staged per pass of the final walk */
+constexpr int kFpBestWords = kFpWords < 4 ? 4 : 8; /* words per entry of the survivor table: bits, start state, pad */
+constexpr int kFpChainBlocks = 160 / kFpBestWords;  /* blocks of the survivor table staged per pass of the final walk */
 
 struct FpArgs {
     int T;                     /* segments of the packet */
@@ -52,9 +56,9 @@ struct FpArgs {
     const uint8_t *metricsIn;  /* [64] path metrics before the packet */
     const uint8_t *segs;       /* 16-byte aligned, readable up to nBlocks * 32 bytes */
     uint8_t *cost;             /* [nBlocks][64 e][64 s] */
-    uint32_t *bitsLo, *bitsHi; /* [nBlocks][64 e][64 s]: input bits of steps 0-31 / 32-63 of the block */
+    uint32_t *bits[kFpWords];  /* each [nBlocks][64 e][64 s]: input bits of steps 32w .. 32w+31 of the block */
     int *v;                    /* [nBlocks + 1][64] */
-    uint4 *best;               /* [nBlocks][64 e] = {bitsLo, bitsHi, start state, -} */
+    uint32_t *best;            /* [nBlocks][64 e][kFpBestWords] = {bits words, start state, -} */
     unsigned int *tickets;     /* [2], zero between calls */
     uint8_t *out;              /* (T - 6 - 1) / 8 + 1 decoded bytes, MSb first (:249) */
     int stampAll;              /* also the grid-wide (atomic, slow over PCIe) stamps */
@@ -91,24 +95,24 @@ __device__ __forceinline__ int fpLaneBitRole(int b, int r)
  * = (own.lo, partner.lo) or (partner.hi, own.hi).  The two candidates of a successor then sit in the two halves
  * of one register: one add forms both, VIMNMX.U16x2 against the half-swapped copy gives the minimum in both halves
  * and the predicate a0 <= a1, i.e. the reference's tie rule (keep the lower predecessor unless strictly greater,
- * :129-130).  21-27 instructions + 2-3 shuffles per step (the scalar form needed 35: the passes are ALU-pipe bound,
+ * :129-130).  21-33 instructions + 2-5 shuffles per step (more as the survivors' bit words fill up) (the scalar form needed 35: the passes are ALU-pipe bound,
  * profiles/r1_packet_kernels_ncu.txt).
  */
 template <int T0>
 __device__ __forceinline__ void fpStep(const uint32_t (&seg)[kFpBlock / 4], const uint2 *dist, const uint32_t (&selLH)[5],
-                                       const uint32_t (&upMask)[5], uint32_t &M, uint32_t (&p0)[2], uint32_t (&p1)[2])
+                                       const uint32_t (&upMask)[5], uint32_t &M, uint32_t (&p0)[kFpWords],
+                                       uint32_t (&p1)[kFpWords])
 {
     constexpr int r = T0 % 5, q = 4 - r;
-    constexpr bool kHigh = T0 >= 32; /* before step 32 the high words are still zero: nothing to move */
+    constexpr int kLive = T0 / 32 + 1; /* words above are still zero: nothing to move */
     const uint32_t um = upMask[r];
     const uint32_t recvM = __shfl_xor_sync(0xFFFFFFFFu, M, 1 << q);
-    const uint32_t recvL = __shfl_xor_sync(0xFFFFFFFFu, (p0[0] & um) | (p1[0] & ~um), 1 << q);
-    const uint32_t pLoL = (recvL & um) | (p0[0] & ~um), pHiL = (p1[0] & um) | (recvL & ~um);
-    uint32_t pLoH = 0, pHiH = 0;
-    if (kHigh) {
-        const uint32_t recvH = __shfl_xor_sync(0xFFFFFFFFu, (p0[1] & um) | (p1[1] & ~um), 1 << q);
-        pLoH = (recvH & um) | (p0[1] & ~um);
-        pHiH = (p1[1] & um) | (recvH & ~um);
+    uint32_t pLo[kLive], pHi[kLive];
+#pragma unroll
+    for (int w = 0; w < kLive; w++) {
+        const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, (p0[w] & um) | (p1[w] & ~um), 1 << q);
+        pLo[w] = (recv & um) | (p0[w] & ~um);
+        pHi[w] = (p1[w] & um) | (recv & ~um);
     }
     const uint32_t LH = __byte_perm(M, recvM, selLH[r]);
     const uint32_t rx = (seg[T0 >> 2] >> (8 * (T0 & 3))) & 3u; /* calcHammingDist(.., n = 2) looks at two bits */
@@ -118,17 +122,17 @@ __device__ __forceinline__ void fpStep(const uint32_t (&seg)[kFpBlock / 4], cons
     const uint32_t RA = __vibmin_u16x2(A, __byte_perm(A, 0, 0x1032), &aHi, &aLo);
     const uint32_t RB = __vibmin_u16x2(B, __byte_perm(B, 0, 0x1032), &bHi, &bLo);
     M = __byte_perm(RA, RB, 0x5410);
-    p0[0] = aLo ? pLoL : pHiL;
-    p1[0] = (bLo ? pLoL : pHiL) | (kHigh ? 0u : 1u << (T0 & 31));
-    if (kHigh) {
-        p0[1] = aLo ? pLoH : pHiH;
-        p1[1] = (bLo ? pLoH : pHiH) | 1u << (T0 & 31);
+#pragma unroll
+    for (int w = 0; w < kLive; w++) {
+        p0[w] = aLo ? pLo[w] : pHi[w];
+        p1[w] = (bLo ? pLo[w] : pHi[w]) | (w == T0 / 32 ? 1u << (T0 & 31) : 0u);
     }
 }
 
 template <int T0>
 __device__ __forceinline__ void fpSteps(const uint32_t (&seg)[kFpBlock / 4], const uint2 *dist, const uint32_t (&selLH)[5],
-                                        const uint32_t (&upMask)[5], uint32_t &M, uint32_t (&p0)[2], uint32_t (&p1)[2])
+                                        const uint32_t (&upMask)[5], uint32_t &M, uint32_t (&p0)[kFpWords],
+                                        uint32_t (&p1)[kFpWords])
 {
     if constexpr (T0 < kFpBlock) {
         fpStep<T0>(seg, dist, selLH, upMask, M, p0, p1);
@@ -137,27 +141,31 @@ __device__ __forceinline__ void fpSteps(const uint32_t (&seg)[kFpBlock / 4], con
 }
 
 /* the same step with the step index at run time: the last, shorter block of a packet */
-__device__ __forceinline__ void fpStepDyn(int t, int lane, uint32_t rx, const uint2 *dist, uint32_t &M, uint32_t (&p0)[2],
-                                          uint32_t (&p1)[2])
+__device__ __forceinline__ void fpStepDyn(int t, int lane, uint32_t rx, const uint2 *dist, uint32_t &M,
+                                          uint32_t (&p0)[kFpWords], uint32_t (&p1)[kFpWords])
 {
     const int r = t % 5, q = 4 - r;
     const bool up = (lane >> q) & 1;
     const uint32_t recvM = __shfl_xor_sync(0xFFFFFFFFu, M, 1 << q);
-    const uint32_t recvL = __shfl_xor_sync(0xFFFFFFFFu, up ? p0[0] : p1[0], 1 << q);
-    const uint32_t recvH = __shfl_xor_sync(0xFFFFFFFFu, up ? p0[1] : p1[1], 1 << q);
+    uint32_t pLo[kFpWords], pHi[kFpWords];
+#pragma unroll
+    for (int w = 0; w < kFpWords; w++) {
+        const uint32_t recv = __shfl_xor_sync(0xFFFFFFFFu, up ? p0[w] : p1[w], 1 << q);
+        pLo[w] = up ? recv : p0[w];
+        pHi[w] = up ? p1[w] : recv;
+    }
     const uint32_t LH = __byte_perm(M, recvM, up ? 0x3276u : 0x5410u);
-    const uint32_t pLoL = up ? recvL : p0[0], pHiL = up ? p1[0] : recvL;
-    const uint32_t pLoH = up ? recvH : p0[1], pHiH = up ? p1[1] : recvH;
     const uint2 d = dist[(r * 4 + (rx & 3u)) * 32];
     const uint32_t A = LH + d.x, B = LH + d.y;
     bool aHi, aLo, bHi, bLo;
     const uint32_t RA = __vibmin_u16x2(A, __byte_perm(A, 0, 0x1032), &aHi, &aLo);
     const uint32_t RB = __vibmin_u16x2(B, __byte_perm(B, 0, 0x1032), &bHi, &bLo);
     M = __byte_perm(RA, RB, 0x5410);
-    p0[0] = aLo ? pLoL : pHiL;
-    p0[1] = aLo ? pLoH : pHiH;
-    p1[0] = (bLo ? pLoL : pHiL) | (t < 32 ? 1u << t : 0u);
-    p1[1] = (bLo ? pLoH : pHiH) | (t < 32 ? 0u : 1u << (t - 32));
+#pragma unroll
+    for (int w = 0; w < kFpWords; w++) {
+        p0[w] = aLo ? pLo[w] : pHi[w];
+        p1[w] = (bLo ? pLo[w] : pHi[w]) | (w == (t >> 5) ? 1u << (t & 31) : 0u);
+    }
 }
 
 /*
@@ -222,7 +230,7 @@ __device__ __forceinline__ void fpChain(const FpArgs &a, uint32_t (&sV)[2][32], 
 #pragma unroll
                 for (int i = 0; i < 16; i++) {
                     uint32_t x = (w[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-                    x += x >= (uint32_t)kFpUnreach ? (uint32_t)kFpBig : 0u;
+                    x += x >= (uint32_t)kFpNoPath ? (uint32_t)kFpBig : 0u;
                     m = min(m, ((vs[8 * p + (i >> 1)] >> (16 * (i & 1))) & 0xFFFFu) + x);
                 }
             }
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     __shared__ uint2 sDist[5 * 4 * 32]; /* [phase][rx][lane] -> {d00 | d0h << 16, d10 | d1h << 16} */
     __shared__ __align__(16) uint8_t sEdge[128];
     __shared__ __align__(16) uint8_t sOutCost[64][kFpThreads / 32];  /* [e][s - s0] of this CTA's 8 passes */
-    __shared__ __align__(16) uint32_t sOutBits[2][64][kFpThreads / 32]; /* low / high word */
+    __shared__ __align__(16) uint32_t sOutBits[kFpWords][64][kFpThreads / 32];
     __shared__ __align__(16) uint32_t sV[2][32];                     /* v as u16x2 pairs (s = 2k, 2k + 1) */
     __shared__ uint4 sCost[kFpAhead][256];                           /* ring of the sequential part */
     __shared__ int sLast;
@@ -256,7 +264,10 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
     const int c = wid >> 6, s = wid & 63;
     const uint4 *sp = reinterpret_cast<const uint4 *>(a.segs + (size_t)c * kFpBlock);
     fpStamp(a, 0, -1);
-    const uint4 s0 = sp[0], s1 = sp[1], s2 = sp[2], s3 = sp[3]; /* in flight while the table is built */
+    uint4 sq[kFpBlock / 16]; /* in flight while the table is built */
+#pragma unroll
+    for (int i = 0; i < kFpBlock / 16; i++)
+        sq[i] = sp[i];
     const int metric0 = tid < 64 ? a.metricsIn[tid] : 0; /* only the CTA that runs the sequential part uses it */
     if (tid < 32)
         reinterpret_cast<uint32_t *>(sEdge)[tid] = reinterpret_cast<const uint32_t *>(a.edge)[tid];
@@ -278,10 +289,16 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 
     {
         const int steps = min(kFpBlock, a.T - c * kFpBlock);
-        const uint32_t seg[16] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w,
-                                  s2.x, s2.y, s2.z, s2.w, s3.x, s3.y, s3.z, s3.w};
+        uint32_t seg[kFpBlock / 4];
+#pragma unroll
+        for (int i = 0; i < kFpBlock / 16; i++) {
+            seg[4 * i] = sq[i].x;
+            seg[4 * i + 1] = sq[i].y;
+            seg[4 * i + 2] = sq[i].z;
+            seg[4 * i + 3] = sq[i].w;
+        }
         uint32_t M = ((2 * lane == s) ? 0u : (uint32_t)kFpUnreach) | ((2 * lane + 1 == s) ? 0u : (uint32_t)kFpUnreach) << 16;
-        uint32_t p0[2] = {0, 0}, p1[2] = {0, 0};
+        uint32_t p0[kFpWords] = {}, p1[kFpWords] = {};
         uint32_t selLH[5], upMask[5];
 #pragma unroll
         for (int ph = 0; ph < 5; ph++) {
@@ -300,22 +317,23 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
         int e = 0;
         for (int b = 0; b < 5; b++)
             e |= ((lane >> b) & 1) << fpLaneBitRole(b, r);
-        sOutCost[e][warp] = (uint8_t)m0;
-        sOutCost[e + 1][warp] = (uint8_t)m1;
-        sOutBits[0][e][warp] = p0[0];
-        sOutBits[0][e + 1][warp] = p1[0];
-        sOutBits[1][e][warp] = p0[1];
-        sOutBits[1][e + 1][warp] = p1[1];
+        sOutCost[e][warp] = (uint8_t)min(m0, (uint32_t)kFpNoPath);
+        sOutCost[e + 1][warp] = (uint8_t)min(m1, (uint32_t)kFpNoPath);
+#pragma unroll
+        for (int w = 0; w < kFpWords; w++) {
+            sOutBits[w][e][warp] = p0[w];
+            sOutBits[w][e + 1][warp] = p1[w];
+        }
     }
     __syncthreads();
-    { /* rows of 8 start states: per end state one 8-byte piece of costs and two whole 32-byte sectors of bits */
+    { /* rows of 8 start states: per end state one 8-byte piece of costs and whole 32-byte sectors of bits */
         const size_t row = (size_t)c * 64, sBase = (size_t)(blockIdx.x * kWarps) & 63;
-        for (int w = tid; w < 64 + 256; w += kFpThreads) {
+        for (int w = tid; w < 64 + 128 * kFpWords; w += kFpThreads) {
             if (w < 64) {
                 *reinterpret_cast<uint2 *>(a.cost + (row + w) * 64 + sBase) = *reinterpret_cast<const uint2 *>(sOutCost[w]);
             } else {
                 const int hw = (w - 64) >> 7, e = ((w - 64) >> 1) & 63, h = w & 1;
-                *reinterpret_cast<uint4 *>((hw ? a.bitsHi : a.bitsLo) + (row + e) * 64 + sBase + 4 * h) =
+                *reinterpret_cast<uint4 *>(a.bits[hw] + (row + e) * 64 + sBase + 4 * h) =
                     *reinterpret_cast<const uint4 *>(&sOutBits[hw][e][4 * h]);
             }
         }
@@ -351,9 +369,9 @@ __global__ void __launch_bounds__(kFpThreads) fpBlockKernel(FpArgs a)
 
 __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
 {
-    __shared__ __align__(16) uint4 sBest[kFpChainBlocks * 64];
-    __shared__ uint32_t sWord[kFpChainBlocks * 2];
-    __shared__ __align__(16) uint4 sOut[kFpThreads / 32];
+    __shared__ __align__(16) uint32_t sBest[kFpChainBlocks * 64 * kFpBestWords];
+    __shared__ uint32_t sWord[kFpChainBlocks * kFpWords];
+    __shared__ __align__(16) uint32_t sOut[kFpThreads / 32][kFpBestWords];
     __shared__ int sState, sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wid = blockIdx.x * (kFpThreads / 32) + warp;
@@ -363,35 +381,65 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
     else if (blockIdx.x == 0)
         fpStamp(a, 5, 0);
     if (c < a.nBlocks) {
-        /* key = (total cost, in-block bits with later steps more significant, rev6(start state)) as two words */
+        /* key = (total cost, in-block bits with later steps more significant, rev6(start state)), most significant
+         * word first: k[0] = total | top bits word, then pairs of bits words, k[kKeys - 1] = lowest bits word | rev6 */
+        constexpr int kKeys = kFpWords / 2 + 1;
         const size_t row = ((size_t)c * 64 + e) * 64;
-        unsigned long long k1 = ~0ull, k2 = ~0ull;
+        unsigned long long k[kKeys];
+        auto less = [](const unsigned long long (&x)[kKeys], const unsigned long long (&y)[kKeys]) {
+            bool lt = false, eq = true;
+#pragma unroll
+            for (int i = 0; i < kKeys; i++) {
+                lt = lt || (eq && x[i] < y[i]);
+                eq = eq && x[i] == y[i];
+            }
+            return lt;
+        };
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int s = lane + 32 * h;
             const int x = a.cost[row + s];
-            const unsigned long long tot = (unsigned long long)(a.v[c * 64 + s] + x + (x >= kFpUnreach ? kFpBig : 0));
-            const unsigned long long n1 = tot << 32 | a.bitsHi[row + s];
-            const unsigned long long n2 = (unsigned long long)a.bitsLo[row + s] << 6 | (__brev(s) >> 26);
-            if (n1 < k1 || (n1 == k1 && n2 < k2)) {
-                k1 = n1;
-                k2 = n2;
+            const unsigned long long tot = (unsigned long long)(a.v[c * 64 + s] + x + (x >= kFpNoPath ? kFpBig : 0));
+            unsigned long long n[kKeys];
+            n[0] = tot << 32 | a.bits[kFpWords - 1][row + s];
+#pragma unroll
+            for (int i = 1; i < kKeys - 1; i++)
+                n[i] = (unsigned long long)a.bits[kFpWords - 2 * i][row + s] << 32 | a.bits[kFpWords - 2 * i - 1][row + s];
+            n[kKeys - 1] = (unsigned long long)a.bits[0][row + s] << 6 | (__brev(s) >> 26);
+            if (h == 0 || less(n, k)) {
+#pragma unroll
+                for (int i = 0; i < kKeys; i++)
+                    k[i] = n[i];
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, o), o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, o);
-            if (o1 < k1 || (o1 == k1 && o2 < k2)) {
-                k1 = o1;
-                k2 = o2;
+            unsigned long long n[kKeys];
+#pragma unroll
+            for (int i = 0; i < kKeys; i++)
+                n[i] = __shfl_xor_sync(0xFFFFFFFFu, k[i], o);
+            if (less(n, k)) {
+#pragma unroll
+                for (int i = 0; i < kKeys; i++)
+                    k[i] = n[i];
             }
         }
-        if (lane == 0)
-            sOut[warp] = make_uint4((uint32_t)(k2 >> 6), (uint32_t)k1, __brev((uint32_t)k2 & 63u) >> 26, 0u);
+        if (lane == 0) {
+            sOut[warp][kFpWords - 1] = (uint32_t)k[0];
+#pragma unroll
+            for (int i = 1; i < kKeys - 1; i++) {
+                sOut[warp][kFpWords - 2 * i] = (uint32_t)(k[i] >> 32);
+                sOut[warp][kFpWords - 2 * i - 1] = (uint32_t)k[i];
+            }
+            sOut[warp][0] = (uint32_t)(k[kKeys - 1] >> 6);
+            sOut[warp][kFpWords] = __brev((uint32_t)k[kKeys - 1] & 63u) >> 26;
+        }
     }
     __syncthreads();
-    if (tid < kFpThreads / 32 && c < a.nBlocks) /* the CTA's 8 entries as whole sectors */
-        a.best[(size_t)blockIdx.x * (kFpThreads / 32) + tid] = sOut[tid];
+    /* the CTA's 8 entries as whole sectors */
+    if (tid < (kFpThreads / 32) * kFpBestWords / 4 && c < a.nBlocks)
+        reinterpret_cast<uint4 *>(a.best + (size_t)blockIdx.x * (kFpThreads / 32) * kFpBestWords)[tid] =
+            reinterpret_cast<const uint4 *>(&sOut[0][0])[tid];
 
     fpStamp(a, 6, 1);
     __threadfence();
@@ -408,9 +456,10 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
     const int L = a.T - 6, outBytes = (L - 1) / 8 + 1;
     for (int hi = a.nBlocks; hi > 0; hi -= kFpChainBlocks) {
         const int lo = max(0, hi - kFpChainBlocks);
-        { /* 10 entries per thread and round, all loads of a round in flight together */
-            const uint4 *src = a.best + (size_t)lo * 64;
-            const int n4 = (hi - lo) * 64;
+        { /* 10 loads per thread and round, all loads of a round in flight together */
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.best + (size_t)lo * 64 * kFpBestWords);
+            uint4 *dst = reinterpret_cast<uint4 *>(sBest);
+            const int n4 = (hi - lo) * 64 * kFpBestWords / 4;
             for (int base = 0; base < n4; base += 10 * kFpThreads) {
                 uint4 r[10];
 #pragma unroll
@@ -420,23 +469,24 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
 #pragma unroll
                 for (int k = 0; k < 10; k++)
                     if (base + k * kFpThreads + tid < n4)
-                        sBest[base + k * kFpThreads + tid] = r[k];
+                        dst[base + k * kFpThreads + tid] = r[k];
             }
         }
         __syncthreads();
         if (tid == 0) {
             int st = sState;
             for (int cb = hi - 1; cb >= lo; cb--) {
-                const uint4 b = sBest[(cb - lo) * 64 + st];
-                sWord[2 * (cb - lo)] = b.x;
-                sWord[2 * (cb - lo) + 1] = b.y;
-                st = (int)b.z;
+                const uint32_t *b = &sBest[((cb - lo) * 64 + st) * kFpBestWords];
+#pragma unroll
+                for (int w = 0; w < kFpWords; w++)
+                    sWord[kFpWords * (cb - lo) + w] = b[w];
+                st = (int)b[kFpWords];
             }
             sState = st;
         }
         __syncthreads();
-        for (int i = tid; i < (hi - lo) * 8; i += kFpThreads) {
-            const int idx = lo * 8 + i; /* output byte; input bit t of a block is bit t % 32 of its word t / 32 */
+        for (int i = tid; i < (hi - lo) * kFpBlock / 8; i += kFpThreads) {
+            const int idx = lo * (kFpBlock / 8) + i; /* output byte; input bit t of a block is bit t % 32 of its word t / 32 */
             if (idx < outBytes) {
                 uint32_t by = __brev((sWord[i >> 2] >> (8 * (i & 3))) & 0xFFu) >> 24; /* MSb first (:249) */
                 const int valid = L - idx * 8;
@@ -454,18 +504,21 @@ __global__ void __launch_bounds__(kFpThreads) fpSelectKernel(FpArgs a)
 
 /* bytes of device scratch for packets of up to maxSteps segments, and the carve-up */
 struct FpScratch {
-    size_t cost, bitsLo, bitsHi, v, best, tickets, total;
+    size_t cost, bits[kFpWords], v, best, tickets, total;
 };
 inline FpScratch fpScratchLayout(int maxSteps)
 {
     const size_t nb = (size_t)(maxSteps + kFpBlock - 1) / kFpBlock;
     FpScratch s;
     s.cost = 0;
-    s.bitsLo = s.cost + nb * 4096;
-    s.bitsHi = s.bitsLo + nb * 4096 * 4;
-    s.v = s.bitsHi + nb * 4096 * 4;
+    size_t at = nb * 4096;
+    for (int w = 0; w < kFpWords; w++) {
+        s.bits[w] = at;
+        at += nb * 4096 * 4;
+    }
+    s.v = at;
     s.best = s.v + (nb + 1) * 64 * 4;
-    s.tickets = s.best + nb * 64 * 16;
+    s.tickets = s.best + nb * 64 * kFpBestWords * 4;
     s.total = s.tickets + 16;
     return s;
 }

@@ -15,7 +15,7 @@ rev6(s) compares the six input bits that precede the block, newest first.
 """
 import numpy as np
 
-BLOCK = 64
+BLOCK = 128
 INF = 1 << 20
 
 
@@ -32,16 +32,17 @@ def edge_symm(g=(0o113, 0o171), K=7):
 
 
 def block_transfer(sym, rx):
-    """cost[s][e], bits[s][e] of the best in-block path from s to e (64 single-start passes)."""
+    """cost[s][e], bits[w][s][e] (64-bit words, w = 0 lowest) of the best in-block path from s to e:
+    64 single-start passes."""
     N = 64
     m = np.full((N, N), INF, dtype=np.int64)
     m[np.arange(N), np.arange(N)] = 0
-    bits = np.zeros((N, N), dtype=np.uint64)
+    bits = np.zeros((BLOCK // 64, N, N), dtype=np.uint64)
     for t, r in enumerate(rx):
         x = sym ^ (int(r) & 3)
         d = (x & 1) + (x >> 1)                      # calcHammingDist(.., n = 2)
         lo, hi = m[:, :32], m[:, 32:]
-        blo, bhi = bits[:, :32], bits[:, 32:]
+        blo, bhi = bits[:, :, :32], bits[:, :, 32:]
         a0, a1 = lo + d, hi + (2 - d)
         b0, b1 = lo + (2 - d), hi + d
         da, db = a0 > a1, b0 > b1
@@ -49,8 +50,9 @@ def block_transfer(sym, rx):
         nb = np.empty_like(bits)
         nm[:, 0::2] = np.where(da, a1, a0)
         nm[:, 1::2] = np.where(db, b1, b0)
-        nb[:, 0::2] = np.where(da, bhi, blo)
-        nb[:, 1::2] = np.where(db, bhi, blo) | np.uint64(1 << t)
+        nb[:, :, 0::2] = np.where(da, bhi, blo)
+        nb[:, :, 1::2] = np.where(db, bhi, blo)
+        nb[t // 64, :, 1::2] |= np.uint64(1 << (t % 64))
         m, bits = nm, nb
     return m, bits
 
@@ -77,9 +79,11 @@ def decode(segs, T, init_metrics=None, g=(0o113, 0o171)):
     e = 0
     u = np.zeros(nb * BLOCK, dtype=np.uint8)
     for c in range(nb - 1, -1, -1):
-        keys = [(int(vs[c][s] + costs[c][s][e]), int(bitss[c][s][e]), rev6(s)) for s in range(64)]
+        def bits_of(s):
+            return sum(int(bitss[c][w][s][e]) << (64 * w) for w in range(BLOCK // 64))
+        keys = [(int(vs[c][s] + costs[c][s][e]), bits_of(s), rev6(s)) for s in range(64)]
         s = min(range(64), key=lambda i: keys[i])
-        w = int(bitss[c][s][e])
+        w = bits_of(s)
         for t in range(BLOCK):
             u[c * BLOCK + t] = (w >> t) & 1
         e = s

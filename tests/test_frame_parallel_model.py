@@ -8,7 +8,7 @@ import oracle
 import frame_parallel_model as fp
 
 
-@pytest.mark.parametrize("T", [13, 14, 33, 38, 65, 69, 70, 134, 262, 1030])
+@pytest.mark.parametrize("T", [13, 14, 33, 38, 65, 70, 129, 133, 134, 262, 1030])
 def test_block_decomposition_equals_the_sequential_decoder(T):
     P = oracle.port()
     rng = np.random.default_rng(T)

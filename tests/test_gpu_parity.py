@@ -468,7 +468,7 @@ def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
     assert np.array_equal(dec.VITERBI_DECODER_HARD(big[:0], True, max_bytes=4096), want)
 
 
-@pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 66, 69, 70, 134, 262, 1030, 2054, 2055, 4102, 16390])
+@pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
 def test_one_shot_packets_take_the_frame_parallel_kernels(port, T):
     """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs fpBlockKernel / fpSelectKernel
     (csrc/frame_parallel.cuh): same bytes as the sequential decoder for clean, noisy, all-zero and
