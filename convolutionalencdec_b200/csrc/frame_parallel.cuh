@@ -95,8 +95,8 @@ __device__ __forceinline__ int fpLaneBitRole(int b, int r)
  * = (own.lo, partner.lo) or (partner.hi, own.hi).  The two candidates of a successor then sit in the two halves
  * of one register: one add forms both, VIMNMX.U16x2 against the half-swapped copy gives the minimum in both halves
  * and the predicate a0 <= a1, i.e. the reference's tie rule (keep the lower predecessor unless strictly greater,
- * :129-130).  21-33 instructions + 2-5 shuffles per step (more as the survivors' bit words fill up) (the scalar form needed 35: the passes are ALU-pipe bound,
- * profiles/r1_packet_kernels_ncu.txt).
+ * :129-130).  21-33 instructions + 2-5 shuffles per step, more as the survivors' bit words fill up (the first,
+ * scalar form needed 35 with one bit word: the passes are ALU-pipe bound, profiles/r1_packet_kernels_ncu.txt).
  */
 template <int T0>
 __device__ __forceinline__ void fpStep(const uint32_t (&seg)[kFpBlock / 4], const uint2 *dist, const uint32_t (&selLH)[5],
