@@ -15,7 +15,10 @@ Prints ONE JSON line on rank 0.  `value` is device-timed (CUDA events on the
 launching stream) with inputs resident in HBM; `e2e` is the same metric through
 ced_decode_batch_host with pinned HOST buffers (H2D + D2H inside the timed
 region); `roofline` is the forward ACS kernel against the measured INT-ALU peak;
-`cpu_baseline` is the reference's own C decoder (oracle/_ref) on the box's cores.
+`cpu_baseline` is the reference's own C decoder (oracle/_ref) on the box's cores;
+`per_packet` is the reference driver's own call shape (ONE 2048-bit packet per
+synchronous VITERBI_DECODER_HARD call, speedDecode.c:79) through the drop-in host
+library, with the reference C on one core beside it in `cpu_baseline`.
 """
 import argparse
 import json

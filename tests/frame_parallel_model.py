@@ -31,13 +31,13 @@ def edge_symm(g=(0o113, 0o171), K=7):
     return out
 
 
-def block_transfer(sym, rx):
+def block_transfer(sym, rx, block=BLOCK):
     """cost[s][e], bits[w][s][e] (64-bit words, w = 0 lowest) of the best in-block path from s to e:
     64 single-start passes."""
     N = 64
     m = np.full((N, N), INF, dtype=np.int64)
     m[np.arange(N), np.arange(N)] = 0
-    bits = np.zeros((BLOCK // 64, N, N), dtype=np.uint64)
+    bits = np.zeros(((block + 63) // 64, N, N), dtype=np.uint64)
     for t, r in enumerate(rx):
         x = sym ^ (int(r) & 3)
         d = (x & 1) + (x >> 1)                      # calcHammingDist(.., n = 2)
@@ -61,31 +61,31 @@ def rev6(s):
     return int(format(s, "06b")[::-1], 2)
 
 
-def decode(segs, T, init_metrics=None, g=(0o113, 0o171)):
+def decode(segs, T, init_metrics=None, g=(0o113, 0o171), block=BLOCK):
     """Decoded bytes of one K=7 n=2 packet of T segments (L = T - 6 information bits)."""
     sym = edge_symm(g)
     v = np.full(64, 65, dtype=np.int64)
     v[0] = 0
     if init_metrics is not None:
         v = np.asarray(init_metrics, dtype=np.int64)
-    nb = (T + BLOCK - 1) // BLOCK
+    nb = (T + block - 1) // block
     costs, bitss, vs = [], [], [v]
     for c in range(nb):
-        cost, bits = block_transfer(sym, segs[c * BLOCK:min(T, (c + 1) * BLOCK)])
+        cost, bits = block_transfer(sym, segs[c * block:min(T, (c + 1) * block)], block)
         costs.append(cost)
         bitss.append(bits)
         v = (v[:, None] + cost).min(axis=0)
         vs.append(v)
     e = 0
-    u = np.zeros(nb * BLOCK, dtype=np.uint8)
+    u = np.zeros(nb * block, dtype=np.uint8)
     for c in range(nb - 1, -1, -1):
         def bits_of(s):
-            return sum(int(bitss[c][w][s][e]) << (64 * w) for w in range(BLOCK // 64))
+            return sum(int(bitss[c][w][s][e]) << (64 * w) for w in range((block + 63) // 64))
         keys = [(int(vs[c][s] + costs[c][s][e]), bits_of(s), rev6(s)) for s in range(64)]
         s = min(range(64), key=lambda i: keys[i])
         w = bits_of(s)
-        for t in range(BLOCK):
-            u[c * BLOCK + t] = (w >> t) & 1
+        for t in range(block):
+            u[c * block + t] = (w >> t) & 1
         e = s
     L = T - 6
     u[L:] = 0

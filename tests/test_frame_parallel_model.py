@@ -34,3 +34,14 @@ def test_other_starting_metrics():
     segs = rng.integers(0, 4, (1, 102), dtype=np.uint8)
     want = P.decode_batch(7, oracle.K7_G, segs, 102)[0]
     assert np.array_equal(fp.decode(segs[0], 102, init_metrics=[0] + [65] * 63), want)
+
+
+@pytest.mark.parametrize("block", [8, 32, 64, 128, 256])
+def test_any_block_length_gives_the_same_bytes(block):
+    """The decomposition does not depend on where the packet is cut (the kernel uses 128-step blocks)."""
+    P = oracle.port()
+    rng = np.random.default_rng(block)
+    for T in (block + 3, 3 * block + 7, 518):
+        segs = rng.integers(0, 4, (1, T), dtype=np.uint8)      # pure noise: ties everywhere
+        want = P.decode_batch(7, oracle.K7_G, segs, T)[0][:(T - 7) // 8 + 1]
+        assert np.array_equal(fp.decode(segs[0], T, block=block), want), (block, T)
