@@ -1481,8 +1481,10 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
      * wrap from reset-like starting values, which is what makes plain ints equivalent. */
     bool parallel = K == 7 && n == 2 && last && it0 == 0 && *renormCounter == 0 && segmentsIn > 2 * S &&
                     streamParallelEnabled();
-    for (int i = 0; parallel && i < N; i++)
-        parallel = metrics[i] <= N + 1;
+    for (int i = 0; parallel && i < N; i++) /* + the two branches out of a state carry complementary labels (both
+                                             * generators tap the newest bit): a free step then costs at most 1, which
+                                             * bounds the reference's metrics and the in-block costs stored as bytes */
+        parallel = metrics[i] <= N + 1 && ((edge[i] ^ edge[N + i]) & 3u) == 3u;
     int rc = c->sIn.ensure(1024 + kStreamMaxSteps + 2 * ced::kFpBlock);
     if (rc == CED_OK) rc = c->sOut.ensure(272 + kStreamMaxSteps / 8 + 16);
     if (rc == CED_OK && parallel && !c->sParallel.p) {

@@ -42,7 +42,8 @@ constexpr int kFpWords = kFpBlock / 32; /* registers holding the input bits of o
 constexpr int kFpThreads = 256;     /* 8 warps per CTA */
 constexpr int kFpUnreach = 0x1000;  /* starting metric of the 63 states a pass does not start in (u16 lanes) */
 constexpr int kFpNoPath = 255;      /* stored cost of an (s, e) pair without a path; real in-block costs stay below
-                                     * (kFpBlock - 6) + 12: a free step costs at most 1 */
+                                     * (kFpBlock - 6) + 12: a free step costs at most 1 when the two branches out of
+                                     * a state carry complementary labels, which the host checks */
 static_assert(kFpBlock + 6 < kFpNoPath, "costs are stored as bytes");
 constexpr int kFpBig = 1 << 20;     /* added to candidates that do not start in s (short last block) */
 constexpr int kFpAhead = 8;        /* blocks of costs in flight ahead of the sequential min-plus chain */
@@ -51,10 +52,10 @@ constexpr int kFpChainBlocks = 160 / kFpBestWords;  /* blocks of the survivor ta
 
 struct FpArgs {
     int T;                     /* segments of the packet */
-    int nBlocks;               /* ceil(T / 32) */
+    int nBlocks;               /* ceil(T / kFpBlock) */
     const uint8_t *edge;       /* [2][64] edge labels, as StreamArgs.edge */
     const uint8_t *metricsIn;  /* [64] path metrics before the packet */
-    const uint8_t *segs;       /* 16-byte aligned, readable up to nBlocks * 32 bytes */
+    const uint8_t *segs;       /* 16-byte aligned, readable up to nBlocks * kFpBlock bytes */
     uint8_t *cost;             /* [nBlocks][64 e][64 s] */
     uint32_t *bits[kFpWords];  /* each [nBlocks][64 e][64 s]: input bits of steps 32w .. 32w+31 of the block */
     int *v;                    /* [nBlocks + 1][64] */
