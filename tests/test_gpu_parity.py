@@ -737,7 +737,7 @@ def test_driver_bertestk7_reproduces_golden_integers():
 def test_speed_drivers_run(name, word):
     path = _driver(name)
     try:
-        r = subprocess.run(["timeout", "-s", "INT", "6", "stdbuf", "-oL", path], capture_output=True, text=True, timeout=60)
+        r = subprocess.run(["timeout", "-s", "INT", "9", "stdbuf", "-oL", path], capture_output=True, text=True, timeout=60)
     except subprocess.TimeoutExpired:
         pytest.fail("%s did not stop" % name)
     assert "Could not" not in r.stdout, r.stdout
