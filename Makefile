@@ -71,9 +71,15 @@ drivers:
 	@echo "drivers: $(CED_REF) not present; using prebuilt drivers/_bin if any"
 endif
 
+# measurement probes (not part of the library): tools/_bin/{write_probe,latency_probe}
+tools: tools/_bin/write_probe tools/_bin/latency_probe
+tools/_bin/%: tools/%.cu
+	mkdir -p tools/_bin
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -o $@ $<
+
 clean:
 	rm -f $(PKG)/*.so tests/hostsim/*.so
 	rm -rf $(DRV) examples/_bin
 	$(MAKE) -C oracle clean
 
-.PHONY: all cuda host oracle hostsim drivers examples clean
+.PHONY: all cuda host oracle hostsim drivers examples tools clean
