@@ -19,9 +19,19 @@ CUDA_HDRS := $(wildcard $(CSRC)/*.cuh) include/ced_abi.h
 
 all: cuda host oracle hostsim drivers examples
 
+# one object per translation unit (build/ is git-ignored), so `make -j` compiles them side by side
+CUDA_SRCS := $(wildcard $(CSRC)/*.cu)
+CUDA_OBJS := $(patsubst $(CSRC)/%.cu,build/%.o,$(CUDA_SRCS)) build/host_pack.o
+
 cuda: $(PKG)/libced_cuda.so
-$(PKG)/libced_cuda.so: $(CSRC)/ced_abi.cu $(CSRC)/host_pack.cpp $(CUDA_HDRS)
-	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared -o $@ $(CSRC)/ced_abi.cu $(CSRC)/host_pack.cpp
+build/%.o: $(CSRC)/%.cu $(CUDA_HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -c -o $@ $<
+build/host_pack.o: $(CSRC)/host_pack.cpp
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -c -o $@ $<
+$(PKG)/libced_cuda.so: $(CUDA_OBJS)
+	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared -o $@ $(CUDA_OBJS) -ldl
 
 host: $(PKG)/libconvencdec_k7.so $(PKG)/libconvencdec_k3.so
 $(PKG)/libconvencdec_k7.so: $(HOST_SRCS) $(CSRC)/host/params/default/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)
@@ -78,7 +88,7 @@ tools/_bin/%: tools/%.cu
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -o $@ $<
 
 clean:
-	rm -f $(PKG)/*.so tests/hostsim/*.so
+	rm -f $(PKG)/*.so tests/hostsim/*.so build/*.o
 	rm -rf $(DRV) examples/_bin
 	$(MAKE) -C oracle clean
 

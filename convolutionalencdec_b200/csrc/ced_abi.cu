@@ -4,7 +4,7 @@
  * Everything here runs kernels; there is no host implementation of any
  * encode/decode arithmetic in this file.
  */
-#include "../../include/ced_abi.h"
+#include "ced_internal.cuh"
 #include "channel_kernels.cuh"
 #include "decode_batch.cuh"
 #include "encode_batch.cuh"
@@ -22,19 +22,9 @@
 #include <thread>
 #include <vector>
 
-namespace ced_host {
-struct Packer;
-Packer *packerCreate(int threads);
-void packerDestroy(Packer *p);
-int packerThreads(const Packer *p);
-void packerRun(Packer *p, const uint8_t *in, size_t inStride, int nRows, int segs, uint8_t *out, size_t outStride);
-} // namespace ced_host
+static thread_local char gLastError[512] = "";
 
-namespace {
-
-thread_local char gLastError[512] = "";
-
-void setError(const char *fmt, ...)
+void cedSetError(const char *fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -42,165 +32,58 @@ void setError(const char *fmt, ...)
     va_end(ap);
 }
 
-#define CED_CUDA(expr)                                                                          \
-    do {                                                                                        \
-        cudaError_t e__ = (expr);                                                               \
-        if (e__ != cudaSuccess) {                                                               \
-            setError("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
-            return CED_ERR_CUDA;                                                                \
-        }                                                                                       \
-    } while (0)
 
-constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave            */
-constexpr size_t kMaxWaveFrames = 1u << 20;       /* bounds the scheduler state (2 KB per 32 frames) */
-constexpr int kHostChunkFrames = 8192;            /* frames per H2D/kernel/D2H pipeline stage */
-constexpr int kPipeDepth = 4;                     /* chunks in flight in the host pipeline      */
-constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
+/* How many GPUs share this host's cores and memory right now: CED_ACTIVE_GPUS if set, else the ranks of a
+ * one-process-per-GPU launch on this node (LOCAL_WORLD_SIZE, set by torchrun), else the devices this process
+ * holds contexts on.  (Round 1 divided by cudaGetDeviceCount(): on an 8-GPU node a single rank then saw 4 cores
+ * per GPU and never packed -- 53 Gbit/s where the 16-core 1-GPU box reached 76.) */
+static std::mutex gActiveMu;
+static int gCtxPerDevice[64] = {};
 
-template <typename T>
-struct DeviceBuf {
-    T *p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need)
-    {
-        if (need <= bytes)
-            return CED_OK;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), need);
-        if (e != cudaSuccess) {
-            setError("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
-            return CED_ERR_NOMEM;
-        }
-        bytes = need;
-        return CED_OK;
-    }
-    void release()
-    {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-struct PinnedBuf {
-    uint8_t *p = nullptr;
-    size_t bytes = 0;
-    int ensure(size_t need)
-    {
-        if (need <= bytes)
-            return CED_OK;
-        if (p)
-            cudaFreeHost(p);
-        p = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), need);
-        if (e != cudaSuccess) {
-            setError("cudaMallocHost(%zu) failed: %s", need, cudaGetErrorString(e));
-            return CED_ERR_NOMEM;
-        }
-        bytes = need;
-        return CED_OK;
-    }
-    void release()
-    {
-        if (p)
-            cudaFreeHost(p);
-        p = nullptr;
-        bytes = 0;
-    }
-};
-
-enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171, K7_Runtime, K7_RuntimeN3 };
-
-CodeId classify(const ced_code_t *c)
+static int activeGpus()
 {
-    /* generators that tap the newest and the oldest bit (the butterfly symmetry the reference itself
-     * requires, src/viterbiDecoder.c:20-24) */
-    auto bothEnds = [](uint64_t g) { return g < 128 && (g & 1u) && ((g >> 6) & 1u); };
-    if (c && c->constraintLen == 7 && c->codedBits == 3 && bothEnds(c->gen[0]) && bothEnds(c->gen[1]) &&
-        bothEnds(c->gen[2]))
-        return CodeId::K7_RuntimeN3;
-    if (!c || c->constraintLen != 7 || c->codedBits != 2)
-        return CodeId::Unsupported;
-    if (c->gen[0] == 0113 && c->gen[1] == 0171)
-        return CodeId::K7_0113_0171;
-    if (c->gen[0] == 0133 && c->gen[1] == 0171)
-        return CodeId::K7_0133_0171;
-    /* any other symmetric pair: SWAR kernel driven by a step table */
-    if (bothEnds(c->gen[0]) && bothEnds(c->gen[1]))
-        return CodeId::K7_Runtime;
-    return CodeId::Unsupported;
+    for (const char *name : {"CED_ACTIVE_GPUS", "LOCAL_WORLD_SIZE"}) {
+        const char *e = getenv(name);
+        if (e && atoi(e) > 0)
+            return atoi(e);
+    }
+    std::lock_guard<std::mutex> lock(gActiveMu);
+    int n = 0;
+    for (int d = 0; d < 64; d++)
+        n += gCtxPerDevice[d] > 0 ? 1 : 0;
+    return std::max(1, n);
 }
 
-uint32_t reverseBits(uint64_t g, int K)
+static int hostCoresPerActiveGpu()
 {
-    uint32_t r = 0;
-    for (int i = 0; i < K; i++)
-        r |= (uint32_t)((g >> i) & 1u) << (K - 1 - i);
-    return r;
+    return std::max(1, (int)std::thread::hardware_concurrency() / activeGpus());
 }
 
-} // namespace
-
-struct ced_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;   /* compute */
-    cudaStream_t h2d = nullptr, d2h = nullptr;
-    cudaEvent_t inReady[kPipeDepth] = {}, inFree[kPipeDepth] = {}, outReady[kPipeDepth] = {}, outFree[kPipeDepth] = {};
-    /* decode working set: slot 0 serves direct calls, slots 1-2 the two chunks the host pipeline keeps
-     * in flight on its two compute streams */
-    struct Work {
-        DeviceBuf<uint4> scratch;    /* survivor words of the wave in flight */
-        DeviceBuf<uint4> schedState; /* FwdSched.state */
-        DeviceBuf<int> schedFlags;   /* [0] unit counter, [1 + g] FwdSched.done */
-        cudaEvent_t idle = nullptr;  /* recorded after the last kernel that used this working set */
-        cudaStream_t lastStream = nullptr;
-    } work[1 + kPipeDepth];
-    cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
-    /* host-side transfer compression (host_pack.cpp): pinned packed staging + worker threads */
-    ced_host::Packer *packer = nullptr;
-    PinnedBuf packStage[kPipeDepth];
-    PinnedBuf outStage[kPipeDepth];  /* results on their way to a pageable caller buffer */
-    cudaEvent_t stageFree[kPipeDepth] = {};
-    int packHoldoff = 0, packPenalty = 1; /* adaptive transfer compression: back-off after the link ran dry */
-    int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
-    int sms = 0, fwdResident = 0;
-    size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
-    DeviceBuf<uint8_t> hostIn[kPipeDepth], hostOut[kPipeDepth];
-    /* streaming path */
-    DeviceBuf<uint8_t> sIn, sOut;
-    DeviceBuf<uint32_t> sSurv;
-    DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
-    cudaGraphExec_t fpGraph = nullptr; /* copy in + fpBlockKernel + fpSelectKernel for packets of fpGraphSegs segments */
-    int fpGraphSegs = 0;
-    PinnedBuf sPinIn, sPinOut;
-    std::recursive_mutex mu;
-    uint64_t launches = 0;
-    ced::BmTable bm0113, bm0133;
-    /* step tables of run-time K=7 codes (ced::buildStepTable), built on first use and kept */
-    struct StepTable {
-        int n;
-        uint64_t g[3];
-        uint2 *dev;
-    };
-    std::vector<StepTable> stepTables;
-    /* optional kernel timing (ced_ctx_set_profiling) */
-    bool profiling = false;
-    static constexpr int kMaxProfWaves = 64;
-    cudaEvent_t prof[kMaxProfWaves][3] = {};
-    int profWaves = 0;
+/* Frames per wave and the working set of one wave of the SWAR decoder: the same computation sizes the
+ * buffers in decodeBatchImpl and answers ced_decode_scratch_bytes. */
+struct DecodeWorkingSet {
+    size_t waveMax, firstGroups, perFrame, scratchBytes, stateBytes, flagBytes;
 };
-
-using Code0113 = ced::K7Code<0113, 0171>;
-using Code0133 = ced::K7Code<0133, 0171>;
-static_assert(Code0113::symmetric && Code0133::symmetric, "SWAR butterflies need symmetric generators");
-static_assert(Code0113::tap0 == 0x69 && Code0113::tap1 == 0x4F, "SURVEY 8(c) KAT: taps of 0113/0171");
+static size_t maxWaveFramesSetting()
+{
+    const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES"); /* tests force several waves with it */
+    return (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
+}
+static DecodeWorkingSet decodeWorkingSet(size_t nFrames, int T, size_t maxWaveFrames)
+{
+    DecodeWorkingSet w;
+    w.perFrame = (size_t)(T / 2) * sizeof(uint4);
+    w.waveMax = std::min<size_t>(maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / w.perFrame)) / 64 * 64;
+    w.firstGroups = (std::min<size_t>(nFrames, w.waveMax) + 31) / 32;
+    w.scratchBytes = w.firstGroups * 32 * w.perFrame;
+    w.stateBytes = w.firstGroups * 4 * 32 * sizeof(uint4);
+    w.flagBytes = (w.firstGroups + 1) * sizeof(int);
+    return w;
+}
 
 extern "C" {
+
+static int ctxInit(ced_ctx *c, int device);
 
 int ced_device_count(void)
 {
@@ -229,6 +112,25 @@ int ced_ctx_create(int device, ced_ctx **out)
     CED_CUDA(cudaSetDevice(device));
     ced_ctx *c = new ced_ctx();
     c->device = device;
+    const int rc = ctxInit(c, device);
+    if (rc != CED_OK) {
+        char keep[512];
+        snprintf(keep, sizeof(keep), "%s", ced_last_error());
+        ced_ctx_destroy(c);   /* releases whatever was created so far */
+        setError("%s", keep);
+        return rc;
+    }
+    {
+        std::lock_guard<std::mutex> lock(gActiveMu);
+        gCtxPerDevice[device & 63]++;
+    }
+    c->counted = true;
+    *out = c;
+    return CED_OK;
+}
+
+static int ctxInit(ced_ctx *c, int device)
+{
     c->bm0113 = ced::makeBmTable<Code0113>();
     c->bm0133 = ced::makeBmTable<Code0133>();
     CED_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -253,8 +155,7 @@ int ced_ctx_create(int device, ced_ctx **out)
          * sub-partition), never more than the kernel's resident capacity */
         int sms = 0, resident = 0;
         CED_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES");
-        c->maxWaveFrames = (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
+        c->maxWaveFrames = maxWaveFramesSetting();
         CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
             &resident, ced::k7ForwardKernel<Code0113, ced::PackedSymbols, false>, ced::kFwdThreads, 0));
         const char *env = getenv("CED_FWD_BLOCKS_PER_SM");
@@ -262,7 +163,6 @@ int ced_ctx_create(int device, ced_ctx **out)
         c->fwdResident = std::max(1, resident);
         c->fwdBlocks = env ? sms * std::max(1, std::min(atoi(env), c->fwdResident)) : 0;
     }
-    *out = c;
     return CED_OK;
 }
 
@@ -292,10 +192,9 @@ void ced_ctx_destroy(ced_ctx *c)
     for (int i = 0; i < kPipeDepth; i++) {
         c->hostIn[i].release();
         c->hostOut[i].release();
-        cudaEventDestroy(c->inReady[i]);
-        cudaEventDestroy(c->inFree[i]);
-        cudaEventDestroy(c->outReady[i]);
-        cudaEventDestroy(c->outFree[i]);
+        for (cudaEvent_t e : {c->inReady[i], c->inFree[i], c->outReady[i], c->outFree[i]})
+            if (e)
+                cudaEventDestroy(e);
     }
     for (auto &t : c->stepTables)
         cudaFree(t.dev);
@@ -310,10 +209,16 @@ void ced_ctx_destroy(ced_ctx *c)
     c->sPinOut.release();
     for (int w = 0; w < ced_ctx::kMaxProfWaves; w++)
         for (int e = 0; e < 3; e++)
-            cudaEventDestroy(c->prof[w][e]);
-    cudaStreamDestroy(c->stream);
-    cudaStreamDestroy(c->h2d);
-    cudaStreamDestroy(c->d2h);
+            if (c->prof[w][e])
+                cudaEventDestroy(c->prof[w][e]);
+    for (cudaStream_t st : {c->stream, c->h2d, c->d2h})
+        if (st)
+            cudaStreamDestroy(st);
+    if (c->counted) {
+        std::lock_guard<std::mutex> lock(gActiveMu);
+        gCtxPerDevice[c->device & 63]--;
+    }
+    cudaGetLastError();
     delete c;
 }
 
@@ -399,12 +304,8 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits)
 {
     if (nFrames <= 0 || frameBits <= 0)
         return 0;
-    const size_t T = (size_t)frameBits + ced::kTailSteps;
-    const size_t perFrame = (T / 2) * sizeof(uint4);
-    size_t wave = std::min<size_t>(kMaxWaveFrames, std::max<size_t>(32, kMaxScratchBytes / perFrame));
-    wave = std::min<size_t>((size_t)nFrames, wave / 32 * 32);
-    const size_t groups = (wave + 63) / 64 * 2;
-    return groups * 32 * perFrame + groups * 4 * 32 * sizeof(uint4) + (groups + 1) * sizeof(int);
+    const DecodeWorkingSet ws = decodeWorkingSet((size_t)nFrames, frameBits + ced::kTailSteps, maxWaveFramesSetting());
+    return ws.scratchBytes + ws.stateBytes + ws.flagBytes;
 }
 
 /* device copy of the step table of a run-time K=7 code (caller holds c->mu, device is current) */
@@ -543,19 +444,15 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (rc != CED_OK)
             return rc;
     }
-    const size_t perFrame = (size_t)(T / 2) * sizeof(uint4);
-    size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame));
-    waveMax = waveMax / 64 * 64;
-    const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax);
-    const size_t firstGroups = (firstWave + 31) / 32;
+    const DecodeWorkingSet ws = decodeWorkingSet((size_t)nFrames, T, c->maxWaveFrames);
+    const size_t waveMax = ws.waveMax;
     ced_ctx::Work &wk = c->work[slot];
-    if (wk.scratch.bytes < firstGroups * 32 * perFrame || wk.schedState.bytes < firstGroups * 4 * 32 * sizeof(uint4) ||
-        wk.schedFlags.bytes < (firstGroups + 1) * sizeof(int)) {
+    if (wk.scratch.bytes < ws.scratchBytes || wk.schedState.bytes < ws.stateBytes || wk.schedFlags.bytes < ws.flagBytes) {
         /* growing means freeing: make sure nothing still uses the old blocks */
         CED_CUDA(cudaDeviceSynchronize());
-        int rc = wk.scratch.ensure(firstGroups * 32 * perFrame);
-        if (rc == CED_OK) rc = wk.schedState.ensure(firstGroups * 4 * 32 * sizeof(uint4));
-        if (rc == CED_OK) rc = wk.schedFlags.ensure((firstGroups + 1) * sizeof(int));
+        int rc = wk.scratch.ensure(ws.scratchBytes);
+        if (rc == CED_OK) rc = wk.schedState.ensure(ws.stateBytes);
+        if (rc == CED_OK) rc = wk.schedFlags.ensure(ws.flagBytes);
         if (rc != CED_OK)
             return rc;
     }
@@ -799,7 +696,7 @@ int ced_pack_symbols(ced_ctx *c, const uint8_t *dSegs, size_t segStride, int nFr
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)c->sms * 32);
     const int aligned = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0 &&
                          (reinterpret_cast<uintptr_t>(dPacked) & 3u) == 0 && (packedStride & 3u) == 0) ? 1 : 0;
     ced::packSymbolsKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
@@ -1002,7 +899,7 @@ int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, i
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)c->sms * 32);
     const int aligned = ((reinterpret_cast<uintptr_t>(dSoft) & 15u) == 0 && (softStride & 15u) == 0 &&
                          (reinterpret_cast<uintptr_t>(dPacked) & 3u) == 0 && (packedStride & 3u) == 0) ? 1 : 0;
     ced::sliceSoftSymbolsKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
@@ -1029,10 +926,8 @@ static bool isPageable(const void *p)
 static int ensurePacker(ced_ctx *c)
 {
     if (!c->packer) {
-        int nDev = 1;
-        cudaGetDeviceCount(&nDev);
         const char *envT = getenv("CED_HOST_THREADS");
-        int threads = envT ? atoi(envT) : (int)std::thread::hardware_concurrency() / std::max(1, nDev);
+        int threads = envT ? atoi(envT) : hostCoresPerActiveGpu();
         c->packer = ced_host::packerCreate(std::max(1, std::min(threads, envT ? 64 : 8)));
     }
     return c->packer ? CED_OK : CED_ERR_NOMEM;
@@ -1043,7 +938,7 @@ static int ensurePacker(ced_ctx *c)
  * the bottleneck and the mix gains 45 % (53.6 -> 77 Gbit/s); on the 8-GPU box (32 cores, 4 per GPU, all links
  * sharing the host memory) raw copies already run at a third of the link rate and packing loses 9 % (156 -> 142
  * Gbit/s in total; with every rank calibrating at once the measurement below is also too noisy there: 3 of 8 ranks
- * chose packing, 146 Gbit/s).  So (1) hosts with fewer than 8 cores per visible GPU always copy raw, and (2) elsewhere
+ * chose packing, 146 Gbit/s).  So (1) hosts with fewer than 8 cores per ACTIVE GPU (activeGpus()) always copy raw, and (2) elsewhere
  * every process measures it once per device: the first 16 eligible calls alternate four raw,
  * four adaptive (the first of each four is a transition and not counted), then the faster mode is kept -- adaptive
  * only if it is at least 5 % faster -- and re-measured after 512 calls.  CED_HOST_PACK = 0 / 1 / 2 bypasses this.
@@ -1100,9 +995,35 @@ static void packTunerEnd(int device, int ticket, int mode, double bytesPerSecond
     }
 }
 
+static int hostPipelineBody(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
+                            size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
+                            size_t outRowBytes);
+
+/* On failure nothing may still be reading or writing the caller's buffers when the call returns: drain the copy
+ * and compute streams first (the error text of the failing call is kept). */
 static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
                         size_t outRowBytes)
+{
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    const int rc = hostPipelineBody(c, code, op, hIn, inStride, inRowBytes, nFrames, frameParam, hOut, outStride,
+                                    outRowBytes);
+    if (rc != CED_OK) {
+        char keep[512];
+        snprintf(keep, sizeof(keep), "%s", ced_last_error());
+        cudaStreamSynchronize(c->h2d);
+        for (int i = 0; i < kPipeDepth; i++)
+            cudaStreamSynchronize(c->pipe[i]);
+        cudaStreamSynchronize(c->d2h);
+        cudaGetLastError();
+        setError("%s", keep);
+    }
+    return rc;
+}
+
+static int hostPipelineBody(ced_ctx *c, const ced_code_t *code, HostOp op, const uint8_t *hIn, size_t inStride,
+                            size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
+                            size_t outRowBytes)
 {
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
@@ -1121,7 +1042,7 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
             return rc;
     }
     for (int b = 0; b < kPipeDepth; b++) {
-        int rc = c->hostIn[b].ensure((size_t)chunk * inStride + 16);
+        int rc = c->hostIn[b].ensure((size_t)chunk * std::max(inStride, packStride) + 16);
         if (rc == CED_OK)
             rc = c->hostOut[b].ensure((size_t)chunk * outStride + 16);
         if (rc != CED_OK)
@@ -1245,6 +1166,10 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
         setError("ced_decode_batch_host: bad argument");
         return CED_ERR_ARG;
     }
+    if (segStride < (size_t)frameBits + code->constraintLen - 1 || outStride < (size_t)frameBits / 8) {
+        setError("ced_decode_batch_host: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
     if (nFrames == 0)
         return CED_OK;
     /* Transfer compression: worker threads pack the symbols to 2 bits into page-locked staging and a quarter of
@@ -1268,11 +1193,7 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
         int mode = envP ? atoi(envP) : (pageable ? 1 : 2);
         if (!envP && !pageable) {
             /* page-locked buffers: adaptive packing only where this machine gains from it (PackTuner) */
-            static const int coresPerGpu = [] {
-                int nDev = 1;
-                cudaGetDeviceCount(&nDev);
-                return (int)std::thread::hardware_concurrency() / std::max(1, nDev);
-            }();
+            const int coresPerGpu = hostCoresPerActiveGpu();
             if (nFrames >= 4 * kHostChunkFrames && coresPerGpu >= 8)
                 tuned = true;
             else
@@ -1307,6 +1228,10 @@ int ced_decode_batch_packed_host(ced_ctx *c, const ced_code_t *code, const uint8
         setError("ced_decode_batch_packed_host: bad argument");
         return CED_ERR_ARG;
     }
+    if (packedStride < ((size_t)frameBits + code->constraintLen - 1 + 3) / 4 || outStride < (size_t)frameBits / 8) {
+        setError("ced_decode_batch_packed_host: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
     if (nFrames == 0)
         return CED_OK;
     return hostPipeline(c, code, HostOp::DecodePacked, hPacked, packedStride,
@@ -1319,6 +1244,10 @@ int ced_encode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hMs
 {
     if (!c || !code || !hMsg || !hSegs || nFrames < 0 || frameBytes <= 0) {
         setError("ced_encode_batch_host: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (msgStride < (size_t)frameBytes || segStride < (size_t)frameBytes * 8 + code->constraintLen - 1) {
+        setError("ced_encode_batch_host: stride shorter than a frame");
         return CED_ERR_ARG;
     }
     if (nFrames == 0)
@@ -1341,7 +1270,7 @@ int ced_ber_count(ced_ctx *c, const uint8_t *dA, size_t strideA, const uint8_t *
     const int aligned4 = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(dB) | strideA | strideB |
                            (size_t)bytesPerFrame) & 3u) == 0;
     const long long work = (long long)nFrames * (aligned4 ? bytesPerFrame / 4 : bytesPerFrame);
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)c->sms * 16);
     ced::berCountKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
         dA, strideA, dB, strideB, nFrames, bytesPerFrame, reinterpret_cast<unsigned long long *>(dCounters), aligned4);
     c->launches += 1;
@@ -1363,7 +1292,7 @@ int ced_bsc_channel(ced_ctx *c, uint8_t *dSegs, size_t segStride, int nFrames, i
     CED_CUDA(cudaSetDevice(c->device));
     const uint32_t threshold = (uint32_t)(p * 4294967296.0);
     const long long work = (long long)nFrames * ((segsPerFrame + 15) / 16);
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 32);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)c->sms * 32);
     const int aligned16 = ((reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0) ? 1 : 0;
     ced::bscChannelKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(
         dSegs, segStride, nFrames, segsPerFrame, codedBits, threshold, seed, firstFrameIndex,
@@ -1385,7 +1314,7 @@ int ced_random_bytes(ced_ctx *c, uint8_t *dMsg, size_t msgStride, int nFrames, i
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     const long long work = (long long)nFrames * ((frameBytes + 7) / 8);
-    const int blocks = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+    const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)c->sms * 16);
     ced::randomBytesKernel<<<blocks, 256, 0, stream ? (cudaStream_t)stream : c->stream>>>(dMsg, msgStride, nFrames,
                                                                                          frameBytes, seed,
                                                                                          firstFrameIndex);
@@ -1565,7 +1494,10 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         };
         if (streamGraphEnabled()) {
             /* per-packet loops call with one packet length: the three submissions become one graph launch */
-            if (!c->fpGraph || c->fpGraphSegs != segmentsIn) {
+            /* the graph holds raw pointers into the staging buffers, which ced_stream_encode may have regrown
+             * (ensure() frees and reallocates): the cache is keyed on them as well as on the packet length */
+            const void *key[5] = {c->sIn.p, c->sOut.p, c->sParallel.p, c->sPinIn.p, c->sPinOut.p};
+            if (!c->fpGraph || c->fpGraphSegs != segmentsIn || memcmp(key, c->fpGraphKey, sizeof(key)) != 0) {
                 if (c->fpGraph)
                     cudaGraphExecDestroy(c->fpGraph);
                 c->fpGraph = nullptr;
@@ -1579,6 +1511,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                 cudaGraphDestroy(g);
                 CED_CUDA(e3);
                 c->fpGraphSegs = segmentsIn;
+                memcpy(c->fpGraphKey, key, sizeof(key));
             }
             CED_CUDA(cudaGraphLaunch(c->fpGraph, c->stream));
         } else {

@@ -1,0 +1,182 @@
+/*
+ * ced_internal.cuh -- what the translation units behind include/ced_abi.h share: the per-GPU context
+ * (ced_ctx), the device / pinned buffer helpers and the error convention.  Not part of the ABI.
+ */
+#pragma once
+#include "../../include/ced_abi.h"
+#include "decode_batch.cuh"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
+
+namespace ced_host {
+struct Packer;
+Packer *packerCreate(int threads);
+void packerDestroy(Packer *p);
+int packerThreads(const Packer *p);
+void packerRun(Packer *p, const uint8_t *in, size_t inStride, int nRows, int segs, uint8_t *out, size_t outStride);
+} // namespace ced_host
+
+/* text behind ced_last_error(), one buffer per thread (defined in ced_abi.cu) */
+void cedSetError(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
+#define setError cedSetError
+
+#define CED_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            setError("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return CED_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave            */
+constexpr size_t kMaxWaveFrames = 1u << 20;       /* bounds the scheduler state (2 KB per 32 frames) */
+constexpr int kHostChunkFrames = 8192;            /* frames per H2D/kernel/D2H pipeline stage */
+constexpr int kPipeDepth = 4;                     /* chunks in flight in the host pipeline      */
+constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
+
+template <typename T>
+struct DeviceBuf {
+    T *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes)
+            return CED_OK;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), need);
+        if (e != cudaSuccess) {
+            setError("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+            return CED_ERR_NOMEM;
+        }
+        bytes = need;
+        return CED_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+struct PinnedBuf {
+    uint8_t *p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes)
+            return CED_OK;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), need);
+        if (e != cudaSuccess) {
+            setError("cudaMallocHost(%zu) failed: %s", need, cudaGetErrorString(e));
+            return CED_ERR_NOMEM;
+        }
+        bytes = need;
+        return CED_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+enum class CodeId { Unsupported, K7_0113_0171, K7_0133_0171, K7_Runtime, K7_RuntimeN3 };
+
+inline CodeId classify(const ced_code_t *c)
+{
+    /* generators that tap the newest and the oldest bit (the butterfly symmetry the reference itself
+     * requires, src/viterbiDecoder.c:20-24) */
+    auto bothEnds = [](uint64_t g) { return g < 128 && (g & 1u) && ((g >> 6) & 1u); };
+    if (c && c->constraintLen == 7 && c->codedBits == 3 && bothEnds(c->gen[0]) && bothEnds(c->gen[1]) &&
+        bothEnds(c->gen[2]))
+        return CodeId::K7_RuntimeN3;
+    if (!c || c->constraintLen != 7 || c->codedBits != 2)
+        return CodeId::Unsupported;
+    if (c->gen[0] == 0113 && c->gen[1] == 0171)
+        return CodeId::K7_0113_0171;
+    if (c->gen[0] == 0133 && c->gen[1] == 0171)
+        return CodeId::K7_0133_0171;
+    /* any other symmetric pair: SWAR kernel driven by a step table */
+    if (bothEnds(c->gen[0]) && bothEnds(c->gen[1]))
+        return CodeId::K7_Runtime;
+    return CodeId::Unsupported;
+}
+
+inline uint32_t reverseBits(uint64_t g, int K)
+{
+    uint32_t r = 0;
+    for (int i = 0; i < K; i++)
+        r |= (uint32_t)((g >> i) & 1u) << (K - 1 - i);
+    return r;
+}
+
+
+struct ced_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;   /* compute */
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t inReady[kPipeDepth] = {}, inFree[kPipeDepth] = {}, outReady[kPipeDepth] = {}, outFree[kPipeDepth] = {};
+    /* decode working set: slot 0 serves direct calls, slots 1-2 the two chunks the host pipeline keeps
+     * in flight on its two compute streams */
+    struct Work {
+        DeviceBuf<uint4> scratch;    /* survivor words of the wave in flight */
+        DeviceBuf<uint4> schedState; /* FwdSched.state */
+        DeviceBuf<int> schedFlags;   /* [0] unit counter, [1 + g] FwdSched.done */
+        cudaEvent_t idle = nullptr;  /* recorded after the last kernel that used this working set */
+        cudaStream_t lastStream = nullptr;
+    } work[1 + kPipeDepth];
+    cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
+    /* host-side transfer compression (host_pack.cpp): pinned packed staging + worker threads */
+    ced_host::Packer *packer = nullptr;
+    PinnedBuf packStage[kPipeDepth];
+    PinnedBuf outStage[kPipeDepth];  /* results on their way to a pageable caller buffer */
+    cudaEvent_t stageFree[kPipeDepth] = {};
+    int packHoldoff = 0, packPenalty = 1; /* adaptive transfer compression: back-off after the link ran dry */
+    int fwdBlocks = 0;               /* persistent grid of k7ForwardKernel (0 = adaptive) */
+    int sms = 0, fwdResident = 0;
+    size_t maxWaveFrames = 0;        /* frames per wave cap (CED_MAX_WAVE_FRAMES overrides, for tests) */
+    DeviceBuf<uint8_t> hostIn[kPipeDepth], hostOut[kPipeDepth];
+    /* streaming path */
+    DeviceBuf<uint8_t> sIn, sOut;
+    DeviceBuf<uint32_t> sSurv;
+    DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
+    cudaGraphExec_t fpGraph = nullptr; /* copy in + fpBlockKernel + fpSelectKernel for packets of fpGraphSegs segments */
+    int fpGraphSegs = 0;
+    const void *fpGraphKey[5] = {};  /* staging pointers baked into fpGraph */
+    PinnedBuf sPinIn, sPinOut;
+    std::recursive_mutex mu;
+    uint64_t launches = 0;
+    ced::BmTable bm0113, bm0133;
+    /* step tables of run-time K=7 codes (ced::buildStepTable), built on first use and kept */
+    struct StepTable {
+        int n;
+        uint64_t g[3];
+        uint2 *dev;
+    };
+    std::vector<StepTable> stepTables;
+    /* optional kernel timing (ced_ctx_set_profiling) */
+    bool profiling = false;
+    static constexpr int kMaxProfWaves = 64;
+    cudaEvent_t prof[kMaxProfWaves][3] = {};
+    int profWaves = 0;
+    bool counted = false;            /* this context is in the per-device census (activeGpus) */
+};
+
+using Code0113 = ced::K7Code<0113, 0171>;
+using Code0133 = ced::K7Code<0133, 0171>;
+static_assert(Code0113::symmetric && Code0133::symmetric, "SWAR butterflies need symmetric generators");
+static_assert(Code0113::tap0 == 0x69 && Code0113::tap1 == 0x4F, "SURVEY 8(c) KAT: taps of 0113/0171");
