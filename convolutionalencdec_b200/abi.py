@@ -88,6 +88,9 @@ def load_abi():
     lib.ced_pack_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_host_pack_symbols.argtypes = [_u8p, sz, i, i, _u8p, sz, i]
     lib.ced_slice_soft_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_soft.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_slice_soft_to_bytes.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_awgn_channel.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, C.c_double, C.c_double, u64, u64, vp, vp]
     lib.ced_encode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
@@ -247,6 +250,44 @@ class Context:
         _check(self.lib, self.lib.ced_slice_soft_symbols(self.h, soft.data_ptr(), soft.stride(0), nf, segs_per_frame,
                                                          out.data_ptr(), out.stride(0), _stream_handle(stream)),
                "ced_slice_soft_symbols")
+        return out
+
+    def decode_batch_soft(self, code, soft, frame_bits, out=None, stream=None):
+        """soft: int8 CUDA tensor [frames, >= 2*(frame_bits+6)], 16-byte aligned rows -> decoded bytes
+        (true soft-decision decoding, ced_decode_batch_soft)."""
+        import torch
+        nf = soft.shape[0]
+        if out is None:
+            out = torch.empty((nf, frame_bits // 8), dtype=torch.uint8, device=soft.device)
+        _check(self.lib, self.lib.ced_decode_batch_soft(self.h, C.byref(code._c), soft.data_ptr(), soft.stride(0), nf,
+                                                        frame_bits, out.data_ptr(), out.stride(0),
+                                                        _stream_handle(stream)), "ced_decode_batch_soft")
+        return out
+
+    def slice_soft_to_bytes(self, soft, segs_per_frame, out=None, stream=None, seg_stride=None):
+        import torch
+        nf = soft.shape[0]
+        if out is None:
+            out = torch.zeros((nf, seg_stride or segs_per_frame), dtype=torch.uint8, device=soft.device)
+        _check(self.lib, self.lib.ced_slice_soft_to_bytes(self.h, soft.data_ptr(), soft.stride(0), nf, segs_per_frame,
+                                                          out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_slice_soft_to_bytes")
+        return out
+
+    def awgn_channel(self, segs, segs_per_frame, ebn0_db, seed, amplitude=32.0, first_frame=0, counters=None, out=None,
+                     stream=None, soft_stride=None, rate=0.5):
+        """BPSK + AWGN at Eb/N0 (dB) on byte-per-segment symbols -> int8 soft symbols [frames, soft_stride]."""
+        import torch
+        nf = segs.shape[0]
+        if out is None:
+            stride = soft_stride or (2 * segs_per_frame + 15) // 16 * 16
+            out = torch.zeros((nf, stride), dtype=torch.int8, device=segs.device)
+        sigma = (2.0 * rate * 10.0 ** (ebn0_db / 10.0)) ** -0.5
+        _check(self.lib, self.lib.ced_awgn_channel(self.h, segs.data_ptr(), segs.stride(0), nf, segs_per_frame,
+                                                   out.data_ptr(), out.stride(0), float(amplitude), float(sigma),
+                                                   int(seed), int(first_frame),
+                                                   counters.data_ptr() if counters is not None else None,
+                                                   _stream_handle(stream)), "ced_awgn_channel")
         return out
 
     def encode_batch_packed(self, code, msgs, out=None, stream=None, packed_stride=None):

@@ -59,28 +59,6 @@ static int hostCoresPerActiveGpu()
     return std::max(1, (int)std::thread::hardware_concurrency() / activeGpus());
 }
 
-/* Frames per wave and the working set of one wave of the SWAR decoder: the same computation sizes the
- * buffers in decodeBatchImpl and answers ced_decode_scratch_bytes. */
-struct DecodeWorkingSet {
-    size_t waveMax, firstGroups, perFrame, scratchBytes, stateBytes, flagBytes;
-};
-static size_t maxWaveFramesSetting()
-{
-    const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES"); /* tests force several waves with it */
-    return (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
-}
-static DecodeWorkingSet decodeWorkingSet(size_t nFrames, int T, size_t maxWaveFrames)
-{
-    DecodeWorkingSet w;
-    w.perFrame = (size_t)(T / 2) * sizeof(uint4);
-    w.waveMax = std::min<size_t>(maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / w.perFrame)) / 64 * 64;
-    w.firstGroups = (std::min<size_t>(nFrames, w.waveMax) + 31) / 32;
-    w.scratchBytes = w.firstGroups * 32 * w.perFrame;
-    w.stateBytes = w.firstGroups * 4 * 32 * sizeof(uint4);
-    w.flagBytes = (w.firstGroups + 1) * sizeof(int);
-    return w;
-}
-
 extern "C" {
 
 static int ctxInit(ced_ctx *c, int device);
@@ -513,7 +491,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
 #undef CED_LAUNCH_FWD
         if (prof)
             CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
-        ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+        ced::k7TracebackKernel<ced::Lanes8><<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
             wk.scratch.p, wave, T, out, outStride);
         if (prof) {
             CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
@@ -667,7 +645,7 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
 #undef CED_LAUNCH_WIN
         c->launches += 1;
         if (bytesOut > 0) {
-            ced::k7TracebackKernel<<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+            ced::k7TracebackKernel<ced::Lanes8><<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
                 wk.scratch.p, wave, Tl, dOut + f0 * outStride, outStride, last ? nullptr : win.startPos,
                 last ? ced::kTailSteps : depth, emitLo);
             c->launches += 1;

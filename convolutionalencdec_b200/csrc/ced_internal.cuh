@@ -6,6 +6,8 @@
 #include "../../include/ced_abi.h"
 #include "decode_batch.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <mutex>
 #include <vector>
@@ -180,3 +182,26 @@ using Code0113 = ced::K7Code<0113, 0171>;
 using Code0133 = ced::K7Code<0133, 0171>;
 static_assert(Code0113::symmetric && Code0133::symmetric, "SWAR butterflies need symmetric generators");
 static_assert(Code0113::tap0 == 0x69 && Code0113::tap1 == 0x4F, "SURVEY 8(c) KAT: taps of 0113/0171");
+
+/* Frames per wave and the working set of one wave of the SWAR decoder: the same computation sizes the
+ * buffers in decodeBatchImpl and answers ced_decode_scratch_bytes. */
+struct DecodeWorkingSet {
+    size_t waveMax, firstGroups, perFrame, scratchBytes, stateBytes, flagBytes;
+};
+inline size_t maxWaveFramesSetting()
+{
+    const char *waveEnv = getenv("CED_MAX_WAVE_FRAMES"); /* tests force several waves with it */
+    return (waveEnv && atoll(waveEnv) >= 64) ? (size_t)atoll(waveEnv) / 64 * 64 : kMaxWaveFrames;
+}
+inline DecodeWorkingSet decodeWorkingSet(size_t nFrames, int T, size_t maxWaveFrames)
+{
+    DecodeWorkingSet w;
+    w.perFrame = (size_t)(T / 2) * sizeof(uint4);
+    w.waveMax = std::min<size_t>(maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / w.perFrame)) / 64 * 64;
+    w.firstGroups = (std::min<size_t>(nFrames, w.waveMax) + 31) / 32;
+    w.scratchBytes = w.firstGroups * 32 * w.perFrame;
+    w.stateBytes = w.firstGroups * 4 * 32 * sizeof(uint4);
+    w.flagBytes = (w.firstGroups + 1) * sizeof(int);
+    return w;
+}
+

@@ -406,10 +406,10 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
 }
 
 /* backward step with the phase known at compile time */
-template <int PH>
+template <class Lay, int PH>
 __device__ __forceinline__ uint32_t tracebackStepC(uint32_t &b, uint32_t w0, uint32_t w1)
 {
-    constexpr int qb = pairBitInB(PH);
+    constexpr int qb = Lay::pairBit(PH);
     const uint32_t word = (b & 32u) ? w1 : w0;
     const uint32_t dec = (word >> (b & 31u)) & 1u;
     const uint32_t bit = (b >> qb) & 1u;
@@ -419,18 +419,18 @@ __device__ __forceinline__ uint32_t tracebackStepC(uint32_t &b, uint32_t w0, uin
 
 /* 8 steps = 4 pairs = one output byte; pair i of the group holds steps (base+6-2i, base+7-2i),
  * PH0 = phase of the group's first step (step base, a multiple of 8 inside a 24-step block). */
-template <int PH0>
+template <class Lay, int PH0>
 __device__ __forceinline__ uint32_t tracebackByteC(uint32_t &b, const uint4 (&w)[4])
 {
     uint32_t acc = 0;
-    acc |= tracebackStepC<(PH0 + 7) % 6>(b, w[0].z, w[0].w) << 0;
-    acc |= tracebackStepC<(PH0 + 6) % 6>(b, w[0].x, w[0].y) << 1;
-    acc |= tracebackStepC<(PH0 + 5) % 6>(b, w[1].z, w[1].w) << 2;
-    acc |= tracebackStepC<(PH0 + 4) % 6>(b, w[1].x, w[1].y) << 3;
-    acc |= tracebackStepC<(PH0 + 3) % 6>(b, w[2].z, w[2].w) << 4;
-    acc |= tracebackStepC<(PH0 + 2) % 6>(b, w[2].x, w[2].y) << 5;
-    acc |= tracebackStepC<(PH0 + 1) % 6>(b, w[3].z, w[3].w) << 6;
-    acc |= tracebackStepC<(PH0 + 0) % 6>(b, w[3].x, w[3].y) << 7;
+    acc |= tracebackStepC<Lay, (PH0 + 7) % 6>(b, w[0].z, w[0].w) << 0;
+    acc |= tracebackStepC<Lay, (PH0 + 6) % 6>(b, w[0].x, w[0].y) << 1;
+    acc |= tracebackStepC<Lay, (PH0 + 5) % 6>(b, w[1].z, w[1].w) << 2;
+    acc |= tracebackStepC<Lay, (PH0 + 4) % 6>(b, w[1].x, w[1].y) << 3;
+    acc |= tracebackStepC<Lay, (PH0 + 3) % 6>(b, w[2].z, w[2].w) << 4;
+    acc |= tracebackStepC<Lay, (PH0 + 2) % 6>(b, w[2].x, w[2].y) << 5;
+    acc |= tracebackStepC<Lay, (PH0 + 1) % 6>(b, w[3].z, w[3].w) << 6;
+    acc |= tracebackStepC<Lay, (PH0 + 0) % 6>(b, w[3].x, w[3].y) << 7;
     return acc;
 }
 
@@ -453,6 +453,7 @@ __device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
 /* Window form (continuous streams): start at the position startPos[frame] instead of state 0, drop the top
  * `skip` steps instead of the S tail steps, and stop above step `emitLo` (a multiple of 24), whose bit is
  * the first one of the output row. */
+template <class Lay = Lanes8>
 __global__ void __launch_bounds__(kTbThreads)
 k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride,
                   const uint32_t *__restrict__ startPos = nullptr, int skip = kTailSteps, int emitLo = 0)
@@ -485,9 +486,9 @@ k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *_
     for (int m = T / 2 - 1; m >= blocks24 * 12; m--) {
         const uint4 w = __ldg(s + (size_t)m * 32);
         const int t = 2 * m;
-        const uint32_t b1 = tracebackStep(b, w.z, w.w, ph);
+        const uint32_t b1 = tracebackStep<Lay>(b, w.z, w.w, ph);
         ph = ph ? ph - 1 : 5;
-        const uint32_t b0 = tracebackStep(b, w.x, w.y, ph);
+        const uint32_t b0 = tracebackStep<Lay>(b, w.x, w.y, ph);
         ph = ph ? ph - 1 : 5;
         if (t < L && t >= emitLo) { /* the S = 6 tail steps carry no output (:208-223) */
             acc = (acc >> 2) | (b1 << 6) | (b0 << 7);   /* first visited (t%8 == 7) ends as the LSb (:249) */
@@ -510,13 +511,13 @@ k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *_
         uint4 g[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) g[i] = sW[buf][i][tid];          /* steps 24blk+16 .. +23 */
-        const uint32_t o2 = tracebackByteC<16 % 6>(b, g);
+        const uint32_t o2 = tracebackByteC<Lay, 16 % 6>(b, g);
 #pragma unroll
         for (int i = 0; i < 4; i++) g[i] = sW[buf][4 + i][tid];      /* steps 24blk+8  .. +15 */
-        const uint32_t o1 = tracebackByteC<8 % 6>(b, g);
+        const uint32_t o1 = tracebackByteC<Lay, 8 % 6>(b, g);
 #pragma unroll
         for (int i = 0; i < 4; i++) g[i] = sW[buf][8 + i][tid];      /* steps 24blk    .. +7  */
-        const uint32_t o0 = tracebackByteC<0>(b, g);
+        const uint32_t o0 = tracebackByteC<Lay, 0>(b, g);
         dst[3 * blk + 2] = (uint8_t)o2;
         dst[3 * blk + 1] = (uint8_t)o1;
         dst[3 * blk + 0] = (uint8_t)o0;

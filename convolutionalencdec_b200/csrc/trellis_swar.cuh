@@ -410,6 +410,17 @@ CED_HDC int pairBitInB(int ph)
     return (int)((0x340125u >> (4 * ph)) & 7u);
 }
 
+/* The two lane layouts of the packed metrics, as far as the traceback is concerned: where position bit
+ * q = 5 - ph sits in the survivor bit index b.
+ *   Lanes8  (this file):            b = 32*(p>>5) + 8*(p&3)  + ((p>>2)&7)
+ *   Lanes16 (trellis_swar16.cuh):   b = 32*(p>>5) + 16*(p&1) + ((p>>1)&15)    q = 5..0 -> b bit 5,3,2,1,0,4 */
+struct Lanes8 {
+    static CED_HDC int pairBit(int ph) { return pairBitInB(ph); }
+};
+struct Lanes16 {
+    static CED_HDC int pairBit(int ph) { return (int)((0x401235u >> (4 * ph)) & 7u); }
+};
+
 /* Windowed traceback start (continuous streams): after renorm() the smallest metric is 0; returns, in b form, the
  * lowest position holding it.  Called between slices, where the next phase is 0 and position == state, so ties go
  * to the lowest state.  The zero-byte finder is exact for bytes < 128 up to and including the lowest zero lane. */
@@ -435,9 +446,10 @@ CED_HD uint32_t bestPositionB(const uint32_t (&R)[16])
  * survivor state after step t; returns that state's newest bit (the decoded bit
  * of step t, src/viterbiDecoderButterflyk1.c:244-249) and moves b to the
  * predecessor (:252). */
+template <class L = Lanes8>
 CED_HD uint32_t tracebackStep(uint32_t &b, uint32_t w0, uint32_t w1, int ph)
 {
-    const int qb = pairBitInB(ph);
+    const int qb = L::pairBit(ph);
     const uint32_t word = (b & 32u) ? w1 : w0;
     const uint32_t dec = (word >> (b & 31u)) & 1u;
     const uint32_t bit = (b >> qb) & 1u;

@@ -122,11 +122,32 @@ int ced_host_pack_symbols(const uint8_t *segs, size_t segStride, int nFrames, in
 /* Encoder writing the packed format directly (n = 2 codes). */
 int ced_encode_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride,
                             int nFrames, int frameBytes, uint8_t *dPacked, size_t packedStride, void *stream);
-/* Soft symbols (two int8 per segment: coded bit 0 then coded bit 1; BPSK bit 0 -> +, bit 1 -> -) are
- * hard-sliced (sign bit; 0 slices to bit 0) into the packed format; decode with ced_decode_batch_packed.
- * The reference is hard-decision only, so this slicing IS the definition of soft input here. */
+/* Soft symbols: two int8 per segment (coded bit 0 then coded bit 1; BPSK bit 0 -> +, bit 1 -> -), rows of
+ * 2 * (frameBits + K - 1) bytes.
+ *
+ * ced_decode_batch_soft is a true soft-decision decoder (north_star kernel (1) "soft or hard symbols"): the
+ * branch cost of an edge is the reference's calcHammingDist (src/viterbiDecoder.c:260-285, used at
+ * src/viterbiDecoderButterflyk1.c:104-115) with every disagreeing coded bit weighted by its reliability |s|;
+ * trellis, tie rule, traceback and output format are the hard decoder's.  Definition: oracle/ced_oracle.c
+ * orc_dec_step_soft.  Inputs of one constant magnitude give exactly the hard decoder's output.  16-bit path
+ * metrics (k7SoftForwardKernel); codes 0113/0171 and 0133/0171; dSoft and softStride multiples of 16 bytes.
+ *
+ * ced_slice_soft_symbols / ced_slice_soft_to_bytes only keep the sign (0 slices to bit 0) and produce the
+ * packed / byte-per-segment hard format -- what a receiver without soft information would decode. */
+int ced_decode_batch_soft(ced_ctx *ctx, const ced_code_t *code, const int8_t *dSoft, size_t softStride, int nFrames,
+                          int frameBits, uint8_t *dOut, size_t outStride, void *stream);
 int ced_slice_soft_symbols(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
                            uint8_t *dPacked, size_t packedStride, void *stream);
+int ced_slice_soft_to_bytes(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
+                            uint8_t *dSegs, size_t segStride, void *stream);
+/* BPSK over AWGN with int8 soft output (the BER sweep's channel, berTestK7/berTestK7.c:29-43 generalised):
+ * soft = clamp(round(amplitude * ((1 - 2 bit) + sigma * N(0,1))), -127, 127) for both coded bits of every
+ * byte-per-segment symbol; for rate 1/2, sigma = 1 / sqrt(Eb/N0).  Counter-based generator keyed by (seed,
+ * frame index, segment), independent of sharding.  dCounters (may be NULL): [0] += coded bits whose sign came
+ * out wrong, [1] += coded bits. */
+int ced_awgn_channel(ced_ctx *ctx, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame, int8_t *dSoft,
+                     size_t softStride, double amplitude, double sigma, uint64_t seed, uint64_t firstFrameIndex,
+                     uint64_t *dCounters, void *stream);
 
 /* Same operations on HOST buffers: chunked H2D / kernel / D2H pipelined on a copy-in stream, four compute
  * streams and a copy-out stream; host worker threads pack part of the symbol chunks to 2 bits while the copy

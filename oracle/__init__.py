@@ -77,6 +77,9 @@ class Port:
                                          C.c_double, C.POINTER(C.c_double)]
         lib.orc_hamming.restype = C.c_uint8
         lib.orc_hamming.argtypes = [C.c_uint8, C.c_uint8, C.c_int]
+        lib.orc_decode_soft_batch.restype = C.c_int
+        lib.orc_decode_soft_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
+                                              _u8p, C.c_size_t]
 
     @staticmethod
     def _g(g):
@@ -110,6 +113,17 @@ class Port:
         out = np.zeros((nf, nbytes), dtype=np.uint8)
         rc = self.lib.orc_decode_batch(K, len(g), self._g(g), int(symmetric), _p(segs), stride, nf, T, _p(out),
                                        nbytes)
+        assert rc == 0
+        return out
+
+    def decode_soft_batch(self, K, g, soft, T):
+        """soft: int8 [frames, >= n*T], n values per segment (generator 0 first); semantics in
+        ced_oracle.c:orc_dec_step_soft (reliability-weighted calcHammingDist, otherwise orc_dec_step)."""
+        soft = np.ascontiguousarray(soft, dtype=np.int8)
+        nf, stride = soft.shape
+        nbytes = (T - (K - 1) - 1) // 8 + 1
+        out = np.zeros((nf, nbytes), dtype=np.uint8)
+        rc = self.lib.orc_decode_soft_batch(K, len(g), self._g(g), soft.ctypes.data, stride, nf, T, _p(out), nbytes)
         assert rc == 0
         return out
 

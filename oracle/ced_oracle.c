@@ -338,6 +338,127 @@ int orc_encode_batch(int K, int n, const uint64_t *g, const uint8_t *in, size_t 
 }
 
 /*
+ * Soft-decision decoding (north_star kernel (1) "soft or hard symbols").  The reference is a
+ * hard-decision decoder, so this restatement EXTENDS it; it is pinned to the reference by reduction:
+ *   - trellis, butterfly order, tie rule (strict '>' keeps the lower predecessor, :129-130), traceback from
+ *     state 0 and MSb-first packing are exactly orc_dec_step's (src/viterbiDecoderButterflyk1.c:101-149,200-260);
+ *   - a received segment is n int8 values s_0..s_{n-1} (s_i for generator i; BPSK bit 0 -> +, bit 1 -> -).
+ *     The cost of an edge labelled c is  sum_i |s_i| * [hard(s_i) != c_i]  with hard(s) = (s < 0), i.e. the
+ *     reference's calcHammingDist(c, rx, n) (src/viterbiDecoder.c:260-285) with every disagreeing bit
+ *     weighted by its reliability.  When all |s_i| equal one constant A this is A * calcHammingDist(c,
+ *     hard(rx), n): every comparison (ties included) is the hard decoder's, so the output must equal
+ *     orc_dec_step's on the sliced symbols bit for bit -- tests/test_oracle.py checks that, and the CUDA
+ *     path is held to both this function and that reduction;
+ *   - metrics are 32-bit ints and never renormalised (16390 steps * n * 128 < 2^31); decisions depend on
+ *     metric differences only, so any non-overflowing renormalisation schedule is equivalent.
+ * Start metrics: 0 for state 0, "never wins" for the rest (the reference's NUM_STATES+1 plays that role for
+ * costs <= n; here n * 128 * K).
+ */
+typedef struct {
+    int K, n, S, N;
+    uint8_t edge[2][ORC_MAX_STATES];
+    int32_t metric[ORC_MAX_STATES];
+    uint32_t iteration, capacity;
+    uint8_t *surv;
+} orc_soft_decoder_t;
+
+orc_soft_decoder_t *orc_soft_new(int K, int n, const uint64_t *g, int maxSegments)
+{
+    orc_soft_decoder_t *d = (orc_soft_decoder_t *)calloc(1, sizeof(*d));
+    uint32_t taps[ORC_MAX_N];
+    if (!d)
+        return NULL;
+    d->K = K;
+    d->n = n;
+    d->S = K - 1;
+    d->N = 1 << (K - 1);
+    orc_taps(K, n, g, taps);
+    const uint32_t keep = (1u << K) - 1u;
+    for (int b = 0; b < 2; b++)
+        for (int s = 0; s < d->N; s++)
+            d->edge[b][s] = orc_segment((((uint32_t)s << 1) | (uint32_t)b) & keep, taps, n);
+    d->capacity = (uint32_t)maxSegments;
+    d->surv = (uint8_t *)malloc((size_t)maxSegments * (size_t)d->N);
+    if (!d->surv) {
+        free(d);
+        return NULL;
+    }
+    d->metric[0] = 0;
+    for (int i = 1; i < d->N; i++)
+        d->metric[i] = n * 128 * K;
+    return d;
+}
+
+void orc_soft_free(orc_soft_decoder_t *d)
+{
+    if (d) {
+        free(d->surv);
+        free(d);
+    }
+}
+
+/* soft: n int8 per segment, segment after segment */
+int orc_dec_step_soft(orc_soft_decoder_t *d, const int8_t *soft, int segmentsIn, uint8_t *uncoded, int last)
+{
+    const int N = d->N, H = N / 2, n = d->n;
+    int32_t next[ORC_MAX_STATES];
+    for (int i = 0; i < segmentsIn; i++) {
+        if (d->iteration >= d->capacity)
+            return -1;
+        int32_t cost[1 << ORC_MAX_N];
+        for (int c = 0; c < (1 << n); c++) {
+            cost[c] = 0;
+            for (int b = 0; b < n; b++) {
+                const int s = soft[(size_t)i * (size_t)n + (size_t)b];
+                const int hard = s < 0, mag = s < 0 ? -s : s;
+                if (hard != ((c >> b) & 1))
+                    cost[c] += mag;
+            }
+        }
+        uint8_t *row = d->surv + (size_t)d->iteration * (size_t)N;
+        for (int j = 0; j < H; j++) {
+            const int32_t a0 = d->metric[j] + cost[d->edge[0][j]];
+            const int32_t a1 = d->metric[j + H] + cost[d->edge[0][j + H]];
+            const int32_t b0 = d->metric[j] + cost[d->edge[1][j]];
+            const int32_t b1 = d->metric[j + H] + cost[d->edge[1][j + H]];
+            const uint8_t da = a0 > a1, db = b0 > b1; /* ties keep the lower predecessor (:129-130) */
+            next[2 * j] = da ? a1 : a0;
+            next[2 * j + 1] = db ? b1 : b0;
+            row[2 * j] = da;
+            row[2 * j + 1] = db;
+        }
+        memcpy(d->metric, next, (size_t)N * sizeof(int32_t));
+        d->iteration++;
+    }
+    if (!last)
+        return 0;
+    const uint32_t T = d->iteration, S = (uint32_t)d->S;
+    uint32_t state = 0;
+    memset(uncoded, 0, (size_t)((T - S - 1) / 8 + 1));
+    for (uint32_t i = 0; i < T; i++) {
+        const uint32_t t = T - 1 - i;
+        const uint32_t dec = d->surv[(size_t)t * (size_t)N + state];
+        if (i >= S && (state & 1u))
+            uncoded[t / 8] |= (uint8_t)(0x80u >> (t % 8));
+        state = (state >> 1) | (dec << (S - 1));
+    }
+    return (int)((T - S - 1) / 8 + 1);
+}
+
+int orc_decode_soft_batch(int K, int n, const uint64_t *g, const int8_t *soft, size_t softStride, int nFrames,
+                          int segsPerFrame, uint8_t *out, size_t outStride)
+{
+    for (int f = 0; f < nFrames; f++) {
+        orc_soft_decoder_t *d = orc_soft_new(K, n, g, segsPerFrame);
+        if (!d)
+            return -1;
+        orc_dec_step_soft(d, soft + (size_t)f * softStride, segsPerFrame, out + (size_t)f * outStride, 1);
+        orc_soft_free(d);
+    }
+    return 0;
+}
+
+/*
  * berTestK7/berTestK7.c:22-53,109-165 restated: glibc rand() stream, BSC with
  * `flip = frand() > p ? 0 : 1`, MSb of the segment drawn first.  counts =
  * {channel flips, coded bits, decoded bit errors, decoded bits}.  `pktsOut`, if

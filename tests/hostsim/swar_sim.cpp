@@ -3,6 +3,7 @@
 // rotating-label algebra can be checked against the oracle without a GPU.
 // It is never linked into the product library.
 #include "trellis_swar.cuh"
+#include "trellis_swar16.cuh"
 #include <vector>
 
 using Code = ced::DefaultK7;
@@ -161,4 +162,52 @@ extern "C" int swar_sim_decision(const uint32_t *surv, int t, int s)
     uint32_t word = surv[2 * t + (p >> 5)];
     uint32_t bit = 8 * (p & 3) + ((p >> 2) & 7);
     return (word >> bit) & 1;
+}
+
+// Soft-decision decode of one frame with the 16-bit-lane step functions of trellis_swar16.cuh (what
+// k7SoftForwardKernel runs per thread) and the generic traceback step for the Lanes16 survivor layout.
+template <int PH>
+static void softPhase(uint32_t (&R)[32], uint32_t W, uint32_t &t0, uint32_t &t1)
+{
+    uint32_t X[4], E[4];
+    ced::softBranchWords<Code, PH>(W, 0xFFFFFFFEu, X, E);
+    ced::acsStep16<Code, PH>(R, X, E, 0xFFFFFFFFu, t0, t1);
+}
+
+extern "C" int swar_sim_decode_soft(const int8_t *soft, int T, uint8_t *out, uint32_t *maxMetric)
+{
+    uint32_t R[32];
+    ced::initMetrics16(R);
+    std::vector<uint32_t> surv(2 * (size_t)T);
+    uint32_t mx = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t t0 = 0, t1 = 0;
+        const uint32_t W = ced::softWord(soft[2 * t], soft[2 * t + 1]);
+        switch (t % 6) {
+        case 0: softPhase<0>(R, W, t0, t1); break;
+        case 1: softPhase<1>(R, W, t0, t1); break;
+        case 2: softPhase<2>(R, W, t0, t1); break;
+        case 3: softPhase<3>(R, W, t0, t1); break;
+        case 4: softPhase<4>(R, W, t0, t1); break;
+        default: softPhase<5>(R, W, t0, t1); break;
+        }
+        surv[2 * t] = t0;
+        surv[2 * t + 1] = t1;
+        for (int r = 0; r < 32; r++) {
+            if ((R[r] & 0xFFFFu) > mx) mx = R[r] & 0xFFFFu;
+            if ((R[r] >> 16) > mx) mx = R[r] >> 16;
+        }
+        if ((t + 1) % ced::kSoftRenormPeriod == 0)
+            ced::renorm16(R);
+    }
+    if (maxMetric) *maxMetric = mx;
+    const int L = T - 6;
+    uint32_t b = 0;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        uint32_t bit = ced::tracebackStep<ced::Lanes16>(b, surv[2 * t], surv[2 * t + 1], t % 6);
+        if (t < L)
+            out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
+    }
+    return (L + 7) / 8;
 }

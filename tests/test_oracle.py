@@ -6,7 +6,9 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import bsc
+import os
+
+from conftest import ROOT, bsc
 
 K7, K3 = oracle.K7_G, oracle.K3_G
 
@@ -111,3 +113,59 @@ def test_against_live_reference(port, ref):
         s, reg = port.encode(7, K7, msg[lo:lo + 7], last=(lo + 7 >= 100), reg=reg)
         parts.append(s)
     assert np.array_equal(np.concatenate(parts), ref.encode(msg, chunk=7))
+
+
+# ------------------------------------------------------------------ soft decisions
+def _bpsk_soft(rng, segs, T, amp, sigma, lo=-127):
+    """int8 soft symbols [frames, 2T] of byte-per-segment symbols: amp * (+-1 + sigma * N(0,1)), rounded, clamped."""
+    bits = np.stack([segs[:, :T] & 1, (segs[:, :T] >> 1) & 1], axis=-1).reshape(segs.shape[0], 2 * T)
+    y = amp * ((1.0 - 2.0 * bits) + sigma * rng.standard_normal(bits.shape))
+    return np.clip(np.round(y), lo, 127).astype(np.int8)
+
+
+def test_soft_oracle_reduces_to_the_reference_for_constant_magnitudes(port, ref):
+    """The pin of orc_dec_step_soft: with every |s| equal, its costs are A * calcHammingDist
+    (src/viterbiDecoder.c:260-285), so its output must be the UNMODIFIED reference decoder's on the
+    sliced symbols -- pure-noise frames included, where nearly every comparison is a tie."""
+    rng = np.random.default_rng(21)
+    for bits in (8, 96, 2048):
+        msgs = rng.integers(0, 256, (24, bits // 8), dtype=np.uint8)
+        segs = port.encode_batch(7, K7, msgs)
+        T = bits + 6
+        for p in (0.0, 0.04, 0.5):
+            noisy = bsc(rng, segs, p)
+            want = ref.decode_batch(noisy, T)
+            assert np.array_equal(want, port.decode_batch(7, K7, noisy, T))
+            for A in (1, 7, 64, 127):
+                hard = np.stack([noisy & 1, (noisy >> 1) & 1], axis=-1).reshape(24, 2 * T).astype(np.int16)
+                soft = np.where(hard == 1, -A, A).astype(np.int8)
+                assert np.array_equal(port.decode_soft_batch(7, K7, soft, T), want), (bits, p, A)
+
+
+def test_soft_lane_arithmetic_matches_soft_oracle(port):
+    """trellis_swar16.cuh (what k7SoftForwardKernel runs per thread: correlation-form branch words, 16-bit
+    guard-bit compare, Lanes16 survivor layout and traceback) on the host against orc_dec_step_soft."""
+    import ctypes as C
+    import subprocess
+    subprocess.run(["make", "-C", ROOT, "hostsim"], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libswar_sim.so"))
+    rng = np.random.default_rng(5)
+    worst = 0
+    for bits in (8, 48, 96, 512, 4096):
+        T = bits + 6
+        segs = port.encode_batch(7, K7, rng.integers(0, 256, (5, bits // 8), dtype=np.uint8))
+        shape = (5, 2 * T)
+        cases = [_bpsk_soft(rng, segs, T, 32, 0.8), _bpsk_soft(rng, segs, T, 90, 1.5, lo=-128),
+                 rng.integers(-128, 128, shape).astype(np.int8),             # pure noise, full range
+                 rng.choice([-128, 127], shape).astype(np.int8),             # extremes only
+                 np.zeros(shape, dtype=np.int8),                             # all erasures: every compare ties
+                 rng.integers(-2, 3, shape).astype(np.int8)]                 # tiny magnitudes, many ties
+        for soft in cases:
+            want = port.decode_soft_batch(7, K7, soft, T)
+            for f in range(5):
+                out, mx = np.zeros(bits // 8, dtype=np.uint8), C.c_uint32(0)
+                row = np.ascontiguousarray(soft[f])
+                lib.swar_sim_decode_soft(row.ctypes.data_as(C.c_void_p), T, out.ctypes.data_as(C.c_void_p), C.byref(mx))
+                assert np.array_equal(out, want[f])
+                worst = max(worst, mx.value)
+    assert worst < 15872   # the bound the 16-bit guard-bit compare relies on (trellis_swar16.cuh)
