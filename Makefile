@@ -32,6 +32,7 @@ build/host_pack.o: $(CSRC)/host_pack.cpp
 	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -c -o $@ $<
 $(PKG)/libced_cuda.so: $(CUDA_OBJS)
 	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared -o $@ $(CUDA_OBJS) -ldl
+	python tools/sass_loop_stats.py   # instruction counts of the hot loops of THIS binary (bench.py reads them)
 
 host: $(PKG)/libconvencdec_k7.so $(PKG)/libconvencdec_k3.so
 $(PKG)/libconvencdec_k7.so: $(HOST_SRCS) $(CSRC)/host/params/default/convCodeParams.c $(PKG)/libced_cuda.so $(wildcard include/*.h)
@@ -41,7 +42,10 @@ $(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCode
 	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
 	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
 
-examples: examples/_bin/batch_roundtrip examples/_bin/speed_queued
+examples: examples/_bin/batch_roundtrip examples/_bin/speed_queued examples/_bin/multi_gpu_roundtrip
+examples/_bin/multi_gpu_roundtrip: examples/multi_gpu_roundtrip.c include/ced_abi.h $(PKG)/libced_cuda.so
+	mkdir -p examples/_bin
+	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude -o $@ $< -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 examples/_bin/speed_queued: examples/speed_queued.c $(wildcard include/*.h) $(PKG)/libconvencdec_k7.so
 	mkdir -p examples/_bin
 	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude/params/default -Iinclude -o $@ $< -L$(PKG) -lconvencdec_k7 -lced_cuda -pthread \

@@ -13,9 +13,9 @@ This Python package is only a ctypes view of those libraries for tests and
 bench.py (PyTorch supplies device memory, streams and torch.distributed).  There
 is no CPU fallback: importing :mod:`.abi` without the built library raises.
 """
-from .abi import (CedError, Context, K7_DEFAULT, K7_TEXTBOOK, Code, lib_path, load_abi,
-                  exported_abi_symbols)
+from .abi import (CedError, Context, MultiContext, K7_DEFAULT, K7_TEXTBOOK, Code, lib_path, load_abi,
+                  exported_abi_symbols, shard_range)
 from .refapi import RefApi
 
-__all__ = ["CedError", "Context", "Code", "K7_DEFAULT", "K7_TEXTBOOK", "RefApi", "lib_path", "load_abi",
+__all__ = ["CedError", "Context", "MultiContext", "shard_range", "Code", "K7_DEFAULT", "K7_TEXTBOOK", "RefApi", "lib_path", "load_abi",
            "exported_abi_symbols"]

@@ -91,6 +91,25 @@ def load_abi():
     lib.ced_decode_batch_soft.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_slice_soft_to_bytes.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_awgn_channel.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, C.c_double, C.c_double, u64, u64, vp, vp]
+    lib.ced_shard_range.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    lib.ced_shard_range.restype = None
+    lib.ced_multi_create.argtypes = [C.POINTER(i), i, C.POINTER(vp)]
+    lib.ced_multi_destroy.argtypes = [vp]
+    lib.ced_multi_destroy.restype = None
+    lib.ced_multi_device_count.argtypes = [vp]
+    lib.ced_multi_ctx.argtypes = [vp, i]
+    lib.ced_multi_ctx.restype = vp
+    lib.ced_decode_batch_host_multi.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
+    lib.ced_encode_batch_host_multi.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
+    lib.ced_ber_allreduce.argtypes = [vp, C.POINTER(vp), i]
+    lib.ced_nccl_version.restype = i
+    lib.ced_probe_copy_ceiling.argtypes = [vp, sz, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ced_multi_probe_copy_ceiling.argtypes = [vp, sz, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.ced_device_alloc.argtypes = [vp, sz, C.POINTER(vp)]
+    lib.ced_device_free.argtypes = [vp, vp]
+    lib.ced_device_free.restype = None
+    lib.ced_copy_to_device.argtypes = [vp, vp, vp, sz]
+    lib.ced_copy_to_host.argtypes = [vp, vp, vp, sz]
     lib.ced_encode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_encode_batch_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
@@ -156,6 +175,71 @@ class WindowDecoder:
         return out[:, :rc]
 
 
+def shard_range(n_frames, n_shards, shard):
+    """(first, count) of the contiguous frame range a shard owns (ced_shard_range; no GPU involved)."""
+    first, count = C.c_int(0), C.c_int(0)
+    load_abi().ced_shard_range(int(n_frames), int(n_shards), int(shard), C.byref(first), C.byref(count))
+    return first.value, count.value
+
+
+class MultiContext:
+    """ced_multi: one process, several GPUs -- host batches sharded by the C library itself."""
+
+    def __init__(self, devices=None):
+        self.lib = load_abi()
+        h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self.lib, self.lib.ced_multi_create(arr, len(devices), C.byref(h)), "ced_multi_create")
+        else:
+            _check(self.lib, self.lib.ced_multi_create(None, 0, C.byref(h)), "ced_multi_create")
+        self.h = h
+        self.n_devices = int(self.lib.ced_multi_device_count(h))
+
+    def ctx(self, i):
+        """Borrowed Context of the i-th device (do not close it)."""
+        c = Context.__new__(Context)
+        c.lib, c.h, c.device, c.borrowed = self.lib, C.c_void_p(self.lib.ced_multi_ctx(self.h, i)), None, True
+        c.device = int(self.lib.ced_ctx_device(c.h))
+        return c
+
+    def decode_batch_host(self, code, segs, frame_bits, out):
+        sp, ss, sshape = Context._host(segs)
+        op, os_, _ = Context._host(out)
+        _check(self.lib, self.lib.ced_decode_batch_host_multi(self.h, C.byref(code._c), sp, ss, sshape[0], frame_bits,
+                                                              op, os_), "ced_decode_batch_host_multi")
+        return out
+
+    def encode_batch_host(self, code, msgs, out):
+        mp, ms, mshape = Context._host(msgs)
+        op, os_, _ = Context._host(out)
+        _check(self.lib, self.lib.ced_encode_batch_host_multi(self.h, C.byref(code._c), mp, ms, mshape[0], mshape[1],
+                                                              op, os_), "ced_encode_batch_host_multi")
+        return out
+
+    def ber_allreduce(self, counters):
+        """counters: one CUDA int64/uint64 tensor per device (same length), summed in place over NCCL."""
+        ptrs = (C.c_void_p * len(counters))(*[c.data_ptr() for c in counters])
+        _check(self.lib, self.lib.ced_ber_allreduce(self.h, ptrs, int(counters[0].numel())), "ced_ber_allreduce")
+
+    def probe_copy_ceiling(self, bytes_per_device=256 << 20, reps=3):
+        up, down = C.c_double(0), C.c_double(0)
+        _check(self.lib, self.lib.ced_multi_probe_copy_ceiling(self.h, bytes_per_device, reps, C.byref(up), C.byref(down)),
+               "ced_multi_probe_copy_ceiling")
+        return up.value, down.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ced_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One per GPU (ced_ctx): owns the compute/copy streams and survivor scratch."""
 
@@ -166,9 +250,16 @@ class Context:
         self.h, self.device = h, int(device)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "borrowed", False):
             self.lib.ced_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
+
+    def probe_copy_ceiling(self, nbytes=256 << 20, reps=3):
+        """(H2D, D2H) bytes per second of raw page-locked copies to / from this device."""
+        up, down = C.c_double(0), C.c_double(0)
+        _check(self.lib, self.lib.ced_probe_copy_ceiling(self.h, nbytes, reps, C.byref(up), C.byref(down)),
+               "ced_probe_copy_ceiling")
+        return up.value, down.value
 
     def __del__(self):
         try:

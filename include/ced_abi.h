@@ -210,6 +210,45 @@ int ced_bsc_channel(ced_ctx *ctx, uint8_t *dSegs, size_t segStride, int nFrames,
 int ced_random_bytes(ced_ctx *ctx, uint8_t *dMsg, size_t msgStride, int nFrames, int frameBytes,
                      uint64_t seed, uint64_t firstFrameIndex, void *stream);
 
+/* ------------------------------------------------ one process, several GPUs
+ * Frames are independent packets (the reference resets its state per packet,
+ * src/viterbiDecoderButterflyk1.c:259), so a batch shards over the GPUs of a box with no traffic between
+ * them: device g of G takes the contiguous range ced_shard_range(nFrames, G, g) of the caller's HOST arrays
+ * and runs its own host pipeline (ced_decode_batch_host) on a worker thread that is pinned to the CPUs of the
+ * device's NUMA node, so its page-locked staging buffers are NUMA-local.  The loop these calls replace is
+ * `for pkt: VITERBI_DECODER_HARD(..., last=true)` of speedDecode/speedDecode.c:78-79 / the convEnc loop of
+ * speedEncode/speedEncode.c:65-67, for a batch that is larger than one GPU should take.
+ *
+ * ced_ber_allreduce is the only collective: the uint64 counters that ced_ber_count / ced_bsc_channel /
+ * ced_awgn_channel accumulated on every device (dCounters[g] = device pointer on device g, `count` words each)
+ * are summed in place over NCCL (communicator from ncclCommInitAll on first use, one ncclAllReduce per device
+ * inside a group, NVLink / NVSwitch).  NCCL is opened with dlopen at that point; without it the call returns
+ * CED_ERR_UNSUPPORTED -- there is no host-side substitute.
+ */
+typedef struct ced_multi ced_multi;
+void ced_shard_range(int nFrames, int nShards, int shard, int *first, int *count);
+int ced_multi_create(const int *devices, int nDevices, ced_multi **out); /* nDevices = 0: every visible GPU */
+void ced_multi_destroy(ced_multi *m);
+int ced_multi_device_count(const ced_multi *m);
+ced_ctx *ced_multi_ctx(ced_multi *m, int i);                             /* context of the i-th device */
+int ced_decode_batch_host_multi(ced_multi *m, const ced_code_t *code, const uint8_t *hSegs, size_t segStride,
+                                int nFrames, int frameBits, uint8_t *hOut, size_t outStride);
+int ced_encode_batch_host_multi(ced_multi *m, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride,
+                                int nFrames, int frameBytes, uint8_t *hSegs, size_t segStride);
+int ced_ber_allreduce(ced_multi *m, uint64_t *const *dCounters, int count);
+int ced_nccl_version(void); /* 0 if NCCL could not be opened */
+/* Device memory for C callers that keep batches resident (BER mode): zero-filled allocation on the context's
+ * device, synchronous copies on its stream. */
+int ced_device_alloc(ced_ctx *ctx, size_t bytes, void **out);
+void ced_device_free(ced_ctx *ctx, void *p);
+int ced_copy_to_device(ced_ctx *ctx, void *dDst, const void *hSrc, size_t bytes);
+int ced_copy_to_host(ced_ctx *ctx, void *hDst, const void *dSrc, size_t bytes);
+/* Raw copy rate between page-locked host memory and the device(s), no kernels: the ceiling for every
+ * host-buffer figure (best of `reps`, bytes per second; the multi form runs all devices at once and sums). */
+int ced_probe_copy_ceiling(ced_ctx *ctx, size_t bytes, int reps, double *h2dBytesPerSecond, double *d2hBytesPerSecond);
+int ced_multi_probe_copy_ceiling(ced_multi *m, size_t bytesPerDevice, int reps, double *h2dBytesPerSecond,
+                                 double *d2hBytesPerSecond);
+
 /* ------------------------------------------------ per-frame streaming path
  * One frame, fed in arbitrary chunks exactly like the reference API
  * (SURVEY A.6).  All decoder state lives in caller memory (the host struct

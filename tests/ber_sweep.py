@@ -35,6 +35,47 @@ def bsc_probability(ebn0_db, rate=0.5):
     return q_function(math.sqrt(2.0 * rate * 10.0 ** (ebn0_db / 10.0)))
 
 
+def run_point_soft(ctx, code, ebn0_db, frames, seed, first_frame, subset, checker, soft_checker):
+    """One Eb/N0 point on the AWGN channel with int8 soft output: the SAME channel realisation is decoded by the
+    soft-decision decoder (ced_decode_batch_soft) and, after slicing to signs, by the hard-decision decoder.
+    counters = {sign errors, coded bits, hard decoded errors, bits, soft decoded errors, bits}."""
+    import numpy as np
+    import torch
+    T = PKT_BITS + code.S
+    stride = (T + 15) // 16 * 16
+    msgs = torch.empty((frames, PKT_BITS // 8), dtype=torch.uint8, device="cuda")
+    segs = torch.zeros((frames, stride), dtype=torch.uint8, device="cuda")
+    counters = torch.zeros(6, dtype=torch.int64, device="cuda")
+    ctx.random_bytes(msgs, seed=seed, first_frame=first_frame)
+    ctx.encode_batch(code, msgs, out=segs)
+    soft = ctx.awgn_channel(segs, T, ebn0_db, seed=seed + 1, first_frame=first_frame, counters=counters[:2])
+    dec_soft = ctx.decode_batch_soft(code, soft, PKT_BITS)
+    hard = ctx.slice_soft_to_bytes(soft, T, seg_stride=stride)
+    dec = ctx.decode_batch(code, hard, PKT_BITS)
+    ctx.ber_count(dec, msgs, counters[2:4])
+    ctx.ber_count(dec_soft, msgs, counters[4:6])
+    ctx.sync()
+    check = None
+    if subset and checker is not None:
+        m, ms = min(subset, frames), min(max(subset // 10, 1), frames)
+        want = checker(hard[:m, :T].cpu().numpy(), T)
+        want_soft = soft_checker(soft[:ms, :2 * T].cpu().numpy(), T)
+        check = {"frames": m, "bytes_identical": bool(np.array_equal(want, dec[:m].cpu().numpy())),
+                 "reference_decoded_errors": int(np.bitwise_count(want ^ msgs[:m].cpu().numpy()).sum()),
+                 "gpu_decoded_errors": int(np.bitwise_count((dec[:m] ^ msgs[:m]).cpu().numpy()).sum()),
+                 "soft_frames": ms, "soft_bytes_identical": bool(np.array_equal(want_soft, dec_soft[:ms].cpu().numpy()))}
+    return counters, check
+
+
+def crossing_db(rows, key, target):
+    """Eb/N0 at which the BER curve rows[*][key] crosses `target` (log-linear interpolation), or None."""
+    pts = [(r["ebn0_db"], r[key]) for r in rows if r[key] > 0]
+    for (d0, b0), (d1, b1) in zip(pts, pts[1:]):
+        if b0 >= target >= b1:
+            return d0 + (d1 - d0) * (math.log(b0) - math.log(target)) / (math.log(b0) - math.log(b1))
+    return None
+
+
 def run_point(ctx, code, p, frames, seed, first_frame, subset, checker):
     import numpy as np
     import torch
@@ -67,6 +108,8 @@ def main(argv=None):
     ap.add_argument("--subset", type=int, default=10000, help="frames per point re-decoded by the reference (rank 0)")
     ap.add_argument("--points", default="0,1,2,3,4,5,6,7,8")
     ap.add_argument("--out", default="")
+    ap.add_argument("--soft", action="store_true",
+                    help="AWGN channel with int8 soft output: soft- and hard-decision decoding of the same noise")
     args = ap.parse_args(argv)
 
     import torch
@@ -81,9 +124,10 @@ def main(argv=None):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    checker, kind = None, None
+    checker, kind, soft_checker = None, None, None
     if rank == 0 and args.subset:
         import oracle
+        soft_checker = lambda soft, T: oracle.port().decode_soft_batch(7, oracle.K7_G, soft, T)
         R = oracle.ref()
         if R is not None:
             checker, kind = (lambda noisy, T: R.decode_batch(noisy, T)), "reference (oracle/_ref)"
@@ -97,6 +141,25 @@ def main(argv=None):
     rows = []
     for i, db in enumerate(float(x) for x in args.points.split(",")):
         p = bsc_probability(db)
+        if args.soft:
+            counters, check = run_point_soft(ctx, code, db, args.frames_per_gpu, seed=1000 + 10 * i,
+                                             first_frame=rank * args.frames_per_gpu,
+                                             subset=args.subset if rank == 0 else 0, checker=checker,
+                                             soft_checker=soft_checker)
+            allreduce_counts(counters)
+            c = [int(x) for x in counters.cpu().tolist()]
+            rows.append({"ebn0_db": db, "bsc_p": p, "sign_errors": c[0], "coded_bits": c[1], "channel_ber": c[0] / c[1],
+                         "hard_decoded_errors": c[2], "soft_decoded_errors": c[4], "decoded_bits": c[3],
+                         "hard_ber": c[2] / c[3], "soft_ber": c[4] / c[5],
+                         "uncoded_bpsk_ber": ber_theory.bpsk_ber(db), "subset_check": check})
+            if rank == 0:
+                print("Eb/N0 %4.1f dB  channel BER %.5e (Q: %.5e)  hard BER %.4e  soft BER %.4e%s"
+                      % (db, c[0] / c[1], p, c[2] / c[3], c[4] / c[5],
+                         "" if not check else "  subset: hard %d frames identical to the reference: %s, soft %d frames "
+                         "identical to the soft oracle: %s" % (check["frames"], check["bytes_identical"],
+                                                              check["soft_frames"], check["soft_bytes_identical"])),
+                      file=sys.stderr)
+            continue
         counters, check = run_point(ctx, code, p, args.frames_per_gpu, seed=1000 + 10 * i,
                                     first_frame=rank * args.frames_per_gpu, subset=args.subset if rank == 0 else 0,
                                     checker=checker)
@@ -112,6 +175,25 @@ def main(argv=None):
                      "" if not check else "  subset %d frames: ref %d == gpu %d : %s"
                      % (check["frames"], check["reference_decoded_errors"], check["gpu_decoded_errors"],
                         check["bytes_identical"])), file=sys.stderr)
+    if args.soft:
+        hard_x, soft_x = crossing_db(rows, "hard_ber", 1e-4), crossing_db(rows, "soft_ber", 1e-4)
+        result = {"config": "K=7 r=1/2 g=(0113,0171), %d-bit packets, BPSK+AWGN quantised to int8 (amplitude 32): "
+                            "soft-decision vs hard-decision decoding of the same channel output" % PKT_BITS,
+                  "n_gpus": world, "frames_per_gpu": args.frames_per_gpu, "checker": kind,
+                  "ebn0_db_at_ber_1e-4": {"hard": hard_x, "soft": soft_x,
+                                          "soft_decision_gain_db": (hard_x - soft_x) if hard_x and soft_x else None},
+                  "points": rows}
+        if rank == 0:
+            text = json.dumps(result, indent=1)
+            if args.out:
+                with open(os.path.join(ROOT, args.out) if not os.path.isabs(args.out) else args.out, "w") as f:
+                    f.write(text + "\n")
+            print(json.dumps(result))
+        ctx.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return result
     result = {"config": "K=7 r=1/2 g=(0113,0171), %d-bit packets, hard-decision BSC from BPSK+AWGN" % PKT_BITS,
               "distance_spectrum": {"dfree": spectrum.dfree, "weight": spectrum.weight, "event": spectrum.event},
               "n_gpus": world, "frames_per_gpu": args.frames_per_gpu, "checker": kind, "points": rows}
