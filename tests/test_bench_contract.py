@@ -50,5 +50,14 @@ def test_our_arm_line():
     assert d["gpu_launches"] >= 2 * 4 and d["clocks"]["sm_mhz"]
     assert d["check"]["decoded_bits"] == 8192 * 4096 and 1e-4 < d["check"]["ber"] < 2e-3
     assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert e["h2d_ceiling_gbs"] > 1.0 and e["frac_of_ceiling"] > 0.0
+    assert rf["issue"]["instr_per_frame_step"] == rf["issue"]["loop_instructions"] / 6.0   # read from the built library
+    # the other BASELINE configs ride on the same line
+    enc, ber, soft = d["encode"], d["ber"], d["soft"]
+    assert enc["config"]["frames"] == 1 << 20 and enc["round_trip_ok"] is True and enc["roofline"]["bound"] == "hbm"
+    assert 0.1 < enc["roofline"]["frac"] < 1.2 and enc["value"] > 100.0
+    assert ber["point"]["decoded_bits"] == 8192 * 4096 and 1e-4 < ber["point"]["decoded_ber"] < 2e-3
+    assert abs(ber["point"]["channel_ber"] - 0.0377) < 0.001
+    assert soft["roofline"]["kernel"] == "k7SoftForwardKernel" and soft["value"] > 1.0 and soft["check"]["ber"] < 2e-3
     pp = d["per_packet"]                       # one 2048-bit packet per call: the two frame-parallel kernels each time
     assert pp["round_trip_ok"] is True and pp["gpu_launches"] == 2 * (pp["calls"] + 64) and pp["value"] > 0
