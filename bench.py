@@ -516,6 +516,8 @@ def main():
 
     if strong and args.mode == "decode":
         # ---- the weak figure beside the strong one: 2^16 frames per GPU, 3 calls in flight (BASELINE configs[1] per GPU) ----
+        weak_out = [torch.empty((sub, bits // 8), dtype=torch.uint8, device="cuda") for _ in lanes]
+
         def weak_pass(n_steps):
             timing = torch.cuda.Stream()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -524,7 +526,7 @@ def main():
                 s_.wait_event(e0)
             for i in range(n_steps):
                 c_, s_ = lanes[i % len(lanes)]
-                c_.decode_batch(code, segs[:sub], bits, out=out[(i % len(lanes)) * sub:(i % len(lanes) + 1) * sub], stream=s_)
+                c_.decode_batch(code, segs[:sub], bits, out=weak_out[i % len(lanes)], stream=s_)
             for _, s_ in lanes:
                 done = torch.cuda.Event()
                 done.record(s_)
