@@ -532,22 +532,24 @@ size_t ced_window_carry_bytes(int nStreams, int depth)
     return (size_t)((nStreams + 31) / 32) * windowCarryGroupBytes(depth);
 }
 
-int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nStreams,
-                            int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
-                            size_t outStride, void *stream)
+static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
+                            int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
+                            uint8_t *dOut, size_t outStride, void *stream)
 {
-    if (!c || nStreams < 0 || nSegments < 0 || depth < 24 || depth % 24 || depth > 8184 || streamPos % 96 ||
+    const int sliceUnit = packed ? ced::PackedSymbols::kChunk : ced::ByteSymbols::kChunk; /* 192 / 96 segments */
+    if (!c || nStreams < 0 || nSegments < 0 || depth < 24 || depth % 24 || depth > 8184 || streamPos % sliceUnit ||
         (nStreams > 0 && (!dSegs || !dOut || !dCarry)) || (reinterpret_cast<uintptr_t>(dCarry) & 15u)) {
         setError("ced_decode_window_batch: bad argument (depth and streamPos must be multiples of 24 / 96)");
         return CED_ERR_ARG;
     }
     const CodeId id = classify(code);
-    if (id == CodeId::Unsupported) {
-        setError("ced_decode_window_batch: K=7 codes with 2 or 3 generators that tap the newest and the oldest bit only");
+    if (id == CodeId::Unsupported || (packed && id == CodeId::K7_RuntimeN3)) {
+        setError("ced_decode_window_batch: K=7 codes with 2 or 3 generators that tap the newest and the oldest bit only "
+                 "(2 generators for the packed format)");
         return CED_ERR_UNSUPPORTED;
     }
     if (last ? (nSegments < ced::kTailSteps || (streamPos + (uint64_t)nSegments - ced::kTailSteps) % 8 != 0)
-             : (nSegments == 0 || nSegments % 96 != 0)) {
+             : (nSegments == 0 || nSegments % sliceUnit != 0)) {
         setError("ced_decode_window_batch: a slice must be a positive multiple of 96 segments; the last one must "
                  "end the stream on a byte boundary plus K-1 tail segments");
         return CED_ERR_ARG;
@@ -561,7 +563,7 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     const int Tl = depth + nSegments;
     const int emitHi = last ? Tl - ced::kTailSteps : nSegments;
     const int bytesOut = emitHi > emitLo ? (emitHi - emitLo) / 8 : 0;
-    if (segStride < (size_t)nSegments || outStride < (size_t)bytesOut) {
+    if (segStride < (packed ? (size_t)(nSegments + 3) / 4 : (size_t)nSegments) || outStride < (size_t)bytesOut) {
         setError("ced_decode_window_batch: stride shorter than a slice");
         return CED_ERR_ARG;
     }
@@ -625,23 +627,29 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
         win.pairOffset = depth / 2;
         const uint8_t *in = dSegs + f0 * segStride;
         const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
-#define CED_LAUNCH_WIN(CODE)                                                                                       \
+#define CED_LAUNCH_WIN(CODE, FMT)                                                                                  \
     do {                                                                                                           \
         if (aligned16)                                                                                             \
-            ced::k7ForwardKernel<CODE, ced::ByteSymbols, true, true><<<blocks, ced::kFwdThreads, 0, s>>>(          \
+            ced::k7ForwardKernel<CODE, ced::FMT, true, true><<<blocks, ced::kFwdThreads, 0, s>>>(                  \
                 in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
         else                                                                                                       \
-            ced::k7ForwardKernel<CODE, ced::ByteSymbols, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(         \
+            ced::k7ForwardKernel<CODE, ced::FMT, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(                 \
                 in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
     } while (0)
         if (id == CodeId::K7_RuntimeN3)
-            CED_LAUNCH_WIN(ced::RuntimeK7<3>);
+            CED_LAUNCH_WIN(ced::RuntimeK7<3>, ByteSymbols);
+        else if (id == CodeId::K7_Runtime && !packed)
+            CED_LAUNCH_WIN(ced::RuntimeK7<2>, ByteSymbols);
         else if (id == CodeId::K7_Runtime)
-            CED_LAUNCH_WIN(ced::RuntimeK7<2>);
+            CED_LAUNCH_WIN(ced::RuntimeK7<2>, PackedSymbols);
+        else if (id == CodeId::K7_0113_0171 && !packed)
+            CED_LAUNCH_WIN(Code0113, ByteSymbols);
         else if (id == CodeId::K7_0113_0171)
-            CED_LAUNCH_WIN(Code0113);
+            CED_LAUNCH_WIN(Code0113, PackedSymbols);
+        else if (!packed)
+            CED_LAUNCH_WIN(Code0133, ByteSymbols);
         else
-            CED_LAUNCH_WIN(Code0133);
+            CED_LAUNCH_WIN(Code0133, PackedSymbols);
 #undef CED_LAUNCH_WIN
         c->launches += 1;
         if (bytesOut > 0) {
@@ -659,6 +667,22 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     wk.lastStream = s;
     CED_CUDA(cudaGetLastError());
     return bytesOut;
+}
+
+int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nStreams,
+                            int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
+                            size_t outStride, void *stream)
+{
+    return decodeWindowImpl(c, code, false, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut,
+                            outStride, stream);
+}
+
+int ced_decode_window_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
+                                   int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
+                                   uint8_t *dOut, size_t outStride, void *stream)
+{
+    return decodeWindowImpl(c, code, true, dPacked, packedStride, nStreams, nSegments, streamPos, depth, last, dCarry,
+                            dOut, outStride, stream);
 }
 
 int ced_pack_symbols(ced_ctx *c, const uint8_t *dSegs, size_t segStride, int nFrames, int segsPerFrame,

@@ -186,11 +186,23 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits);
  *              the caller and passed unchanged from call to call (metrics + the last `depth` decisions)
  * nSegments and streamPos must be multiples of 96 except nSegments of the last call.
  * Returns the number of decoded BYTES written per stream by this call (>= 0), or a negative CED_ERR_*.
+ *
+ * ced_decode_window_batch_packed takes the packed wire format (4 segments per byte); its slices and streamPos are
+ * multiples of 192 segments (48 bytes), the last slice excepted.
+ *
+ * Pinning: the reference's own windowed decoder does not run at HEAD, so the semantics are those of
+ * oracle/ced_oracle.c:orc_decode_window (bit-exact tests).  That definition, run with one-step slices and depth 35,
+ * IS vitdec(..., tblen = 35, 'term', 'hard') and reproduces the MATLAB expectations the reference keeps in
+ * berTestK7/berTestK7.c:98 within its own +-10 % rule (tests/test_oracle.py); with depth >= the stream length it is the
+ * reference's full traceback.
  */
 size_t ced_window_carry_bytes(int nStreams, int depth);
 int ced_decode_window_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
                             int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                             uint8_t *dOut, size_t outStride, void *stream);
+int ced_decode_window_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
+                                   int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
+                                   uint8_t *dOut, size_t outStride, void *stream);
 
 /* dCounters[0] += popcount(dA ^ dB) over nFrames x bytesPerFrame; dCounters[1] +=
  * bits compared.  Device-side uint64 counters, so a BER sweep can all-reduce

@@ -77,6 +77,9 @@ class Port:
                                          C.c_double, C.POINTER(C.c_double)]
         lib.orc_hamming.restype = C.c_uint8
         lib.orc_hamming.argtypes = [C.c_uint8, C.c_uint8, C.c_int]
+        lib.orc_window_ber.restype = C.c_int
+        lib.orc_window_ber.argtypes = [C.c_int, C.c_int, _u64p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int,
+                                       C.c_uint64, C.c_int, _i64p]
         lib.orc_decode_soft_batch.restype = C.c_int
         lib.orc_decode_soft_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                               _u8p, C.c_size_t]
@@ -115,6 +118,13 @@ class Port:
                                        nbytes)
         assert rc == 0
         return out
+
+    def window_ber(self, K, g, pkts, pkt_bytes, p, call_segs, depth, seed=1, threads=None):
+        """BSC Monte-Carlo of orc_decode_window: {channel flips, coded bits, decoded errors, decoded bits}."""
+        counts = np.zeros(4, dtype=np.int64)
+        self.lib.orc_window_ber(K, len(g), self._g(g), pkts, pkt_bytes, float(p), call_segs, depth, seed,
+                                threads or os.cpu_count() or 1, _p(counts, _i64p))
+        return counts
 
     def decode_soft_batch(self, K, g, soft, T):
         """soft: int8 [frames, >= n*T], n values per segment (generator 0 first); semantics in

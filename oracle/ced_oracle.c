@@ -20,9 +20,11 @@
  * code at compile time (src/defaultParams/convCodeParams.h:8-17); here K, n and
  * the generators are run-time fields so one object serves K=3 and K=7.
  */
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define ORC_MAX_STATES 256
 #define ORC_MAX_N 8
@@ -518,13 +520,94 @@ int orc_bertest(int K, int n, const uint64_t *g, int pkts, int pktBytes, double 
 }
 
 /*
+ * Statistical anchor of orc_decode_window to numbers the reference holds.  berTestK7/berTestK7.c:98 keeps MATLAB's
+ * expectations for vitdec(..., tblen = 5*K = 35, 'term', 'hard') (scripts/matlab/viterbiBEREstimate.m:17,99;
+ * generators 133/171): decoded BER 5.295410e-03 / 5.421997e-04 / 3.385010e-05 at channel BER 5.585640e-02 /
+ * 3.716174e-02 / 2.262231e-02.  orc_decode_window with callSegs = 1 IS that decoder: after every step it starts
+ * in the best state, walks back `depth` steps and emits the one bit that became final, and the terminated end is
+ * flushed from state 0.  This loop measures its BER on a BSC (berTestK7.c:29-43 channel, own xorshift stream per
+ * packet so threads are independent) so a test can apply the reference's own +-10 % rule (berTestK7.c:167-172).
+ * counts = {channel flips, coded bits, decoded bit errors, decoded bits}.
+ */
+typedef struct {
+    int K, n, pktBytes, callSegs, depth, first, count;
+    const uint64_t *g;
+    double p;
+    uint64_t seed;
+    int64_t counts[4];
+} orc_wber_arg_t;
+
+static uint64_t orc_xorshift(uint64_t *s)
+{
+    uint64_t x = *s;
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    return *s = x;
+}
+
+static void *orc_wber_thread(void *vp)
+{
+    orc_wber_arg_t *a = (orc_wber_arg_t *)vp;
+    const int T = 8 * a->pktBytes + a->K - 1;
+    uint8_t *msg = (uint8_t *)malloc((size_t)a->pktBytes), *dec = (uint8_t *)malloc((size_t)a->pktBytes + 1);
+    uint8_t *segs = (uint8_t *)malloc((size_t)T);
+    const uint64_t thr = (uint64_t)(a->p * 18446744073709551616.0);
+    for (int it = a->first; it < a->first + a->count; it++) {
+        uint64_t s = (a->seed + 1) * 0x9E3779B97F4A7C15ull + (uint64_t)it * 0xD1B54A32D192ED03ull;
+        for (int w = 0; w < 4; w++)
+            orc_xorshift(&s);
+        for (int j = 0; j < a->pktBytes; j++)
+            msg[j] = (uint8_t)(orc_xorshift(&s) >> 32);
+        uint32_t reg = 0;
+        orc_encode(a->K, a->n, a->g, &reg, msg, a->pktBytes, segs, 1);
+        for (int i = 0; i < T; i++)
+            for (int b = 0; b < a->n; b++)
+                if (orc_xorshift(&s) < thr) {
+                    segs[i] ^= (uint8_t)(1u << b);
+                    a->counts[0]++;
+                }
+        a->counts[1] += (int64_t)T * a->n;
+        orc_decode_window(a->K, a->n, a->g, segs, T, a->callSegs, a->depth, dec);
+        for (int j = 0; j < a->pktBytes; j++)
+            a->counts[2] += __builtin_popcount((unsigned)(msg[j] ^ dec[j]));
+        a->counts[3] += 8 * (int64_t)a->pktBytes;
+    }
+    free(msg);
+    free(dec);
+    free(segs);
+    return NULL;
+}
+
+int orc_window_ber(int K, int n, const uint64_t *g, int pkts, int pktBytes, double p, int callSegs, int depth,
+                   uint64_t seed, int nThreads, int64_t *counts)
+{
+    if (nThreads < 1)
+        nThreads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nThreads);
+    orc_wber_arg_t *args = (orc_wber_arg_t *)calloc((size_t)nThreads, sizeof(orc_wber_arg_t));
+    for (int i = 0; i < nThreads; i++) {
+        const int lo = (int)((int64_t)pkts * i / nThreads), hi = (int)((int64_t)pkts * (i + 1) / nThreads);
+        args[i] = (orc_wber_arg_t){K, n, pktBytes, callSegs, depth, lo, hi - lo, g, p, seed, {0, 0, 0, 0}};
+        pthread_create(&th[i], NULL, orc_wber_thread, &args[i]);
+    }
+    memset(counts, 0, 4 * sizeof(int64_t));
+    for (int i = 0; i < nThreads; i++) {
+        pthread_join(th[i], NULL);
+        for (int c = 0; c < 4; c++)
+            counts[c] += args[i].counts[c];
+    }
+    free(th);
+    free(args);
+    return 0;
+}
+
+/*
  * CPU-baseline loop for bench.py ("port" kind): speedDecode.c:72-110 semantics
  * (frames pre-encoded, decode only, one-shot last=true calls, CLOCK_MONOTONIC),
  * one thread per requested core, each with a private decoder.  Returns decoded
  * information bits summed over threads; *seconds receives the wall time.
  */
-#include <pthread.h>
-#include <time.h>
 
 typedef struct {
     int K, n, segsPerFrame, nFrames, first;

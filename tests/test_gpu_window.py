@@ -1,7 +1,10 @@
 """Continuous streams with windowed traceback through the C ABI, against the oracle's definition
-(oracle/ced_oracle.c orc_decode_window).  PARITY UNPINNED against the reference -- its windowed decoder does not
-run at HEAD -- so two anchors tie it back to the pinned path: the forward recursion is shared with
-ced_decode_batch, and with a depth longer than the stream the output must equal the reference's full traceback."""
+(oracle/ced_oracle.c orc_decode_window), bit-exact.  The reference's own windowed decoder does not run at HEAD;
+the definition is tied to the reference three ways: the forward recursion is shared with ced_decode_batch, a depth
+longer than the stream must equal the reference's full traceback, and -- statistically -- the definition with
+one-step slices and depth 35 reproduces the MATLAB vitdec(tblen = 35) expectations held in berTestK7.c:98
+(tests/test_oracle.py::test_window_definition_reproduces_matlab_tblen_expectations), while the GPU decoder at its
+own slice shapes reproduces the full-traceback expectations of berTestK7.c:96-97 (last test of this file)."""
 import numpy as np
 import pytest
 
@@ -152,3 +155,64 @@ def test_outputs_stay_inside_their_rows(ctx, port):
         got.append(piece.clone())
     assert bool((cflat[:32] == 0xA5).all() and (cflat[-32:] == 0xA5).all())
     assert torch.equal(torch.cat(got, dim=1), d_msgs)
+
+
+def run_window_packed(ctx, code, noisy, call_segs, depth):
+    """the same streams in the packed wire format (4 segments per byte), slices of call_segs (a multiple of 192)"""
+    import torch
+    n_streams, total = noisy.shape
+    d = ctx.pack_symbols(torch.from_numpy(noisy).cuda(), total, packed_stride=((total + 3) // 4 + 15) // 16 * 16)
+    dec = ctx.window_decoder(code, n_streams, depth, packed=True)
+    pieces, pos = [], 0
+    while pos < total:
+        n = total - pos if total - pos <= call_segs else call_segs
+        pieces.append(dec.push(d[:, pos // 4:], last=(pos + n == total), n_segments=n).clone())
+        pos += n
+    ctx.sync()
+    return torch.cat(pieces, dim=1).cpu().numpy()
+
+
+@pytest.mark.parametrize("n_streams,total,call,depth,p", [
+    (100, 4902, 960, 48, 0.04), (33, 192 * 15 + 6, 192, 384, 0.06), (5, 192 * 6 + 38, 576, 48, 0.10),
+    (1, 192 + 6, 192, 24, 0.02), (40, 1926, 192 * 20, 48, 0.05),
+])
+def test_packed_window_decode_matches_oracle_definition(ctx, port, n_streams, total, call, depth, p):
+    rng = np.random.default_rng(total * 3 + depth)
+    msgs, noisy = make_streams(port, rng, n_streams, total, p)
+    got = run_window_packed(ctx, ced.K7_DEFAULT, noisy, call, depth)
+    for i in range(n_streams):
+        assert np.array_equal(got[i], port.decode_window(7, K7, noisy[i], call, depth)), i
+    with pytest.raises(ced.CedError):      # packed slices are multiples of 192 segments
+        run_window_packed(ctx, ced.K7_DEFAULT, noisy, 96, depth)
+
+
+def test_window_ber_meets_the_reference_held_expectations(ctx, port):
+    """berTestK7's three BSC points (berTestK7.c:95-100) through ced_decode_window_batch with the generators the MATLAB
+    expectations were made with (133/171, scripts/matlab/viterbiBEREstimate.m:11): slices of 96 segments at depth 48
+    decide every bit with at least 48 >= 5K steps of traceback, so the BER must meet the full-traceback expectations
+    of berTestK7.c:96-97 under the reference's own +-10 % rule (:167-172).  The same symbols in the packed format give
+    the same bytes; a sample of packets equals the oracle's definition bit for bit."""
+    import torch
+    code, g = ced.K7_TEXTBOOK, (0o133, 0o171)
+    bits, T = 2048, 2054
+    for p, want, pkts in ((5.585640e-02, 4.765898e-03, 1 << 13), (3.716174e-02, 5.184082e-04, 1 << 15),
+                          (2.262231e-02, 3.499023e-05, 1 << 17)):
+        msgs = torch.empty((pkts, bits // 8), dtype=torch.uint8, device="cuda")
+        ctx.random_bytes(msgs, seed=int(p * 1e6))
+        segs = torch.zeros((pkts, 2064), dtype=torch.uint8, device="cuda")
+        ctx.encode_batch(code, msgs, out=segs)
+        ctx.bsc_channel(segs, T, 2, p, seed=17)
+        dec = ctx.window_decoder(code, pkts, 48)
+        pieces = [dec.push(segs[:, a:min(a + 96, T)], last=a + 96 >= T).clone() for a in range(0, T, 96)]
+        out = torch.cat(pieces, dim=1).contiguous()
+        cnt = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ctx.ber_count(out, msgs, cnt)
+        ctx.sync()
+        ber = int(cnt[0]) / int(cnt[1])
+        assert int(cnt[1]) == pkts * bits and abs(ber - want) / want < 0.10, (p, ber, want)
+        noisy = segs[:64, :T].cpu().numpy()
+        for i in range(64):
+            assert np.array_equal(out[i].cpu().numpy(), port.decode_window(7, g, noisy[i], 96, 48))
+        if pkts == 1 << 13:
+            assert np.array_equal(run_window_packed(ctx, code, segs[:512, :T].cpu().numpy(), 192, 48),
+                                  np.stack([port.decode_window(7, g, r, 192, 48) for r in segs[:512, :T].cpu().numpy()]))

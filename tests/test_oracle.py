@@ -169,3 +169,26 @@ def test_soft_lane_arithmetic_matches_soft_oracle(port):
                 assert np.array_equal(out, want[f])
                 worst = max(worst, mx.value)
     assert worst < 15872   # the bound the 16-bit guard-bit compare relies on (trellis_swar16.cuh)
+
+
+# ------------------------------------------------------------------ windowed traceback
+def test_window_definition_reproduces_matlab_tblen_expectations(port):
+    """The statistical pin of orc_decode_window.  The reference's own windowed decoder aborts at HEAD, but
+    berTestK7.c:98 holds MATLAB's vitdec(..., tblen = 5K = 35, 'term', 'hard') expectations (generators 133/171,
+    scripts/matlab/viterbiBEREstimate.m:11,17,99).  orc_decode_window with one-step slices and depth 35 is that
+    decoder; its BER on berTestK7's BSC points must meet them under the reference's own +-10 % rule (:167-172).
+    The same definition with the depth beyond the packet length is the full traceback and meets the full-traceback
+    expectations of :96-97 instead -- the two sets differ by 4-11 %, so the test tells the two decoders apart."""
+    g = (0o133, 0o171)
+    points = ((5.585640e-02, 5.295410e-03, 4.765898e-03, 4000), (3.716174e-02, 5.421997e-04, 5.184082e-04, 20000),
+              (2.262231e-02, 3.385010e-05, 3.499023e-05, 100000))
+    excess = []
+    for p, want_tblen, want_full, pkts in points:
+        c = port.window_ber(7, g, pkts, 256, p, 1, 35, seed=1)
+        assert abs(c[0] / c[1] - p) < 0.01 * p
+        ber = c[2] / c[3]
+        assert abs(ber - want_tblen) / want_tblen < 0.10, (p, ber, want_tblen)
+        full = port.window_ber(7, g, pkts // 2, 256, p, 4096, 4096, seed=1)
+        assert abs(full[2] / full[3] - want_full) / want_full < 0.10, (p, full[2] / full[3], want_full)
+        excess.append(ber / (full[2] / full[3]))
+    assert excess[0] > 1.03 and excess[1] > 1.0     # truncating the traceback at 35 steps costs errors, as in MATLAB's numbers
