@@ -80,6 +80,7 @@ def load_abi():
     lib.ced_launch_count.restype = u64
     lib.ced_ctx_set_profiling.argtypes = [vp, i]
     lib.ced_ctx_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ced_ctx_last_fallback_frames.argtypes = [vp, C.POINTER(i)]
     lib.ced_probe_int_peak.argtypes = [vp, i, C.POINTER(C.c_double)]
     lib.ced_decode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_encode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
@@ -281,6 +282,12 @@ class Context:
         ms = (C.c_float * 2)()
         _check(self.lib, self.lib.ced_ctx_last_kernel_ms(self.h, ms), "ced_ctx_last_kernel_ms")
         return float(ms[0]), float(ms[1])
+
+    def last_fallback_frames(self):
+        """frames of the most recent fused decode that were decoded again by the two-kernel path"""
+        n = C.c_int(0)
+        _check(self.lib, self.lib.ced_ctx_last_fallback_frames(self.h, C.byref(n)), "ced_ctx_last_fallback_frames")
+        return n.value
 
     def probe_int_peak(self, mode=0):
         """32-bit lane-ops/s of a dependent-free LOP3 stream (mode 1: with IMAD co-issue)."""

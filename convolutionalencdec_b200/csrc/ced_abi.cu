@@ -7,6 +7,7 @@
 #include "ced_internal.cuh"
 #include "channel_kernels.cuh"
 #include "decode_batch.cuh"
+#include "decode_fused.cuh"
 #include "encode_batch.cuh"
 #include "frame_parallel.cuh"
 #include "probe_kernels.cuh"
@@ -156,6 +157,10 @@ void ced_ctx_destroy(ced_ctx *c)
         w.scratch.release();
         w.schedState.release();
         w.schedFlags.release();
+        w.ring.release();
+        w.fusedAux.release();
+        w.gatherIn.release();
+        w.gatherOut.release();
     }
     for (int i = 0; i < kPipeDepth; i++) {
         if (c->pipe[i])
@@ -434,6 +439,26 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (rc != CED_OK)
             return rc;
     }
+    /* compile-time codes and batches that fill the GPU take the fused kernel (CED_FUSED=0: always two kernels) */
+    const int envFused = getenv("CED_FUSED") ? atoi(getenv("CED_FUSED")) : 1;   /* read per call: tests flip them */
+    const int envFusedMin = getenv("CED_FUSED_MIN_FRAMES") ? atoi(getenv("CED_FUSED_MIN_FRAMES")) : 16384;
+    const bool fused = envFused != 0 && (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171) && nFrames >= envFusedMin;
+    if (fused) {
+        const size_t wave0 = std::min<size_t>((size_t)nFrames, waveMax), g0 = (wave0 + 31) / 32;
+        const size_t ringBytes = std::min<size_t>(g0, 2 * ced::kCohortGroups) * ced::kRingPairs * 32 * sizeof(uint4);
+        const size_t auxBytes = (2 * (g0 + 1) + 1 + 2 * wave0 + g0 * 32) * sizeof(int);
+        const size_t gInBytes = wave0 * ((rowBytes + 15) / 16 * 16), gOutBytes = wave0 * (size_t)(frameBits / 8);
+        if (wk.ring.bytes < ringBytes || wk.fusedAux.bytes < auxBytes || wk.gatherIn.bytes < gInBytes ||
+            wk.gatherOut.bytes < gOutBytes) {
+            CED_CUDA(cudaDeviceSynchronize());
+            int rc = wk.ring.ensure(ringBytes);
+            if (rc == CED_OK) rc = wk.fusedAux.ensure(auxBytes);
+            if (rc == CED_OK) rc = wk.gatherIn.ensure(gInBytes);
+            if (rc == CED_OK) rc = wk.gatherOut.ensure(gOutBytes);
+            if (rc != CED_OK)
+                return rc;
+        }
+    }
     /* the working set is shared by all calls on this context: a call on another stream first waits for
      * the previous one (use one context per stream to keep several decodes in flight) */
     if (wk.lastStream && wk.lastStream != s)
@@ -460,11 +485,82 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         sched.done = wk.schedFlags.p + 1;
         sched.state = wk.schedState.p;
         CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
-        if (prof)
-            CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
         const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
         static const int envCpu = getenv("CED_FWD_CHUNKS_PER_UNIT") ? atoi(getenv("CED_FWD_CHUNKS_PER_UNIT")) : 0;
         const int cpu = envCpu > 0 ? envCpu : 2; /* chunks a warp runs before handing its group on: 1 / 2 / 4 / 8 -> 1.249 / 1.217 / 1.225 / 1.262 ms */
+        if (fused) {
+            /* one kernel: forward ACS with the traceback inside (decode_fused.cuh); the frames it hands back (failed
+             * pass check; none at useful noise levels) are gathered, decoded by the two-kernel path and scattered */
+            const size_t gStride = (rowBytes + 15) / 16 * 16, outBytes = (size_t)frameBits / 8;
+            int *aux = wk.fusedAux.p;                       /* [counterA doneA[groups]] [counterB doneB[groups]] [count] [flag[wave]] */
+            int *auxB = aux + groups + 1, *count = auxB + groups + 1;
+            unsigned int *flag = reinterpret_cast<unsigned int *>(count + 1);
+            int *list = reinterpret_cast<int *>(flag) + wave;
+            uint32_t *expect = reinterpret_cast<uint32_t *>(list + wave);
+            CED_CUDA(cudaMemsetAsync(aux, 0, (size_t)(2 * (groups + 1) + 1 + wave) * sizeof(int), s));
+            if (prof)
+                CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
+            ced::FwdSched schedA = {reinterpret_cast<unsigned int *>(aux), aux + 1, wk.schedState.p};
+            ced::FwdSched schedB = {reinterpret_cast<unsigned int *>(auxB), auxB + 1, wk.schedState.p};
+            ced::FusedArgs fa;
+            fa.ring = wk.ring.p;
+            fa.expect = expect;
+            fa.flag = flag;
+            fa.list = list;
+            fa.count = count;
+            fa.out = out;
+            fa.outStride = outStride;
+            fa.ringSlots = std::min(groups, 2 * ced::kCohortGroups);
+            static const int envFusedPerSm = getenv("CED_FUSED_BLOCKS_PER_SM") ? atoi(getenv("CED_FUSED_BLOCKS_PER_SM")) : 0;
+            const int perSm = envFusedPerSm > 0 ? envFusedPerSm : std::max(3, std::min(4, groups / (4 * c->sms)));
+            const int fBlocks = std::max(1, std::min(c->sms * perSm, (groups + 3) / 4));
+#define CED_LAUNCH_FUSED(CODE, FMT)                                                                                \
+    do {                                                                                                           \
+        if (aligned16)                                                                                             \
+            ced::k7FusedKernel<CODE, ced::FMT, true><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, \
+                                                                                          schedA, cpu, fa);        \
+        else                                                                                                       \
+            ced::k7FusedKernel<CODE, ced::FMT, false><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, \
+                                                                                           schedA, cpu, fa);       \
+    } while (0)
+            if (id == CodeId::K7_0113_0171 && !packed)
+                CED_LAUNCH_FUSED(Code0113, ByteSymbols);
+            else if (id == CodeId::K7_0113_0171)
+                CED_LAUNCH_FUSED(Code0113, PackedSymbols);
+            else if (!packed)
+                CED_LAUNCH_FUSED(Code0133, ByteSymbols);
+            else
+                CED_LAUNCH_FUSED(Code0133, PackedSymbols);
+#undef CED_LAUNCH_FUSED
+            if (prof)
+                CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
+            const int auxGrid = c->sms * 4;
+            ced::gatherRowsKernel<<<auxGrid, 256, 0, s>>>(in, segStride, list, count, wk.gatherIn.p, gStride, (int)rowBytes);
+            if (id == CodeId::K7_0113_0171 && !packed)
+                ced::k7ForwardKernel<Code0113, ced::ByteSymbols, true><<<blocks, ced::kFwdThreads, 0, s>>>(
+                    wk.gatherIn.p, gStride, wave, T, wk.scratch.p, bm, schedB, cpu, ced::FwdWindow(), nullptr, count);
+            else if (id == CodeId::K7_0113_0171)
+                ced::k7ForwardKernel<Code0113, ced::PackedSymbols, true><<<blocks, ced::kFwdThreads, 0, s>>>(
+                    wk.gatherIn.p, gStride, wave, T, wk.scratch.p, bm, schedB, cpu, ced::FwdWindow(), nullptr, count);
+            else if (!packed)
+                ced::k7ForwardKernel<Code0133, ced::ByteSymbols, true><<<blocks, ced::kFwdThreads, 0, s>>>(
+                    wk.gatherIn.p, gStride, wave, T, wk.scratch.p, bm, schedB, cpu, ced::FwdWindow(), nullptr, count);
+            else
+                ced::k7ForwardKernel<Code0133, ced::PackedSymbols, true><<<blocks, ced::kFwdThreads, 0, s>>>(
+                    wk.gatherIn.p, gStride, wave, T, wk.scratch.p, bm, schedB, cpu, ced::FwdWindow(), nullptr, count);
+            ced::k7TracebackKernel<ced::Lanes8><<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+                wk.scratch.p, wave, T, wk.gatherOut.p, outBytes, nullptr, ced::kTailSteps, 0, count);
+            ced::scatterRowsKernel<<<auxGrid, 256, 0, s>>>(wk.gatherOut.p, outBytes, list, count, out, outStride, (int)outBytes);
+            if (prof) {
+                CED_CUDA(cudaEventRecord(c->prof[pw][2], s));
+                c->profWaves++;
+            }
+            c->launches += 5;
+            c->lastFusedCount = count;
+            continue;
+        }
+        if (prof)
+            CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
 #define CED_LAUNCH_FWD(CODE, FMT)                                                                                  \
     do {                                                                                                           \
         if (aligned16)                                                                                             \
@@ -733,6 +829,20 @@ int ced_ctx_last_kernel_ms(ced_ctx *c, float *ms2)
         ms2[0] += a;
         ms2[1] += b;
     }
+    return CED_OK;
+}
+
+int ced_ctx_last_fallback_frames(ced_ctx *c, int *frames)
+{
+    if (!c || !frames)
+        return CED_ERR_ARG;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    *frames = 0;
+    if (!c->lastFusedCount)
+        return CED_OK;
+    CED_CUDA(cudaDeviceSynchronize());
+    CED_CUDA(cudaMemcpy(frames, c->lastFusedCount, sizeof(int), cudaMemcpyDeviceToHost));
     return CED_OK;
 }
 

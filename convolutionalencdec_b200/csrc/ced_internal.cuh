@@ -138,6 +138,11 @@ struct ced_ctx {
         DeviceBuf<uint4> scratch;    /* survivor words of the wave in flight */
         DeviceBuf<uint4> schedState; /* FwdSched.state */
         DeviceBuf<int> schedFlags;   /* [0] unit counter, [1 + g] FwdSched.done */
+        /* k7FusedKernel (decode_fused.cuh): decision rings, pass-to-pass state + flags, and the dense buffers the
+         * frames it hands back are gathered into */
+        DeviceBuf<uint4> ring;
+        DeviceBuf<int> fusedAux;
+        DeviceBuf<uint8_t> gatherIn, gatherOut;
         cudaEvent_t idle = nullptr;  /* recorded after the last kernel that used this working set */
         cudaStream_t lastStream = nullptr;
     } work[1 + kPipeDepth];
@@ -175,6 +180,7 @@ struct ced_ctx {
     static constexpr int kMaxProfWaves = 64;
     cudaEvent_t prof[kMaxProfWaves][3] = {};
     int profWaves = 0;
+    const int *lastFusedCount = nullptr; /* device counter of the frames the last fused decode handed to the two-kernel path */
     bool counted = false;            /* this context is in the per-device census (activeGpus) */
 };
 

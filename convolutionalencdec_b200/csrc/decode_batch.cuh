@@ -236,8 +236,10 @@ template <class Code, class Fmt, bool ALIGNED, bool CARRY = false>
 __global__ void __launch_bounds__(kFwdThreads)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
                 BmTable table, FwdSched sched, int chunksPerUnit, FwdWindow win = FwdWindow(),
-                const uint2 *__restrict__ stepTable = nullptr)
+                const uint2 *__restrict__ stepTable = nullptr, const int *__restrict__ nFramesDev = nullptr)
 {
+    if (nFramesDev)   /* frame count decided on the device (the frames k7FusedKernel handed back, decode_fused.cuh) */
+        nFrames = *nFramesDev;
     using G = TileGeom<Fmt, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
     __shared__ uint4 sBm[StepTableUint4<Code>::value];
@@ -405,35 +407,6 @@ k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, in
     }
 }
 
-/* backward step with the phase known at compile time */
-template <class Lay, int PH>
-__device__ __forceinline__ uint32_t tracebackStepC(uint32_t &b, uint32_t w0, uint32_t w1)
-{
-    constexpr int qb = Lay::pairBit(PH);
-    const uint32_t word = (b & 32u) ? w1 : w0;
-    const uint32_t dec = (word >> (b & 31u)) & 1u;
-    const uint32_t bit = (b >> qb) & 1u;
-    b = (b & ~(1u << qb)) | (dec << qb);
-    return bit;
-}
-
-/* 8 steps = 4 pairs = one output byte; pair i of the group holds steps (base+6-2i, base+7-2i),
- * PH0 = phase of the group's first step (step base, a multiple of 8 inside a 24-step block). */
-template <class Lay, int PH0>
-__device__ __forceinline__ uint32_t tracebackByteC(uint32_t &b, const uint4 (&w)[4])
-{
-    uint32_t acc = 0;
-    acc |= tracebackStepC<Lay, (PH0 + 7) % 6>(b, w[0].z, w[0].w) << 0;
-    acc |= tracebackStepC<Lay, (PH0 + 6) % 6>(b, w[0].x, w[0].y) << 1;
-    acc |= tracebackStepC<Lay, (PH0 + 5) % 6>(b, w[1].z, w[1].w) << 2;
-    acc |= tracebackStepC<Lay, (PH0 + 4) % 6>(b, w[1].x, w[1].y) << 3;
-    acc |= tracebackStepC<Lay, (PH0 + 3) % 6>(b, w[2].z, w[2].w) << 4;
-    acc |= tracebackStepC<Lay, (PH0 + 2) % 6>(b, w[2].x, w[2].y) << 5;
-    acc |= tracebackStepC<Lay, (PH0 + 1) % 6>(b, w[3].z, w[3].w) << 6;
-    acc |= tracebackStepC<Lay, (PH0 + 0) % 6>(b, w[3].x, w[3].y) << 7;
-    return acc;
-}
-
 constexpr int kTbThreads = 64;
 
 __device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
@@ -456,8 +429,11 @@ __device__ __forceinline__ void cpAsync16(void *smemDst, const void *gmemSrc)
 template <class Lay = Lanes8>
 __global__ void __launch_bounds__(kTbThreads)
 k7TracebackKernel(const uint4 *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride,
-                  const uint32_t *__restrict__ startPos = nullptr, int skip = kTailSteps, int emitLo = 0)
+                  const uint32_t *__restrict__ startPos = nullptr, int skip = kTailSteps, int emitLo = 0,
+                  const int *__restrict__ nFramesDev = nullptr)
 {
+    if (nFramesDev)
+        nFrames = *nFramesDev;
     __shared__ uint4 sW[2][12][kTbThreads];
     const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (frame >= nFrames)

@@ -44,6 +44,10 @@
 #define CED_HDC constexpr
 #endif
 
+#if !defined(__CUDACC__)
+struct uint4 { uint32_t x, y, z, w; }; /* host stand-in for tests/hostsim (never compiled with the CUDA headers) */
+#endif
+
 namespace ced {
 
 CED_HDC uint32_t rotl6(uint32_t x, int r)
@@ -455,6 +459,35 @@ CED_HD uint32_t tracebackStep(uint32_t &b, uint32_t w0, uint32_t w1, int ph)
     const uint32_t bit = (b >> qb) & 1u;
     b = (b & ~(1u << qb)) | (dec << qb);
     return bit;
+}
+
+/* backward step with the phase known at compile time */
+template <class Lay, int PH>
+CED_HD uint32_t tracebackStepC(uint32_t &b, uint32_t w0, uint32_t w1)
+{
+    constexpr int qb = Lay::pairBit(PH);
+    const uint32_t word = (b & 32u) ? w1 : w0;
+    const uint32_t dec = (word >> (b & 31u)) & 1u;
+    const uint32_t bit = (b >> qb) & 1u;
+    b = (b & ~(1u << qb)) | (dec << qb);
+    return bit;
+}
+
+/* 8 steps = 4 pairs = one output byte; pair i of the group holds steps (base+6-2i, base+7-2i),
+ * PH0 = phase of the group's first step (step base, a multiple of 8 inside a 24-step block). */
+template <class Lay, int PH0>
+CED_HD uint32_t tracebackByteC(uint32_t &b, const uint4 (&w)[4])
+{
+    uint32_t acc = 0;
+    acc |= tracebackStepC<Lay, (PH0 + 7) % 6>(b, w[0].z, w[0].w) << 0;
+    acc |= tracebackStepC<Lay, (PH0 + 6) % 6>(b, w[0].x, w[0].y) << 1;
+    acc |= tracebackStepC<Lay, (PH0 + 5) % 6>(b, w[1].z, w[1].w) << 2;
+    acc |= tracebackStepC<Lay, (PH0 + 4) % 6>(b, w[1].x, w[1].y) << 3;
+    acc |= tracebackStepC<Lay, (PH0 + 3) % 6>(b, w[2].z, w[2].w) << 4;
+    acc |= tracebackStepC<Lay, (PH0 + 2) % 6>(b, w[2].x, w[2].y) << 5;
+    acc |= tracebackStepC<Lay, (PH0 + 1) % 6>(b, w[3].z, w[3].w) << 6;
+    acc |= tracebackStepC<Lay, (PH0 + 0) % 6>(b, w[3].x, w[3].y) << 7;
+    return acc;
 }
 
 } // namespace ced

@@ -211,3 +211,54 @@ extern "C" int swar_sim_decode_soft(const int8_t *soft, int T, uint8_t *out, uin
     }
     return (L + 7) / 8;
 }
+
+// The in-kernel traceback of k7FusedKernel for one frame (trellis_fused.cuh): decisions live in a ring of
+// kRingPairs step pairs only; after every 96 steps the chunk pass walks the window, the final pass ends the frame.
+// *flagged = 1 if any pass failed its check (the kernel then hands the frame to the two-kernel path).
+#include "trellis_fused.cuh"
+
+extern "C" int swar_sim_fused(const uint8_t *segs, int T, uint8_t *out, int *flagged, int bestStart)
+{
+    uint32_t R[16];
+    ced::initMetrics(R);
+    std::vector<uint4> ring(ced::kRingPairs);
+    const int L = T - 6;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0xEE; /* every byte must be written by a pass */
+    uint32_t expect = 0;
+    bool ok = true;
+    auto loadBlock = [&](int blk, uint4 (&r)[12]) {
+        for (int i = 0; i < 12; i++)
+            r[i] = ring[(size_t)((12 * blk + 11 - i) % ced::kRingPairs)];
+    };
+    auto storeBytes = [&](int blk, uint32_t o0, uint32_t o1, uint32_t o2) {
+        out[3 * blk] = (uint8_t)o0;
+        out[3 * blk + 1] = (uint8_t)o1;
+        out[3 * blk + 2] = (uint8_t)o2;
+    };
+    for (int t = 0; t < T; t++) {
+        uint32_t t0 = 0, t1 = 0, rx = segs[t];
+        switch (t % 6) {
+        case 0: stepPhase<0>(R, rx, t0, t1); break;
+        case 1: stepPhase<1>(R, rx, t0, t1); break;
+        case 2: stepPhase<2>(R, rx, t0, t1); break;
+        case 3: stepPhase<3>(R, rx, t0, t1); break;
+        case 4: stepPhase<4>(R, rx, t0, t1); break;
+        default: stepPhase<5>(R, rx, t0, t1); break;
+        }
+        uint4 &row = ring[(size_t)((t / 2) % ced::kRingPairs)];
+        if (t & 1) { row.z = t0; row.w = t1; } else { row.x = t0; row.y = t1; }
+        const int now = t + 1;
+        if (now == T) {
+            const int cc = (T - 1) / ced::kFusedE;
+            ok &= ced::fusedFinalPass<ced::Lanes8>(
+                cc, T, 6, expect, [&](int m) { return ring[(size_t)(m % ced::kRingPairs)]; }, loadBlock,
+                [&](int i, uint32_t v) { out[i] = (uint8_t)v; }, storeBytes);
+        } else if (now % ced::kFusedE == 0) {
+            ced::renorm(R);
+            ok &= ced::fusedChunkPass<ced::Lanes8>(now / ced::kFusedE - 1, bestStart ? ced::bestPositionB(R) : 0u, expect,
+                                                   loadBlock, storeBytes);
+        }
+    }
+    *flagged = ok ? 0 : 1;
+    return (L + 7) / 8;
+}
