@@ -325,16 +325,19 @@ def main():
     sass = load_sass_stats()
 
     # ---- synthetic frames, generated on the device, resident in HBM before timing ----
-    # a rank's frames are decoded in sub-batches of 2^16 (one ced_decode_batch call each, BASELINE configs[1]'s shape)
-    sub = min(frames, FRAMES_PER_GPU)
+    # config 2: one ced_decode_batch call of 2^16 frames per step.  config 5 (strong scaling): ONE call over the rank's
+    # whole shard per step -- the library keeps waves of 2^16 frames in flight internally (decodeBatchPipelined).
+    # `sub` = frames per call of a step, `launch` = frames of the single-wave calls used for the roofline / e2e / weak legs
+    launch = min(frames, FRAMES_PER_GPU)
+    sub = frames if strong else launch
     n_sub = (frames + sub - 1) // sub
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
     seg_stride = max(args.stride, T)
     segs = torch.zeros((frames, seg_stride), dtype=torch.uint8, device="cuda")
     out = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()   # allocations / zero-fills ran on torch's default stream
-    for a in range(0, frames, sub):
-        b = min(frames, a + sub)
+    for a in range(0, frames, launch):
+        b = min(frames, a + launch)
         ctx.random_bytes(msgs[a:b], seed=314, first_frame=first_frame + a, stream=stream)
         ctx.encode_batch(code, msgs[a:b], out=segs[a:b], stream=stream)
         ctx.bsc_channel(segs[a:b], T, 2, 0.0377, seed=2718, first_frame=first_frame + a, stream=stream)
@@ -348,13 +351,14 @@ def main():
     # context serialises its own decodes on its survivor scratch).  `value` is this steady-state throughput; the
     # one-decode-at-a-time figure is reported as `single_stream`.
     extra = [ced.Context(local_rank) for _ in range(max(1, args.in_flight) - 1)]
-    lanes = [(ctx, stream)] + [(c_, torch.cuda.Stream()) for c_ in extra]
+    all_lanes = [(ctx, stream)] + [(c_, torch.cuda.Stream()) for c_ in extra]
+    lanes = all_lanes[:1] if strong else all_lanes       # one call covers the shard: nothing to juggle from outside
     counters = torch.zeros(4, dtype=torch.int64, device="cuda")
 
     # one sub-batch per step: every lane decodes into its own output buffer (the same frames are in flight on several
     # lanes at once); several sub-batches per step: each writes its own rows of `out`
     lane_out = {id(ctx): out}
-    if n_sub == 1:
+    if n_sub == 1 and not strong:
         for c_ in extra:
             lane_out[id(c_)] = torch.empty_like(out)
 
@@ -448,21 +452,24 @@ def main():
                        "frame_bits": bits, "segment_stride_bytes": seg_stride,
                        "calls_per_step": n_sub if args.mode == "decode" else 1,
                        "symbol_format": "1 byte per 2-bit segment (reference wire format)", "channel": "BSC p=0.0377 (Eb/N0 5 dB)",
-                       "l2_policy": "inputs (%.0f MB symbols + %.0f MB survivors per call) exceed the 126 MB L2"
-                                    % (sub * seg_stride / 1e6, sub * (T // 2) * 16 / 1e6),
+                       "l2_policy": "inputs (%.0f MB symbols + %.0f MB survivors per wave of 2^16 frames) exceed the 126 MB L2"
+                                    % (launch * seg_stride / 1e6, launch * (T // 2) * 16 / 1e6),
                        "sharding": "frames [rank*F, (rank+1)*F) per rank, no data-path collective"},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall}
     if single is not None:
         line["single_stream"] = single
         line["config"]["in_flight"] = ("%d ced_decode_batch calls in flight (one ced_ctx + CUDA stream each): "
                                        "traceback(i) overlaps forward(i+1)" % len(lanes))
+    elif strong:
+        line["config"]["in_flight"] = ("one ced_decode_batch call per step over the whole shard; the library keeps 3 waves of "
+                                       "2^16 frames in flight on internal streams (decodeBatchPipelined)")
 
     if args.mode == "decode":
         # ---- roofline of the dominant kernel (forward ACS), CUDA events around that kernel alone ----
         ctx.set_profiling(True)
         fwd, tb = [], []
         for _ in range(max(3, min(args.steps, 10))):
-            ctx.decode_batch(code, segs[:sub], bits, out=out[:sub], stream=stream)
+            ctx.decode_batch(code, segs[:launch], bits, out=out[:launch], stream=stream)
             f, t = ctx.last_kernel_ms()
             fwd.append(f)
             tb.append(t)
@@ -470,7 +477,7 @@ def main():
         fwd_ms, tb_ms = sum(fwd) / len(fwd), sum(tb) / len(tb)
         int_peak = ctx.probe_int_peak(0)
         int_peak_dual = ctx.probe_int_peak(1)
-        launch_bits = sub * bits                 # one launch = one sub-batch
+        launch_bits = launch * bits              # one launch = 2^16 frames
         algo_ops = launch_bits * INT_OPS_PER_BIT
         achieved = algo_ops / (fwd_ms * 1e-3) / 1e12
         # DRAM bytes of one launch: ncu --set full capture at 2^16 frames (profiles/roofline_traffic.json), scaled
@@ -482,7 +489,7 @@ def main():
                 tj = json.load(f)
             per_launch = tj.get("k7ForwardKernel_dram_bytes_per_launch")
             if per_launch:
-                traffic = per_launch * sub / float(tj.get("frames_per_launch", FRAMES_PER_GPU))
+                traffic = per_launch * launch / float(tj.get("frames_per_launch", FRAMES_PER_GPU))
         # instruction-level view: SASS instruction count of the kernel's 6-step loop body, read from the BUILT
         # library by tools/sass_loop_stats.py at `make cuda`; an SM sub-partition issues at most one warp-instruction
         # per cycle and the kernel splits them ~50/50 over the ALU and FMA pipes
@@ -491,7 +498,7 @@ def main():
         sm_mhz = (clocks.get("sm_mhz") or 1965.0)
         issue = None
         if ipf:
-            warp_instr = sub * T * ipf / 32.0
+            warp_instr = launch * T * ipf / 32.0
             ipc = warp_instr / (148 * 4 * fwd_ms * 1e-3 * sm_mhz * 1e6)
             issue = {"instr_per_frame_step": ipf, "loop_instructions": loop.get("loop_instructions"),
                      "pipes": loop.get("pipes"), "ipc_per_sm_subpartition": ipc, "peak": 1.0, "frac": ipc,
@@ -503,7 +510,7 @@ def main():
                             "peak": int_peak / 1e12, "unit": "Tiop/s", "frac": achieved / (int_peak / 1e12),
                             "peak_source": "measured live: dependent-free LOP3 stream (ced_probe_int_peak mode 0)",
                             "peak_with_imad_coissue": int_peak_dual / 1e12,
-                            "algorithmic_ops_per_launch": algo_ops, "frames_per_launch": sub, "kernel_ms": fwd_ms,
+                            "algorithmic_ops_per_launch": algo_ops, "frames_per_launch": launch, "kernel_ms": fwd_ms,
                             "kernel_share_of_step": fwd_ms / (fwd_ms + tb_ms), "traceback_ms": tb_ms,
                             "traffic": traffic,
                             "hbm": {"achieved": launch_bits * ALGO_BYTES_PER_BIT / ((fwd_ms + tb_ms) * 1e-3) / 1e9,
@@ -516,30 +523,31 @@ def main():
 
     if strong and args.mode == "decode":
         # ---- the weak figure beside the strong one: 2^16 frames per GPU, 3 calls in flight (BASELINE configs[1] per GPU) ----
-        weak_out = [torch.empty((sub, bits // 8), dtype=torch.uint8, device="cuda") for _ in lanes]
+        lanes_w = all_lanes
+        weak_out = [torch.empty((launch, bits // 8), dtype=torch.uint8, device="cuda") for _ in lanes_w]
 
         def weak_pass(n_steps):
             timing = torch.cuda.Stream()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(timing)
-            for _, s_ in lanes:
+            for _, s_ in lanes_w:
                 s_.wait_event(e0)
             for i in range(n_steps):
-                c_, s_ = lanes[i % len(lanes)]
-                c_.decode_batch(code, segs[:sub], bits, out=weak_out[i % len(lanes)], stream=s_)
-            for _, s_ in lanes:
+                c_, s_ = lanes_w[i % len(lanes_w)]
+                c_.decode_batch(code, segs[:launch], bits, out=weak_out[i % len(lanes_w)], stream=s_)
+            for _, s_ in lanes_w:
                 done = torch.cuda.Event()
                 done.record(s_)
                 timing.wait_event(done)
             e1.record(timing)
             timing.synchronize()
             return e0.elapsed_time(e1)
-        weak_pass(len(lanes))
+        weak_pass(2 * len(lanes_w))
         barrier()
         n_w = max(10, min(args.steps, 30))
         ms_w = max_over_ranks(weak_pass(n_w))
-        line["weak"] = {"value": world * sub * bits * n_w / (ms_w * 1e-3) / 1e9, "unit": "Gbit/s", "frames_per_gpu": sub,
-                        "steps": n_w, "note": "2^16 frames per GPU, %d calls in flight: the N = 1 workload on every GPU" % len(lanes)}
+        line["weak"] = {"value": world * launch * bits * n_w / (ms_w * 1e-3) / 1e9, "unit": "Gbit/s", "frames_per_gpu": launch,
+                        "steps": n_w, "note": "2^16 frames per GPU, %d calls in flight: the N = 1 workload on every GPU" % len(lanes_w)}
 
     def host_calls_in_flight(call, n_calls, n_threads):
         """n_calls synchronous host-buffer calls issued from n_threads host threads (one ced_ctx and one set of
@@ -567,7 +575,7 @@ def main():
         # Host batch = 2^16 frames per rank at every N (BASELINE configs[1] per GPU): page-locking 2^22 frames of
         # symbols (17 GB) per box would measure the host's memory, not the library.
         n_host = 2
-        hf = sub
+        hf = launch
         host_ctx = [ctx] + [ced.Context(local_rank) for _ in range(n_host - 1)]
         h_segs = [torch.empty((hf, seg_stride), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
         h_out = [torch.empty((hf, bits // 8), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
@@ -648,7 +656,7 @@ def main():
                      "ber": float(cnt[0].item()) / max(1, int(cnt[1].item()))}
 
     if world == 1 and args.mode == "decode" and not args.no_subrecords:
-        line.update(sub_records(ctx, ced, torch, stream, msgs[:sub], segs[:sub], out[:sub], bits, T, hbm_peak, peak_src,
+        line.update(sub_records(ctx, ced, torch, stream, msgs[:launch], segs[:launch], out[:launch], bits, T, hbm_peak, peak_src,
                                 line["roofline"]["peak"], sass, clocks))
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.mode == "decode":

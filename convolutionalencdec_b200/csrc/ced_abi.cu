@@ -127,6 +127,9 @@ static int ctxInit(ced_ctx *c, int device)
             CED_CUDA(cudaEventCreate(&c->prof[w][e]));
     for (auto &w : c->work)
         CED_CUDA(cudaEventCreateWithFlags(&w.idle, cudaEventDisableTiming));
+    CED_CUDA(cudaEventCreateWithFlags(&c->waveFork, cudaEventDisableTiming));
+    for (int i = 0; i < kPipeDepth; i++)
+        CED_CUDA(cudaEventCreateWithFlags(&c->waveJoin[i], cudaEventDisableTiming));
     for (int i = 0; i < kPipeDepth; i++)
         CED_CUDA(cudaEventCreateWithFlags(&c->stageFree[i], cudaEventDisableTiming));
     {
@@ -159,6 +162,7 @@ void ced_ctx_destroy(ced_ctx *c)
         w.schedFlags.release();
         w.ring.release();
         w.fusedAux.release();
+        w.wsAux.release();
         w.gatherIn.release();
         w.gatherOut.release();
     }
@@ -170,6 +174,11 @@ void ced_ctx_destroy(ced_ctx *c)
         c->packStage[i].release();
         c->outStage[i].release();
     }
+    if (c->waveFork)
+        cudaEventDestroy(c->waveFork);
+    for (int i = 0; i < kPipeDepth; i++)
+        if (c->waveJoin[i])
+            cudaEventDestroy(c->waveJoin[i]);
     if (c->packer)
         ced_host::packerDestroy(c->packer);
     for (int i = 0; i < kPipeDepth; i++) {
@@ -439,19 +448,24 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         if (rc != CED_OK)
             return rc;
     }
-    /* compile-time codes and batches that fill the GPU take the fused kernel (CED_FUSED=0: always two kernels) */
-    const int envFused = getenv("CED_FUSED") ? atoi(getenv("CED_FUSED")) : 1;   /* read per call: tests flip them */
+    /* CED_FUSED=1 / 2: compile-time codes and batches that fill the GPU take the fused kernel (decode_fused.cuh:
+     * traceback inside the forward warps / on its own warp).  Off by default: measured 1.58 / 1.85 ms against 1.65 ms
+     * for the two kernels one call at a time and 1.355 ms with three calls in flight */
+    const int envFused = getenv("CED_FUSED") ? atoi(getenv("CED_FUSED")) : 0;   /* read per call: tests flip them */
     const int envFusedMin = getenv("CED_FUSED_MIN_FRAMES") ? atoi(getenv("CED_FUSED_MIN_FRAMES")) : 16384;
     const bool fused = envFused != 0 && (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171) && nFrames >= envFusedMin;
     if (fused) {
         const size_t wave0 = std::min<size_t>((size_t)nFrames, waveMax), g0 = (wave0 + 31) / 32;
-        const size_t ringBytes = std::min<size_t>(g0, 2 * ced::kCohortGroups) * ced::kRingPairs * 32 * sizeof(uint4);
+        const size_t ringBytes = std::min<size_t>(g0, 2 * ced::kCohortGroups) * ced::WsGeom<384, 96>::kRingPairs * 32 * sizeof(uint4);
+        const size_t wsPasses = (size_t)(T + 95) / 96;   /* at most one pass per 96 steps */
+        const size_t wsBytes = g0 * wsPasses * (sizeof(int) + 64);
         const size_t auxBytes = (2 * (g0 + 1) + 1 + 2 * wave0 + g0 * 32) * sizeof(int);
         const size_t gInBytes = wave0 * ((rowBytes + 15) / 16 * 16), gOutBytes = wave0 * (size_t)(frameBits / 8);
         if (wk.ring.bytes < ringBytes || wk.fusedAux.bytes < auxBytes || wk.gatherIn.bytes < gInBytes ||
-            wk.gatherOut.bytes < gOutBytes) {
+            wk.gatherOut.bytes < gOutBytes || wk.wsAux.bytes < wsBytes) {
             CED_CUDA(cudaDeviceSynchronize());
             int rc = wk.ring.ensure(ringBytes);
+            if (rc == CED_OK) rc = wk.wsAux.ensure(wsBytes);
             if (rc == CED_OK) rc = wk.fusedAux.ensure(auxBytes);
             if (rc == CED_OK) rc = wk.gatherIn.ensure(gInBytes);
             if (rc == CED_OK) rc = wk.gatherOut.ensure(gOutBytes);
@@ -502,6 +516,43 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
                 CED_CUDA(cudaEventRecord(c->prof[pw][0], s));
             ced::FwdSched schedA = {reinterpret_cast<unsigned int *>(aux), aux + 1, wk.schedState.p};
             ced::FwdSched schedB = {reinterpret_cast<unsigned int *>(auxB), auxB + 1, wk.schedState.p};
+            bool wsLaunched = false;
+            if (envFused == 2 && id == CodeId::K7_0113_0171 && !packed && aligned16) {
+                /* warp-specialised form (k7FusedWsKernel): traceback on its own warp, ring streamed with bulk copies */
+                int wsE = 192, wsD = 72;
+                if (const char *ge = getenv("CED_FUSED_GEOM"))
+                    sscanf(ge, "%d,%d", &wsE, &wsD);
+                const int passes = (T + wsE - 1) / wsE;
+                ced::WsArgs wa;
+                wa.ring = wk.ring.p;
+                wa.passes = passes;
+                wa.out = out;
+                wa.outStride = outStride;
+                wa.ringSlots = std::min(groups, 2 * ced::kCohortGroups);
+                uint8_t *wsAux = reinterpret_cast<uint8_t *>(wk.wsAux.p);
+                wa.passDone = reinterpret_cast<int *>(wsAux);
+                wa.startState = wsAux + (size_t)groups * passes * sizeof(int);
+                wa.arriveState = wa.startState + (size_t)groups * passes * 32;
+                CED_CUDA(cudaMemsetAsync(wa.passDone, 0, (size_t)groups * passes * sizeof(int), s));
+                static const int envWsPerSm = getenv("CED_FUSED_BLOCKS_PER_SM") ? atoi(getenv("CED_FUSED_BLOCKS_PER_SM")) : 0;
+                const int wsBlocks = std::max(1, std::min(c->sms * (envWsPerSm > 0 ? envWsPerSm : 3), (groups + 3) / 4));
+#define CED_WS_CASE(E_, D_)                                                                                          \
+    if (wsE == E_ && wsD == D_) {                                                                                    \
+        ced::k7FusedWsKernel<Code0113, ced::ByteSymbols, true, ced::WsGeom<E_, D_>><<<wsBlocks, ced::kWsThreads, 0, s>>>( \
+            in, segStride, wave, T, bm, schedA, cpu, wa);                                                            \
+        wsLaunched = true;                                                                                           \
+    }
+                CED_WS_CASE(96, 72)
+                CED_WS_CASE(192, 72)
+                CED_WS_CASE(384, 96)
+#undef CED_WS_CASE
+                if (wsLaunched) {
+                    ced::fusedVerifyKernel<<<(wave + 255) / 256, 256, 0, s>>>(wa.startState, wa.arriveState, wave, passes, wsE,
+                                                                             wsD, list, count);
+                    c->launches += 1;
+                }
+            }
+            if (!wsLaunched) {
             ced::FusedArgs fa;
             fa.ring = wk.ring.p;
             fa.expect = expect;
@@ -523,6 +574,20 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             ced::k7FusedKernel<CODE, ced::FMT, false><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, \
                                                                                            schedA, cpu, fa);       \
     } while (0)
+            /* experiments: other ring geometries for the default code, byte format, aligned rows (CED_FUSED_GEOM=E,D) */
+            int geoE = 0, geoD = 0;
+            if (const char *ge = getenv("CED_FUSED_GEOM"))
+                sscanf(ge, "%d,%d", &geoE, &geoD);
+#define CED_FUSED_GEOM_CASE(E_, D_)                                                                                \
+    if (id == CodeId::K7_0113_0171 && !packed && aligned16 && geoE == E_ && geoD == D_)                            \
+        ced::k7FusedKernel<Code0113, ced::ByteSymbols, true, ced::FusedGeom<E_, D_>><<<fBlocks, ced::kFwdThreads, 0, s>>>( \
+            in, segStride, wave, T, bm, schedA, cpu, fa);                                                          \
+    else
+            CED_FUSED_GEOM_CASE(96, 48)
+            CED_FUSED_GEOM_CASE(192, 72)
+            CED_FUSED_GEOM_CASE(192, 96)
+            CED_FUSED_GEOM_CASE(384, 96)
+#undef CED_FUSED_GEOM_CASE
             if (id == CodeId::K7_0113_0171 && !packed)
                 CED_LAUNCH_FUSED(Code0113, ByteSymbols);
             else if (id == CodeId::K7_0113_0171)
@@ -532,6 +597,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             else
                 CED_LAUNCH_FUSED(Code0133, PackedSymbols);
 #undef CED_LAUNCH_FUSED
+            } /* !wsLaunched */
             if (prof)
                 CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
             const int auxGrid = c->sms * 4;
@@ -601,16 +667,57 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     return CED_OK;
 }
 
+/*
+ * A batch of several GPU-fills is decoded as waves of 2^16 frames kept in flight on three internal streams, each with
+ * its own working set: the forward (ACS) kernel is issue-bound and the traceback kernel HBM-bound, so the traceback
+ * of wave w runs under the forward passes of waves w+1 and w+2 -- what bench.py used to arrange from outside with
+ * three contexts (166 -> 198 Gbit/s) now happens inside ONE call.  The caller's stream forks into the
+ * internal streams and joins them again, so the call keeps its stream semantics.  CED_WAVE_PIPELINE=0 turns it off.
+ */
+constexpr int kPipeWaveFrames = 1 << 16;
+constexpr int kPipeWaves = 3;
+
+static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
+                                int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    static const bool enabled = !getenv("CED_WAVE_PIPELINE") || atoi(getenv("CED_WAVE_PIPELINE")) != 0;
+    if (!c || !enabled || nFrames < 2 * kPipeWaveFrames || classify(code) == CodeId::Unsupported || !dSegs || !dOut ||
+        frameBits <= 0 || (frameBits & 7) || frameBits > 8192)
+        return decodeBatchImpl(c, code, packed, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    CED_CUDA(cudaEventRecord(c->waveFork, s));
+    for (int i = 0; i < kPipeWaves; i++)
+        CED_CUDA(cudaStreamWaitEvent(c->pipe[i], c->waveFork, 0));
+    int w = 0;
+    for (long long f0 = 0; f0 < nFrames; f0 += kPipeWaveFrames, w++) {
+        const int cnt = (int)std::min<long long>(kPipeWaveFrames, nFrames - f0);
+        const int rc = decodeBatchImpl(c, code, packed, dSegs + (size_t)f0 * segStride, segStride, cnt, frameBits,
+                                       dOut + (size_t)f0 * outStride, outStride, c->pipe[w % kPipeWaves], 1 + w % kPipeWaves);
+        if (rc != CED_OK) {
+            for (int i = 0; i < kPipeWaves; i++)
+                cudaStreamSynchronize(c->pipe[i]);
+            return rc;
+        }
+    }
+    for (int i = 0; i < kPipeWaves; i++) {
+        CED_CUDA(cudaEventRecord(c->waveJoin[i], c->pipe[i]));
+        CED_CUDA(cudaStreamWaitEvent(s, c->waveJoin[i], 0));
+    }
+    return CED_OK;
+}
+
 int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                      int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    return decodeBatchImpl(c, code, false, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+    return decodeBatchPipelined(c, code, false, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
 }
 
 int ced_decode_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
                             int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    return decodeBatchImpl(c, code, true, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
+    return decodeBatchPipelined(c, code, true, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
 }
 
 /* ------------------------------------------------ continuous streams, windowed traceback */

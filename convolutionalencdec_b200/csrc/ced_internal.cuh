@@ -142,11 +142,13 @@ struct ced_ctx {
          * frames it hands back are gathered into */
         DeviceBuf<uint4> ring;
         DeviceBuf<int> fusedAux;
+        DeviceBuf<int> wsAux;        /* k7FusedWsKernel: pass-done flags and per-pass start / arrival states */
         DeviceBuf<uint8_t> gatherIn, gatherOut;
         cudaEvent_t idle = nullptr;  /* recorded after the last kernel that used this working set */
         cudaStream_t lastStream = nullptr;
     } work[1 + kPipeDepth];
-    cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline */
+    cudaStream_t pipe[kPipeDepth] = {}; /* compute streams of the host pipeline and of the wave pipeline below */
+    cudaEvent_t waveFork = nullptr, waveJoin[kPipeDepth] = {}; /* ced_decode_batch: waves of a large batch in flight */
     /* host-side transfer compression (host_pack.cpp): pinned packed staging + worker threads */
     ced_host::Packer *packer = nullptr;
     PinnedBuf packStage[kPipeDepth];

@@ -420,10 +420,23 @@ CED_HDC int pairBitInB(int ph)
  *   Lanes16 (trellis_swar16.cuh):   b = 32*(p>>5) + 16*(p&1) + ((p>>1)&15)    q = 5..0 -> b bit 5,3,2,1,0,4 */
 struct Lanes8 {
     static CED_HDC int pairBit(int ph) { return pairBitInB(ph); }
+    /* survivor bit index -> position (== state when the next step has phase 0) */
+    static CED_HD uint32_t toPosition(uint32_t b) { return (b & 32u) | ((b & 7u) << 2) | ((b >> 3) & 3u); }
 };
 struct Lanes16 {
     static CED_HDC int pairBit(int ph) { return (int)((0x401235u >> (4 * ph)) & 7u); }
+    static CED_HD uint32_t toPosition(uint32_t b) { return (b & 32u) | ((b & 15u) << 1) | ((b >> 4) & 1u); }
 };
+
+CED_HD uint32_t rotr32(uint32_t x, uint32_t n)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(x, x, n); /* one SHF; only the low 5 bits of n count */
+#else
+    n &= 31u;
+    return n ? (x >> n) | (x << (32u - n)) : x;
+#endif
+}
 
 /* Windowed traceback start (continuous streams): after renorm() the smallest metric is 0; returns, in b form, the
  * lowest position holding it.  Called between slices, where the next phase is 0 and position == state, so ties go

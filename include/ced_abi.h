@@ -77,11 +77,11 @@ uint64_t ced_launch_count(const ced_ctx *ctx);
 int ced_ctx_set_profiling(ced_ctx *ctx, int enable);
 int ced_ctx_last_kernel_ms(ced_ctx *ctx, float *ms2);
 int ced_probe_int_peak(ced_ctx *ctx, int mode, double *laneOpsPerSecond);
-/* ced_decode_batch runs batches of at least 16384 frames of the compiled-in codes as ONE kernel with the traceback
- * inside it (k7FusedKernel; ced_ctx_last_kernel_ms: [0] that kernel, [1] the re-decode below).  A frame whose
- * in-kernel traceback cannot be proven equal to the reference's full traceback is decoded again by the two-kernel
- * path in the same call; this returns how many frames of the (last wave of the) most recent call that was.
- * Synchronises the device.  CED_FUSED=0 disables the fused kernel. */
+/* With CED_FUSED=1 (or 2) in the environment ced_decode_batch runs batches of at least 16384 frames of the compiled-in
+ * codes as ONE kernel with the traceback inside it (k7FusedKernel / k7FusedWsKernel; then
+ * ced_ctx_last_kernel_ms: [0] that kernel, [1] the re-decode below).  A frame whose in-kernel traceback cannot be
+ * proven equal to the reference's full traceback is decoded again by the two-kernel path in the same call; this
+ * returns how many frames of the (last wave of the) most recent call that was.  Synchronises the device. */
 int ced_ctx_last_fallback_frames(ced_ctx *ctx, int *frames);
 
 /* ------------------------------------------------------- batched hot path

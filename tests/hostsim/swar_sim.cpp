@@ -217,18 +217,19 @@ extern "C" int swar_sim_decode_soft(const int8_t *soft, int T, uint8_t *out, uin
 // *flagged = 1 if any pass failed its check (the kernel then hands the frame to the two-kernel path).
 #include "trellis_fused.cuh"
 
-extern "C" int swar_sim_fused(const uint8_t *segs, int T, uint8_t *out, int *flagged, int bestStart)
+template <class Geo>
+static int simFused(const uint8_t *segs, int T, uint8_t *out, int *flagged, int bestStart)
 {
     uint32_t R[16];
     ced::initMetrics(R);
-    std::vector<uint4> ring(ced::kRingPairs);
+    std::vector<uint4> ring(Geo::kRingPairs);
     const int L = T - 6;
     for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0xEE; /* every byte must be written by a pass */
     uint32_t expect = 0;
     bool ok = true;
     auto loadBlock = [&](int blk, uint4 (&r)[12]) {
         for (int i = 0; i < 12; i++)
-            r[i] = ring[(size_t)((12 * blk + 11 - i) % ced::kRingPairs)];
+            r[i] = ring[(size_t)((12 * blk + 11 - i) % Geo::kRingPairs)];
     };
     auto storeBytes = [&](int blk, uint32_t o0, uint32_t o1, uint32_t o2) {
         out[3 * blk] = (uint8_t)o0;
@@ -245,20 +246,32 @@ extern "C" int swar_sim_fused(const uint8_t *segs, int T, uint8_t *out, int *fla
         case 4: stepPhase<4>(R, rx, t0, t1); break;
         default: stepPhase<5>(R, rx, t0, t1); break;
         }
-        uint4 &row = ring[(size_t)((t / 2) % ced::kRingPairs)];
+        uint4 &row = ring[(size_t)((t / 2) % Geo::kRingPairs)];
         if (t & 1) { row.z = t0; row.w = t1; } else { row.x = t0; row.y = t1; }
         const int now = t + 1;
         if (now == T) {
-            const int cc = (T - 1) / ced::kFusedE;
-            ok &= ced::fusedFinalPass<ced::Lanes8>(
-                cc, T, 6, expect, [&](int m) { return ring[(size_t)(m % ced::kRingPairs)]; }, loadBlock,
+            const int cc = (T - 1) / Geo::E;
+            ok &= ced::fusedFinalPass<ced::Lanes8, Geo>(
+                cc, T, 6, expect, [&](int m) { return ring[(size_t)(m % Geo::kRingPairs)]; }, loadBlock,
                 [&](int i, uint32_t v) { out[i] = (uint8_t)v; }, storeBytes);
-        } else if (now % ced::kFusedE == 0) {
+        } else if (now % 96 == 0) {
             ced::renorm(R);
-            ok &= ced::fusedChunkPass<ced::Lanes8>(now / ced::kFusedE - 1, bestStart ? ced::bestPositionB(R) : 0u, expect,
-                                                   loadBlock, storeBytes);
+            if (now % Geo::E == 0)
+                ok &= ced::fusedChunkPass<ced::Lanes8, Geo>(now / Geo::E - 1, bestStart ? ced::bestPositionB(R) : 0u, expect,
+                                                            loadBlock, storeBytes);
         }
     }
     *flagged = ok ? 0 : 1;
     return (L + 7) / 8;
+}
+
+extern "C" int swar_sim_fused(const uint8_t *segs, int T, uint8_t *out, int *flagged, int bestStart, int E, int D)
+{
+    if (E == 96 && D == 72) return simFused<ced::FusedGeom<96, 72>>(segs, T, out, flagged, bestStart);
+    if (E == 96 && D == 48) return simFused<ced::FusedGeom<96, 48>>(segs, T, out, flagged, bestStart);
+    if (E == 192 && D == 72) return simFused<ced::FusedGeom<192, 72>>(segs, T, out, flagged, bestStart);
+    if (E == 192 && D == 96) return simFused<ced::FusedGeom<192, 96>>(segs, T, out, flagged, bestStart);
+    if (E == 384 && D == 96) return simFused<ced::FusedGeom<384, 96>>(segs, T, out, flagged, bestStart);
+    if (E == 384 && D == 120) return simFused<ced::FusedGeom<384, 120>>(segs, T, out, flagged, bestStart);
+    return -1;
 }

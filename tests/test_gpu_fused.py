@@ -27,13 +27,15 @@ def ctx(torch_cuda):
     c = ced.Context(0)
     yield c
     c.close()
-    for k in ("CED_FUSED", "CED_FUSED_MIN_FRAMES"):
+    for k in ("CED_FUSED", "CED_FUSED_MIN_FRAMES", "CED_FUSED_GEOM"):
         os.environ.pop(k, None)
 
 
-def both_paths(ctx, code, segs, bits, packed=False):
-    """(fused output, frames handed back, two-kernel output)"""
-    os.environ["CED_FUSED"] = "1"
+def both_paths(ctx, code, segs, bits, packed=False, mode="1"):
+    """(fused output, frames handed back, two-kernel output); mode 1: traceback inside the forward warps
+    (k7FusedKernel), 2: on its own warp with bulk-copy streaming (k7FusedWsKernel; default code, byte format, aligned
+    rows -- anything else falls back to mode 1)"""
+    os.environ["CED_FUSED"] = mode
     os.environ["CED_FUSED_MIN_FRAMES"] = "1"
     dec = ctx.decode_batch_packed if packed else ctx.decode_batch
     a = dec(code, segs, bits).clone()
@@ -45,11 +47,13 @@ def both_paths(ctx, code, segs, bits, packed=False):
     return a, back, b
 
 
+@pytest.mark.parametrize("mode", ["1", "2"])
 @pytest.mark.parametrize("bits,frames,pad,offset", [
     (8, 1, 0, 0), (40, 33, 0, 0), (88, 127, 10, 0), (96, 128, 2, 0), (184, 129, 6, 0), (192, 100, 0, 0), (280, 64, 0, 0),
-    (1000 // 8 * 8, 200, 0, 0), (2048, 257, 16 - (2054 % 16), 0), (4096, 300, 10, 0), (4096, 70, 0, 3), (16384, 9, 10, 0),
+    (376, 40, 8, 0), (392, 40, 8, 0), (1000 // 8 * 8, 200, 2, 0), (2048, 257, 16 - (2054 % 16), 0), (4096, 300, 10, 0),
+    (4096, 70, 0, 3), (16384, 9, 10, 0),
 ])
-def test_fused_matches_oracle_shapes_and_alignment(torch_cuda, ctx, port, bits, frames, pad, offset):
+def test_fused_matches_oracle_shapes_and_alignment(torch_cuda, ctx, port, bits, frames, pad, offset, mode):
     """Frame lengths around the 96-step segment and the 24-step block, frame counts off the 32 / 128 grid, aligned and
     misaligned rows, the reference's maximum packet length; clean, useful, heavy and pure noise."""
     torch = torch_cuda
@@ -62,7 +66,7 @@ def test_fused_matches_oracle_shapes_and_alignment(torch_cuda, ctx, port, bits, 
         buf = torch.zeros(frames * (T + pad) + 16, dtype=torch.uint8, device="cuda")
         d = buf[offset:offset + frames * (T + pad)].view(frames, T + pad)
         d[:, :T] = torch.from_numpy(noisy).cuda()
-        a, back, b = both_paths(ctx, ced.K7_DEFAULT, d, bits)
+        a, back, b = both_paths(ctx, ced.K7_DEFAULT, d, bits, mode=mode)
         want = port.decode_batch(7, K7, noisy, T)
         assert np.array_equal(a.cpu().numpy(), want), (p, back)
         assert torch.equal(a, b)
@@ -70,8 +74,9 @@ def test_fused_matches_oracle_shapes_and_alignment(torch_cuda, ctx, port, bits, 
             assert back == 0 and np.array_equal(want, msgs)
 
 
-@pytest.mark.parametrize("code,g", [(ced.K7_DEFAULT, K7), (ced.K7_TEXTBOOK, (0o133, 0o171))])
-def test_fused_config2_shape_all_noise_levels(torch_cuda, ctx, port, ref, code, g):
+@pytest.mark.parametrize("code,g,mode", [(ced.K7_DEFAULT, K7, "1"), (ced.K7_TEXTBOOK, (0o133, 0o171), "1"),
+                                         (ced.K7_DEFAULT, K7, "2")])
+def test_fused_config2_shape_all_noise_levels(torch_cuda, ctx, port, ref, code, g, mode):
     """2^16 frames x 4096 bits: identical to the two-kernel path on every frame; a sample against the unmodified
     reference; the number of frames handed back grows with the noise and is ~0 where the code is useful."""
     torch = torch_cuda
@@ -85,7 +90,7 @@ def test_fused_config2_shape_all_noise_levels(torch_cuda, ctx, port, ref, code, 
     for p in (0.0377, 0.06, 0.12, 0.5):
         segs = clean.clone()
         ctx.bsc_channel(segs, T, 2, p, seed=int(p * 1e4))
-        a, back, b = both_paths(ctx, code, segs, bits)
+        a, back, b = both_paths(ctx, code, segs, bits, mode=mode)
         assert torch.equal(a, b), p
         handed[p] = back
         sample = np.arange(0, frames, 701)
@@ -118,10 +123,11 @@ def test_fused_packed_format_and_waves(torch_cuda, ctx, port, monkeypatch):
         c2.close()
 
 
-def test_default_call_takes_the_fused_kernel(torch_cuda, ctx):
-    """ced_decode_batch of a GPU-filling batch = 1 fused launch + 4 (empty) hand-back launches; small batches keep
-    the two-kernel path."""
+def test_fused_call_launch_count(torch_cuda, ctx):
+    """ced_decode_batch of a GPU-filling batch with CED_FUSED=1 = 1 fused launch + 4 (empty) hand-back launches; small
+    batches keep the two-kernel path."""
     torch = torch_cuda
+    os.environ["CED_FUSED"] = "1"
     segs = torch.zeros((1 << 15, 272), dtype=torch.uint8, device="cuda")
     l0 = ctx.launches
     ctx.decode_batch(ced.K7_DEFAULT, segs, 256)

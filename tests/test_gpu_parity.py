@@ -742,3 +742,31 @@ def test_speed_drivers_run(name, word):
         pytest.fail("%s did not stop" % name)
     assert "Could not" not in r.stdout, r.stdout
     assert "Rate:" in r.stdout and "Mbps" in r.stdout, r.stdout[-1500:] + r.stderr[-500:]
+
+
+def test_large_batch_is_decoded_as_waves_in_flight(torch_cuda, ctx, port):
+    """ced_decode_batch of several GPU-fills runs as waves of 2^16 frames on three internal streams
+    (decodeBatchPipelined): same bytes as the same frames decoded in single-wave calls, a sample against the
+    oracle, ragged last wave, caller's stream semantics kept (the result is complete when the caller's stream is)."""
+    torch = torch_cuda
+    frames, bits = 3 * 65536 + 777, 64
+    T = bits + 6
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=21)
+    segs = torch.zeros((frames, 80), dtype=torch.uint8, device="cuda")
+    ctx.encode_batch(ced.K7_DEFAULT, msgs, out=segs)
+    ctx.bsc_channel(segs, T, 2, 0.05, seed=3)
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    out = torch.zeros((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    stream.wait_stream(torch.cuda.current_stream())
+    ctx.decode_batch(ced.K7_DEFAULT, segs, bits, out=out, stream=stream)
+    stream.synchronize()                       # only the caller's stream: the internal streams were joined into it
+    assert ctx.launches - l0 == 2 * 4          # four waves, forward + traceback each
+    pieces = [ctx.decode_batch(ced.K7_DEFAULT, segs[a:a + 100000], bits).clone() for a in range(0, frames, 100000)]
+    ctx.sync()
+    assert torch.equal(out, torch.cat(pieces))
+    sample = np.arange(0, frames, 997)
+    noisy = segs[torch.from_numpy(sample).cuda()][:, :T].cpu().numpy()
+    assert np.array_equal(out.cpu().numpy()[sample], port.decode_batch(7, K7, noisy, T))
