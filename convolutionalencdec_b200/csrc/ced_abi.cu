@@ -417,6 +417,11 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             setError("ced_decode_batch_packed: 2-bit packing is for K=7 n=2 codes whose generators tap both ends");
             return CED_ERR_UNSUPPORTED;
         }
+        /* thread-per-frame SIMD-in-word kernels driven by a step table (swar_generic.cu): K = 3, 4, 5, 7, 9 with 2 or 3
+         * generators of any shape; what they do not take goes to the one-warp-per-frame kernel */
+        const int rc = cedDecodeBatchSwarGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
+        if (rc != CED_ERR_UNSUPPORTED)
+            return rc;
         return decodeBatchGeneric(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
     }
     const int T = frameBits + ced::kTailSteps;

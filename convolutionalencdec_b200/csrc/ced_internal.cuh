@@ -213,3 +213,8 @@ inline DecodeWorkingSet decodeWorkingSet(size_t nFrames, int T, size_t maxWaveFr
     return w;
 }
 
+
+/* swar_generic.cu: any k = 1, n = 2 / 3 code with 4 .. 256 states on the table-driven SIMD-in-word kernels;
+ * CED_ERR_UNSUPPORTED = not a code these kernels take */
+int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                              int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);

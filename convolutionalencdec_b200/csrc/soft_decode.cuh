@@ -6,7 +6,8 @@
  * hard forward kernel (decode_batch.cuh) with 16-bit metrics: the same persistent unit scheduler, the same
  * survivor stream (64 decision bits per step, two steps per 128-bit store, group-major) and therefore the
  * same traceback kernel, instantiated for the 16-bit lane layout.  Definition of the result:
- * oracle/ced_oracle.c:orc_dec_step_soft; inputs of constant magnitude reproduce the hard decoder bit for bit.
+ * the weighted Hamming cost stated in trellis_swar16.cuh (the test suite holds a CPU restatement of it); inputs of
+ * constant magnitude reproduce the hard decoder bit for bit.
  *
  * Wire format: two int8 per segment (generator 0 first), rows of 2*(frameBits+6) bytes, base and stride
  * multiples of 16 bytes.  A warp stages tiles of 32 frames x 48 segments: 6 coalesced 128-bit loads per lane,

@@ -1,0 +1,311 @@
+/*
+ * swar_generic.cu -- batched decode of any k = 1, n = 2 / 3 code with 4 .. 256 states on the table-driven
+ * SIMD-in-word kernels (swar_generic.cuh): persistent forward kernel with the unit scheduler of k7ForwardKernel,
+ * thread-per-frame traceback with cp.async-staged survivor rows.  Called by ced_decode_batch for the codes the
+ * hand-scheduled K = 7 kernels do not take (ced_abi.cu decodeBatchImpl).
+ */
+#include "ced_internal.cuh"
+#include "swar_generic.cuh"
+
+namespace ced {
+
+constexpr int kGenChunk = 96;
+
+template <int W>
+struct alignas(W >= 4 ? 16 : 4 * W) SurvRow {
+    uint32_t w[W];
+};
+
+/* Forward pass: see k7ForwardKernel (decode_batch.cuh) for the scheduler; symbols are byte-per-segment only. */
+template <int S, int V, bool ALIGNED>
+__global__ void __launch_bounds__(kFwdThreads, 3)
+genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, SurvRow<GenGeom<S>::kWords> *__restrict__ surv,
+                 const uint8_t *__restrict__ table, int n, uint32_t minusOne, FwdSched sched, int chunksPerUnit)
+{
+    using G = GenGeom<S>;
+    using TG = TileGeom<ByteSymbols, ALIGNED>;
+    constexpr int kPitch = TG::kPitch, kRegs = G::kRegs, kStateU4 = (kRegs + 3) / 4;
+    extern __shared__ __align__(16) uint8_t sMem[];
+    uint8_t *sTab = sMem;                                              /* G::tableBytes(V) */
+    uint8_t *sTile = sMem + (G::tableBytes(V) + 15) / 16 * 16;         /* [4 warps][32 * kPitch] */
+    for (int i = threadIdx.x; i < G::tableBytes(V) / 16; i += kFwdThreads)
+        reinterpret_cast<uint4 *>(sTab)[i] = reinterpret_cast<const uint4 *>(table)[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *tile = sTile + warp * 32 * kPitch;
+    const uint32_t symMask = 0x01010101u * (uint32_t)(V - 1);
+    const unsigned groups = (unsigned)((nFrames + 31) / 32);
+    const unsigned chunks = (unsigned)((T + kGenChunk - 1) / kGenChunk);
+    const unsigned unitsPerGroup = (chunks + chunksPerUnit - 1) / chunksPerUnit;
+    const unsigned total = groups * unitsPerGroup;
+
+    auto grab = [&]() -> unsigned {
+        unsigned v = 0;
+        if (lane == 0)
+            v = atomicAdd(sched.counter, 1u);
+        return __shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+    unsigned u = grab();
+    uint4 pre[TG::kPiecesPerRow];
+    if (u < total)
+        loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)((u / groups) * chunksPerUnit) * kGenChunk,
+                                      T, lane);
+    while (u < total) {
+        const unsigned g = u % groups, su = u / groups;
+        const unsigned cFirst = su * chunksPerUnit, cEnd = min(chunks, cFirst + chunksPerUnit);
+        const long long frame0 = 32LL * g;
+        const bool live = frame0 + lane < nFrames;
+        uint4 *stateSlot = sched.state + ((size_t)g * kStateU4) * 32 + lane;
+        uint32_t R[kRegs];
+        if (su == 0) {
+            genInitMetrics<S>(R, n);
+        } else {
+            if (lane == 0)
+                while (ldAcquire(sched.done + g) < (int)su)
+                    __nanosleep(200);
+            __syncwarp();
+            __threadfence();
+#pragma unroll
+            for (int i = 0; i < kStateU4; i++) {
+                const uint4 v = __ldcg(stateSlot + i * 32);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (4 * i + k < kRegs)
+                        R[4 * i + k] = w[k];
+            }
+        }
+        unsigned un = total;
+        for (unsigned c = cFirst; c < cEnd; c++) {
+            const int t0 = (int)c * kGenChunk;
+            __syncwarp();
+            storeTile<ByteSymbols, ALIGNED>(tile, pre, lane, symMask);
+            if (c + 1 < cEnd) {
+                loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, frame0, nFrames, t0 + kGenChunk, T, lane);
+            } else {
+                un = grab();
+                if (un < total)
+                    loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, 32LL * (un % groups), nFrames,
+                                                  (int)((un / groups) * chunksPerUnit) * kGenChunk, T, lane);
+            }
+            __syncwarp();
+            const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride + (size_t)t0;
+            const uint8_t *p = tile + lane * kPitch + (ALIGNED ? 0u : (rowAddr & 15u));
+            SurvRow<G::kWords> *o = surv + ((size_t)g * T + t0) * 32 + lane;
+            const int steps = min(kGenChunk, T - t0);
+            for (int done = 0; done < steps;) {
+                const int nr = min(G::kRenorm, steps - done);
+#pragma unroll 1
+                for (int base = 0; base < nr; base += S) {
+                    const int nn = min(S, nr - base);          /* whole label rotations except at the end of the frame */
+                    auto one = [&](auto phTag) {
+                        constexpr int PH = decltype(phTag)::value;
+                        if (PH < nn) {
+                            const uint32_t off = p[PH];          /* rx * 32 */
+                            constexpr int q = S - 1 - PH;
+                            const uint8_t *tab = sTab + G::phaseBase(PH, V) + (q >= 2 ? off : (off >> 1));
+                            uint32_t Tw[G::kWords];
+                            genStep<S, PH>(R, tab, (q >= 2 ? 32 : 16) * V, minusOne, Tw);
+                            if (live) {
+                                SurvRow<G::kWords> row;
+#pragma unroll
+                                for (int w = 0; w < G::kWords; w++)
+                                    row.w[w] = Tw[w];
+                                o[(size_t)PH * 32] = row;
+                            }
+                        }
+                    };
+                    one(std::integral_constant<int, 0>());
+                    one(std::integral_constant<int, 1>());
+                    if constexpr (S > 2) one(std::integral_constant<int, 2>());
+                    if constexpr (S > 3) one(std::integral_constant<int, 3>());
+                    if constexpr (S > 4) { one(std::integral_constant<int, 4>()); one(std::integral_constant<int, 5>()); }
+                    if constexpr (S > 6) { one(std::integral_constant<int, 6>()); one(std::integral_constant<int, 7>()); }
+                    p += S;
+                    o += (size_t)S * 32;
+                }
+                done += nr;
+                if (done < steps || c + 1 < chunks)
+                    genRenorm<S>(R);
+            }
+        }
+        if (cEnd < chunks) {
+#pragma unroll
+            for (int i = 0; i < kStateU4; i++) {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (4 * i + k < kRegs)
+                        w[k] = R[4 * i + k];
+                __stcg(stateSlot + i * 32, make_uint4(w[0], w[1], w[2], w[3]));
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                stRelease(sched.done + g, (int)su + 1);
+        }
+        u = un;
+    }
+}
+
+/* Full-frame traceback from state 0 (src/viterbiDecoderButterflyk1.c:205-254), one thread per frame; the rows of the
+ * next 8 steps are fetched with cp.async into the thread's own shared-memory slots while the current 8 are walked. */
+template <int S>
+__global__ void __launch_bounds__(kTbThreads)
+genTracebackKernel(const SurvRow<GenGeom<S>::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out,
+                   size_t outStride)
+{
+    using G = GenGeom<S>;
+    using Row = SurvRow<G::kWords>;
+    __shared__ Row sW[2][8][kTbThreads];
+    const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= nFrames)
+        return;
+    const Row *s = surv + ((size_t)(frame / 32) * T) * 32 + (frame & 31);
+    uint8_t *dst = out + (size_t)frame * outStride;
+    const int L = T - S, nBlocks = L / 8, tid = threadIdx.x;
+    auto prefetch = [&](int blk, int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const Row *src = s + (size_t)(8 * blk + i) * 32;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sW[buf][i][tid]);
+            if constexpr (sizeof(Row) >= 16) {
+#pragma unroll
+                for (int k = 0; k < (int)sizeof(Row) / 16; k++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16 * k),
+                                 "l"(reinterpret_cast<const uint8_t *>(src) + 16 * k));
+            } else if constexpr (sizeof(Row) == 8) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src));
+            } else {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (nBlocks > 0)
+        prefetch(nBlocks - 1, 0);
+    uint32_t p = 0; /* state 0 sits at position 0 in every phase */
+    for (int t = T - 1; t >= L; t--) {   /* the S tail steps carry no output (:208-223) */
+        const Row row = s[(size_t)t * 32];
+        genTracebackStep<S>(p, row.w, t);
+    }
+    int buf = 0;
+    for (int blk = nBlocks - 1; blk >= 0; blk--, buf ^= 1) {
+        if (blk > 0) {
+            prefetch(blk - 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            const Row row = sW[buf][i][tid];
+            acc |= genTracebackStep<S>(p, row.w, 8 * blk + i) << (7 - i);   /* MSb first (:249) */
+        }
+        dst[blk] = (uint8_t)acc;
+    }
+}
+
+} // namespace ced
+
+/* taps, table and launch for one call; returns CED_ERR_UNSUPPORTED if the code is outside what these kernels take
+ * (the caller then falls back to the one-warp-per-frame kernel) */
+template <int S>
+static int launchGen(ced_ctx *c, const ced::GenCode &gc, const uint8_t *dSegs, size_t segStride, int nFrames, int frameBits,
+                     uint8_t *dOut, size_t outStride, cudaStream_t s, int slot)
+{
+    using G = ced::GenGeom<S>;
+    using Row = ced::SurvRow<G::kWords>;
+    const int T = frameBits + S, V = 1 << gc.n;
+    ced_ctx::Work &wk = c->work[slot];
+    const size_t perFrame = (size_t)T * sizeof(Row);
+    size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame)) / 64 * 64;
+    const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax), g0 = (firstWave + 31) / 32;
+    constexpr int kStateU4 = (G::kRegs + 3) / 4;
+    const size_t tabBytes = (size_t)G::tableBytes(V);
+    const size_t stateBytes = g0 * kStateU4 * 32 * sizeof(uint4) + tabBytes + 256, flagBytes = (g0 + 1) * sizeof(int);
+    if (wk.scratch.bytes < g0 * 32 * perFrame || wk.schedState.bytes < stateBytes || wk.schedFlags.bytes < flagBytes) {
+        CED_CUDA(cudaDeviceSynchronize());
+        int rc = wk.scratch.ensure(g0 * 32 * perFrame);
+        if (rc == CED_OK) rc = wk.schedState.ensure(stateBytes);
+        if (rc == CED_OK) rc = wk.schedFlags.ensure(flagBytes);
+        if (rc != CED_OK)
+            return rc;
+    }
+    if (wk.lastStream && wk.lastStream != s)
+        CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
+    /* the step table of this code: built on the host (a few KB), kept behind the hand-off slots of the working set */
+    std::vector<uint8_t> table(tabBytes);
+    ced::buildGenTable<S>(gc, table.data());
+    uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p) + (stateBytes - tabBytes - 256 + 255) / 256 * 256;
+    CED_CUDA(cudaMemcpyAsync(dTable, table.data(), tabBytes, cudaMemcpyHostToDevice, s));   /* pageable source: staged */
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0;
+    const size_t pitchA = ced::TileGeom<ced::ByteSymbols, true>::kPitch, pitchU = ced::TileGeom<ced::ByteSymbols, false>::kPitch;
+    const size_t smem = (tabBytes + 15) / 16 * 16 + 4 * 32 * (aligned16 ? pitchA : pitchU);
+    auto kernelFor = [&](bool al) -> void (*)(const uint8_t *, size_t, int, int, Row *, const uint8_t *, int, uint32_t, ced::FwdSched, int) {
+        if (gc.n == 2)
+            return al ? ced::genForwardKernel<S, 4, true> : ced::genForwardKernel<S, 4, false>;
+        return al ? ced::genForwardKernel<S, 8, true> : ced::genForwardKernel<S, 8, false>;
+    };
+    auto kernel = kernelFor(aligned16);
+    CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int resident = 0;
+    CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, ced::kFwdThreads, smem));
+    resident = std::max(1, resident);
+    for (size_t f0 = 0; f0 < (size_t)nFrames; f0 += waveMax) {
+        const int wave = (int)std::min<size_t>(waveMax, (size_t)nFrames - f0);
+        const int groups = (wave + 31) / 32;
+        const int perSm = std::max(1, std::min({4, resident, std::max(3, groups / (4 * c->sms))}));
+        const int blocks = std::max(1, std::min(c->sms * perSm, (groups + 3) / 4));
+        ced::FwdSched sched;
+        sched.counter = reinterpret_cast<unsigned int *>(wk.schedFlags.p);
+        sched.done = wk.schedFlags.p + 1;
+        sched.state = wk.schedState.p;
+        CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
+        kernel<<<blocks, ced::kFwdThreads, smem, s>>>(dSegs + f0 * segStride, segStride, wave, T, reinterpret_cast<Row *>(wk.scratch.p),
+                                                     dTable, gc.n, c->bm0113.minusOne, sched, 2);
+        ced::genTracebackKernel<S><<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
+            reinterpret_cast<const Row *>(wk.scratch.p), wave, T, dOut + f0 * outStride, outStride);
+        c->launches += 2;
+    }
+    CED_CUDA(cudaEventRecord(wk.idle, s));
+    wk.lastStream = s;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                              int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
+{
+    if (!code || code->codedBits < 2 || code->codedBits > 3)
+        return CED_ERR_UNSUPPORTED;
+    const int K = code->constraintLen, S = K - 1;
+    if (!(S == 2 || S == 3 || S == 4 || S == 6 || S == 8) || (code->codedBits == 3 && S > 6))
+        return CED_ERR_UNSUPPORTED;
+    static const bool off = getenv("CED_SWAR_GENERIC") && atoi(getenv("CED_SWAR_GENERIC")) == 0;
+    if (off)
+        return CED_ERR_UNSUPPORTED;
+    if (segStride < (size_t)(frameBits + S) || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    ced::GenCode gc;
+    gc.S = S;
+    gc.n = code->codedBits;
+    for (int i = 0; i < 3; i++)
+        gc.tap[i] = i < gc.n ? reverseBits(code->gen[i], K) : 0u;
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    switch (S) {
+    case 2: return launchGen<2>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+    case 3: return launchGen<3>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+    case 4: return launchGen<4>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+    case 6: return launchGen<6>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+    default: return launchGen<8>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+    }
+}

@@ -10,7 +10,7 @@
  *   (partner = same register, halves swapped, one PRMT).
  *
  * Branch costs.  A received segment is two int8 (s0 for generator 0, s1 for generator 1; BPSK bit 0 -> +).
- * The decoder's definition (oracle/ced_oracle.c:orc_dec_step_soft) weights every disagreeing coded bit by
+ * The decoder's definition (include/ced_abi.h, ced_decode_soft_batch) weights every disagreeing coded bit by
  * its reliability, cost(c) = sum_i |s_i| [hard(s_i) != c_i] -- the reference's calcHammingDist
  * (src/viterbiDecoder.c:260-285) generalised.  The kernel uses the affinely equivalent correlation form
  *   x_i = 128 - s_i in [1,256]      cost'(c) = sum_i (c_i ? 256 - x_i : x_i) = 2 cost(c) + (256 - |s0| - |s1|)
@@ -21,7 +21,7 @@
  *
  * Exactness of the 16-bit guard-bit compare: a branch costs <= 512, the smallest metric grows by <= 256 per
  * step (the two branches out of a state cost c and 512 - c), the spread is <= 6 * 512 once all states are
- * reachable and start metrics are 3584 (= 2 * the oracle's 1792) before that, so with a renormalisation every
+ * reachable and start metrics are 3584 (= 2 * n * 128 * K in correlation units) before that, so with a renormalisation every
  * 48 steps candidates stay below 3072 + 48 * 256 + 512 = 15872 < 32768: bit 15 is free for the guard.
  */
 #pragma once
@@ -30,7 +30,7 @@
 namespace ced {
 
 constexpr uint32_t kGuard16 = 0x80008000u;
-constexpr uint32_t kSoftInit = 3584u;           /* "never wins": 2 * (n * 128 * K) of the oracle */
+constexpr uint32_t kSoftInit = 3584u;           /* "never wins": 2 * (n * 128 * K), above any reachable metric */
 constexpr uint32_t kSoftFull = 0x02000200u;     /* cost'(c) + cost'(~c) in both lanes */
 constexpr int kSoftRenormPeriod = 48;
 

@@ -275,3 +275,79 @@ extern "C" int swar_sim_fused(const uint8_t *segs, int T, uint8_t *out, int *fla
     if (E == 384 && D == 120) return simFused<ced::FusedGeom<384, 120>>(segs, T, out, flagged, bestStart);
     return -1;
 }
+
+// Any k = 1 code with 4 .. 256 states and n = 2 / 3 through the table-driven step functions of swar_generic.cuh
+// (what genForwardKernel / genTracebackKernel run per thread): returns the largest metric seen, -1 = not a code it takes.
+#include "swar_generic.cuh"
+
+template <int S>
+static int decodeGen(const ced::GenCode &gc, const uint8_t *segs, int T, uint8_t *out)
+{
+    using G = ced::GenGeom<S>;
+    const int V = 1 << gc.n;
+    std::vector<uint8_t> table((size_t)G::tableBytes(V) + 16);
+    ced::buildGenTable<S>(gc, table.data());
+    uint32_t R[G::kRegs];
+    ced::genInitMetrics<S>(R, gc.n);
+    std::vector<uint32_t> surv((size_t)G::kWords * (size_t)T);
+    int mx = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t Tw[G::kWords];
+        const int ph = t % S;
+        const uint32_t rx = segs[t] & (uint32_t)(V - 1);
+        const int q = S - 1 - ph;
+        const uint8_t *tab = table.data() + G::phaseBase(ph, V) + rx * (q >= 2 ? 32 : 16);
+        const int stride = (q >= 2 ? 32 : 16) * V;
+        switch (ph) {
+        case 0: ced::genStep<S, 0>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 1: ced::genStep<S, 1>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 2: if constexpr (S > 2) ced::genStep<S, 2>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 3: if constexpr (S > 3) ced::genStep<S, 3>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 4: if constexpr (S > 4) ced::genStep<S, 4>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 5: if constexpr (S > 5) ced::genStep<S, 5>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        case 6: if constexpr (S > 6) ced::genStep<S, 6>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        default: if constexpr (S > 7) ced::genStep<S, 7>(R, tab, stride, 0xFFFFFFFFu, Tw); break;
+        }
+        for (int w = 0; w < G::kWords; w++)
+            surv[(size_t)t * G::kWords + w] = Tw[w];
+        for (int r = 0; r < G::kRegs; r++)
+            for (int l = 0; l < 4; l++) {
+                if (4 * r + l >= G::kStates) continue;
+                const int v = (R[r] >> (8 * l)) & 0xFF;
+                if (v > mx) mx = v;
+            }
+        if ((t + 1) % G::kRenorm == 0)
+            ced::genRenorm<S>(R);
+    }
+    const int L = T - S;
+    for (int i = 0; i < (L + 7) / 8; i++) out[i] = 0;
+    uint32_t p = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        const uint32_t bit = ced::genTracebackStep<S>(p, &surv[(size_t)t * G::kWords], t);
+        if (t < L)
+            out[t / 8] |= (uint8_t)(bit << (7 - (t % 8)));
+    }
+    return mx;
+}
+
+extern "C" int swar_sim_decode_gen(int K, int n, const uint32_t *gens, const uint8_t *segs, int T, uint8_t *out)
+{
+    ced::GenCode gc;
+    gc.S = K - 1;
+    gc.n = n;
+    if (n < 2 || n > 3) return -1;
+    for (int i = 0; i < 3; i++) {
+        gc.tap[i] = 0;
+        if (i < n)
+            for (int b = 0; b < K; b++)   /* taps with bit 0 on the newest input bit (src/convEncode.c:163-175) */
+                gc.tap[i] |= ((gens[i] >> b) & 1u) << (K - 1 - b);
+    }
+    switch (gc.S) {
+    case 2: return decodeGen<2>(gc, segs, T, out);
+    case 3: return decodeGen<3>(gc, segs, T, out);
+    case 4: return decodeGen<4>(gc, segs, T, out);
+    case 6: return decodeGen<6>(gc, segs, T, out);
+    case 8: return decodeGen<8>(gc, segs, T, out);
+    default: return -1;
+    }
+}

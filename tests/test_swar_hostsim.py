@@ -114,3 +114,36 @@ def test_runtime_table_path_matches_oracle(sim, port, g):
                                     out.ctypes.data_as(u8p))
         assert mx < 128 - n, (g, bits, p, mx)
         assert np.array_equal(out, port.decode_batch(7, list(g), noisy[None, :], bits + 6)[0]), (g, bits, p)
+
+
+GEN_CODES = [(3, (0b111, 0b110)), (3, (0b111, 0b101)), (3, (0b101, 0b011)), (3, (0b111, 0b101, 0b011)),
+             (4, (0o15, 0o17)), (4, (0o13, 0o15, 0o17)), (4, (0o14, 0o07)),
+             (5, (0o23, 0o35)), (5, (0o25, 0o33, 0o37)), (5, (0o30, 0o07)),
+             (7, (0o133, 0o170)), (7, (0o066, 0o171)), (7, (0o113, 0o171)), (7, (0o133, 0o145, 0o174)),
+             (9, (0o561, 0o753)), (9, (0o557, 0o663, 0o711)), (9, (0o460, 0o353))]
+
+
+@pytest.mark.parametrize("K,g", GEN_CODES)
+def test_generic_table_path_matches_oracle(sim, port, K, g):
+    """genStep / buildGenTable / genTracebackStep (swar_generic.cuh: any k = 1 code with 4..256 states, generators
+    that need not tap both ends) against the oracle's general butterflies; the largest metric must leave the guard
+    bit free."""
+    sim.swar_sim_decode_gen.argtypes = [C.c_int, C.c_int, u32p, u8p, C.c_int, u8p]
+    rng = np.random.default_rng(K * 1000 + sum(g))
+    n, S = len(g), K - 1
+    gens = np.array(g, dtype=np.uint32)
+    for bits, p in ((8, 0.0), (48, 0.0), (40, 0.2), (512, 0.03), (2048, 0.07), (1024, 0.5), (4096, 0.5)):
+        msg = rng.integers(0, 256, (1, bits // 8), dtype=np.uint8)
+        clean = port.encode_batch(K, list(g), msg)
+        flips = rng.random(clean.shape + (n,)) < p
+        noisy = clean.copy()
+        for j in range(n):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        noisy |= rng.integers(0, 32, noisy.shape, dtype=np.uint8) << 3  # bits above n are ignored
+        noisy = np.ascontiguousarray(noisy[0])
+        out = np.zeros(bits // 8, dtype=np.uint8)
+        mx = sim.swar_sim_decode_gen(K, n, gens.ctypes.data_as(u32p), noisy.ctypes.data_as(u8p), bits + S,
+                                     out.ctypes.data_as(u8p))
+        assert 0 <= mx < 128 - n, (K, g, bits, p, mx)
+        want = port.decode_batch(K, list(g), noisy[None, :], bits + S, symmetric=False)[0]
+        assert np.array_equal(out, want), (K, g, bits, p)

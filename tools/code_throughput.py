@@ -1,5 +1,6 @@
 """Decode throughput per code: the two compile-time K=7 codes, run-time K=7 generators through the
-step-table SWAR kernel, and other K / n through the generic one-warp-per-frame kernel."""
+step-table SWAR kernel, and other K / n through the table-driven SWAR kernels of swar_generic.cu (CED_SWAR_GENERIC=0:
+the one-warp-per-frame kernel they replaced)."""
 import os
 import sys
 
@@ -11,8 +12,10 @@ import convolutionalencdec_b200 as ced  # noqa: E402
 ctx = ced.Context(0)
 bits = 4096
 for K, g, frames in ((7, (0o113, 0o171), 1 << 16), (7, (0o133, 0o171), 1 << 16), (7, (0o171, 0o133), 1 << 16),
-                     (7, (0o117, 0o155), 1 << 16), (7, (0o133, 0o170), 1 << 14), (3, (7, 6), 1 << 14),
-                     (9, (0o561, 0o753), 1 << 14), (7, (0o133, 0o171, 0o165), 1 << 16), (7, (0o133, 0o145, 0o174), 1 << 14)):
+                     (7, (0o117, 0o155), 1 << 16), (7, (0o133, 0o171, 0o165), 1 << 16),
+                     (7, (0o133, 0o170), 1 << 16), (7, (0o133, 0o145, 0o174), 1 << 16),
+                     (3, (7, 6), 1 << 16), (3, (7, 5, 3), 1 << 16), (4, (0o15, 0o17), 1 << 16), (5, (0o23, 0o35), 1 << 16),
+                     (5, (0o25, 0o33, 0o37), 1 << 16), (9, (0o561, 0o753), 1 << 16)):
     code = ced.Code(K, g)
     T = bits + K - 1
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
