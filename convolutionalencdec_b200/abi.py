@@ -85,6 +85,8 @@ def load_abi():
     lib.ced_decode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_encode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_encode_batch_k.argtypes = [vp, codep, i, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_k.argtypes = [vp, codep, i, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_packed_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_pack_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_host_pack_symbols.argtypes = [_u8p, sz, i, i, _u8p, sz, i]
@@ -389,6 +391,28 @@ class Context:
                                                    int(seed), int(first_frame),
                                                    counters.data_ptr() if counters is not None else None,
                                                    _stream_handle(stream)), "ced_awgn_channel")
+        return out
+
+    # ---- rate-k/n codes with k > 1: code.g are the k*K-bit generators, code.K the constraint length ----
+    def encode_batch_k(self, code, k, msgs, out=None, stream=None, seg_stride=None):
+        import torch
+        nf, nb = msgs.shape
+        T = 8 * nb // k + code.S
+        if out is None:
+            out = torch.zeros((nf, seg_stride or T), dtype=torch.uint8, device=msgs.device)
+        _check(self.lib, self.lib.ced_encode_batch_k(self.h, C.byref(code._c), k, msgs.data_ptr(), msgs.stride(0), nf, nb,
+                                                     out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_encode_batch_k")
+        return out
+
+    def decode_batch_k(self, code, k, segs, frame_bits, out=None, stream=None):
+        import torch
+        nf = segs.shape[0]
+        if out is None:
+            out = torch.empty((nf, frame_bits // 8), dtype=torch.uint8, device=segs.device)
+        _check(self.lib, self.lib.ced_decode_batch_k(self.h, C.byref(code._c), k, segs.data_ptr(), segs.stride(0), nf,
+                                                     frame_bits, out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_decode_batch_k")
         return out
 
     def encode_batch_packed(self, code, msgs, out=None, stream=None, packed_stride=None):

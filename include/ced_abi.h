@@ -99,8 +99,10 @@ int ced_ctx_last_fallback_frames(ced_ctx *ctx, int *frames);
  * alignment is accepted.
  * Codes: any k=1 code with constraintLen 2..9 and 1..8 coded bits.  K=7 codes with
  * 2 or 3 generators that all tap the newest and the oldest bit (src/viterbiDecoder.c:20-24)
- * run on the SIMD-in-word kernel -- 0113/0171 and 0133/0171 compiled in, any other
- * set through a table built on first use; everything else on a generic kernel.
+ * run on the hand-scheduled SIMD-in-word kernel -- 0113/0171 and 0133/0171 compiled in, any
+ * other set through a table built on first use; K = 3, 4, 5, 7, 9 with 2 or 3 generators of
+ * ANY shape on table-driven SIMD-in-word kernels (swar_generic.cu); the rest on a
+ * one-warp-per-frame kernel.  (k > 1: ced_decode_batch_k.)
  */
 int ced_decode_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
                      int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream);
@@ -227,6 +229,22 @@ int ced_bsc_channel(ced_ctx *ctx, uint8_t *dSegs, size_t segStride, int nFrames,
 /* Uniform random message bytes keyed by (seed, frame index, byte index). */
 int ced_random_bytes(ced_ctx *ctx, uint8_t *dMsg, size_t msgStride, int nFrames, int frameBytes,
                      uint64_t seed, uint64_t firstFrameIndex, void *stream);
+
+/* ------------------------------------------------ rate-k/n codes with k > 1
+ * The reference's headers describe a code by K, k, n and n generators of k*K bits: ONE shift register of k*K bits that
+ * takes inputBits = k message bits per coded segment (src/convEncode.h:8-18, src/convEncode.c:46-130), decoded on a
+ * trellis of 2^(k*(K-1)) states with 2^k branches into every state (src/viterbiDecoder.c:95-128; the lowest edgeIn keeps
+ * a tie).  code->gen[i] is generator i as the reference writes it (MSb = newest input bit, k*K bits wide).
+ * A frame of frameBytes*8 message bits is frameBytes*8/k + K-1 segments, one byte per segment (low n bits).
+ * The decoder is the reference's add-compare-select followed by the full traceback from state 0 that its butterfly
+ * decoder performs (src/viterbiDecoderButterflyk1.c:200-256, formulas for general k) -- the reference's own k > 1
+ * traceback does not run at HEAD; encoder, trellis labels and per-step path metrics are pinned to the unmodified
+ * reference built with k = 2 parameters (tests/test_oracle_k.py).
+ * inputBits in {1, 2, 4} (1 forwards to ced_encode_batch / ced_decode_batch), k*(K-1) <= 8, k*K <= 32. */
+int ced_encode_batch_k(ced_ctx *ctx, const ced_code_t *code, int inputBits, const uint8_t *dMsg, size_t msgStride,
+                       int nFrames, int frameBytes, uint8_t *dSegs, size_t segStride, void *stream);
+int ced_decode_batch_k(ced_ctx *ctx, const ced_code_t *code, int inputBits, const uint8_t *dSegs, size_t segStride,
+                       int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream);
 
 /* ------------------------------------------------ one process, several GPUs
  * Frames are independent packets (the reference resets its state per packet,

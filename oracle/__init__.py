@@ -84,9 +84,52 @@ class Port:
         lib.orc_decode_soft_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                               _u8p, C.c_size_t]
 
+        _u32p = C.POINTER(C.c_uint32)
+        lib.orck_encode_batch.restype = C.c_int
+        lib.orck_encode_batch.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u8p, C.c_size_t, C.c_int, C.c_int, _u8p,
+                                          C.c_size_t]
+        lib.orck_decode_batch.restype = C.c_int
+        lib.orck_decode_batch.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u8p, C.c_size_t, C.c_int, C.c_int, _u8p,
+                                          C.c_size_t]
+        lib.orck_edges.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u8p]
+        lib.orck_metrics.restype = C.c_int
+        lib.orck_metrics.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u8p, C.c_int, _u32p]
+
     @staticmethod
     def _g(g):
         return (C.c_uint64 * len(g))(*g)
+
+    # ---- k > 1 (ced_oracle_k.c): one k*K-bit shift register, k bits per segment ----
+    def encode_batch_k(self, K, k, g, msgs, seg_stride=None):
+        msgs = np.ascontiguousarray(msgs, dtype=np.uint8)
+        nf, nb = msgs.shape
+        T = 8 * nb // k + K - 1
+        stride = seg_stride or T
+        segs = np.zeros((nf, stride), dtype=np.uint8)
+        assert self.lib.orck_encode_batch(K, k, len(g), self._g(g), _p(msgs), nb, nf, nb, _p(segs), stride) == 0
+        return segs
+
+    def decode_batch_k(self, K, k, g, segs, T):
+        segs = np.ascontiguousarray(segs, dtype=np.uint8)
+        nf, stride = segs.shape
+        nbytes = (T - (K - 1)) * k // 8
+        out = np.zeros((nf, nbytes), dtype=np.uint8)
+        assert self.lib.orck_decode_batch(K, k, len(g), self._g(g), _p(segs), stride, nf, T, _p(out), nbytes) == 0
+        return out
+
+    def edges_k(self, K, k, g):
+        N = 1 << (k * (K - 1))
+        out = np.zeros((1 << k, N), dtype=np.uint8)
+        self.lib.orck_edges(K, k, len(g), self._g(g), _p(out))
+        return out
+
+    def metrics_k(self, K, k, g, segs):
+        segs = np.ascontiguousarray(segs, dtype=np.uint8)
+        N = 1 << (k * (K - 1))
+        out = np.zeros((segs.size, N), dtype=np.uint32)
+        assert self.lib.orck_metrics(K, k, len(g), self._g(g), _p(segs), segs.size,
+                                     out.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+        return out
 
     def taps(self, K, g):
         out = (C.c_uint32 * len(g))()
@@ -315,6 +358,52 @@ class Ref:
         el = C.c_double(0)
         bits = self.lib.refh_speed_encode(_p(msgs), nf, nb, threads, float(seconds), C.byref(el))
         return bits, el.value
+
+
+class RefK:
+    """The unmodified reference built with k = 2 parameters (oracle/params/<name>/) behind ref_harness_k.c: encoder,
+    edge labels and per-step path metrics of its generic decoder (whose traceback does not run at HEAD)."""
+
+    def __init__(self, name):
+        path = os.path.join(HERE, "_ref", "libced_refk_%s.so" % name)
+        if not os.path.exists(path):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = lib = C.CDLL(path)
+        lib.refk_g.restype = C.c_uint64
+        lib.refk_g.argtypes = [C.c_int]
+        lib.refk_encode.restype = C.c_int
+        lib.refk_encode.argtypes = [_u8p, C.c_int, _u8p]
+        lib.refk_edges.argtypes = [_u8p]
+        lib.refk_metrics.argtypes = [_u8p, C.c_int, C.POINTER(C.c_uint32)]
+        self.K, self.k, self.n, self.N = lib.refk_K(), lib.refk_k(), lib.refk_n(), lib.refk_states()
+        self.g = [int(lib.refk_g(i)) for i in range(self.n)]
+
+    def encode(self, msg):
+        msg = np.ascontiguousarray(msg, dtype=np.uint8)
+        segs = np.zeros(8 * msg.size // self.k + self.K + 8, dtype=np.uint8)
+        cnt = self.lib.refk_encode(_p(msg), msg.size, _p(segs))
+        return segs[:cnt].copy()
+
+    def edges(self):
+        out = np.zeros((1 << self.k, self.N), dtype=np.uint8)
+        self.lib.refk_edges(_p(out))
+        return out
+
+    def metrics(self, segs):
+        segs = np.ascontiguousarray(segs, dtype=np.uint8)
+        out = np.zeros((segs.size, self.N), dtype=np.uint32)
+        self.lib.refk_metrics(_p(segs), segs.size, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return out
+
+
+def refk(name):
+    """Reference built with the k = 2 parameters `name`, or None when oracle/_ref was never built."""
+    try:
+        return RefK(name)
+    except (FileNotFoundError, OSError, subprocess.CalledProcessError):
+        return None
 
 
 _PORT = None

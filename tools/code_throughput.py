@@ -35,3 +35,24 @@ for K, g, frames in ((7, (0o113, 0o171), 1 << 16), (7, (0o133, 0o171), 1 << 16),
     print("K=%d g=%s frames=%d: %8.1f Gbit/s (%.3f ms), %d wrong bytes" % (
         K, [oct(x) for x in g], frames, frames * bits / ms / 1e6, ms, errs))
 ctx.close()
+
+# rate-k/n codes with k > 1 (csrc/radix_k.cu, one warp per frame)
+ctx = ced.Context(0)
+for K, k, g, frames in ((3, 2, (0o27, 0o75, 0o72), 1 << 14), (4, 2, (0o236, 0o155, 0o337), 1 << 14),
+                        (5, 2, (0o1236, 0o0155, 0o1337), 1 << 13)):
+    code = ced.Code(K, g)
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=3)
+    segs = ctx.encode_batch_k(code, k, msgs)
+    out = torch.empty_like(msgs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(3):
+        if rep == 1:
+            e0.record()
+        ctx.decode_batch_k(code, k, segs, bits, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    print("K=%d k=%d g=%s frames=%d: %8.1f Gbit/s (%.3f ms), %d wrong bytes" % (
+        K, k, [oct(x) for x in g], frames, frames * bits / ms / 1e6, ms, int((out != msgs).sum())))
+ctx.close()
