@@ -169,7 +169,7 @@ def _cpu_reference_rate(seconds, threads=None, frames=None):
         kind = "port"
         how = "oracle/ced_oracle.c (C restatement)"
     return {"value": bits / el / 1e9, "unit": "Gbit/s", "cores": threads, "kind": kind,
-            "sample": "%d noisy frames x %d bits decoded round-robin for %.1f s wall on %d threads, %s"
+            "sample": "%d noisy frames x %d bits decoded round-robin for %.1f s wall on %d threads (one pinned per CPU), %s"
                       % (frames, FRAME_BITS, el, threads, how)}, bits, el
 
 

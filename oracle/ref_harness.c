@@ -13,6 +13,7 @@
 #include "convEncode.h"
 #include "viterbiDecoder.h"
 #include <pthread.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -190,9 +191,27 @@ int64_t refh_speed_decode(const uint8_t *segs, size_t stride, int nFrames, int s
     pthread_t *th = malloc(sizeof(pthread_t) * (size_t)nThreads);
     refh_speed_arg_t *args = calloc((size_t)nThreads, sizeof(refh_speed_arg_t));
     const double t0 = refh_now();
+    /* one thread per host core, each pinned to its own CPU of this process's affinity mask (the way
+     * speedDecode.c:23,147 pins its worker); with more threads than CPUs the extra ones share round-robin */
+    cpu_set_t allowed;
+    int cpus[CPU_SETSIZE], nCpus = 0;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &allowed))
+                cpus[nCpus++] = c;
     for (int i = 0; i < nThreads; i++) {
         args[i] = (refh_speed_arg_t){segs, stride, nFrames, segsPerFrame, i * 7, budgetSeconds, 0, 0};
-        pthread_create(&th[i], NULL, refh_speed_thread, &args[i]);
+        pthread_attr_t attr;
+        pthread_attr_init(&attr);
+        if (nCpus > 0) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(cpus[i % nCpus], &one);
+            pthread_attr_setaffinity_np(&attr, sizeof(one), &one);
+        }
+        if (pthread_create(&th[i], &attr, refh_speed_thread, &args[i]) != 0)
+            pthread_create(&th[i], NULL, refh_speed_thread, &args[i]);
+        pthread_attr_destroy(&attr);
     }
     int64_t bits = 0;
     for (int i = 0; i < nThreads; i++) {
