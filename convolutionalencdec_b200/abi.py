@@ -85,6 +85,7 @@ def load_abi():
     lib.ced_decode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_encode_batch.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_stream_server_stats.argtypes = [C.POINTER(u64), C.POINTER(u64)]
     lib.ced_encode_batch_k.argtypes = [vp, codep, i, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_k.argtypes = [vp, codep, i, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_packed_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]

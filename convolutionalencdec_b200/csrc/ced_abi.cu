@@ -10,10 +10,12 @@
 #include "decode_fused.cuh"
 #include "encode_batch.cuh"
 #include "frame_parallel.cuh"
+#include "frame_server.cuh"
 #include "probe_kernels.cuh"
 #include "stream_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
@@ -22,6 +24,11 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+
+static std::atomic<ced_ctx *> gServerCtx{nullptr}; /* context that owns the resident packet decoder */
+extern "C" {
+static void fsStop(ced_ctx *c);
+}
 
 static thread_local char gLastError[512] = "";
 
@@ -153,7 +160,16 @@ void ced_ctx_destroy(ced_ctx *c)
     if (!c)
         return;
     cudaSetDevice(c->device);
+    if (gServerCtx.load() == c)
+        gServerCtx.store(nullptr);
+    fsStop(c);
     cudaDeviceSynchronize();
+    if (c->fsMailbox)
+        cudaFreeHost(c->fsMailbox);
+    if (c->fsCtl)
+        cudaFree(c->fsCtl);
+    if (c->fsStream)
+        cudaStreamDestroy(c->fsStream);
     for (auto &w : c->work) {
         if (w.idle)
             cudaEventDestroy(w.idle);
@@ -407,6 +423,7 @@ static int decodeBatchGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
 static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
                            int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0)
 {
+    cedStopPacketServer();
     if (!c || nFrames < 0 || frameBits <= 0 || (frameBits & 7) || (nFrames > 0 && (!dSegs || !dOut))) {
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
@@ -1066,6 +1083,7 @@ static int launchEncode(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg,
 int ced_encode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dMsg, size_t msgStride, int nFrames,
                      int frameBytes, uint8_t *dSegs, size_t segStride, void *stream)
 {
+    cedStopPacketServer();
     if (!c || !code || nFrames < 0 || frameBytes <= 0 || (nFrames > 0 && (!dMsg || !dSegs))) {
         setError("ced_encode_batch: bad argument");
         return CED_ERR_ARG;
@@ -1229,6 +1247,7 @@ static int hostPipeline(ced_ctx *c, const ced_code_t *code, HostOp op, const uin
                         size_t inRowBytes, int nFrames, int frameParam, uint8_t *hOut, size_t outStride,
                         size_t outRowBytes)
 {
+    cedStopPacketServer();
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     const int rc = hostPipelineBody(c, code, op, hIn, inStride, inRowBytes, nFrames, frameParam, hOut, outStride,
                                     outRowBytes);
@@ -1593,6 +1612,155 @@ static bool streamParallelEnabled()
     return on;
 }
 
+/* ------------------------------------------------ resident packet decoder (frame_server.cuh) */
+/* CED_STREAM_SERVER=0: one graph launch per packet (the round-1 path) instead of the resident kernel */
+static bool streamServerEnabled()
+{
+    const char *e = getenv("CED_STREAM_SERVER"); /* read per call: tests flip it */
+    return !e || atoi(e) != 0;
+}
+
+int ced_stream_server_stats(uint64_t *requests, uint64_t *launches)
+{
+    ced_ctx *c = gServerCtx.load(std::memory_order_acquire);
+    if (requests)
+        *requests = c ? c->fsRequests : 0;
+    if (launches)
+        *launches = c ? c->fsLaunches : 0;
+    return c && !c->fsDisabled ? 1 : 0;
+}
+
+static void fsStop(ced_ctx *c)
+{
+    ced::FsMailbox *mb = static_cast<ced::FsMailbox *>(c->fsMailbox);
+    if (!mb || !c->fsLaunched)
+        return;
+    mb->seq = ced::kFsExit;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    cudaStreamSynchronize(c->fsStream);
+    mb->seq = c->fsSeq;
+    c->fsLaunched = false;
+}
+
+void cedStopPacketServer()
+{
+    ced_ctx *c = gServerCtx.load(std::memory_order_acquire);
+    if (!c || !c->fsLaunched)
+        return;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    cudaSetDevice(c->device);
+    fsStop(c);
+}
+
+static int fsLaunch(ced_ctx *c, const ced::FpArgs &f, uint32_t lastSeq)
+{
+    ced::FsMailbox *mb = static_cast<ced::FsMailbox *>(c->fsMailbox);
+    unsigned int init[4] = {lastSeq, 0u, 0u, 0u}; /* FsCtl: cmd, T, barrier, gaveUp */
+    mb->state = 1;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    static_assert(sizeof(init) == ced::kFsCtlInitBytes, "FsCtl header");
+    CED_CUDA(cudaMemcpyAsync(c->fsCtl, init, sizeof(init), cudaMemcpyHostToDevice, c->fsStream));
+    ced::FsMailbox *mbDev = static_cast<ced::FsMailbox *>(c->fsMailboxDev);
+    ced::FsCtl *ctl = static_cast<ced::FsCtl *>(c->fsCtl);
+    ced::FpArgs args = f;
+    void *params[] = {&mbDev, &ctl, &args, &lastSeq};
+    CED_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(ced::fpServerKernel), dim3(c->sms), dim3(ced::kFpThreads),
+                                         params, sizeof(ced::FsShared), c->fsStream));
+    c->fsLaunched = true;
+    c->fsLaunches++;
+    c->launches++;
+    return CED_OK;
+}
+
+/* one packet through the resident kernel; CED_ERR_UNSUPPORTED = not available (the caller takes the launch path) */
+static int fsDecode(ced_ctx *c, const ced::FpArgs &scratch, const uint8_t *edge, const uint8_t *metrics, const uint8_t *segs,
+                    int T, uint8_t *uncoded, size_t decodedBytes)
+{
+    if (c->fsDisabled || T > ced::kFsMaxSegs - 2 * ced::kFpBlock)
+        return CED_ERR_UNSUPPORTED;
+    if (!c->fsMailbox) {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        void *mb = nullptr;
+        if (!coop || cudaHostAlloc(&mb, sizeof(ced::FsMailbox), cudaHostAllocMapped) != cudaSuccess) {
+            cudaGetLastError();
+            c->fsDisabled = true;
+            return CED_ERR_UNSUPPORTED;
+        }
+        memset(mb, 0, sizeof(ced::FsMailbox));
+        c->fsMailbox = mb;
+        if (cudaHostGetDevicePointer(&c->fsMailboxDev, mb, 0) != cudaSuccess || cudaMalloc(&c->fsCtl, sizeof(ced::FsCtl)) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&c->fsStream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaFuncSetAttribute(ced::fpServerKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ced::FsShared)) !=
+                cudaSuccess) {
+            cudaGetLastError();
+            c->fsDisabled = true;
+            return CED_ERR_UNSUPPORTED;
+        }
+        gServerCtx.store(c, std::memory_order_release);
+    }
+    ced::FsMailbox *mb = static_cast<ced::FsMailbox *>(c->fsMailbox);
+    memcpy(mb->edge, edge, 128);
+    memcpy(mb->metrics, metrics, 64);
+    memcpy(mb->segs, segs, (size_t)T);
+    mb->T = (uint32_t)T;
+    uint32_t s = c->fsSeq + 1;
+    if (s == ced::kFsExit)
+        s = 1;
+    const uint32_t lastSeq = c->fsSeq;
+    c->fsSeq = s;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    mb->seq = s;
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    auto giveUp = [&](const char *why) {
+        mb->seq = ced::kFsExit;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        cudaStreamSynchronize(c->fsStream);
+        cudaGetLastError();
+        c->fsLaunched = false;
+        c->fsDisabled = true;
+        fprintf(stderr, "convolutionalencdec: resident packet decoder switched off (%s); using one launch per packet\n", why);
+        return CED_ERR_UNSUPPORTED;
+    };
+    if (!c->fsLaunched || mb->state != 1) {
+        if (c->fsLaunched)
+            CED_CUDA(cudaStreamSynchronize(c->fsStream));
+        if (fsLaunch(c, scratch, lastSeq) != CED_OK) {
+            cudaGetLastError();
+            c->fsDisabled = true;
+            return CED_ERR_UNSUPPORTED;
+        }
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (unsigned spins = 0;; spins++) {
+        if (mb->done == s)
+            break;
+        const uint32_t st = mb->state;
+        if (st == 3)
+            return giveUp("a wait inside the kernel timed out");
+        if (st == 2) { /* it left (idle time-out) while this request was on its way: start it again */
+            CED_CUDA(cudaStreamSynchronize(c->fsStream));
+            if (mb->done == s)
+                break;
+            if (fsLaunch(c, scratch, lastSeq) != CED_OK)
+                return giveUp("relaunch failed");
+        }
+        if ((spins & 1023u) == 1023u) {
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2))
+                return giveUp("no answer within 2 s");
+            if (cudaStreamQuery(c->fsStream) != cudaErrorNotReady && mb->done != s && mb->state == 1)
+                return giveUp("kernel ended without an answer");
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    memcpy(uncoded, mb->out, decodedBytes);
+    c->fsRequests++;
+    return CED_OK;
+}
+
 int ced_stream_surv_words(int nStates)
 {
     const int H = nStates / 2;
@@ -1651,6 +1819,26 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
     if (rc != CED_OK)
         return rc;
+
+    if (parallel && streamServerEnabled() && !c->fsDisabled) {
+        /* the resident kernel (frame_server.cuh): no launch, no copy node, no stream synchronise per packet */
+        const ced::FpScratch lay = ced::fpScratchLayout(kStreamMaxSteps);
+        ced::FpArgs f = {};
+        f.cost = c->sParallel.p + lay.cost;
+        for (int w = 0; w < ced::kFpWords; w++)
+            f.bits[w] = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.bits[w]);
+        f.v = reinterpret_cast<int *>(c->sParallel.p + lay.v);
+        f.best = reinterpret_cast<uint32_t *>(c->sParallel.p + lay.best);
+        f.tickets = reinterpret_cast<unsigned int *>(c->sParallel.p + lay.tickets);
+        const size_t nb = (size_t)((total - S - 1) / 8 + 1);
+        const int rs = fsDecode(c, f, edge, metrics, segs, segmentsIn, uncoded, nb);
+        if (rs == CED_OK)
+            return (int)nb;
+        if (rs != CED_ERR_UNSUPPORTED)
+            return rs;
+    } else if (c->fsLaunched) {
+        fsStop(c); /* another kind of call: the kernels below should not wait for the idle time-out */
+    }
 
     /* mailbox in : [0,512) edge  [512,768) metrics  [1024,...) segments          (one H2D)
      * mailbox out: [0,256) metrics [256,272) renormCounter [272,...) decoded bytes (one D2H) */

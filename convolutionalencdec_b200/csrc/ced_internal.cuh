@@ -167,6 +167,12 @@ struct ced_ctx {
     int fpGraphSegs = 0;
     const void *fpGraphKey[5] = {};  /* staging pointers baked into fpGraph */
     PinnedBuf sPinIn, sPinOut;
+    /* resident packet decoder (frame_server.cuh): mailbox in mapped page-locked memory, control words on the device */
+    void *fsMailbox = nullptr, *fsMailboxDev = nullptr, *fsCtl = nullptr;
+    cudaStream_t fsStream = nullptr;
+    uint32_t fsSeq = 0;
+    bool fsLaunched = false, fsDisabled = false;
+    uint64_t fsRequests = 0, fsLaunches = 0;
     std::recursive_mutex mu;
     uint64_t launches = 0;
     ced::BmTable bm0113, bm0133;
@@ -213,6 +219,10 @@ inline DecodeWorkingSet decodeWorkingSet(size_t nFrames, int T, size_t maxWaveFr
     return w;
 }
 
+
+/* ced_abi.cu: asks the resident packet decoder of the default context (if one is running) to leave; batch entry
+ * points call it so that their kernels and allocations do not wait for its idle time-out */
+extern "C" void cedStopPacketServer();
 
 /* swar_generic.cu: any k = 1, n = 2 / 3 code with 4 .. 256 states on the table-driven SIMD-in-word kernels;
  * CED_ERR_UNSUPPORTED = not a code these kernels take */

@@ -502,11 +502,12 @@ def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
 
 
 @pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
-def test_one_shot_packets_take_the_frame_parallel_kernels(port, T):
+def test_one_shot_packets_take_the_frame_parallel_kernels(port, T, monkeypatch):
     """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs fpBlockKernel / fpSelectKernel
-    (csrc/frame_parallel.cuh): same bytes as the sequential decoder for clean, noisy, all-zero and
-    pure-noise packets, for lengths that leave a short last block or a partial last byte, and the decoder
-    is usable for chunked packets afterwards."""
+    (csrc/frame_parallel.cuh; CED_STREAM_SERVER=0 = one launch per packet): same bytes as the sequential decoder for
+    clean, noisy, all-zero and pure-noise packets, for lengths that leave a short last block or a partial last byte,
+    and the decoder is usable for chunked packets afterwards."""
+    monkeypatch.setenv("CED_STREAM_SERVER", "0")
     api = ced.RefApi("k7")
     dec = api.decoder()
     dec.VITERBI_RESET()
@@ -533,6 +534,80 @@ def test_one_shot_packets_take_the_frame_parallel_kernels(port, T):
     # the same packet in two calls goes through the sequential kernel and gives the same bytes
     assert dec.VITERBI_DECODER_HARD(segs[0, :7], False).size == 0
     assert np.array_equal(dec.VITERBI_DECODER_HARD(segs[0, 7:], True, max_bytes=4096), want)
+
+
+def server_stats():
+    import ctypes as C
+    lib = ced.load_abi()
+    req, lau = C.c_uint64(0), C.c_uint64(0)
+    on = lib.ced_stream_server_stats(C.byref(req), C.byref(lau))
+    return on, req.value, lau.value
+
+
+@pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
+def test_one_shot_packets_through_the_resident_kernel(port, T):
+    """The same packets through fpServerKernel (csrc/frame_server.cuh): the packet goes into the mailbox, the resident
+    kernel answers; no launch per call.  Same bytes as the sequential decoder."""
+    api = ced.RefApi("k7")
+    dec = api.decoder()
+    dec.VITERBI_RESET()
+    dec.VITERBI_INIT()
+    rng = np.random.default_rng(1000 + T)
+    L = T - 6
+    for rep, p in enumerate((0.0, 0.04, 0.12, 0.5, None, "zero")):
+        msg = rng.integers(0, 256, (1, (L + 7) // 8), dtype=np.uint8)
+        segs = port.encode_batch(7, K7, msg)[:, :T].copy()
+        if p is None:
+            segs[:] = rng.integers(0, 256, segs.shape)
+        elif p == "zero":
+            segs[:] = 0
+        else:
+            segs = bsc(rng, segs, p)
+        want = port.decode_batch(7, K7, segs, T)[0][:(L - 1) // 8 + 1]
+        _, req0, _ = server_stats()
+        got = dec.VITERBI_DECODER_HARD(segs[0], True, max_bytes=4096)
+        on, req1, _ = server_stats()
+        assert on == 1 and req1 - req0 == 1, "expected the resident packet decoder to answer"
+        assert np.array_equal(got, want), (T, rep)
+        assert dec.nodeMetricsCur().tolist() == [0] + [65] * 63
+    assert dec.VITERBI_DECODER_HARD(segs[0, :7], False).size == 0
+    assert np.array_equal(dec.VITERBI_DECODER_HARD(segs[0, 7:], True, max_bytes=4096), want)
+
+
+def test_resident_kernel_coexists_with_the_rest_of_the_library(torch_cuda, ctx, port):
+    """Packets through the resident kernel interleaved with per-frame encodes, chunked decodes, batch decodes on another
+    context, idle periods longer than its time-out, and device-wide synchronisation: it steps aside and comes back."""
+    import time
+    torch = torch_cuda
+    api = ced.RefApi("k7")
+    dec, enc = api.decoder(), api.encoder()
+    dec.VITERBI_RESET(); dec.VITERBI_INIT()
+    enc.resetConvEncoder(); enc.initConvEncoder()
+    rng = np.random.default_rng(99)
+    msgs = rng.integers(0, 256, (40, 256), dtype=np.uint8)
+    clean = port.encode_batch(7, K7, msgs)
+    noisy = bsc(rng, clean, 0.03)
+    want = port.decode_batch(7, K7, noisy, 2054)
+    d_noisy = torch.from_numpy(noisy).cuda()
+    _, req0, lau0 = server_stats()
+    for i in range(40):
+        if i % 5 == 1:
+            assert np.array_equal(enc.convEnc(msgs[i], True), clean[i])
+        if i % 7 == 2:
+            time.sleep(0.01)                                   # longer than the idle time-out: it has left
+        if i % 9 == 3:
+            out = ctx.decode_batch(ced.K7_DEFAULT, d_noisy, 2048)
+            ctx.sync()
+            assert np.array_equal(out.cpu().numpy(), want)
+        if i % 11 == 4:
+            torch.cuda.synchronize()
+        if i % 6 == 5:                                         # a chunked packet in between
+            assert dec.VITERBI_DECODER_HARD(noisy[i, :1000], False).size == 0
+            assert np.array_equal(dec.VITERBI_DECODER_HARD(noisy[i, 1000:], True, max_bytes=4096), want[i])
+        assert np.array_equal(dec.VITERBI_DECODER_HARD(noisy[i], True, max_bytes=4096), want[i]), i
+    on, req1, lau1 = server_stats()
+    assert on == 1 and req1 - req0 == 40
+    assert 2 <= lau1 - lau0 <= 30
 
 
 def test_streaming_encoder_chunks_and_kat(golden, port):
