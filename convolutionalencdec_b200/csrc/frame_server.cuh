@@ -22,7 +22,7 @@
  * the mailbox with ld.volatile.
  *
  * Exactness: the arithmetic is frame_parallel.cuh's (same device functions); tests/test_gpu_parity.py runs the same
- * packets through both and against the oracle.
+ * packets through both paths and against the sequential CPU decoder.
  */
 #pragma once
 #include "frame_parallel.cuh"
