@@ -248,6 +248,54 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank's host threads -- and therefore place its page-locked buffers, which are
+    allocated first-touch -- on the CPUs of the NUMA node the GPU hangs off (sysfs local_cpulist of its PCI device).
+    Without it every rank's host buffers may sit on one socket and the other socket's GPUs pull their symbols across
+    the inter-socket link (round 1: e2e flat from 2 to 4 GPUs).  CED_BENCH_NUMA=0 turns it off.  Returns a note."""
+    if os.environ.get("CED_BENCH_NUMA", "1") == "0":
+        return "off (CED_BENCH_NUMA=0)"
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                idx = int(ids[local_rank])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        bus = nv.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        with open(base + "/local_cpulist") as f:
+            text = f.read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = sorted(cpus & allowed)
+        node = "?"
+        try:
+            with open(base + "/numa_node") as f:
+                node = f.read().strip()
+        except OSError:
+            pass
+        if not use or len(use) == len(allowed):
+            return "node %s: all %d allowed CPUs are local" % (node, len(allowed))
+        os.sched_setaffinity(0, use)
+        return "node %s: bound to %d of %d CPUs (%s)" % (node, len(use), len(allowed), text)
+    except Exception as e:  # noqa: BLE001
+        return "unavailable (%s)" % type(e).__name__
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,6 +339,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a GPU (there is no CPU fallback); use --impl reference for the CPU arm")
+    numa_note = bind_to_gpu_numa_node(local_rank)   # before the CUDA context and any page-locked allocation
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -454,7 +503,8 @@ def main():
                        "symbol_format": "1 byte per 2-bit segment (reference wire format)", "channel": "BSC p=0.0377 (Eb/N0 5 dB)",
                        "l2_policy": "inputs (%.0f MB symbols + %.0f MB survivors per wave of 2^16 frames) exceed the 126 MB L2"
                                     % (launch * seg_stride / 1e6, launch * (T // 2) * 16 / 1e6),
-                       "sharding": "frames [rank*F, (rank+1)*F) per rank, no data-path collective"},
+                       "sharding": "frames [rank*F, (rank+1)*F) per rank, no data-path collective",
+                       "host_numa": numa_note},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall}
     if single is not None:
         line["single_stream"] = single

@@ -1613,11 +1613,14 @@ static bool streamParallelEnabled()
 }
 
 /* ------------------------------------------------ resident packet decoder (frame_server.cuh) */
-/* CED_STREAM_SERVER=0: one graph launch per packet (the round-1 path) instead of the resident kernel */
+/* CED_STREAM_SERVER=1: the resident kernel instead of one graph launch per packet.  Off by default: measured on B200 it
+ * takes the host-visible overhead of a call from ~20 us to 2.5 us, but the device-side phases of a 2048-bit packet then
+ * add up to 27 us (request staged over PCIe 4.4, passes 6.7 -- they are bound by the ALU work of 64 start states per
+ * block --, three grid barriers ~1.3 each, chain 4, select 1.5, walk 2.2): 31.7 us per call either way */
 static bool streamServerEnabled()
 {
     const char *e = getenv("CED_STREAM_SERVER"); /* read per call: tests flip it */
-    return !e || atoi(e) != 0;
+    return e && atoi(e) != 0;
 }
 
 int ced_stream_server_stats(uint64_t *requests, uint64_t *launches)
@@ -1758,6 +1761,14 @@ static int fsDecode(ced_ctx *c, const ced::FpArgs &scratch, const uint8_t *edge,
     std::atomic_thread_fence(std::memory_order_seq_cst);
     memcpy(uncoded, mb->out, decodedBytes);
     c->fsRequests++;
+    if (getenv("CED_FP_STAMPS") && c->fsRequests % 1000 == 2) {
+        const double host = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+        const volatile unsigned long long *st = mb->stamp;
+        fprintf(stderr, "resident T=%d: host post->answer %.1f us | device: stage %.1f  passes+barrier %.1f  chain %.1f  "
+                        "barrier+select+barrier %.1f  walk+write %.1f  (seen->answered %.1f; table built +%.1f, first pass done +%.1f after staging)\n",
+                T, host, (st[1] - st[0]) * 1e-3, (st[2] - st[1]) * 1e-3, (st[3] - st[2]) * 1e-3, (st[4] - st[3]) * 1e-3,
+                (st[5] - st[4]) * 1e-3, (st[5] - st[0]) * 1e-3, (st[6] - st[1]) * 1e-3, (st[7] - st[1]) * 1e-3);
+    }
     return CED_OK;
 }
 

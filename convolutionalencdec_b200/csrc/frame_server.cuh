@@ -41,7 +41,8 @@ struct FsMailbox {
     uint32_t pad0[30];
     volatile uint32_t done;      /* device -> host: number of the last request answered */
     volatile uint32_t state;     /* 1 running, 2 left (idle / asked to), 3 gave up on a wait */
-    uint32_t pad1[30];
+    uint32_t pad1[14];
+    volatile unsigned long long stamp[8]; /* %globaltimer of CTA 0: request seen, staged, passes, chain, select, answered */
     uint8_t edge[128];           /* [2][64] edge labels */
     uint8_t metrics[64];         /* path metrics before the packet */
     uint8_t pad2[64];
@@ -173,6 +174,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
         __syncthreads();
         if (blockIdx.x == 0) {
             /* the request travels host -> device once, as 16-byte pieces all in flight together */
+            if (tid == 0)
+                mb->stamp[0] = fpNow();
             if (sm.cmd != kFsExit) {
                 const int nSeg = ((int)sm.T + 15) / 16, nAll = nSeg + (128 + 64) / 16;
                 for (int i = tid; i < nAll; i += kFpThreads) {
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
             if (tid == 0) {
                 ctl->T = sm.T;
                 fsStRelease(&ctl->cmd, sm.cmd);
+                mb->stamp[1] = fpNow();
             }
         }
         if (sm.cmd == kFsExit) {
@@ -221,6 +225,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
             sm.dist[i] = make_uint2(hd(sm.edge[j]) | hd(sm.edge[j + 32]) << 16, hd(sm.edge[64 + j]) | hd(sm.edge[64 + j + 32]) << 16);
         }
         __syncthreads();
+        if (blockIdx.x == 0 && tid == 0)
+            mb->stamp[6] = fpNow();
 
         /* ---- phase 1: the passes (fpBlockKernel) ---- */
         for (int vb = blockIdx.x; vb < nVirtual; vb += gridDim.x) {
@@ -249,6 +255,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
                 for (int t = 0; t < steps; t++)
                     fpStepDyn(t, lane, sm.seg[t], sm.dist + lane, M, p0, p1);
             }
+            if (blockIdx.x == 0 && tid == 0 && vb == 0)
+                mb->stamp[7] = fpNow();
             const uint32_t m0 = M & 0xFFFFu, m1 = M >> 16;
             const int r = steps % 5;
             int e = 0;
@@ -279,6 +287,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
 
         /* ---- the sequential part on CTA 0 (fpChain), everybody else waits at the next barrier ---- */
         if (blockIdx.x == 0) {
+            if (tid == 0)
+                mb->stamp[2] = fpNow();
             if (tid < 64) {
                 const int metric0 = (int)__ldcg(ctl->metrics + tid);
                 reinterpret_cast<uint16_t *>(sm.v[0])[tid] = (uint16_t)metric0;
@@ -287,6 +297,8 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
             __syncthreads();
             fpChain<4, kFpAhead>(a, sm.v, &sm.u.cost[0][0], tid);
             __syncthreads();
+            if (tid == 0)
+                mb->stamp[3] = fpNow();
         }
         if (!fsGridBarrier(ctl, target, sm))
             break;
@@ -357,8 +369,10 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
 
         /* ---- CTA 0 walks the table back from state 0 (src/viterbiDecoderButterflyk1.c:205) and answers ---- */
         if (blockIdx.x == 0) {
-            if (tid == 0)
+            if (tid == 0) {
                 sm.state = 0;
+                mb->stamp[4] = fpNow();
+            }
             __syncthreads();
             const int L = a.T - 6, outBytes = (L - 1) / 8 + 1;
             for (int hi = a.nBlocks; hi > 0; hi -= kFpChainBlocks) {
@@ -410,6 +424,7 @@ __global__ void __launch_bounds__(kFpThreads, 1) fpServerKernel(FsMailbox *mb, F
             __threadfence_system();
             __syncthreads();
             if (tid == 0) {
+                mb->stamp[5] = fpNow();
                 mb->done = seq;
                 __threadfence_system();
             }

@@ -301,11 +301,12 @@ int ced_multi_probe_copy_ceiling(ced_multi *m, size_t bytesPerDevice, int reps, 
  * Returns the number of decoded bytes written (0 unless last), <0 on error.
  */
 int ced_stream_surv_words(int nStates);
-/* One-shot K=7 n=2 packets (last = true on the first call of a packet) are decoded by a RESIDENT kernel that takes
- * packet after packet from a mailbox in page-locked host memory -- no launch, copy or stream synchronise per call
- * (frame_server.cuh; it leaves by itself after 2 ms without a request and whenever another entry point of the library
- * needs the GPU).  CED_STREAM_SERVER=0 selects one graph launch per packet instead.  Returns 1 if the resident path is
- * in use; *requests = packets it has answered, *launches = times the kernel was started. */
+/* With CED_STREAM_SERVER=1 one-shot K=7 n=2 packets (last = true on the first call of a packet) are decoded by a
+ * RESIDENT kernel that takes packet after packet from a mailbox in page-locked host memory -- no launch, copy or stream
+ * synchronise per call (frame_server.cuh; it leaves by itself after 2 ms without a request and whenever another entry
+ * point of the library needs the GPU).  Default: one graph launch per packet (measured equally fast at the reference's
+ * packet length).  Returns 1 if the resident path has been used and is healthy; *requests = packets it
+ * has answered, *launches = times the kernel was started. */
 int ced_stream_server_stats(uint64_t *requests, uint64_t *launches);
 
 int ced_stream_decode(int constraintLen, int codedBits, const uint8_t *edge, uint8_t *metrics, uint32_t *iteration,

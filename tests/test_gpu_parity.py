@@ -504,7 +504,7 @@ def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
 @pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
 def test_one_shot_packets_take_the_frame_parallel_kernels(port, T, monkeypatch):
     """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs fpBlockKernel / fpSelectKernel
-    (csrc/frame_parallel.cuh; CED_STREAM_SERVER=0 = one launch per packet): same bytes as the sequential decoder for
+    (csrc/frame_parallel.cuh; one graph launch per packet, the default): same bytes as the sequential decoder for
     clean, noisy, all-zero and pure-noise packets, for lengths that leave a short last block or a partial last byte,
     and the decoder is usable for chunked packets afterwards."""
     monkeypatch.setenv("CED_STREAM_SERVER", "0")
@@ -545,9 +545,10 @@ def server_stats():
 
 
 @pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
-def test_one_shot_packets_through_the_resident_kernel(port, T):
-    """The same packets through fpServerKernel (csrc/frame_server.cuh): the packet goes into the mailbox, the resident
-    kernel answers; no launch per call.  Same bytes as the sequential decoder."""
+def test_one_shot_packets_through_the_resident_kernel(port, T, monkeypatch):
+    """The same packets through fpServerKernel (csrc/frame_server.cuh, CED_STREAM_SERVER=1): the packet goes into the
+    mailbox, the resident kernel answers; no launch per call.  Same bytes as the sequential decoder."""
+    monkeypatch.setenv("CED_STREAM_SERVER", "1")
     api = ced.RefApi("k7")
     dec = api.decoder()
     dec.VITERBI_RESET()
@@ -574,10 +575,11 @@ def test_one_shot_packets_through_the_resident_kernel(port, T):
     assert np.array_equal(dec.VITERBI_DECODER_HARD(segs[0, 7:], True, max_bytes=4096), want)
 
 
-def test_resident_kernel_coexists_with_the_rest_of_the_library(torch_cuda, ctx, port):
+def test_resident_kernel_coexists_with_the_rest_of_the_library(torch_cuda, ctx, port, monkeypatch):
     """Packets through the resident kernel interleaved with per-frame encodes, chunked decodes, batch decodes on another
     context, idle periods longer than its time-out, and device-wide synchronisation: it steps aside and comes back."""
     import time
+    monkeypatch.setenv("CED_STREAM_SERVER", "1")
     torch = torch_cuda
     api = ced.RefApi("k7")
     dec, enc = api.decoder(), api.encoder()
