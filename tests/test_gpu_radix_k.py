@@ -109,7 +109,7 @@ def test_k_waves_and_argument_checks(torch_cuda, ctx, port, monkeypatch):
     with pytest.raises(ced.CedError):
         ctx.decode_batch_k(ced.Code(6, g), 2, d, 64)   # 2^(k(K-1)) = 1024 states
     with pytest.raises(ced.CedError):
-        ctx.decode_batch_k(code, 2, d[:, :20], 64)     # stride shorter than a frame
+        ctx.decode_batch_k(code, 2, torch.zeros((4, 20), dtype=torch.uint8, device="cuda"), 64)   # stride shorter than a frame
     # k = 1 forwards to the k = 1 entry points
     m1 = rng.integers(0, 256, (9, 8), dtype=np.uint8)
     s1 = ctx.encode_batch_k(ced.K7_DEFAULT, 1, torch.from_numpy(m1).cuda())
