@@ -161,41 +161,61 @@ CED_HD void genStep(uint32_t (&R)[GenGeom<S>::kRegs], const uint8_t *tab, int st
 #pragma unroll
     for (int w = 0; w < G::kWords; w++)
         T[w] = 0;
+    /* Table entries are fetched in batches of eight before they are used.  (Written this way after ncu showed
+     * short_scoreboard as the top stall, profiles/r2_gen_*_ncu.txt; ptxas schedules the loads of the one-pair-at-a-time
+     * form the same way -- 83.6 vs 83.8 Gbit/s for non-symmetric K=7 -- so the stall is the latency of the first
+     * entry of a step with three warps per sub-partition, not the order of the loads.) */
     if constexpr (q >= 2) {
         constexpr int rb = q - 2;
-        int idx = 0;
+        constexpr int kBatch = G::kPairs < 8 ? G::kPairs : 8;
+        static_assert(G::kPairs % kBatch == 0, "whole batches");
 #pragma unroll
-        for (int r = 0; r < G::kRegs; r++) {
-            if ((r >> rb) & 1)
-                continue;
-            const int rh = r | (1 << rb);
-            const uint4 x = *reinterpret_cast<const uint4 *>(tab + (size_t)idx * stride);
-            const uint32_t ea = *reinterpret_cast<const uint32_t *>(tab + (size_t)idx * stride + 16);
-            const uint32_t eb = *reinterpret_cast<const uint32_t *>(tab + (size_t)idx * stride + 20);
-            idx++;
-            const uint32_t lo = R[r], hi = R[rh];
-            const uint32_t a0 = lo + x.x, a1 = hi + x.y;
-            const uint32_t b0 = lo + x.z, b1 = hi + x.w;
-            const uint32_t delta = subOnFma(hi, lo, minusOne);
-            const uint32_t ma = signMask(delta + ea);      /* FF: keep the lower predecessor */
-            const uint32_t mb = signMask(delta + eb);
-            R[r] = sel(ma, a0, a1);
-            R[rh] = sel(mb, b0, b1);
-            T[r >> 3] |= ~ma & (0x01010101u << (r & 7));
-            T[rh >> 3] |= ~mb & (0x01010101u << (rh & 7));
+        for (int b0 = 0; b0 < G::kPairs; b0 += kBatch) {
+            uint4 x[kBatch];
+            uint2 e[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; i++) {
+                x[i] = *reinterpret_cast<const uint4 *>(tab + (size_t)(b0 + i) * stride);
+                e[i] = *reinterpret_cast<const uint2 *>(tab + (size_t)(b0 + i) * stride + 16);
+            }
+#pragma unroll
+            for (int i = 0; i < kBatch; i++) {
+                /* pair number idx -> its lower register: the idx-th register index with bit rb clear */
+                constexpr int low = (1 << rb) - 1;
+                const int idx = b0 + i;
+                const int r = ((idx & ~low) << 1) | (idx & low), rh = r | (1 << rb);
+                const uint32_t lo = R[r], hi = R[rh];
+                const uint32_t a0 = lo + x[i].x, a1 = hi + x[i].y;
+                const uint32_t b0v = lo + x[i].z, b1 = hi + x[i].w;
+                const uint32_t delta = subOnFma(hi, lo, minusOne);
+                const uint32_t ma = signMask(delta + e[i].x);      /* FF: keep the lower predecessor */
+                const uint32_t mb = signMask(delta + e[i].y);
+                R[r] = sel(ma, a0, a1);
+                R[rh] = sel(mb, b0v, b1);
+                T[r >> 3] |= ~ma & (0x01010101u << (r & 7));
+                T[rh >> 3] |= ~mb & (0x01010101u << (rh & 7));
+            }
         }
     } else {
         constexpr uint32_t swapSel = (q == 1) ? 0x1032u : 0x2301u;
         constexpr uint32_t upper = (q == 1) ? 0xFFFF0000u : 0xFF00FF00u;
+        constexpr int kBatch = G::kRegs < 8 ? G::kRegs : 8;
 #pragma unroll
-        for (int r = 0; r < G::kRegs; r++) {
-            const uint4 e = *reinterpret_cast<const uint4 *>(tab + (size_t)r * stride);   /* xself xcross e pad */
-            const uint32_t self = R[r] + e.x;
-            const uint32_t swapped = prmt(R[r], 0u, swapSel);
-            const uint32_t cross = swapped + e.y;
-            const uint32_t m = signMask(subOnFma(swapped, R[r], minusOne) + e.z);
-            R[r] = sel(m, self, cross);
-            T[r >> 3] |= ~m & (0x01010101u << (r & 7));
+        for (int b0 = 0; b0 < G::kRegs; b0 += kBatch) {
+            uint4 e[kBatch];   /* xself xcross e pad */
+#pragma unroll
+            for (int i = 0; i < kBatch; i++)
+                e[i] = *reinterpret_cast<const uint4 *>(tab + (size_t)(b0 + i) * stride);
+#pragma unroll
+            for (int i = 0; i < kBatch; i++) {
+                const int r = b0 + i;
+                const uint32_t self = R[r] + e[i].x;
+                const uint32_t swapped = prmt(R[r], 0u, swapSel);
+                const uint32_t cross = swapped + e[i].y;
+                const uint32_t m = signMask(subOnFma(swapped, R[r], minusOne) + e[i].z);
+                R[r] = sel(m, self, cross);
+                T[r >> 3] |= ~m & (0x01010101u << (r & 7));
+            }
         }
         constexpr uint32_t used = G::kRegs >= 8 ? 0xFFFFFFFFu : (0x01010101u * ((1u << G::kRegs) - 1u));
 #pragma unroll

@@ -45,7 +45,8 @@
 #endif
 
 #if !defined(__CUDACC__)
-struct uint4 { uint32_t x, y, z, w; }; /* host stand-in for tests/hostsim (never compiled with the CUDA headers) */
+struct uint4 { uint32_t x, y, z, w; }; /* host stand-ins for tests/hostsim (never compiled with the CUDA headers) */
+struct uint2 { uint32_t x, y; };
 #endif
 
 namespace ced {
