@@ -587,23 +587,51 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             static const int envFusedPerSm = getenv("CED_FUSED_BLOCKS_PER_SM") ? atoi(getenv("CED_FUSED_BLOCKS_PER_SM")) : 0;
             const int perSm = envFusedPerSm > 0 ? envFusedPerSm : std::max(3, std::min(4, groups / (4 * c->sms)));
             const int fBlocks = std::max(1, std::min(c->sms * perSm, (groups + 3) / 4));
+#define CED_LAUNCH_FUSED_ONE(...)                                                                                  \
+    ced::k7FusedKernel<__VA_ARGS__><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, schedA, cpu, fa)
 #define CED_LAUNCH_FUSED(CODE, FMT)                                                                                \
     do {                                                                                                           \
         if (aligned16)                                                                                             \
-            ced::k7FusedKernel<CODE, ced::FMT, true><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, \
-                                                                                          schedA, cpu, fa);        \
+            CED_LAUNCH_FUSED_ONE(CODE, ced::FMT, true);                                                            \
         else                                                                                                       \
-            ced::k7FusedKernel<CODE, ced::FMT, false><<<fBlocks, ced::kFwdThreads, 0, s>>>(in, segStride, wave, T, bm, \
-                                                                                           schedA, cpu, fa);       \
+            CED_LAUNCH_FUSED_ONE(CODE, ced::FMT, false);                                                           \
     } while (0)
             /* experiments: other ring geometries for the default code, byte format, aligned rows (CED_FUSED_GEOM=E,D) */
             int geoE = 0, geoD = 0;
             if (const char *ge = getenv("CED_FUSED_GEOM"))
                 sscanf(ge, "%d,%d", &geoE, &geoD);
+            /* keep the decision rings in L2: a persisting access-policy window over them, so that the symbol stream
+             * (269 MB per decode, read once) does not evict them (CED_FUSED_PERSIST=0 turns it off) */
+            static const int envPersist = getenv("CED_FUSED_PERSIST") ? atoi(getenv("CED_FUSED_PERSIST")) : 1;
+            bool windowSet = false;
+            if (envPersist) {
+                int maxPersist = 0, maxWin = 0;
+                cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+                cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+                const int pairs = geoE > 0 ? (geoE + geoD) / 2 : ced::kRingPairs;
+                const size_t ringUsed = (size_t)fa.ringSlots * pairs * 32 * sizeof(uint4);
+                if (maxPersist > 0 && maxWin > 0) {
+                    static bool limitSet = false;
+                    if (!limitSet) {
+                        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxPersist);
+                        limitSet = true;
+                        if (getenv("CED_FUSED_DEBUG"))
+                            fprintf(stderr, "fused: persisting L2 up to %.1f MB, window up to %.1f MB, rings %.1f MB\n",
+                                    maxPersist / 1e6, maxWin / 1e6, ringUsed / 1e6);
+                    }
+                    cudaStreamAttrValue v = {};
+                    v.accessPolicyWindow.base_ptr = wk.ring.p;
+                    v.accessPolicyWindow.num_bytes = std::min<size_t>(ringUsed, (size_t)maxWin);
+                    v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)maxPersist / (double)ringUsed);
+                    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    windowSet = cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
+                    cudaGetLastError();
+                }
+            }
 #define CED_FUSED_GEOM_CASE(E_, D_)                                                                                \
     if (id == CodeId::K7_0113_0171 && !packed && aligned16 && geoE == E_ && geoD == D_)                            \
-        ced::k7FusedKernel<Code0113, ced::ByteSymbols, true, ced::FusedGeom<E_, D_>><<<fBlocks, ced::kFwdThreads, 0, s>>>( \
-            in, segStride, wave, T, bm, schedA, cpu, fa);                                                          \
+        CED_LAUNCH_FUSED_ONE(Code0113, ced::ByteSymbols, true, ced::FusedGeom<E_, D_>);                            \
     else
             CED_FUSED_GEOM_CASE(96, 48)
             CED_FUSED_GEOM_CASE(192, 72)
@@ -619,6 +647,13 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
             else
                 CED_LAUNCH_FUSED(Code0133, PackedSymbols);
 #undef CED_LAUNCH_FUSED
+#undef CED_LAUNCH_FUSED_ONE
+            if (windowSet) { /* the kernels that follow on this stream are not to inherit the window */
+                cudaStreamAttrValue v = {};
+                v.accessPolicyWindow.num_bytes = 0;
+                cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+                cudaGetLastError();
+            }
             } /* !wsLaunched */
             if (prof)
                 CED_CUDA(cudaEventRecord(c->prof[pw][1], s));
