@@ -67,7 +67,68 @@ soft = torch.randint(-128, 128, (20, 2 * 262 + 4), dtype=torch.int8, device="cud
 pk = ctx.slice_soft_symbols(soft, 262)
 ctx.decode_batch_packed(code, pk, 256)
 ctx.sync()
+# round 2: true soft-decision decoder, AWGN channel, table-driven SIMD-in-word kernels for other codes, k > 1 codes,
+# packed windowed decoder, fused kernels, resident packet decoder -- exactly sized buffers again
+for frames, bits in ((1, 8), (33, 96), (70, 1000 // 8 * 8)):
+    T = bits + 6
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=frames)
+    segs = ctx.encode_batch(code, msgs, seg_stride=(T + 15) // 16 * 16)
+    softb = ctx.awgn_channel(segs, T, 9.0, seed=7)       # 9 dB: practically noise-free, rows of exactly ceil16(2 T) bytes
+    d = ctx.decode_batch_soft(code, softb, bits)
+    ctx.sync()
+    good = bool(torch.equal(d, msgs))
+    ok &= good
+    print("soft-decision round trip %d x %d:" % (frames, bits), good)
+for K, g in ((3, (7, 5, 3)), (4, (0o15, 0o17)), (5, (0o23, 0o35)), (7, (0o133, 0o170)), (9, (0o557, 0o663, 0o711))):
+    c4 = ced.Code(K, g)
+    frames, bits = 67, 200
+    T = bits + K - 1
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=K + 50)
+    flat = torch.zeros(frames * T + 1, dtype=torch.uint8, device="cuda")
+    segs = flat[1:].view(frames, T)                      # misaligned base, no slack
+    ctx.encode_batch(c4, msgs, out=segs)
+    d = ctx.decode_batch(c4, segs, bits)
+    ctx.sync()
+    good = bool(torch.equal(d, msgs))
+    ok &= good
+    print("table-driven SWAR K=%d n=%d round trip:" % (K, len(g)), good)
+for K, k, g in ((3, 2, (0o27, 0o75, 0o72)), (5, 2, (0o1236, 0o0155, 0o1337, 0o1701)), (2, 4, (0o357, 0o261, 0o173, 0o225, 0o316))):
+    c5 = ced.Code(K, g)
+    msgs = torch.empty((41, 24), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=K * 10 + k)
+    segs = ctx.encode_batch_k(c5, k, msgs)
+    d = ctx.decode_batch_k(c5, k, segs, 192)
+    ctx.sync()
+    good = bool(torch.equal(d, msgs))
+    ok &= good
+    print("k=%d K=%d round trip:" % (k, K), good)
+for mode in ("1", "2"):
+    os.environ["CED_FUSED"], os.environ["CED_FUSED_MIN_FRAMES"] = mode, "1"
+    frames, bits = 130, 96 * 6 + 40
+    T = bits + 6
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=11)
+    segs = ctx.encode_batch(code, msgs, seg_stride=(T + 15) // 16 * 16)
+    d = ctx.decode_batch(code, segs, bits)
+    ctx.sync()
+    good = bool(torch.equal(d, msgs))
+    ok &= good
+    print("fused kernel mode %s round trip:" % mode, good)
+os.environ.pop("CED_FUSED")
+os.environ.pop("CED_FUSED_MIN_FRAMES")
 # per-frame API
+os.environ["CED_STREAM_SERVER"] = "1"
+apis = ced.RefApi("k7")
+encs = apis.encoder(); encs.resetConvEncoder(); encs.initConvEncoder()
+decs = apis.decoder(); decs.VITERBI_RESET(); decs.VITERBI_INIT()
+for nbytes in (1, 17, 256):
+    m = np.arange(nbytes, dtype=np.uint8)
+    good = bool(np.array_equal(decs.VITERBI_DECODER_HARD(encs.convEnc(m, True), True, max_bytes=4096), m))
+    ok &= good
+    print("resident packet decoder, %d bytes:" % nbytes, good)
+os.environ["CED_STREAM_SERVER"] = "0"
 api = ced.RefApi("k7")
 enc = api.encoder(); enc.resetConvEncoder(); enc.initConvEncoder()
 dec = api.decoder(); dec.VITERBI_RESET(); dec.VITERBI_INIT()
