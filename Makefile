@@ -58,7 +58,7 @@ oracle:
 	$(MAKE) -C oracle CED_REF=$(CED_REF) all
 
 hostsim: tests/hostsim/libswar_sim.so
-tests/hostsim/libswar_sim.so: tests/hostsim/swar_sim.cpp $(CSRC)/trellis_swar.cuh $(CSRC)/trellis_swar16.cuh $(CSRC)/trellis_fused.cuh $(CSRC)/swar_generic.cuh
+tests/hostsim/libswar_sim.so: tests/hostsim/swar_sim.cpp $(CSRC)/trellis_swar.cuh $(CSRC)/trellis_swar16.cuh $(CSRC)/trellis_fused.cuh $(CSRC)/swar_generic.cuh $(CSRC)/swar_radix4.cuh
 	g++ -O2 -std=c++17 -Wno-unknown-pragmas -fPIC -shared -x c++ -I$(CSRC) -o $@ $<
 
 # Reference drivers, sources untouched.  speedDecode/speedEncode pin their worker

@@ -226,6 +226,11 @@ int ced_decode_batch_k(ced_ctx *c, const ced_code_t *code, int inputBits, const 
     }
     if (nFrames == 0)
         return CED_OK;
+    if (kc.k == 2) { /* thread-per-frame SIMD-in-word kernels with radix-4 butterflies (swar_radix4.cuh) take n = 2, 3 */
+        const int rr = cedDecodeBatchSwarRadix4(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+        if (rr != CED_ERR_UNSUPPORTED)
+            return rr;
+    }
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;

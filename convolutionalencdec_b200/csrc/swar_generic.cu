@@ -6,6 +6,7 @@
  */
 #include "ced_internal.cuh"
 #include "swar_generic.cuh"
+#include "swar_radix4.cuh"
 
 namespace ced {
 
@@ -17,12 +18,13 @@ struct alignas(W >= 4 ? 16 : 4 * W) SurvRow {
 };
 
 /* Forward pass: see k7ForwardKernel (decode_batch.cuh) for the scheduler; symbols are byte-per-segment only. */
-template <int S, int V, bool ALIGNED>
+template <class P, int V, bool ALIGNED>
 __global__ void __launch_bounds__(kFwdThreads, 3)
-genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, SurvRow<GenGeom<S>::kWords> *__restrict__ surv,
+genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, SurvRow<P::kWords> *__restrict__ surv,
                  const uint8_t *__restrict__ table, int n, uint32_t minusOne, FwdSched sched, int chunksPerUnit)
 {
-    using G = GenGeom<S>;
+    using G = P;
+    constexpr int S = P::kPhases;   /* steps per label rotation */
     using TG = TileGeom<ByteSymbols, ALIGNED>;
     constexpr int kPitch = TG::kPitch, kRegs = G::kRegs, kStateU4 = (kRegs + 3) / 4;
     extern __shared__ __align__(16) uint8_t sMem[];
@@ -59,7 +61,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
         uint4 *stateSlot = sched.state + ((size_t)g * kStateU4) * 32 + lane;
         uint32_t R[kRegs];
         if (su == 0) {
-            genInitMetrics<S>(R, n);
+            P::init(R, n);
         } else {
             if (lane == 0)
                 while (ldAcquire(sched.done + g) < (int)su)
@@ -103,10 +105,9 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
                         constexpr int PH = decltype(phTag)::value;
                         if (PH < nn) {
                             const uint32_t off = p[PH];          /* rx * 32 */
-                            constexpr int q = S - 1 - PH;
-                            const uint8_t *tab = sTab + G::phaseBase(PH, V) + (q >= 2 ? off : (off >> 1));
+                            const uint8_t *tab = sTab + G::phaseBase(PH, V) + G::rxOffset(PH, off);
                             uint32_t Tw[G::kWords];
-                            genStep<S, PH>(R, tab, (q >= 2 ? 32 : 16) * V, minusOne, Tw);
+                            P::template step<PH>(R, tab, V, minusOne, Tw);
                             if (live) {
                                 SurvRow<G::kWords> row;
 #pragma unroll
@@ -117,7 +118,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
                         }
                     };
                     one(std::integral_constant<int, 0>());
-                    one(std::integral_constant<int, 1>());
+                    if constexpr (S > 1) one(std::integral_constant<int, 1>());
                     if constexpr (S > 2) one(std::integral_constant<int, 2>());
                     if constexpr (S > 3) one(std::integral_constant<int, 3>());
                     if constexpr (S > 4) { one(std::integral_constant<int, 4>()); one(std::integral_constant<int, 5>()); }
@@ -127,7 +128,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
                 }
                 done += nr;
                 if (done < steps || c + 1 < chunks)
-                    genRenorm<S>(R);
+                    P::renorm(R);
             }
         }
         if (cEnd < chunks) {
@@ -150,21 +151,24 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
 }
 
 /* Full-frame traceback from state 0 (src/viterbiDecoderButterflyk1.c:205-254), one thread per frame; the rows of the
- * next 8 steps are fetched with cp.async into the thread's own shared-memory slots while the current 8 are walked. */
-template <int S>
+ * next 8 steps are fetched with cp.async into the thread's own shared-memory slots while the current 8 are walked.
+ * A step yields P::kStepBits decoded bits, MSb first within the byte (:249). */
+template <class P>
+__host__ __device__ constexpr int genTbThreads() { return sizeof(SurvRow<P::kWords>) >= 64 ? 32 : kTbThreads; } /* staging fits 48 KB */
+
+template <class P>
 __global__ void __launch_bounds__(kTbThreads)
-genTracebackKernel(const SurvRow<GenGeom<S>::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out,
-                   size_t outStride)
+genTracebackKernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride)
 {
-    using G = GenGeom<S>;
-    using Row = SurvRow<G::kWords>;
-    __shared__ Row sW[2][8][kTbThreads];
+    using Row = SurvRow<P::kWords>;
+    constexpr int kb = P::kStepBits, spb = 8 / kb;   /* bits per step, steps per output byte */
+    __shared__ Row sW[2][8][genTbThreads<P>()];
     const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (frame >= nFrames)
         return;
     const Row *s = surv + ((size_t)(frame / 32) * T) * 32 + (frame & 31);
     uint8_t *dst = out + (size_t)frame * outStride;
-    const int L = T - S, nBlocks = L / 8, tid = threadIdx.x;
+    const int L = T - P::kTail, nBlocks = L / 8, tid = threadIdx.x;
     auto prefetch = [&](int blk, int buf) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -186,9 +190,17 @@ genTracebackKernel(const SurvRow<GenGeom<S>::kWords> *__restrict__ surv, int nFr
     if (nBlocks > 0)
         prefetch(nBlocks - 1, 0);
     uint32_t p = 0; /* state 0 sits at position 0 in every phase */
-    for (int t = T - 1; t >= L; t--) {   /* the S tail steps carry no output (:208-223) */
+    uint32_t acc = 0;
+    for (int t = T - 1; t >= 8 * nBlocks; t--) {   /* the tail steps carry no output (:208-223); then < 8 ragged steps */
         const Row row = s[(size_t)t * 32];
-        genTracebackStep<S>(p, row.w, t);
+        const uint32_t v = P::tbStep(p, row.w, t);
+        if (t < L) {
+            acc = (acc >> kb) | (v << (8 - kb));
+            if (t % spb == 0) {
+                dst[t / spb] = (uint8_t)acc;
+                acc = 0;
+            }
+        }
     }
     int buf = 0;
     for (int blk = nBlocks - 1; blk >= 0; blk--, buf ^= 1) {
@@ -198,34 +210,115 @@ genTracebackKernel(const SurvRow<GenGeom<S>::kWords> *__restrict__ surv, int nFr
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        uint32_t acc = 0;
 #pragma unroll
         for (int i = 7; i >= 0; i--) {
             const Row row = sW[buf][i][tid];
-            acc |= genTracebackStep<S>(p, row.w, 8 * blk + i) << (7 - i);   /* MSb first (:249) */
+            const uint32_t v = P::tbStep(p, row.w, 8 * blk + i);
+            acc = (acc >> kb) | (v << (8 - kb));
+            if (i % spb == 0) {
+                dst[(8 * blk + i) / spb] = (uint8_t)acc;
+                acc = 0;
+            }
         }
-        dst[blk] = (uint8_t)acc;
+    }
+}
+
+/*
+ * The same walk for narrow survivor rows (<= 16 bytes per step), in blocks of 24 steps like k7TracebackKernel: 24 is a
+ * multiple of every label rotation (S = 1, 2, 3, 4, 6, 8), so inside a block the phase of a step -- and with it every shift
+ * count -- is a compile-time constant, and a block is a whole number of output bytes (3 for k = 1, 6 for k = 2).  The rows
+ * of the next block are fetched with cp.async while the current one is walked.  (The 8-step kernel above computed
+ * t mod S and variable shifts per step: for K = 3 its 0.42 ms were as long as the forward pass.)
+ */
+template <class P>
+__host__ __device__ constexpr int genTb24Threads() { return sizeof(SurvRow<P::kWords>) >= 16 ? 32 : 64; }
+
+template <class P, int I>
+__device__ __forceinline__ void genWalk24(uint32_t &p, uint32_t &acc, const SurvRow<P::kWords> *rows, int stride, uint8_t *dst, int blk)
+{
+    if constexpr (I >= 0) {
+        constexpr int kb = P::kStepBits, spb = 8 / kb;
+        const SurvRow<P::kWords> row = rows[(size_t)I * stride];
+        const uint32_t v = P::template tbStepC<I % P::kPhases>(p, row.w);
+        acc = (acc >> kb) | (v << (8 - kb));
+        if constexpr (I % spb == 0) {
+            dst[(24 * blk + I) / spb] = (uint8_t)acc;
+            acc = 0;
+        }
+        genWalk24<P, I - 1>(p, acc, rows, stride, dst, blk);
+    }
+}
+
+template <class P>
+__global__ void __launch_bounds__(genTb24Threads<P>())
+genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride)
+{
+    using Row = SurvRow<P::kWords>;
+    constexpr int kb = P::kStepBits, spb = 8 / kb, kThreads = genTb24Threads<P>();
+    static_assert(24 % P::kPhases == 0, "a block holds whole label rotations");
+    __shared__ Row sW[2][24][kThreads];
+    const long long frame = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= nFrames)
+        return;
+    const Row *s = surv + ((size_t)(frame / 32) * T) * 32 + (frame & 31);
+    uint8_t *dst = out + (size_t)frame * outStride;
+    const int L = T - P::kTail, nBlocks = L / 24, tid = threadIdx.x;
+    auto prefetch = [&](int blk, int buf) {
+#pragma unroll
+        for (int i = 0; i < 24; i++) {
+            const Row *src = s + (size_t)(24 * blk + i) * 32;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(&sW[buf][i][tid]);
+            if constexpr (sizeof(Row) == 16)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src));
+            else if constexpr (sizeof(Row) == 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src));
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (nBlocks > 0)
+        prefetch(nBlocks - 1, 0);
+    uint32_t p = 0, acc = 0;
+    for (int t = T - 1; t >= 24 * nBlocks; t--) {   /* tail steps (no output, :208-223) and the ragged top */
+        const Row row = s[(size_t)t * 32];
+        const uint32_t v = P::tbStep(p, row.w, t);
+        if (t < L) {
+            acc = (acc >> kb) | (v << (8 - kb));
+            if (t % spb == 0) {
+                dst[t / spb] = (uint8_t)acc;
+                acc = 0;
+            }
+        }
+    }
+    int buf = 0;
+    for (int blk = nBlocks - 1; blk >= 0; blk--, buf ^= 1) {
+        if (blk > 0) {
+            prefetch(blk - 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        genWalk24<P, 23>(p, acc, &sW[buf][0][tid], kThreads, dst, blk);
     }
 }
 
 } // namespace ced
 
-/* taps, table and launch for one call; returns CED_ERR_UNSUPPORTED if the code is outside what these kernels take
- * (the caller then falls back to the one-warp-per-frame kernel) */
-template <int S>
-static int launchGen(ced_ctx *c, const ced::GenCode &gc, const uint8_t *dSegs, size_t segStride, int nFrames, int frameBits,
+/* table and launch for one call of a trellis policy P; T = trellis steps per frame, V = 2^n received symbols */
+template <class P, class BuildTable>
+static int launchGen(ced_ctx *c, int n, int T, BuildTable buildTable, const uint8_t *dSegs, size_t segStride, int nFrames,
                      uint8_t *dOut, size_t outStride, cudaStream_t s, int slot)
 {
-    using G = ced::GenGeom<S>;
-    using Row = ced::SurvRow<G::kWords>;
-    const int T = frameBits + S, V = 1 << gc.n;
+    using Row = ced::SurvRow<P::kWords>;
+    const int V = 1 << n;
     ced_ctx::Work &wk = c->work[slot];
     const size_t perFrame = (size_t)T * sizeof(Row);
     size_t waveMax = std::min<size_t>(c->maxWaveFrames, std::max<size_t>(64, kMaxScratchBytes / perFrame)) / 64 * 64;
     const size_t firstWave = std::min<size_t>((size_t)nFrames, waveMax), g0 = (firstWave + 31) / 32;
-    constexpr int kStateU4 = (G::kRegs + 3) / 4;
-    const size_t tabBytes = (size_t)G::tableBytes(V);
-    const size_t stateBytes = g0 * kStateU4 * 32 * sizeof(uint4) + tabBytes + 256, flagBytes = (g0 + 1) * sizeof(int);
+    constexpr int kStateU4 = (P::kRegs + 3) / 4;
+    const size_t tabBytes = ((size_t)P::tableBytes(V) + 15) / 16 * 16;
+    const size_t stateBytes = g0 * kStateU4 * 32 * sizeof(uint4) + tabBytes + 512, flagBytes = (g0 + 1) * sizeof(int);
     if (wk.scratch.bytes < g0 * 32 * perFrame || wk.schedState.bytes < stateBytes || wk.schedFlags.bytes < flagBytes) {
         CED_CUDA(cudaDeviceSynchronize());
         int rc = wk.scratch.ensure(g0 * 32 * perFrame);
@@ -238,16 +331,16 @@ static int launchGen(ced_ctx *c, const ced::GenCode &gc, const uint8_t *dSegs, s
         CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
     /* the step table of this code: built on the host (a few KB), kept behind the hand-off slots of the working set */
     std::vector<uint8_t> table(tabBytes);
-    ced::buildGenTable<S>(gc, table.data());
-    uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p) + (stateBytes - tabBytes - 256 + 255) / 256 * 256;
+    buildTable(table.data());
+    uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p) + (g0 * kStateU4 * 32 * sizeof(uint4) + 255) / 256 * 256;
     CED_CUDA(cudaMemcpyAsync(dTable, table.data(), tabBytes, cudaMemcpyHostToDevice, s));   /* pageable source: staged */
     const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0;
     const size_t pitchA = ced::TileGeom<ced::ByteSymbols, true>::kPitch, pitchU = ced::TileGeom<ced::ByteSymbols, false>::kPitch;
-    const size_t smem = (tabBytes + 15) / 16 * 16 + 4 * 32 * (aligned16 ? pitchA : pitchU);
+    const size_t smem = tabBytes + 4 * 32 * (aligned16 ? pitchA : pitchU);
     auto kernelFor = [&](bool al) -> void (*)(const uint8_t *, size_t, int, int, Row *, const uint8_t *, int, uint32_t, ced::FwdSched, int) {
-        if (gc.n == 2)
-            return al ? ced::genForwardKernel<S, 4, true> : ced::genForwardKernel<S, 4, false>;
-        return al ? ced::genForwardKernel<S, 8, true> : ced::genForwardKernel<S, 8, false>;
+        if (n == 2)
+            return al ? ced::genForwardKernel<P, 4, true> : ced::genForwardKernel<P, 4, false>;
+        return al ? ced::genForwardKernel<P, 8, true> : ced::genForwardKernel<P, 8, false>;
     };
     auto kernel = kernelFor(aligned16);
     CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -265,9 +358,16 @@ static int launchGen(ced_ctx *c, const ced::GenCode &gc, const uint8_t *dSegs, s
         sched.state = wk.schedState.p;
         CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
         kernel<<<blocks, ced::kFwdThreads, smem, s>>>(dSegs + f0 * segStride, segStride, wave, T, reinterpret_cast<Row *>(wk.scratch.p),
-                                                     dTable, gc.n, c->bm0113.minusOne, sched, 2);
-        ced::genTracebackKernel<S><<<(wave + ced::kTbThreads - 1) / ced::kTbThreads, ced::kTbThreads, 0, s>>>(
-            reinterpret_cast<const Row *>(wk.scratch.p), wave, T, dOut + f0 * outStride, outStride);
+                                                     dTable, n, c->bm0113.minusOne, sched, 2);
+        if constexpr (sizeof(Row) <= 16) {
+            constexpr int tbT = ced::genTb24Threads<P>();
+            ced::genTraceback24Kernel<P><<<(wave + tbT - 1) / tbT, tbT, 0, s>>>(reinterpret_cast<const Row *>(wk.scratch.p), wave, T,
+                                                                             dOut + f0 * outStride, outStride);
+        } else {
+            constexpr int tbT = ced::genTbThreads<P>();
+            ced::genTracebackKernel<P><<<(wave + tbT - 1) / tbT, tbT, 0, s>>>(reinterpret_cast<const Row *>(wk.scratch.p), wave, T,
+                                                                           dOut + f0 * outStride, outStride);
+        }
         c->launches += 2;
     }
     CED_CUDA(cudaEventRecord(wk.idle, s));
@@ -301,11 +401,59 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    const int T = frameBits + S;
+#define CED_GEN_CASE(S_)                                                                                                 \
+    case S_:                                                                                                             \
+        return launchGen<ced::GenPolicy<S_>>(c, gc.n, T, [&](uint8_t *t) { ced::buildGenTable<S_>(gc, t); }, dSegs, segStride, \
+                                             nFrames, dOut, outStride, s, slot)
     switch (S) {
-    case 2: return launchGen<2>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
-    case 3: return launchGen<3>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
-    case 4: return launchGen<4>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
-    case 6: return launchGen<6>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
-    default: return launchGen<8>(c, gc, dSegs, segStride, nFrames, frameBits, dOut, outStride, s, slot);
+        CED_GEN_CASE(2);
+        CED_GEN_CASE(3);
+        CED_GEN_CASE(4);
+        CED_GEN_CASE(6);
+    default:
+        return launchGen<ced::GenPolicy<8>>(c, gc.n, T, [&](uint8_t *t) { ced::buildGenTable<8>(gc, t); }, dSegs, segStride, nFrames,
+                                            dOut, outStride, s, slot);
     }
+#undef CED_GEN_CASE
+}
+
+/* rate-2/n codes (k = 2), n = 2 or 3, 4 .. 256 states: radix-4 SIMD-in-word kernels; CED_ERR_UNSUPPORTED = not a code
+ * they take (ced_decode_batch_k then runs the one-warp-per-frame kernel of radix_k.cu) */
+int cedDecodeBatchSwarRadix4(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                             int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    if (!code || code->codedBits < 2 || code->codedBits > 3 || code->constraintLen < 2 || code->constraintLen > 5 || (frameBits & 7))
+        return CED_ERR_UNSUPPORTED;
+    static const bool off = getenv("CED_SWAR_GENERIC") && atoi(getenv("CED_SWAR_GENERIC")) == 0;
+    if (off)
+        return CED_ERR_UNSUPPORTED;
+    const int K = code->constraintLen, S = K - 1, T = frameBits / 2 + S;
+    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch_k: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    ced::R4Code rc;
+    rc.S = S;
+    rc.n = code->codedBits;
+    for (int i = 0; i < 3; i++)
+        rc.tap[i] = i < rc.n ? reverseBits(code->gen[i], 2 * K) : 0u;
+    if (nFrames == 0)
+        return CED_OK;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+#define CED_R4_CASE(S_)                                                                                                  \
+    case S_:                                                                                                             \
+        return launchGen<ced::R4Policy<S_>>(c, rc.n, T, [&](uint8_t *t) { ced::buildR4Table<S_>(rc, t); }, dSegs, segStride,  \
+                                            nFrames, dOut, outStride, s, 0)
+    switch (S) {
+        CED_R4_CASE(1);
+        CED_R4_CASE(2);
+        CED_R4_CASE(3);
+    default:
+        return launchGen<ced::R4Policy<4>>(c, rc.n, T, [&](uint8_t *t) { ced::buildR4Table<4>(rc, t); }, dSegs, segStride, nFrames,
+                                           dOut, outStride, s, 0);
+    }
+#undef CED_R4_CASE
 }

@@ -73,6 +73,12 @@ struct GenGeom {
     static constexpr int kPairs = kRegs / 2;
     static constexpr int kWords = kRegs >= 8 ? kRegs / 8 : 1;    /* decision words per step */
     static constexpr int kRenorm = 24;
+    static constexpr int kPhases = S;
+    static constexpr int kTail = S;          /* tail segments */
+    static constexpr int kStepBits = 1;      /* decoded bits per trellis step */
+    /* byte offset of the received symbol's variant inside an entry row; `off` = rx * 32 as staged in the tile */
+    CED_HD static constexpr uint32_t rxOffset(int ph, uint32_t off) { return ph < kRegPhases ? off : off >> 1; }
+    CED_HD static constexpr int entryStride(int ph, int V) { return (ph < kRegPhases ? 32 : 16) * V; }
     /* bytes of step table for V received symbols: 32 per (register phase, pair, rx), 16 per (lane phase, register, rx) */
     CED_HD static constexpr int tableBytes(int V) { return (kRegPhases * kPairs * 32 + 2 * kRegs * 16) * V; }
     CED_HD static constexpr int phaseBase(int ph, int V)               /* byte offset of phase ph's entries */
@@ -251,5 +257,44 @@ CED_HD uint32_t genTracebackStep(uint32_t &p, const uint32_t *words, int t)
     p = (p & ~(1u << q)) | (dec << q);
     return bit;
 }
+
+/* words[idx] of N words without indexing the (register) array dynamically for N <= 2 */
+template <int N>
+CED_HD uint32_t pickWord(const uint32_t *words, uint32_t idx)
+{
+    if (N == 1)
+        return words[0];
+    if (N == 2)
+        return idx ? words[1] : words[0];
+    return words[idx];
+}
+
+/* the same step with the phase known at compile time (shift counts become immediates) */
+template <int S, int PH>
+CED_HD uint32_t genTracebackStepC(uint32_t &p, const uint32_t *words)
+{
+    constexpr int q = S - 1 - PH;
+    const uint32_t r = p >> 2, l = p & 3u;
+    const uint32_t dec = (pickWord<GenGeom<S>::kWords>(words, r >> 3) >> (8u * l + (r & 7u))) & 1u;
+    const uint32_t bit = (p >> q) & 1u;
+    p = (p & ~(1u << q)) | (dec << q);
+    return bit;
+}
+
+/* what genForwardKernel / genTracebackKernel (swar_generic.cu) need to know about a trellis */
+template <int S>
+struct GenPolicy : GenGeom<S> {
+    using G = GenGeom<S>;
+    template <int PH>
+    CED_HD static void step(uint32_t (&R)[G::kRegs], const uint8_t *tab, int V, uint32_t minusOne, uint32_t (&T)[G::kWords])
+    {
+        genStep<S, PH>(R, tab, G::entryStride(PH, V), minusOne, T);
+    }
+    CED_HD static void init(uint32_t (&R)[G::kRegs], int n) { genInitMetrics<S>(R, n); }
+    CED_HD static void renorm(uint32_t (&R)[G::kRegs]) { genRenorm<S>(R); }
+    CED_HD static uint32_t tbStep(uint32_t &p, const uint32_t *words, int t) { return genTracebackStep<S>(p, words, t); }
+    template <int PH>
+    CED_HD static uint32_t tbStepC(uint32_t &p, const uint32_t *words) { return genTracebackStepC<S, PH>(p, words); }
+};
 
 } // namespace ced

@@ -351,3 +351,70 @@ extern "C" int swar_sim_decode_gen(int K, int n, const uint32_t *gens, const uin
     default: return -1;
     }
 }
+
+// k = 2 codes through the radix-4 step functions of swar_radix4.cuh (what genForwardKernel<R4Policy> runs per thread):
+// returns the largest metric seen, -1 = not a code it takes.  out: (T - S) * 2 / 8 bytes.
+#include "swar_radix4.cuh"
+
+template <int S>
+static int decodeR4(const ced::R4Code &c, const uint8_t *segs, int T, uint8_t *out)
+{
+    using G = ced::R4Geom<S>;
+    const int V = 1 << c.n;
+    std::vector<uint8_t> table((size_t)G::tableBytes(V) + 16);
+    ced::buildR4Table<S>(c, table.data());
+    uint32_t R[G::kRegs];
+    ced::r4InitMetrics<S>(R, c.n);
+    std::vector<uint32_t> surv((size_t)G::kWords * (size_t)T);
+    int mx = 0;
+    for (int t = 0; t < T; t++) {
+        uint32_t Tw[G::kWords];
+        const int ph = t % S;
+        const uint32_t rx = segs[t] & (uint32_t)(V - 1);
+        const uint8_t *tab = table.data() + G::phaseBase(ph, V) + G::rxOffset(ph, rx * 32u);
+        switch (ph) {
+        case 0: ced::R4Policy<S>::template step<0>(R, tab, V, 0xFFFFFFFFu, Tw); break;
+        case 1: if constexpr (S > 1) ced::R4Policy<S>::template step<1>(R, tab, V, 0xFFFFFFFFu, Tw); break;
+        case 2: if constexpr (S > 2) ced::R4Policy<S>::template step<2>(R, tab, V, 0xFFFFFFFFu, Tw); break;
+        default: if constexpr (S > 3) ced::R4Policy<S>::template step<3>(R, tab, V, 0xFFFFFFFFu, Tw); break;
+        }
+        for (int w = 0; w < G::kWords; w++)
+            surv[(size_t)t * G::kWords + w] = Tw[w];
+        for (int r = 0; r < G::kRegs; r++)
+            for (int l = 0; l < 4; l++) {
+                const int v = (R[r] >> (8 * l)) & 0xFF;
+                if (v > mx) mx = v;
+            }
+        if ((t + 1) % G::kRenorm == 0)
+            ced::r4Renorm<S>(R);
+    }
+    const int L = T - S;                         /* information segments, 2 bits each */
+    for (int i = 0; i < (2 * L + 7) / 8; i++) out[i] = 0;
+    uint32_t p = 0;
+    for (int t = T - 1; t >= 0; t--) {
+        const uint32_t two = ced::r4TracebackStep<S>(p, &surv[(size_t)t * G::kWords], t);
+        if (t < L)
+            out[t / 4] |= (uint8_t)(two << (6 - 2 * (t % 4)));
+    }
+    return mx;
+}
+
+extern "C" int swar_sim_decode_r4(int K, int n, const uint32_t *gens, const uint8_t *segs, int T, uint8_t *out)
+{
+    ced::R4Code c;
+    c.S = K - 1;
+    c.n = n;
+    if (n < 2 || n > 3 || K < 2 || K > 5) return -1;
+    for (int i = 0; i < 3; i++) {
+        c.tap[i] = 0;
+        if (i < n)
+            for (int b = 0; b < 2 * K; b++)   /* taps with bit 0 on the newest input bit (src/convEncode.c:163-175, k*K bits) */
+                c.tap[i] |= ((gens[i] >> b) & 1u) << (2 * K - 1 - b);
+    }
+    switch (c.S) {
+    case 1: return decodeR4<1>(c, segs, T, out);
+    case 2: return decodeR4<2>(c, segs, T, out);
+    case 3: return decodeR4<3>(c, segs, T, out);
+    default: return decodeR4<4>(c, segs, T, out);
+    }
+}

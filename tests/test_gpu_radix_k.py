@@ -11,7 +11,8 @@ from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
 
-CODES = [(3, 2, (0o27, 0o75, 0o72)), (4, 2, (0o236, 0o155, 0o337)), (2, 2, (0o17, 0o06, 0o15)),
+CODES = [(3, 2, (0o27, 0o75, 0o72)), (4, 2, (0o236, 0o155, 0o337)), (2, 2, (0o17, 0o06, 0o15)), (3, 2, (0o53, 0o75)),
+         (5, 2, (0o1236, 0o0155, 0o1337)), (4, 2, (0o321, 0o256, 0o177)),
          (5, 2, (0o1236, 0o0155, 0o1337, 0o1701)), (3, 4, (0o7531, 0o6427, 0o5173, 0o3355, 0o1777)), (2, 4, (0o357, 0o261, 0o173, 0o225, 0o316))]
 
 

@@ -147,3 +147,33 @@ def test_generic_table_path_matches_oracle(sim, port, K, g):
         assert 0 <= mx < 128 - n, (K, g, bits, p, mx)
         want = port.decode_batch(K, list(g), noisy[None, :], bits + S, symmetric=False)[0]
         assert np.array_equal(out, want), (K, g, bits, p)
+
+
+R4_CODES = [(2, (0o17, 0o06, 0o15)), (3, (0o27, 0o75, 0o72)), (4, (0o236, 0o155, 0o337)), (5, (0o1236, 0o0155, 0o1337)),
+            (3, (0o53, 0o75)), (2, (0o13, 0o07, 0o15)), (4, (0o321, 0o256, 0o177))]
+
+
+@pytest.mark.parametrize("K,g", R4_CODES)
+def test_radix4_step_functions_match_the_k2_restatement(sim, port, K, g):
+    """r4Step / buildR4Table / r4TracebackStep (swar_radix4.cuh, k = 2: four branches into every state, lowest edgeIn
+    keeps a tie) against oracle/ced_oracle_k.c, which is pinned to the reference's own add-compare-select; the largest
+    metric must leave the guard bit free."""
+    sim.swar_sim_decode_r4.argtypes = [C.c_int, C.c_int, u32p, u8p, C.c_int, u8p]
+    rng = np.random.default_rng(K * 100 + sum(g))
+    n, S = len(g), K - 1
+    gens = np.array(g, dtype=np.uint32)
+    for nbytes, p in ((1, 0.0), (6, 0.0), (5, 0.2), (64, 0.03), (256, 0.07), (128, 0.5), (512, 0.5)):
+        msg = rng.integers(0, 256, (1, nbytes), dtype=np.uint8)
+        clean = port.encode_batch_k(K, 2, g, msg)
+        T = clean.shape[1]
+        flips = rng.random(clean.shape + (n,)) < p
+        noisy = clean.copy()
+        for j in range(n):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        want = port.decode_batch_k(K, 2, g, noisy, T)[0]
+        junk = noisy | (rng.integers(0, 16, noisy.shape, dtype=np.uint8) << 4)    # bits above n are ignored
+        row = np.ascontiguousarray(junk[0])
+        out = np.zeros(nbytes, dtype=np.uint8)
+        mx = sim.swar_sim_decode_r4(K, n, gens.ctypes.data_as(u32p), row.ctypes.data_as(u8p), T, out.ctypes.data_as(u8p))
+        assert 0 <= mx < 128 - n, (K, g, nbytes, p, mx)
+        assert np.array_equal(out, want), (K, g, nbytes, p)

@@ -38,8 +38,8 @@ ctx.close()
 
 # rate-k/n codes with k > 1 (csrc/radix_k.cu, one warp per frame)
 ctx = ced.Context(0)
-for K, k, g, frames in ((3, 2, (0o27, 0o75, 0o72), 1 << 14), (4, 2, (0o236, 0o155, 0o337), 1 << 14),
-                        (5, 2, (0o1236, 0o0155, 0o1337), 1 << 13)):
+for K, k, g, frames in ((3, 2, (0o27, 0o75, 0o72), 1 << 16), (3, 2, (0o53, 0o75), 1 << 16), (4, 2, (0o236, 0o155, 0o337), 1 << 16),
+                        (5, 2, (0o1236, 0o0155, 0o1337), 1 << 15), (5, 2, (0o1236, 0o0155, 0o1337, 0o1701), 1 << 13)):
     code = ced.Code(K, g)
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
     ctx.random_bytes(msgs, seed=3)
