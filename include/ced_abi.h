@@ -240,7 +240,9 @@ int ced_random_bytes(ced_ctx *ctx, uint8_t *dMsg, size_t msgStride, int nFrames,
  * decoder performs (src/viterbiDecoderButterflyk1.c:200-256, formulas for general k) -- the reference's own k > 1
  * traceback does not run at HEAD; encoder, trellis labels and per-step path metrics are pinned to the unmodified
  * reference built with k = 2 parameters (tests/test_oracle_k.py).
- * inputBits in {1, 2, 4} (1 forwards to ced_encode_batch / ced_decode_batch), k*(K-1) <= 8, k*K <= 32. */
+ * inputBits in {1, 2, 4} (1 forwards to ced_encode_batch / ced_decode_batch), k*(K-1) <= 8, k*K <= 32.  k = 2 with 2 or 3
+ * generators runs on thread-per-frame SIMD-in-word kernels with radix-4 butterflies, the rest on a one-warp-per-frame
+ * kernel. */
 int ced_encode_batch_k(ced_ctx *ctx, const ced_code_t *code, int inputBits, const uint8_t *dMsg, size_t msgStride,
                        int nFrames, int frameBytes, uint8_t *dSegs, size_t segStride, void *stream);
 int ced_decode_batch_k(ced_ctx *ctx, const ced_code_t *code, int inputBits, const uint8_t *dSegs, size_t segStride,
