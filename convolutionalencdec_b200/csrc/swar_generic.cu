@@ -19,7 +19,7 @@ struct alignas(W >= 4 ? 16 : 4 * W) SurvRow {
 
 /* Forward pass: see k7ForwardKernel (decode_batch.cuh) for the scheduler; symbols are byte-per-segment only. */
 template <class P, int V, bool ALIGNED>
-__global__ void __launch_bounds__(kFwdThreads, 3)
+__global__ void __launch_bounds__(kFwdThreads, P::kRegs >= 64 ? 2 : 3)
 genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, SurvRow<P::kWords> *__restrict__ surv,
                  const uint8_t *__restrict__ table, int n, uint32_t minusOne, FwdSched sched, int chunksPerUnit)
 {
@@ -382,7 +382,7 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
     if (!code || code->codedBits < 2 || code->codedBits > 3)
         return CED_ERR_UNSUPPORTED;
     const int K = code->constraintLen, S = K - 1;
-    if (!(S == 2 || S == 3 || S == 4 || S == 6 || S == 8) || (code->codedBits == 3 && S > 6))
+    if (!(S == 2 || S == 3 || S == 4 || S == 6 || S == 8))
         return CED_ERR_UNSUPPORTED;
     static const bool off = getenv("CED_SWAR_GENERIC") && atoi(getenv("CED_SWAR_GENERIC")) == 0;
     if (off)

@@ -1,6 +1,6 @@
 /*
  * swar_generic.cuh -- the SIMD-in-word forward pass of trellis_swar.cuh for ANY rate-1/n, k = 1 code with 2^S states,
- * S = K - 1 in {2, 3, 4, 6, 8} and n = 2 or 3 (n = 3 up to S = 6): generators that do NOT tap both ends included
+ * S = K - 1 in {2, 3, 4, 6, 8} and n = 2 or 3: generators that do NOT tap both ends included
  * (the reference's headers advertise generic K / n, src/convEncode.h:8-18, src/viterbiDecoder.h:47-62,
  * and its own handTracedTest code g = {7, 6} is one of them).  K = 7 codes whose generators tap the newest and the oldest
  * bit keep the hand-scheduled kernel (decode_batch.cuh); everything else used to run on a one-warp-per-frame kernel
