@@ -738,6 +738,11 @@ static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed,
                                 int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
     static const bool enabled = !getenv("CED_WAVE_PIPELINE") || atoi(getenv("CED_WAVE_PIPELINE")) != 0;
+    /* experiments: CED_PIPE_WAVE_FRAMES (frames per wave), CED_PIPE_WAVES (waves in flight, <= kPipeDepth - 1) */
+    static const int envWaveFrames = getenv("CED_PIPE_WAVE_FRAMES") ? atoi(getenv("CED_PIPE_WAVE_FRAMES")) : 0;
+    static const int envWaves = getenv("CED_PIPE_WAVES") ? atoi(getenv("CED_PIPE_WAVES")) : 0;
+    const int kPipeWaveFrames = envWaveFrames >= 4096 ? envWaveFrames / 64 * 64 : ::kPipeWaveFrames;
+    const int kPipeWaves = envWaves >= 1 ? std::min(envWaves, kPipeDepth) : ::kPipeWaves;
     if (!c || !enabled || nFrames < 2 * kPipeWaveFrames || classify(code) == CodeId::Unsupported || !dSegs || !dOut ||
         frameBits <= 0 || (frameBits & 7) || frameBits > 8192)
         return decodeBatchImpl(c, code, packed, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
