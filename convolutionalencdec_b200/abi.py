@@ -93,6 +93,8 @@ def load_abi():
     lib.ced_host_pack_symbols.argtypes = [_u8p, sz, i, i, _u8p, sz, i]
     lib.ced_slice_soft_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_soft.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_softq.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_quantize_soft.argtypes = [vp, _u8p, sz, i, i, C.c_double, _u8p, sz, vp]
     lib.ced_slice_soft_to_bytes.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_awgn_channel.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, C.c_double, C.c_double, u64, u64, vp, vp]
     lib.ced_shard_range.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
@@ -366,6 +368,28 @@ class Context:
         _check(self.lib, self.lib.ced_decode_batch_soft(self.h, C.byref(code._c), soft.data_ptr(), soft.stride(0), nf,
                                                         frame_bits, out.data_ptr(), out.stride(0),
                                                         _stream_handle(stream)), "ced_decode_batch_soft")
+        return out
+
+    def decode_batch_softq(self, code, syms, frame_bits, out=None, stream=None):
+        """syms: uint8 CUDA tensor [frames, >= frame_bits+6], one byte per segment x0 | x1 << 3 (3-bit soft decisions)."""
+        import torch
+        nf = syms.shape[0]
+        if out is None:
+            out = torch.empty((nf, frame_bits // 8), dtype=torch.uint8, device=syms.device)
+        _check(self.lib, self.lib.ced_decode_batch_softq(self.h, C.byref(code._c), syms.data_ptr(), syms.stride(0), nf,
+                                                         frame_bits, out.data_ptr(), out.stride(0),
+                                                         _stream_handle(stream)), "ced_decode_batch_softq")
+        return out
+
+    def quantize_soft(self, soft, segs_per_frame, delta, out=None, stream=None, sym_stride=None):
+        """int8 reliabilities [frames, >= 2*segs] -> 3-bit soft symbols [frames, sym_stride] (ced_quantize_soft)."""
+        import torch
+        nf = soft.shape[0]
+        if out is None:
+            out = torch.zeros((nf, sym_stride or (segs_per_frame + 15) // 16 * 16), dtype=torch.uint8, device=soft.device)
+        _check(self.lib, self.lib.ced_quantize_soft(self.h, soft.data_ptr(), soft.stride(0), nf, segs_per_frame,
+                                                    float(delta), out.data_ptr(), out.stride(0), _stream_handle(stream)),
+               "ced_quantize_soft")
         return out
 
     def slice_soft_to_bytes(self, soft, segs_per_frame, out=None, stream=None, seg_stride=None):

@@ -183,6 +183,7 @@ struct ced_ctx {
         uint2 *dev;
     };
     std::vector<StepTable> stepTables;
+    DeviceBuf<uint4> softqTable[2];  /* softq_decode.cuh cost tables of 0113/0171 and 0133/0171, built on first use */
     /* optional kernel timing (ced_ctx_set_profiling) */
     bool profiling = false;
     static constexpr int kMaxProfWaves = 64;

@@ -148,6 +148,17 @@ int ced_slice_soft_symbols(ced_ctx *ctx, const int8_t *dSoft, size_t softStride,
                            uint8_t *dPacked, size_t packedStride, void *stream);
 int ced_slice_soft_to_bytes(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame,
                             uint8_t *dSegs, size_t segStride, void *stream);
+/* 3-bit soft decisions at (nearly) the hard decoder's speed and wire size: one byte per segment x0 | x1 << 3, x in 0..7
+ * (0 = surely bit 0 ... 7 = surely bit 1; generator 0 in the low field), i.e. the reliabilities s = 7 - 2x of
+ * ced_decode_batch_soft's definition; the decoded bytes equal ced_decode_batch_soft's on those int8 values.  Byte path
+ * metrics, the hard kernel's survivor stream and traceback (k7SoftQForwardKernel).  Codes 0113/0171 and
+ * 0133/0171; any base / stride (16-byte aligned rows are fastest).  ced_quantize_soft turns int8 reliabilities (two per
+ * segment) into this format with a uniform 8-level quantiser of step `delta` (thresholds 0, +-delta, +-2 delta,
+ * +-3 delta; about 0.6 sigma of the channel noise in int8 units is the usual choice). */
+int ced_decode_batch_softq(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
+                           int frameBits, uint8_t *dOut, size_t outStride, void *stream);
+int ced_quantize_soft(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame, double delta,
+                      uint8_t *dSyms, size_t symStride, void *stream);
 /* BPSK over AWGN with int8 soft output (the BER sweep's channel, berTestK7/berTestK7.c:29-43 generalised):
  * soft = clamp(round(amplitude * ((1 - 2 bit) + sigma * N(0,1))), -127, 127) for both coded bits of every
  * byte-per-segment symbol; for rate 1/2, sigma = 1 / sqrt(Eb/N0).  Counter-based generator keyed by (seed,

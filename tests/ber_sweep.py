@@ -38,14 +38,15 @@ def bsc_probability(ebn0_db, rate=0.5):
 def run_point_soft(ctx, code, ebn0_db, frames, seed, first_frame, subset, checker, soft_checker):
     """One Eb/N0 point on the AWGN channel with int8 soft output: the SAME channel realisation is decoded by the
     soft-decision decoder (ced_decode_batch_soft) and, after slicing to signs, by the hard-decision decoder.
-    counters = {sign errors, coded bits, hard decoded errors, bits, soft decoded errors, bits}."""
+    and, quantised to 3 bits (step 0.6 sigma), by the byte-metric soft decoder (ced_decode_batch_softq).
+    counters = {sign errors, coded bits, hard decoded errors, bits, soft decoded errors, bits, 3-bit soft errors, bits}."""
     import numpy as np
     import torch
     T = PKT_BITS + code.S
     stride = (T + 15) // 16 * 16
     msgs = torch.empty((frames, PKT_BITS // 8), dtype=torch.uint8, device="cuda")
     segs = torch.zeros((frames, stride), dtype=torch.uint8, device="cuda")
-    counters = torch.zeros(6, dtype=torch.int64, device="cuda")
+    counters = torch.zeros(8, dtype=torch.int64, device="cuda")
     ctx.random_bytes(msgs, seed=seed, first_frame=first_frame)
     ctx.encode_batch(code, msgs, out=segs)
     soft = ctx.awgn_channel(segs, T, ebn0_db, seed=seed + 1, first_frame=first_frame, counters=counters[:2])
@@ -54,6 +55,10 @@ def run_point_soft(ctx, code, ebn0_db, frames, seed, first_frame, subset, checke
     dec = ctx.decode_batch(code, hard, PKT_BITS)
     ctx.ber_count(dec, msgs, counters[2:4])
     ctx.ber_count(dec_soft, msgs, counters[4:6])
+    sigma_i8 = 32.0 * 10.0 ** (-ebn0_db / 20.0)            # rate 1/2: sigma = 1 / sqrt(Eb/N0), amplitude 32
+    syms = ctx.quantize_soft(soft, T, 0.6 * sigma_i8, sym_stride=stride)
+    dec_q = ctx.decode_batch_softq(code, syms, PKT_BITS)
+    ctx.ber_count(dec_q, msgs, counters[6:8])
     ctx.sync()
     check = None
     if subset and checker is not None:
@@ -64,6 +69,11 @@ def run_point_soft(ctx, code, ebn0_db, frames, seed, first_frame, subset, checke
                  "reference_decoded_errors": int(np.bitwise_count(want ^ msgs[:m].cpu().numpy()).sum()),
                  "gpu_decoded_errors": int(np.bitwise_count((dec[:m] ^ msgs[:m]).cpu().numpy()).sum()),
                  "soft_frames": ms, "soft_bytes_identical": bool(np.array_equal(want_soft, dec_soft[:ms].cpu().numpy()))}
+        sy = syms[:ms, :T].cpu().numpy()
+        q8 = np.empty((ms, 2 * T), dtype=np.int8)
+        q8[:, 0::2] = 7 - 2 * (sy & 7).astype(np.int16)
+        q8[:, 1::2] = 7 - 2 * ((sy >> 3) & 7).astype(np.int16)
+        check["softq_bytes_identical"] = bool(np.array_equal(soft_checker(q8, T), dec_q[:ms].cpu().numpy()))
     return counters, check
 
 
@@ -150,14 +160,16 @@ def main(argv=None):
             c = [int(x) for x in counters.cpu().tolist()]
             rows.append({"ebn0_db": db, "bsc_p": p, "sign_errors": c[0], "coded_bits": c[1], "channel_ber": c[0] / c[1],
                          "hard_decoded_errors": c[2], "soft_decoded_errors": c[4], "decoded_bits": c[3],
-                         "hard_ber": c[2] / c[3], "soft_ber": c[4] / c[5],
+                         "hard_ber": c[2] / c[3], "soft_ber": c[4] / c[5], "softq_decoded_errors": c[6],
+                         "softq_ber": c[6] / c[7],
                          "uncoded_bpsk_ber": ber_theory.bpsk_ber(db), "subset_check": check})
             if rank == 0:
-                print("Eb/N0 %4.1f dB  channel BER %.5e (Q: %.5e)  hard BER %.4e  soft BER %.4e%s"
-                      % (db, c[0] / c[1], p, c[2] / c[3], c[4] / c[5],
+                print("Eb/N0 %4.1f dB  channel BER %.5e (Q: %.5e)  hard BER %.4e  soft BER %.4e  3-bit soft BER %.4e%s"
+                      % (db, c[0] / c[1], p, c[2] / c[3], c[4] / c[5], c[6] / c[7],
                          "" if not check else "  subset: hard %d frames identical to the reference: %s, soft %d frames "
-                         "identical to the soft oracle: %s" % (check["frames"], check["bytes_identical"],
-                                                              check["soft_frames"], check["soft_bytes_identical"])),
+                         "identical to the soft oracle: %s, 3-bit soft: %s"
+                         % (check["frames"], check["bytes_identical"], check["soft_frames"], check["soft_bytes_identical"],
+                            check["softq_bytes_identical"])),
                       file=sys.stderr)
             continue
         counters, check = run_point(ctx, code, p, args.frames_per_gpu, seed=1000 + 10 * i,
@@ -177,11 +189,13 @@ def main(argv=None):
                         check["bytes_identical"])), file=sys.stderr)
     if args.soft:
         hard_x, soft_x = crossing_db(rows, "hard_ber", 1e-4), crossing_db(rows, "soft_ber", 1e-4)
+        softq_x = crossing_db(rows, "softq_ber", 1e-4)
         result = {"config": "K=7 r=1/2 g=(0113,0171), %d-bit packets, BPSK+AWGN quantised to int8 (amplitude 32): "
                             "soft-decision vs hard-decision decoding of the same channel output" % PKT_BITS,
                   "n_gpus": world, "frames_per_gpu": args.frames_per_gpu, "checker": kind,
-                  "ebn0_db_at_ber_1e-4": {"hard": hard_x, "soft": soft_x,
-                                          "soft_decision_gain_db": (hard_x - soft_x) if hard_x and soft_x else None},
+                  "ebn0_db_at_ber_1e-4": {"hard": hard_x, "soft": soft_x, "soft_3bit": softq_x,
+                                          "soft_decision_gain_db": (hard_x - soft_x) if hard_x and soft_x else None,
+                                          "soft_3bit_gain_db": (hard_x - softq_x) if hard_x and softq_x else None},
                   "points": rows}
         if rank == 0:
             text = json.dumps(result, indent=1)

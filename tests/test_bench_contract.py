@@ -54,6 +54,8 @@ def test_our_arm_line():
     assert rf["issue"]["instr_per_frame_step"] == rf["issue"]["loop_instructions"] / 6.0   # read from the built library
     # the other BASELINE configs ride on the same line
     enc, ber, soft = d["encode"], d["ber"], d["soft"]
+    q3 = soft["soft_3bit"]
+    assert q3["value"] > soft["value"] and q3["check"]["decoded_bits"] == 8192 * 4096 and q3["check"]["ber"] < 5e-3
     assert enc["config"]["frames"] == 1 << 20 and enc["round_trip_ok"] is True and enc["roofline"]["bound"] == "hbm"
     assert 0.1 < enc["roofline"]["frac"] < 1.2 and enc["value"] > 100.0
     assert ber["point"]["decoded_bits"] == 8192 * 4096 and 1e-4 < ber["point"]["decoded_ber"] < 2e-3

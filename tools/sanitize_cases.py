@@ -80,6 +80,14 @@ for frames, bits in ((1, 8), (33, 96), (70, 1000 // 8 * 8)):
     good = bool(torch.equal(d, msgs))
     ok &= good
     print("soft-decision round trip %d x %d:" % (frames, bits), good)
+    flatq = torch.zeros(frames * T + 2, dtype=torch.uint8, device="cuda")
+    symq = flatq[2:].view(frames, T)                     # misaligned, exactly sized
+    ctx.quantize_soft(softb, T, 8.0, out=symq)
+    dq = ctx.decode_batch_softq(code, symq, bits)
+    ctx.sync()
+    goodq = bool(torch.equal(dq, msgs))
+    ok &= goodq
+    print("3-bit soft round trip %d x %d:" % (frames, bits), goodq)
 for K, g in ((3, (7, 5, 3)), (4, (0o15, 0o17)), (5, (0o23, 0o35)), (7, (0o133, 0o170)), (9, (0o557, 0o663, 0o711))):
     c4 = ced.Code(K, g)
     frames, bits = 67, 200

@@ -39,3 +39,25 @@ ctx.sync()
 fm, tm = sum(fwd) / n, sum(tb) / n
 print(json.dumps({"frames": frames, "forward_ms": fm, "traceback_ms": tm, "gbit_s": frames * bits / ((fm + tm) * 1e-3) / 1e9,
                   "forward_only_gbit_s": frames * bits / (fm * 1e-3) / 1e9, "bit_errors": int(cnt[0]), "bits": int(cnt[1])}))
+
+# the same channel output quantised to 3 bits: byte metrics, one byte per segment (ced_decode_batch_softq)
+sigma_i8 = 32.0 * 10 ** (-3.0 / 20)
+syms = ctx.quantize_soft(soft, T, 0.6 * sigma_i8, sym_stride=4112)
+hard = ctx.decode_batch(ced.K7_DEFAULT, ctx.slice_soft_to_bytes(soft, T, seg_stride=4112), bits)
+for _ in range(3):
+    ctx.decode_batch_softq(ced.K7_DEFAULT, syms, bits, out=out)
+fwd, tb = [], []
+for _ in range(n):
+    ctx.decode_batch_softq(ced.K7_DEFAULT, syms, bits, out=out)
+    f, t = ctx.last_kernel_ms()
+    fwd.append(f)
+    tb.append(t)
+torch.cuda.synchronize()
+cnt = torch.zeros(4, dtype=torch.int64, device="cuda")
+ctx.ber_count(out, msgs, cnt[:2])
+ctx.ber_count(hard, msgs, cnt[2:])
+ctx.sync()
+fm, tm = sum(fwd) / n, sum(tb) / n
+print(json.dumps({"softq": True, "frames": frames, "forward_ms": fm, "traceback_ms": tm,
+                  "gbit_s": frames * bits / ((fm + tm) * 1e-3) / 1e9, "forward_only_gbit_s": frames * bits / (fm * 1e-3) / 1e9,
+                  "bit_errors": int(cnt[0]), "hard_bit_errors": int(cnt[2]), "bits": int(cnt[1])}))
