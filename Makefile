@@ -42,7 +42,10 @@ $(PKG)/libconvencdec_k3.so: $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCode
 	$(CC) $(CFLAGS) -Iinclude/params/handTraced -shared -o $@ $(HOST_SRCS) $(CSRC)/host/params/handTraced/convCodeParams.c \
 	    -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN' -Wl,-Bsymbolic
 
-examples: examples/_bin/batch_roundtrip examples/_bin/speed_queued examples/_bin/multi_gpu_roundtrip
+examples: examples/_bin/batch_roundtrip examples/_bin/speed_queued examples/_bin/multi_gpu_roundtrip examples/_bin/soft_decisions
+examples/_bin/soft_decisions: examples/soft_decisions.c include/ced_abi.h $(PKG)/libced_cuda.so
+	mkdir -p examples/_bin
+	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude -o $@ $< -L$(PKG) -lced_cuda -lm -Wl,-rpath,'$$ORIGIN/../../$(PKG)'
 examples/_bin/multi_gpu_roundtrip: examples/multi_gpu_roundtrip.c include/ced_abi.h $(PKG)/libced_cuda.so
 	mkdir -p examples/_bin
 	$(CC) -O2 -g -std=gnu11 -Wall -Iinclude -o $@ $< -L$(PKG) -lced_cuda -Wl,-rpath,'$$ORIGIN/../../$(PKG)'

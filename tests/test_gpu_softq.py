@@ -112,3 +112,17 @@ def test_softq_argument_checks(torch_cuda, ctx):
         ctx.decode_batch_softq(ced.K7_DEFAULT, d, 64)          # 70 segments do not fit a 64-byte row
     with pytest.raises(ced.CedError):
         ctx.decode_batch_softq(ced.K7_DEFAULT, d, 12)
+
+
+def test_plain_c_soft_decisions_example():
+    """examples/soft_decisions.c: a C program (no CUDA headers) sends one batch through the AWGN channel and decodes it
+    with hard, int8-soft and 3-bit-soft decisions; the error rates must order as expected."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "examples", "_bin", "soft_decisions")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_bin/soft_decisions not built")
+    r = subprocess.run([exe, "3.0"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3-bit soft" in r.stdout
