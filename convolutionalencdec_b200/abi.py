@@ -94,6 +94,7 @@ def load_abi():
     lib.ced_slice_soft_symbols.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_soft.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_decode_batch_softq.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz, vp]
+    lib.ced_decode_batch_softq_host.argtypes = [vp, codep, _u8p, sz, i, i, _u8p, sz]
     lib.ced_quantize_soft.argtypes = [vp, _u8p, sz, i, i, C.c_double, _u8p, sz, vp]
     lib.ced_slice_soft_to_bytes.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, vp]
     lib.ced_awgn_channel.argtypes = [vp, _u8p, sz, i, i, _u8p, sz, C.c_double, C.c_double, u64, u64, vp, vp]
@@ -379,6 +380,14 @@ class Context:
         _check(self.lib, self.lib.ced_decode_batch_softq(self.h, C.byref(code._c), syms.data_ptr(), syms.stride(0), nf,
                                                          frame_bits, out.data_ptr(), out.stride(0),
                                                          _stream_handle(stream)), "ced_decode_batch_softq")
+        return out
+
+    def decode_batch_softq_host(self, code, syms, frame_bits, out):
+        """syms / out: host uint8 arrays (numpy or CPU tensors), 2-D; synchronous (ced_decode_batch_softq_host)."""
+        sp, ss, sshape = Context._host(syms)
+        op, os_, _ = Context._host(out)
+        _check(self.lib, self.lib.ced_decode_batch_softq_host(self.h, C.byref(code._c), sp, ss, sshape[0], frame_bits, op, os_),
+               "ced_decode_batch_softq_host")
         return out
 
     def quantize_soft(self, soft, segs_per_frame, delta, out=None, stream=None, sym_stride=None):

@@ -1192,7 +1192,7 @@ int ced_slice_soft_symbols(ced_ctx *c, const int8_t *dSoft, size_t softStride, i
 }
 
 /* H2D -> kernels -> D2H over two buffers; `encode` selects the direction of the sizes. */
-enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack, DecodeAdaptive };
+enum class HostOp { Encode, Decode, DecodePacked, DecodeViaPack, DecodeAdaptive, DecodeSoftQ };
 
 /* ordinary malloc'ed / stack memory, i.e. neither page-locked by CUDA nor registered */
 static bool isPageable(const void *p)
@@ -1404,6 +1404,8 @@ static int hostPipelineBody(ced_ctx *c, const ced_code_t *code, HostOp op, const
         int rc;
         if (op == HostOp::Encode)
             rc = ced_encode_batch(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride, cs);
+        else if (op == HostOp::DecodeSoftQ)
+            rc = cedDecodeBatchSoftQ(c, code, c->hostIn[b].p, inStride, cnt, frameParam, c->hostOut[b].p, outStride, cs, 1 + b);
         else if (packThis)
             rc = decodeBatchImpl(c, code, true, c->hostIn[b].p, packStride, cnt, frameParam, c->hostOut[b].p, outStride,
                                  cs, 1 + b);
@@ -1520,6 +1522,23 @@ int ced_decode_batch_packed_host(ced_ctx *c, const ced_code_t *code, const uint8
     return hostPipeline(c, code, HostOp::DecodePacked, hPacked, packedStride,
                         ((size_t)frameBits + code->constraintLen - 1 + 3) / 4, nFrames, frameBits, hOut, outStride,
                         (size_t)frameBits / 8);
+}
+
+int ced_decode_batch_softq_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSyms, size_t symStride, int nFrames,
+                                int frameBits, uint8_t *hOut, size_t outStride)
+{
+    if (!c || !code || !hSyms || !hOut || nFrames < 0 || frameBits <= 0 || (frameBits & 7) || code->constraintLen != 7) {
+        setError("ced_decode_batch_softq_host: bad argument");
+        return CED_ERR_ARG;
+    }
+    if (symStride < (size_t)frameBits + 6 || outStride < (size_t)frameBits / 8) {
+        setError("ced_decode_batch_softq_host: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    if (nFrames == 0)
+        return CED_OK;
+    return hostPipeline(c, code, HostOp::DecodeSoftQ, hSyms, symStride, (size_t)frameBits + 6, nFrames, frameBits, hOut,
+                        outStride, (size_t)frameBits / 8);
 }
 
 int ced_encode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hMsg, size_t msgStride, int nFrames,

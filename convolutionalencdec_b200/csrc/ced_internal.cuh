@@ -229,6 +229,10 @@ extern "C" void cedStopPacketServer();
  * CED_ERR_UNSUPPORTED = not a code these kernels take */
 int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                               int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
+/* softq_decode.cu: ced_decode_batch_softq on working-set `slot` (the host pipeline keeps several chunks in flight) */
+int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
+                        int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
+
 /* swar_generic.cu: rate-2/n codes on the radix-4 SIMD-in-word kernels (swar_radix4.cuh); same convention */
 int cedDecodeBatchSwarRadix4(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                              int frameBits, uint8_t *dOut, size_t outStride, void *stream);

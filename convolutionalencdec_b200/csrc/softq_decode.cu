@@ -23,10 +23,8 @@ static int softqTableFor(ced_ctx *c, int slot, cudaStream_t s, const uint4 **out
     return CED_OK;
 }
 
-extern "C" {
-
-int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
-                           int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
+                        int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
 {
     if (!c || nFrames < 0 || frameBits <= 0 || (frameBits & 7) || (nFrames > 0 && (!dSyms || !dOut))) {
         setError("ced_decode_batch_softq: bad argument (frameBits must be a positive multiple of 8)");
@@ -53,7 +51,7 @@ int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dS
     if (rc != CED_OK)
         return rc;
     const DecodeWorkingSet ws = decodeWorkingSet((size_t)nFrames, T, c->maxWaveFrames);
-    ced_ctx::Work &wk = c->work[0];
+    ced_ctx::Work &wk = c->work[slot];
     if (wk.scratch.bytes < ws.scratchBytes || wk.schedState.bytes < ws.stateBytes || wk.schedFlags.bytes < ws.flagBytes) {
         CED_CUDA(cudaDeviceSynchronize());
         rc = wk.scratch.ensure(ws.scratchBytes);
@@ -104,6 +102,14 @@ int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dS
     wk.lastStream = s;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
+}
+
+extern "C" {
+
+int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
+                           int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    return cedDecodeBatchSoftQ(c, code, dSyms, symStride, nFrames, frameBits, dOut, outStride, stream, 0);
 }
 
 int ced_quantize_soft(ced_ctx *c, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame, double delta,

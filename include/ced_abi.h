@@ -159,6 +159,9 @@ int ced_decode_batch_softq(ced_ctx *ctx, const ced_code_t *code, const uint8_t *
                            int frameBits, uint8_t *dOut, size_t outStride, void *stream);
 int ced_quantize_soft(ced_ctx *ctx, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame, double delta,
                       uint8_t *dSyms, size_t symStride, void *stream);
+/* the same decode on HOST buffers through the chunked H2D / kernel / D2H pipeline of ced_decode_batch_host (synchronous) */
+int ced_decode_batch_softq_host(ced_ctx *ctx, const ced_code_t *code, const uint8_t *hSyms, size_t symStride, int nFrames,
+                                int frameBits, uint8_t *hOut, size_t outStride);
 /* BPSK over AWGN with int8 soft output (the BER sweep's channel, berTestK7/berTestK7.c:29-43 generalised):
  * soft = clamp(round(amplitude * ((1 - 2 bit) + sigma * N(0,1))), -127, 127) for both coded bits of every
  * byte-per-segment symbol; for rate 1/2, sigma = 1 / sqrt(Eb/N0).  Counter-based generator keyed by (seed,

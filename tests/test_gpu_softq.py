@@ -103,6 +103,26 @@ def test_softq_config2_shape_second_code_and_waves(torch_cuda, ctx, port, monkey
         c2.close()
 
 
+def test_softq_host_buffers_match_device_path(torch_cuda, ctx, port):
+    """ced_decode_batch_softq_host: pageable and page-locked host arrays through the chunked pipeline (20000 frames =
+    three chunks) give the device path's bytes."""
+    torch = torch_cuda
+    rng = np.random.default_rng(12)
+    frames, bits, T = 20000, 512, 518
+    syms = rng.integers(0, 64, (frames, T + 2), dtype=np.uint8)
+    want = ctx.decode_batch_softq(ced.K7_DEFAULT, torch.from_numpy(syms).cuda(), bits)
+    ctx.sync()
+    out = np.zeros((frames, bits // 8), dtype=np.uint8)
+    ctx.decode_batch_softq_host(ced.K7_DEFAULT, syms, bits, out)                 # pageable numpy arrays
+    assert np.array_equal(out, want.cpu().numpy())
+    h_in = torch.from_numpy(syms).pin_memory()
+    h_out = torch.zeros((frames, bits // 8), dtype=torch.uint8).pin_memory()
+    ctx.decode_batch_softq_host(ced.K7_DEFAULT, h_in, bits, h_out)               # page-locked
+    assert torch.equal(h_out, want.cpu())
+    sample = np.arange(0, frames, 401)
+    assert np.array_equal(out[sample], port.decode_soft_batch(7, K7, to_int8_pairs(syms[sample], T), T))
+
+
 def test_softq_argument_checks(torch_cuda, ctx):
     torch = torch_cuda
     d = torch.zeros((4, 64), dtype=torch.uint8, device="cuda")
