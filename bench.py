@@ -8,8 +8,8 @@ over this rank's synthetic frames.
     configs: `encode` (configs[2], 2^20 frames), `ber` (configs[3] pipeline + a BER point) and `soft`
     (soft-decision decoder).
   * --gpus N > 1 (under torchrun, one rank per GPU): BASELINE.json configs[4] -- 2^22 frames sharded,
-    2^22 / N per rank, "scaling": "strong"; no collective on the data path.  The weak figure (2^16 frames
-    per GPU) is kept in `weak`.
+    2^22 / N per rank, "scaling": "strong"; no collective on the data path; one ced_decode_batch call per
+    step over the rank's shard, two steps in flight.  The weak figure (2^16 frames per GPU) is kept in `weak`.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm
     python bench.py --impl reference [...]                         # reference CPU arm
@@ -401,14 +401,16 @@ def main():
     # one-decode-at-a-time figure is reported as `single_stream`.
     extra = [ced.Context(local_rank) for _ in range(max(1, args.in_flight) - 1)]
     all_lanes = [(ctx, stream)] + [(c_, torch.cuda.Stream()) for c_ in extra]
-    lanes = all_lanes[:1] if strong else all_lanes       # one call covers the shard: nothing to juggle from outside
+    # config 5: one call covers the shard and keeps its waves in flight by itself; two calls (steps) in flight so that
+    # the ramp of a call -- first wave's forward pass alone, last wave's traceback alone -- overlaps the neighbouring step
+    lanes = all_lanes[:2] if strong else all_lanes
     counters = torch.zeros(4, dtype=torch.int64, device="cuda")
 
     # one sub-batch per step: every lane decodes into its own output buffer (the same frames are in flight on several
     # lanes at once); several sub-batches per step: each writes its own rows of `out`
     lane_out = {id(ctx): out}
-    if n_sub == 1 and not strong:
-        for c_ in extra:
+    if n_sub == 1:
+        for c_, _s in lanes[1:]:
             lane_out[id(c_)] = torch.empty_like(out)
 
     def decode_pass(use, first_lane=0):
@@ -479,7 +481,8 @@ def main():
         ms1 = max_over_ranks(timed_run(args.steps, 1))
         single = {"value": world * units * args.steps / (ms1 * 1e-3) / 1e9, "unit": "Gbit/s",
                   "ms_per_step": ms1 / args.steps,
-                  "note": "one ced_decode_batch at a time on one context and stream (forward then traceback, no overlap)"}
+                  "note": ("one ced_decode_batch call at a time over the whole shard (waves pipelined inside the call)" if strong
+                           else "one ced_decode_batch at a time on one context and stream (forward then traceback, no overlap)")}
 
     total_frames = world * frames
     if args.mode == "encode":
@@ -508,11 +511,13 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": wall}
     if single is not None:
         line["single_stream"] = single
+    if single is not None and not strong:
         line["config"]["in_flight"] = ("%d ced_decode_batch calls in flight (one ced_ctx + CUDA stream each): "
                                        "traceback(i) overlaps forward(i+1)" % len(lanes))
     elif strong:
         line["config"]["in_flight"] = ("one ced_decode_batch call per step over the whole shard; the library keeps 3 waves of "
-                                       "2^16 frames in flight on internal streams (decodeBatchPipelined)")
+                                       "2^16 frames in flight on internal streams (decodeBatchPipelined); %d steps in flight "
+                                       "(one ced_ctx + stream each)" % len(lanes))
 
     if args.mode == "decode":
         # ---- roofline of the dominant kernel (forward ACS), CUDA events around that kernel alone ----
