@@ -10,7 +10,6 @@
 
 namespace ced {
 
-constexpr int kGenChunk = 96;
 
 template <int W>
 struct alignas(W >= 4 ? 16 : 4 * W) SurvRow {
@@ -38,7 +37,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
     uint8_t *tile = sTile + warp * 32 * kPitch;
     const uint32_t symMask = 0x01010101u * (uint32_t)(V - 1);
     const unsigned groups = (unsigned)((nFrames + 31) / 32);
-    const unsigned chunks = (unsigned)((T + kGenChunk - 1) / kGenChunk);
+    const unsigned chunks = (unsigned)((T + P::kChunk - 1) / P::kChunk);
     const unsigned unitsPerGroup = (chunks + chunksPerUnit - 1) / chunksPerUnit;
     const unsigned total = groups * unitsPerGroup;
 
@@ -51,7 +50,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
     unsigned u = grab();
     uint4 pre[TG::kPiecesPerRow];
     if (u < total)
-        loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)((u / groups) * chunksPerUnit) * kGenChunk,
+        loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, 32LL * (u % groups), nFrames, (int)((u / groups) * chunksPerUnit) * P::kChunk,
                                       T, lane);
     while (u < total) {
         const unsigned g = u % groups, su = u / groups;
@@ -80,22 +79,22 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
         }
         unsigned un = total;
         for (unsigned c = cFirst; c < cEnd; c++) {
-            const int t0 = (int)c * kGenChunk;
+            const int t0 = (int)c * P::kChunk;
             __syncwarp();
             storeTile<ByteSymbols, ALIGNED>(tile, pre, lane, symMask);
             if (c + 1 < cEnd) {
-                loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, frame0, nFrames, t0 + kGenChunk, T, lane);
+                loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, frame0, nFrames, t0 + P::kChunk, T, lane);
             } else {
                 un = grab();
                 if (un < total)
                     loadTile<ByteSymbols, ALIGNED>(pre, segs, stride, 32LL * (un % groups), nFrames,
-                                                  (int)((un / groups) * chunksPerUnit) * kGenChunk, T, lane);
+                                                  (int)((un / groups) * chunksPerUnit) * P::kChunk, T, lane);
             }
             __syncwarp();
             const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride + (size_t)t0;
             const uint8_t *p = tile + lane * kPitch + (ALIGNED ? 0u : (rowAddr & 15u));
             SurvRow<G::kWords> *o = surv + ((size_t)g * T + t0) * 32 + lane;
-            const int steps = min(kGenChunk, T - t0);
+            const int steps = min(P::kChunk, T - t0);
             for (int done = 0; done < steps;) {
                 const int nr = min(G::kRenorm, steps - done);
 #pragma unroll 1
@@ -121,8 +120,10 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
                     if constexpr (S > 1) one(std::integral_constant<int, 1>());
                     if constexpr (S > 2) one(std::integral_constant<int, 2>());
                     if constexpr (S > 3) one(std::integral_constant<int, 3>());
-                    if constexpr (S > 4) { one(std::integral_constant<int, 4>()); one(std::integral_constant<int, 5>()); }
-                    if constexpr (S > 6) { one(std::integral_constant<int, 6>()); one(std::integral_constant<int, 7>()); }
+                    if constexpr (S > 4) one(std::integral_constant<int, 4>());
+                    if constexpr (S > 5) one(std::integral_constant<int, 5>());
+                    if constexpr (S > 6) one(std::integral_constant<int, 6>());
+                    if constexpr (S > 7) one(std::integral_constant<int, 7>());
                     p += S;
                     o += (size_t)S * 32;
                 }
@@ -334,7 +335,8 @@ static int launchGen(ced_ctx *c, int n, int T, BuildTable buildTable, const uint
     buildTable(table.data());
     uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p) + (g0 * kStateU4 * 32 * sizeof(uint4) + 255) / 256 * 256;
     CED_CUDA(cudaMemcpyAsync(dTable, table.data(), tabBytes, cudaMemcpyHostToDevice, s));   /* pageable source: staged */
-    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0;
+    /* a tile that is not a whole number of 16-byte pieces (S = 5, 7: 95 / 91 steps) starts at any alignment */
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0 && P::kChunk % 16 == 0;
     const size_t pitchA = ced::TileGeom<ced::ByteSymbols, true>::kPitch, pitchU = ced::TileGeom<ced::ByteSymbols, false>::kPitch;
     const size_t smem = tabBytes + 4 * 32 * (aligned16 ? pitchA : pitchU);
     auto kernelFor = [&](bool al) -> void (*)(const uint8_t *, size_t, int, int, Row *, const uint8_t *, int, uint32_t, ced::FwdSched, int) {
@@ -359,7 +361,7 @@ static int launchGen(ced_ctx *c, int n, int T, BuildTable buildTable, const uint
         CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
         kernel<<<blocks, ced::kFwdThreads, smem, s>>>(dSegs + f0 * segStride, segStride, wave, T, reinterpret_cast<Row *>(wk.scratch.p),
                                                      dTable, n, c->bm0113.minusOne, sched, 2);
-        if constexpr (sizeof(Row) <= 16) {
+        if constexpr (sizeof(Row) <= 16 && 24 % P::kPhases == 0) {
             constexpr int tbT = ced::genTb24Threads<P>();
             ced::genTraceback24Kernel<P><<<(wave + tbT - 1) / tbT, tbT, 0, s>>>(reinterpret_cast<const Row *>(wk.scratch.p), wave, T,
                                                                              dOut + f0 * outStride, outStride);
@@ -382,7 +384,7 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
     if (!code || code->codedBits < 2 || code->codedBits > 3)
         return CED_ERR_UNSUPPORTED;
     const int K = code->constraintLen, S = K - 1;
-    if (!(S == 2 || S == 3 || S == 4 || S == 6 || S == 8))
+    if (S < 2 || S > 8)
         return CED_ERR_UNSUPPORTED;
     static const bool off = getenv("CED_SWAR_GENERIC") && atoi(getenv("CED_SWAR_GENERIC")) == 0;
     if (off)
@@ -410,7 +412,9 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
         CED_GEN_CASE(2);
         CED_GEN_CASE(3);
         CED_GEN_CASE(4);
+        CED_GEN_CASE(5);
         CED_GEN_CASE(6);
+        CED_GEN_CASE(7);
     default:
         return launchGen<ced::GenPolicy<8>>(c, gc.n, T, [&](uint8_t *t) { ced::buildGenTable<8>(gc, t); }, dSegs, segStride, nFrames,
                                             dOut, outStride, s, slot);

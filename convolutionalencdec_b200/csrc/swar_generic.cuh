@@ -1,6 +1,6 @@
 /*
  * swar_generic.cuh -- the SIMD-in-word forward pass of trellis_swar.cuh for ANY rate-1/n, k = 1 code with 2^S states,
- * S = K - 1 in {2, 3, 4, 6, 8} and n = 2 or 3: generators that do NOT tap both ends included
+ * S = K - 1 in 2 .. 8 and n = 2 or 3: generators that do NOT tap both ends included
  * (the reference's headers advertise generic K / n, src/convEncode.h:8-18, src/viterbiDecoder.h:47-62,
  * and its own handTracedTest code g = {7, 6} is one of them).  K = 7 codes whose generators tap the newest and the oldest
  * bit keep the hand-scheduled kernel (decode_batch.cuh); everything else used to run on a one-warp-per-frame kernel
@@ -19,12 +19,11 @@
  * keeps the lower predecessor, src/viterbiDecoderButterflyk1.c:129-130).
  *
  * Exactness of 8-bit metrics: the start metrics are the reference's, 0 for state 0 and (uint8_t)(NUM_STATES + 1) for
- * the rest (src/viterbiDecoderButterflyk1.c:59-67) -- 5 / 9 / 17 / 65 play "never wins" for K = 3 / 4 / 5 / 7, and for
- * K = 9 the reference's uint8_t METRIC_TYPE turns 257 into 1, which this kernel reproduces.  Any state
- * is reachable from state 0 within S steps at cost <= n*S, so the largest value seen is <= 65 + n*S in the first S
- * steps, the spread is <= n*S afterwards and the minimum grows by <= n per step: with a renormalisation every 24
- * steps candidates stay <= n*S + 24*n + n <= 93 (or <= 65 + n*S + n = 86 at the start) < 128 for every supported
- * (S, n).  tests/hostsim asserts the largest metric seen.
+ * the rest (src/viterbiDecoderButterflyk1.c:59-67), capped at n*S + 1 where that changes no decision (genInitMetrics);
+ * for K = 9 the reference's uint8_t METRIC_TYPE turns 257 into 1, which this kernel reproduces.  Any state is reachable
+ * from state 0 within S steps at cost <= n*S, so the largest value seen is <= 2 n*S + 1 in the first S steps, the
+ * spread is <= n*S afterwards and the minimum grows by <= n per step: with a renormalisation every <= 24 steps
+ * candidates stay <= n*S + 24*n + n <= 99 < 128 for every supported (S, n).  tests/hostsim asserts the largest metric.
  *
  * Survivors: W = max(1, 2^S / 32) decision words per step and frame, [group][step][lane] rows of W words (4, 8 or 32
  * bytes per lane): position p = (register r, lane l) -> word r >> 3, bit 8 l + (r & 7).
@@ -66,13 +65,14 @@ CED_HD uint32_t hdN(uint32_t a, uint32_t b, int n)
 
 template <int S>
 struct GenGeom {
-    static_assert(S == 2 || S == 3 || S == 4 || S == 6 || S == 8, "96-step tiles hold whole label rotations");
+    static_assert(S >= 2 && S <= 8, "4 .. 256 states");
     static constexpr int kStates = 1 << S;
     static constexpr int kRegs = kStates >= 4 ? kStates / 4 : 1;
     static constexpr int kRegPhases = S - 2;                     /* phases whose pair bit is a register bit */
     static constexpr int kPairs = kRegs / 2;
     static constexpr int kWords = kRegs >= 8 ? kRegs / 8 : 1;    /* decision words per step */
-    static constexpr int kRenorm = 24;
+    static constexpr int kRenorm = 24 / S * S;   /* whole label rotations: 24, or 20 / 21 for S = 5 / 7 */
+    static constexpr int kChunk = 96 / S * S;    /* trellis steps per staged tile: 96, or 95 / 91 for S = 5 / 7 */
     static constexpr int kPhases = S;
     static constexpr int kTail = S;          /* tail segments */
     static constexpr int kStepBits = 1;      /* decoded bits per trellis step */
@@ -146,8 +146,12 @@ inline void buildGenTable(const GenCode &c, uint8_t *table)
 template <int S>
 CED_HD void genInitMetrics(uint32_t (&R)[GenGeom<S>::kRegs], int n)
 {
-    (void)n;
-    const uint32_t never = (uint32_t)((GenGeom<S>::kStates + 1) & 0xFF) * 0x01010101u;   /* METRIC_TYPE forceNot, :59-60 */
+    /* METRIC_TYPE forceNot = NUM_STATES + 1 (:59-60) as a uint8_t.  Where that exceeds n S + 1 it is a true "never wins" (a
+     * path from another start state costs more than the path from state 0 with the same inputs, which merges with it after
+     * S steps at <= n S) and n S + 1 gives the same decisions while leaving the guard bit free (K = 8: 129 would not);
+     * where it does not (K = 3 with n = 3: 5; K = 9: 257 wraps to 1) the reference's value is kept as it is. */
+    const uint32_t ref = (uint32_t)((GenGeom<S>::kStates + 1) & 0xFF), cap = (uint32_t)(n * S + 1);
+    const uint32_t never = (ref < cap ? ref : cap) * 0x01010101u;
 #pragma unroll
     for (int r = 0; r < GenGeom<S>::kRegs; r++)
         R[r] = never;

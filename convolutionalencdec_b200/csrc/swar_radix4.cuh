@@ -75,6 +75,7 @@ struct R4Geom {
     static constexpr int kHalfWords = kRegs >= 8 ? kRegs / 8 : 1;
     static constexpr int kWords = 2 * kHalfWords;
     static constexpr int kRenorm = 24;
+    static constexpr int kChunk = 96;        /* trellis steps per staged tile (a multiple of S) */
     static constexpr int kTail = S;          /* tail segments */
     static constexpr int kStepBits = 2;      /* decoded bits per trellis step */
     CED_HD static constexpr int tableBytes(int V) { return ((S - 1) * kQuads * 96 + kRegs * 16) * V; }

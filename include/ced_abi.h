@@ -100,7 +100,7 @@ int ced_ctx_last_fallback_frames(ced_ctx *ctx, int *frames);
  * Codes: any k=1 code with constraintLen 2..9 and 1..8 coded bits.  K=7 codes with
  * 2 or 3 generators that all tap the newest and the oldest bit (src/viterbiDecoder.c:20-24)
  * run on the hand-scheduled SIMD-in-word kernel -- 0113/0171 and 0133/0171 compiled in, any
- * other set through a table built on first use; K = 3, 4, 5, 7, 9 with 2 or 3 generators of
+ * other set through a table built on first use; K = 3 .. 9 with 2 or 3 generators of
  * ANY shape on table-driven SIMD-in-word kernels (swar_generic.cu); the rest on a
  * one-warp-per-frame kernel.  (k > 1: ced_decode_batch_k.)
  */

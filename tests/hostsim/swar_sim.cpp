@@ -346,7 +346,9 @@ extern "C" int swar_sim_decode_gen(int K, int n, const uint32_t *gens, const uin
     case 2: return decodeGen<2>(gc, segs, T, out);
     case 3: return decodeGen<3>(gc, segs, T, out);
     case 4: return decodeGen<4>(gc, segs, T, out);
+    case 5: return decodeGen<5>(gc, segs, T, out);
     case 6: return decodeGen<6>(gc, segs, T, out);
+    case 7: return decodeGen<7>(gc, segs, T, out);
     case 8: return decodeGen<8>(gc, segs, T, out);
     default: return -1;
     }

@@ -120,7 +120,9 @@ GEN_CODES = [(3, (0b111, 0b110)), (3, (0b111, 0b101)), (3, (0b101, 0b011)), (3, 
              (4, (0o15, 0o17)), (4, (0o13, 0o15, 0o17)), (4, (0o14, 0o07)),
              (5, (0o23, 0o35)), (5, (0o25, 0o33, 0o37)), (5, (0o30, 0o07)),
              (7, (0o133, 0o170)), (7, (0o066, 0o171)), (7, (0o113, 0o171)), (7, (0o133, 0o145, 0o174)),
-             (9, (0o561, 0o753)), (9, (0o557, 0o663, 0o711)), (9, (0o460, 0o353))]
+             (9, (0o561, 0o753)), (9, (0o557, 0o663, 0o711)), (9, (0o460, 0o353)),
+             (6, (0o53, 0o75)), (6, (0o47, 0o53, 0o75)), (6, (0o60, 0o17)), (8, (0o247, 0o371)), (8, (0o225, 0o331, 0o367)),
+             (8, (0o300, 0o073))]
 
 
 @pytest.mark.parametrize("K,g", GEN_CODES)

@@ -15,7 +15,8 @@ for K, g, frames in ((7, (0o113, 0o171), 1 << 16), (7, (0o133, 0o171), 1 << 16),
                      (7, (0o117, 0o155), 1 << 16), (7, (0o133, 0o171, 0o165), 1 << 16),
                      (7, (0o133, 0o170), 1 << 16), (7, (0o133, 0o145, 0o174), 1 << 16),
                      (3, (7, 6), 1 << 16), (3, (7, 5, 3), 1 << 16), (4, (0o15, 0o17), 1 << 16), (5, (0o23, 0o35), 1 << 16),
-                     (5, (0o25, 0o33, 0o37), 1 << 16), (9, (0o561, 0o753), 1 << 16), (9, (0o557, 0o663, 0o711), 1 << 16)):
+                     (5, (0o25, 0o33, 0o37), 1 << 16), (6, (0o53, 0o75), 1 << 16), (8, (0o247, 0o371), 1 << 16),
+                     (9, (0o561, 0o753), 1 << 16), (9, (0o557, 0o663, 0o711), 1 << 16)):
     code = ced.Code(K, g)
     T = bits + K - 1
     msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
