@@ -734,9 +734,16 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
 constexpr int kPipeWaveFrames = 1 << 16;
 constexpr int kPipeWaves = 3;
 
-static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
+enum class WireKind { Bytes, Packed, SoftQ };   /* hard symbols, 4 hard symbols per byte, 3-bit soft symbols */
+
+static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, WireKind kind, const uint8_t *dSegs, size_t segStride,
                                 int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
+    auto one = [&](const uint8_t *in, int cnt, uint8_t *out, void *st, int slot) -> int {
+        if (kind == WireKind::SoftQ)
+            return cedDecodeBatchSoftQ(c, code, in, segStride, cnt, frameBits, out, outStride, st, slot);
+        return decodeBatchImpl(c, code, kind == WireKind::Packed, in, segStride, cnt, frameBits, out, outStride, st, slot);
+    };
     static const bool enabled = !getenv("CED_WAVE_PIPELINE") || atoi(getenv("CED_WAVE_PIPELINE")) != 0;
     /* experiments: CED_PIPE_WAVE_FRAMES (frames per wave), CED_PIPE_WAVES (waves in flight, <= kPipeDepth - 1) */
     static const int envWaveFrames = getenv("CED_PIPE_WAVE_FRAMES") ? atoi(getenv("CED_PIPE_WAVE_FRAMES")) : 0;
@@ -745,7 +752,7 @@ static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed,
     const int kPipeWaves = envWaves >= 1 ? std::min(envWaves, kPipeDepth) : ::kPipeWaves;
     if (!c || !enabled || nFrames < 2 * kPipeWaveFrames || classify(code) == CodeId::Unsupported || !dSegs || !dOut ||
         frameBits <= 0 || (frameBits & 7) || frameBits > 8192)
-        return decodeBatchImpl(c, code, packed, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+        return one(dSegs, nFrames, dOut, stream, 0);
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
@@ -755,8 +762,8 @@ static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed,
     int w = 0;
     for (long long f0 = 0; f0 < nFrames; f0 += kPipeWaveFrames, w++) {
         const int cnt = (int)std::min<long long>(kPipeWaveFrames, nFrames - f0);
-        const int rc = decodeBatchImpl(c, code, packed, dSegs + (size_t)f0 * segStride, segStride, cnt, frameBits,
-                                       dOut + (size_t)f0 * outStride, outStride, c->pipe[w % kPipeWaves], 1 + w % kPipeWaves);
+        const int rc = one(dSegs + (size_t)f0 * segStride, cnt, dOut + (size_t)f0 * outStride, c->pipe[w % kPipeWaves],
+                           1 + w % kPipeWaves);
         if (rc != CED_OK) {
             for (int i = 0; i < kPipeWaves; i++)
                 cudaStreamSynchronize(c->pipe[i]);
@@ -773,13 +780,19 @@ static int decodeBatchPipelined(ced_ctx *c, const ced_code_t *code, bool packed,
 int ced_decode_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                      int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    return decodeBatchPipelined(c, code, false, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+    return decodeBatchPipelined(c, code, WireKind::Bytes, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
 }
 
 int ced_decode_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
                             int nFrames, int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    return decodeBatchPipelined(c, code, true, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
+    return decodeBatchPipelined(c, code, WireKind::Packed, dPacked, packedStride, nFrames, frameBits, dOut, outStride, stream);
+}
+
+int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
+                           int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    return decodeBatchPipelined(c, code, WireKind::SoftQ, dSyms, symStride, nFrames, frameBits, dOut, outStride, stream);
 }
 
 /* ------------------------------------------------ continuous streams, windowed traceback */

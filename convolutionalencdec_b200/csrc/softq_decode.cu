@@ -1,6 +1,6 @@
 /*
- * softq_decode.cu -- ABI entry points of the 3-bit soft-decision path (include/ced_abi.h): ced_decode_batch_softq,
- * ced_quantize_soft.  Kernels in softq_decode.cuh; nothing here computes on the host except the 12 KB cost table of a code.
+ * softq_decode.cu -- the 3-bit soft-decision path (include/ced_abi.h): cedDecodeBatchSoftQ (behind ced_decode_batch_softq,
+ * which ced_abi.cu wraps in its wave pipeline) and ced_quantize_soft.  Kernels in softq_decode.cuh; nothing here computes on the host except the 12 KB cost table of a code.
  */
 #include "ced_internal.cuh"
 #include "softq_decode.cuh"
@@ -105,12 +105,6 @@ int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms
 }
 
 extern "C" {
-
-int ced_decode_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
-                           int frameBits, uint8_t *dOut, size_t outStride, void *stream)
-{
-    return cedDecodeBatchSoftQ(c, code, dSyms, symStride, nFrames, frameBits, dOut, outStride, stream, 0);
-}
 
 int ced_quantize_soft(ced_ctx *c, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame, double delta,
                       uint8_t *dSyms, size_t symStride, void *stream)
