@@ -232,8 +232,11 @@ struct FwdWindow {
     int pairOffset;          /* rows in front of this launch's first step                            */
 };
 
+#ifndef CED_FWD_MIN_BLOCKS
+#define CED_FWD_MIN_BLOCKS 4 /* 128 registers: forward 1.224 vs 1.247 ms with the 96 ptxas picks unconstrained; 3 (162 registers) is slower */
+#endif
 template <class Code, class Fmt, bool ALIGNED, bool CARRY = false>
-__global__ void __launch_bounds__(kFwdThreads)
+__global__ void __launch_bounds__(kFwdThreads, CED_FWD_MIN_BLOCKS)
 k7ForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
                 BmTable table, FwdSched sched, int chunksPerUnit, FwdWindow win = FwdWindow(),
                 const uint2 *__restrict__ stepTable = nullptr, const int *__restrict__ nFramesDev = nullptr)
