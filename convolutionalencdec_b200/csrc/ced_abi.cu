@@ -119,6 +119,12 @@ static int ctxInit(ced_ctx *c, int device)
 {
     c->bm0113 = ced::makeBmTable<Code0113>();
     c->bm0133 = ced::makeBmTable<Code0133>();
+    c->bm0113s = c->bm0113;
+    c->bm0133s = c->bm0133;
+    for (ced::BmTable *t : {&c->bm0113s, &c->bm0133s})   /* generators in the other order: received symbols 01 <-> 10 */
+        for (int ph = 0; ph < 6; ph++)
+            for (int i = 0; i < 2; i++)
+                std::swap(t->x[(ph * 4 + 1) * 2 + i], t->x[(ph * 4 + 2) * 2 + i]);
     CED_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CED_CUDA(cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking));
     CED_CUDA(cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking));
@@ -428,7 +434,15 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
     }
-    const CodeId id = classify(code);
+    CodeId id = classify(code);
+    /* the compiled-in codes with their two generators written the other way round ((0171, 0133) is how the NASA standard
+     * code is often given): the same kernel with the rows of its branch-cost table for the received symbols 01 and 10
+     * exchanged -- HD(rx, swap(label)) = HD(swap(rx), label) -- instead of the step-table kernel (167 vs 151 Gbit/s) */
+    bool swapped = false;
+    if (id == CodeId::K7_Runtime && code->gen[0] == 0171 && (code->gen[1] == 0113 || code->gen[1] == 0133)) {
+        id = code->gen[1] == 0113 ? CodeId::K7_0113_0171 : CodeId::K7_0133_0171;
+        swapped = true;
+    }
     if (id == CodeId::Unsupported || (packed && id == CodeId::K7_RuntimeN3)) {
         if (packed) {
             setError("ced_decode_batch_packed: 2-bit packing is for K=7 n=2 codes whose generators tap both ends");
@@ -475,7 +489,8 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
      * for the two kernels one call at a time and 1.355 ms with three calls in flight */
     const int envFused = getenv("CED_FUSED") ? atoi(getenv("CED_FUSED")) : 0;   /* read per call: tests flip them */
     const int envFusedMin = getenv("CED_FUSED_MIN_FRAMES") ? atoi(getenv("CED_FUSED_MIN_FRAMES")) : 16384;
-    const bool fused = envFused != 0 && (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171) && nFrames >= envFusedMin;
+    const bool fused = envFused != 0 && !swapped && (id == CodeId::K7_0113_0171 || id == CodeId::K7_0133_0171) &&
+                       nFrames >= envFusedMin;
     if (fused) {
         const size_t wave0 = std::min<size_t>((size_t)nFrames, waveMax), g0 = (wave0 + 31) / 32;
         const size_t ringBytes = std::min<size_t>(g0, 2 * ced::kCohortGroups) * ced::WsGeom<384, 96>::kRingPairs * 32 * sizeof(uint4);
@@ -521,7 +536,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         sched.done = wk.schedFlags.p + 1;
         sched.state = wk.schedState.p;
         CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
-        const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? c->bm0113 : c->bm0133;
+        const ced::BmTable &bm = (id == CodeId::K7_0113_0171) ? (swapped ? c->bm0113s : c->bm0113) : (swapped ? c->bm0133s : c->bm0133);
         static const int envCpu = getenv("CED_FWD_CHUNKS_PER_UNIT") ? atoi(getenv("CED_FWD_CHUNKS_PER_UNIT")) : 0;
         const int cpu = envCpu > 0 ? envCpu : 2; /* chunks a warp runs before handing its group on: 1 / 2 / 4 / 8 -> 1.249 / 1.217 / 1.225 / 1.262 ms */
         if (fused) {

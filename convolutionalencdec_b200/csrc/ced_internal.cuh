@@ -175,7 +175,7 @@ struct ced_ctx {
     uint64_t fsRequests = 0, fsLaunches = 0;
     std::recursive_mutex mu;
     uint64_t launches = 0;
-    ced::BmTable bm0113, bm0133;
+    ced::BmTable bm0113, bm0133, bm0113s, bm0133s;   /* ...s: the same code with its generators exchanged */
     /* step tables of run-time K=7 codes (ced::buildStepTable), built on first use and kept */
     struct StepTable {
         int n;
