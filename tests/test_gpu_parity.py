@@ -882,3 +882,12 @@ def test_large_batch_is_decoded_as_waves_in_flight(torch_cuda, ctx, port):
     sample = np.arange(0, frames, 997)
     noisy = segs[torch.from_numpy(sample).cuda()][:, :T].cpu().numpy()
     assert np.array_equal(out.cpu().numpy()[sample], port.decode_batch(7, K7, noisy, T))
+
+
+def test_randomised_parity_soak():
+    """tools/fuzz_parity.py for 25 s: random codes (K = 3..9, k = 1 and 2, n = 2..4, random generators), frame shapes,
+    strides, base offsets and channels through ced_decode_batch / _packed / _soft / _softq / _k and the windowed decoder,
+    every result compared with the oracle (a 240 s run with 49,275 cases is kept in profiles/fuzz_parity_r2.txt)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "fuzz_parity.py"), "25", "7"], capture_output=True,
+                       text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and "fuzz ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
