@@ -48,14 +48,55 @@ t_end = time.time() + seconds
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window"])
+    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window", "enc", "host"])
     frames = int(rng.choice([1, 2, 31, 33, 64, 100, 257]))
     bits = int(rng.choice([8, 16, 40, 96, 104, 200, 512, 1000, 2048]))
     pad, off = int(rng.integers(0, 20)), int(rng.integers(0, 16))
     p = float(rng.choice([0.0, 0.02, 0.06, 0.2, 0.5]))
     msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
     tag = kind
-    if kind in ("k7", "packed", "soft", "softq", "window"):
+    if kind == "enc":
+        k = int(rng.choice([1, 1, 2]))
+        K = int(rng.integers(2, 10)) if k == 1 else int(rng.integers(2, 6))
+        n = int(rng.integers(1, 9)) if k == 1 else int(rng.integers(2, 5))
+        g = [int(rng.integers(1, 1 << (k * K))) for _ in range(n)]
+        code = ced.Code(K, g)
+        d_msgs = torch.from_numpy(msgs).cuda()
+        if k == 1:
+            want = P.encode_batch(K, g, msgs)
+            T = want.shape[1]
+            out_t = torch.full((frames, T + pad), 0xEE, dtype=torch.uint8, device="cuda")
+            ctx.encode_batch(code, d_msgs, out=out_t)
+        else:
+            want = P.encode_batch_k(K, 2, g, msgs)
+            T = want.shape[1]
+            out_t = torch.full((frames, T + pad), 0xEE, dtype=torch.uint8, device="cuda")
+            ctx.encode_batch_k(code, 2, d_msgs, out=out_t)
+        ctx.sync()
+        got = out_t[:, :T]
+        if pad and not bool((out_t[:, T:] == 0xEE).all()):
+            print("ENCODER WROTE PAST THE ROW", dict(K=K, k=k, n=n, frames=frames, bits=bits, pad=pad))
+            sys.exit(1)
+        tag = "enc k=%d" % k
+    elif kind == "host":
+        g = [K7, [0o133, 0o171]][int(rng.integers(0, 2))]
+        code = ced.Code(7, g)
+        T = bits + 6
+        frames = int(rng.choice([1, 100, 9000]))
+        msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+        rx = noisy(P.encode_batch(7, g, msgs), 2, min(p, 0.06))
+        h_in = np.full((frames, T + pad), 0xEE, dtype=np.uint8)
+        h_in[:, :T] = rx
+        h_out = np.zeros((frames, bits // 8), dtype=np.uint8)
+        ctx.decode_batch_host(code, h_in, bits, h_out)
+        want = P.decode_batch(7, g, rx[:200], T)
+        got = torch.from_numpy(h_out[:200])
+        enc_out = np.zeros((frames, T + pad), dtype=np.uint8)
+        ctx.encode_batch_host(code, msgs, enc_out)
+        if not np.array_equal(enc_out[:200, :T], P.encode_batch(7, g, msgs[:200])):
+            print("HOST ENCODE MISMATCH", dict(frames=frames, bits=bits, pad=pad))
+            sys.exit(1)
+    elif kind in ("k7", "packed", "soft", "softq", "window"):
         g = [K7, [0o133, 0o171], [0o171, 0o133]][int(rng.integers(0, 3 if kind in ("k7", "packed") else 2))]
         code = ced.Code(7, g)
         T = bits + 6
