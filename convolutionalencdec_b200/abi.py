@@ -128,6 +128,7 @@ def load_abi():
     lib.ced_window_carry_bytes.restype = sz
     lib.ced_decode_window_batch.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
     lib.ced_decode_window_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
+    lib.ced_decode_window_batch_softq.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
     lib.ced_ber_count.argtypes = [vp, _u8p, sz, _u8p, sz, i, i, vp, vp]
     lib.ced_bsc_channel.argtypes = [vp, _u8p, sz, i, i, i, C.c_double, u64, u64, vp, vp]
     lib.ced_random_bytes.argtypes = [vp, _u8p, sz, i, i, u64, u64, vp]
@@ -159,9 +160,10 @@ def _stream_handle(stream):
 class WindowDecoder:
     """nStreams continuous K=7 streams decoded a slice at a time; owns the carry block between calls."""
 
-    def __init__(self, ctx, code, n_streams, depth, packed=False):
+    def __init__(self, ctx, code, n_streams, depth, packed=False, softq=False):
         import torch
         self.ctx, self.code, self.n, self.depth, self.pos, self.packed = ctx, code, n_streams, depth, 0, packed
+        self.softq = softq
         nbytes = ctx.lib.ced_window_carry_bytes(n_streams, depth)
         if n_streams > 0 and nbytes == 0:
             raise ValueError("depth must be a multiple of 24, at least 24")
@@ -174,7 +176,8 @@ class WindowDecoder:
         n_seg = n_segments if n_segments is not None else segs.shape[1]
         if out is None:
             out = torch.empty((self.n, (n_seg + self.depth) // 8 + 1), dtype=torch.uint8, device=segs.device)
-        fn = self.ctx.lib.ced_decode_window_batch_packed if self.packed else self.ctx.lib.ced_decode_window_batch
+        fn = self.ctx.lib.ced_decode_window_batch_packed if self.packed else (
+            self.ctx.lib.ced_decode_window_batch_softq if self.softq else self.ctx.lib.ced_decode_window_batch)
         rc = fn(self.ctx.h, C.byref(self.code._c), segs.data_ptr(), segs.stride(0),
                                                   self.n, n_seg, self.pos, self.depth, int(bool(last)),
                                                   self.carry.data_ptr(), out.data_ptr(), out.stride(0),
@@ -334,9 +337,9 @@ class Context:
     def host_unregister(self, array):
         _check(self.lib, self.lib.ced_host_unregister(array.ctypes.data), "ced_host_unregister")
 
-    def window_decoder(self, code, n_streams, depth=48, packed=False):
-        """Continuous streams with windowed traceback (ced_decode_window_batch[_packed])."""
-        return WindowDecoder(self, code, n_streams, depth, packed)
+    def window_decoder(self, code, n_streams, depth=48, packed=False, softq=False):
+        """Continuous streams with windowed traceback (ced_decode_window_batch[_packed | _softq])."""
+        return WindowDecoder(self, code, n_streams, depth, packed, softq)
 
     def pack_symbols(self, segs, segs_per_frame, out=None, stream=None, packed_stride=None):
         import torch

@@ -825,10 +825,11 @@ size_t ced_window_carry_bytes(int nStreams, int depth)
     return (size_t)((nStreams + 31) / 32) * windowCarryGroupBytes(depth);
 }
 
-static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, bool packed, const uint8_t *dSegs, size_t segStride,
+static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, WireKind kind, const uint8_t *dSegs, size_t segStride,
                             int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                             uint8_t *dOut, size_t outStride, void *stream)
 {
+    const bool packed = kind == WireKind::Packed, softq = kind == WireKind::SoftQ;
     const int sliceUnit = packed ? ced::PackedSymbols::kChunk : ced::ByteSymbols::kChunk; /* 192 / 96 segments */
     if (!c || nStreams < 0 || nSegments < 0 || depth < 24 || depth % 24 || depth > 8184 || streamPos % sliceUnit ||
         (nStreams > 0 && (!dSegs || !dOut || !dCarry)) || (reinterpret_cast<uintptr_t>(dCarry) & 15u)) {
@@ -836,6 +837,10 @@ static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, bool packed, con
         return CED_ERR_ARG;
     }
     const CodeId id = classify(code);
+    if (softq && id != CodeId::K7_0113_0171 && id != CodeId::K7_0133_0171) {
+        setError("ced_decode_window_batch_softq: K=7 rate-1/2 codes 0113/0171 and 0133/0171 only");
+        return CED_ERR_UNSUPPORTED;
+    }
     if (id == CodeId::Unsupported || (packed && id == CodeId::K7_RuntimeN3)) {
         setError("ced_decode_window_batch: K=7 codes with 2 or 3 generators that tap the newest and the oldest bit only "
                  "(2 generators for the packed format)");
@@ -929,7 +934,12 @@ static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, bool packed, con
             ced::k7ForwardKernel<CODE, ced::FMT, false, true><<<blocks, ced::kFwdThreads, 0, s>>>(                 \
                 in, segStride, wave, nSegments, wk.scratch.p, bm, sched, 2, win, stepTable);                       \
     } while (0)
-        if (id == CodeId::K7_RuntimeN3)
+        if (softq) {
+            const int rq = cedSoftQForwardWindow(c, code, aligned16, blocks, s, in, segStride, wave, nSegments, wk.scratch.p,
+                                                 sched, win);
+            if (rq != CED_OK)
+                return rq;
+        } else if (id == CodeId::K7_RuntimeN3)
             CED_LAUNCH_WIN(ced::RuntimeK7<3>, ByteSymbols);
         else if (id == CodeId::K7_Runtime && !packed)
             CED_LAUNCH_WIN(ced::RuntimeK7<2>, ByteSymbols);
@@ -966,15 +976,23 @@ int ced_decode_window_batch(ced_ctx *c, const ced_code_t *code, const uint8_t *d
                             int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
                             size_t outStride, void *stream)
 {
-    return decodeWindowImpl(c, code, false, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut,
-                            outStride, stream);
+    return decodeWindowImpl(c, code, WireKind::Bytes, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry,
+                            dOut, outStride, stream);
 }
 
 int ced_decode_window_batch_packed(ced_ctx *c, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
                                    int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                                    uint8_t *dOut, size_t outStride, void *stream)
 {
-    return decodeWindowImpl(c, code, true, dPacked, packedStride, nStreams, nSegments, streamPos, depth, last, dCarry,
+    return decodeWindowImpl(c, code, WireKind::Packed, dPacked, packedStride, nStreams, nSegments, streamPos, depth, last,
+                            dCarry, dOut, outStride, stream);
+}
+
+int ced_decode_window_batch_softq(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nStreams,
+                                  int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
+                                  size_t outStride, void *stream)
+{
+    return decodeWindowImpl(c, code, WireKind::SoftQ, dSyms, symStride, nStreams, nSegments, streamPos, depth, last, dCarry,
                             dOut, outStride, stream);
 }
 

@@ -233,6 +233,9 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
 int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nFrames,
                         int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
 
+int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, int blocks, cudaStream_t s, const uint8_t *in,
+                          size_t symStride, int wave, int nSegments, uint4 *scratch, ced::FwdSched sched, ced::FwdWindow win);
+
 /* swar_generic.cu: rate-2/n codes on the radix-4 SIMD-in-word kernels (swar_radix4.cuh); same convention */
 int cedDecodeBatchSwarRadix4(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                              int frameBits, uint8_t *dOut, size_t outStride, void *stream);

@@ -104,6 +104,31 @@ int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms
     return CED_OK;
 }
 
+/* forward pass of one slice of continuous streams (decodeWindowImpl, ced_abi.cu); the caller holds c->mu */
+int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, int blocks, cudaStream_t s, const uint8_t *in,
+                          size_t symStride, int wave, int nSegments, uint4 *scratch, ced::FwdSched sched, ced::FwdWindow win)
+{
+    const CodeId id = classify(code);
+    if (id != CodeId::K7_0113_0171 && id != CodeId::K7_0133_0171) {
+        setError("ced_decode_window_batch_softq: K=7 rate-1/2 codes 0113/0171 and 0133/0171 only");
+        return CED_ERR_UNSUPPORTED;
+    }
+    const uint4 *table = nullptr;
+    const int rc = id == CodeId::K7_0113_0171 ? softqTableFor<Code0113>(c, 0, s, &table) : softqTableFor<Code0133>(c, 1, s, &table);
+    if (rc != CED_OK)
+        return rc;
+#define CED_SOFTQ_WIN(CODE, AL)                                                                                         \
+    ced::k7SoftQForwardKernel<CODE, AL, true><<<blocks, ced::kFwdThreads, 0, s>>>(in, symStride, wave, nSegments, scratch,  \
+                                                                                table, c->bm0113.minusOne, sched, 2, win)
+    if (id == CodeId::K7_0113_0171) {
+        if (aligned16) CED_SOFTQ_WIN(Code0113, true); else CED_SOFTQ_WIN(Code0113, false);
+    } else {
+        if (aligned16) CED_SOFTQ_WIN(Code0133, true); else CED_SOFTQ_WIN(Code0133, false);
+    }
+#undef CED_SOFTQ_WIN
+    return CED_OK;
+}
+
 extern "C" {
 
 int ced_quantize_soft(ced_ctx *c, const int8_t *dSoft, size_t softStride, int nFrames, int segsPerFrame, double delta,

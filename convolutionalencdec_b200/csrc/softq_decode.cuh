@@ -95,10 +95,11 @@ CED_HD void acsStepForced(uint32_t (&R)[16], const uint32_t (&X)[4])
  * table in shared memory, the symbol byte scaled to a table offset at its use, a renormalisation after every 6-step
  * iteration and the forced first iteration.
  */
-template <class Code, bool ALIGNED>
+template <class Code, bool ALIGNED, bool CARRY = false>
 __global__ void __launch_bounds__(kFwdThreads)
 k7SoftQForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, uint4 *__restrict__ surv,
-                     const uint4 *__restrict__ table, uint32_t minusOne, FwdSched sched, int chunksPerUnit)
+                     const uint4 *__restrict__ table, uint32_t minusOne, FwdSched sched, int chunksPerUnit,
+                     FwdWindow win = FwdWindow())
 {
     using G = TileGeom<ByteSymbols, ALIGNED>;
     constexpr int kChunk = G::kChunk, kPitch = G::kPitch;
@@ -111,7 +112,10 @@ k7SoftQForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrame
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *tile = sTile[warp];
     const uint8_t *bmBase = reinterpret_cast<const uint8_t *>(sBm);
-    const size_t pairs = (size_t)(T / 2);
+    /* continuous streams (ced_decode_window_batch_softq): see FwdWindow in decode_batch.cuh */
+    const size_t pairs = CARRY ? (size_t)win.survPairs : (size_t)(T / 2);
+    const size_t pairOffset = CARRY ? (size_t)win.pairOffset : 0;
+    const bool fresh = !CARRY || win.metricsIn == nullptr;     /* the stream starts here: forced first six steps */
     const unsigned groups = (unsigned)((nFrames + 31) / 32);
     const unsigned chunks = (unsigned)((T + kChunk - 1) / kChunk);
     const unsigned unitsPerGroup = (chunks + chunksPerUnit - 1) / chunksPerUnit;
@@ -157,6 +161,18 @@ k7SoftQForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrame
 #pragma unroll
             for (int r = 0; r < 16; r++)
                 R[r] = 0u;
+            if constexpr (CARRY) {
+                if (win.metricsIn) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint4 v = __ldcg(win.metricsIn + ((size_t)g * 4 + i) * 32 + lane);
+                        R[4 * i] = v.x;
+                        R[4 * i + 1] = v.y;
+                        R[4 * i + 2] = v.z;
+                        R[4 * i + 3] = v.w;
+                    }
+                }
+            }
         } else {
             if (lane == 0)
                 while (ldAcquire(sched.done + g) < (int)su)
@@ -188,11 +204,11 @@ k7SoftQForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrame
             __syncwarp();
             const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride + (size_t)t0;
             const uint8_t *p = tile + lane * kPitch + (ALIGNED ? 0u : (rowAddr & 15u));
-            uint4 *o = surv + ((size_t)g * pairs + (size_t)(t0 / 2)) * 32 + lane;
+            uint4 *o = surv + ((size_t)g * pairs + pairOffset + (size_t)(t0 / 2)) * 32 + lane;
             const int steps = min(kChunk, T - t0);
             int done = 0;
             uint32_t X[4], E[4];
-            if (c == 0) {
+            if (c == 0 && fresh) {
                 /* steps 0..5: forced (T > 6 always: a frame has at least 8 information bits) */
                 tableWords(0, p[0], X, E); acsStepForced<Code, 0>(R, X);
                 tableWords(1, p[1], X, E); acsStepForced<Code, 1>(R, X);
@@ -247,6 +263,19 @@ k7SoftQForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrame
             __syncwarp();
             if (lane == 0)
                 stRelease(sched.done + g, (int)su + 1);
+        } else if constexpr (CARRY) {
+            if (win.metricsOut) {
+                /* a slice is a multiple of 96 steps, so the metrics were renormalised by the last iteration (smallest =
+                 * 0) and the next step has phase 0: position == state */
+                const uint32_t best = bestPositionB(R);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        __stcg(win.metricsOut + ((size_t)g * 4 + i) * 32 + lane,
+                               make_uint4(R[4 * i], R[4 * i + 1], R[4 * i + 2], R[4 * i + 3]));
+                    win.startPos[(size_t)g * 32 + lane] = best;
+                }
+            }
         }
         u = un;
     }

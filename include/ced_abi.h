@@ -225,6 +225,12 @@ int ced_decode_window_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t 
 int ced_decode_window_batch_packed(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dPacked, size_t packedStride,
                                    int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                                    uint8_t *dOut, size_t outStride, void *stream);
+/* the same for 3-bit soft symbols (one byte per segment x0 | x1 << 3, see ced_decode_batch_softq): slices and streamPos
+ * multiples of 96 segments; codes 0113/0171 and 0133/0171.  Semantics: orc_decode_window_soft (the windowing of
+ * orc_decode_window around the soft recursion) on the reliabilities s = 7 - 2x. */
+int ced_decode_window_batch_softq(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSyms, size_t symStride, int nStreams,
+                                  int nSegments, uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut,
+                                  size_t outStride, void *stream);
 
 /* dCounters[0] += popcount(dA ^ dB) over nFrames x bytesPerFrame; dCounters[1] +=
  * bits compared.  Device-side uint64 counters, so a BER sweep can all-reduce

@@ -84,6 +84,8 @@ class Port:
         lib.orc_decode_soft_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                               _u8p, C.c_size_t]
 
+        lib.orc_decode_window_soft.restype = C.c_int
+        lib.orc_decode_window_soft.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p]
         _u32p = C.POINTER(C.c_uint32)
         lib.orck_encode_batch.restype = C.c_int
         lib.orck_encode_batch.argtypes = [C.c_int, C.c_int, C.c_int, _u64p, _u8p, C.c_size_t, C.c_int, C.c_int, _u8p,
@@ -178,6 +180,15 @@ class Port:
         out = np.zeros((nf, nbytes), dtype=np.uint8)
         rc = self.lib.orc_decode_soft_batch(K, len(g), self._g(g), soft.ctypes.data, stride, nf, T, _p(out), nbytes)
         assert rc == 0
+        return out
+
+    def decode_window_soft(self, K, g, soft, call_segs, depth):
+        """soft: int8 [n * total segments] of ONE stream; the windowing of decode_window around the soft recursion."""
+        soft = np.ascontiguousarray(soft, dtype=np.int8)
+        total = soft.size // len(g)
+        out = np.zeros((total - (K - 1) + 7) // 8, dtype=np.uint8)
+        rc = self.lib.orc_decode_window_soft(K, len(g), self._g(g), soft.ctypes.data, total, call_segs, depth, _p(out))
+        assert rc == total - (K - 1)
         return out
 
     def decode_window(self, K, g, segs, call_segs, depth):

@@ -447,6 +447,46 @@ int orc_dec_step_soft(orc_soft_decoder_t *d, const int8_t *soft, int segmentsIn,
     return (int)((T - S - 1) / 8 + 1);
 }
 
+/*
+ * orc_decode_window with soft inputs: the windowing procedure of orc_decode_window (same PARITY status: it defines the
+ * semantics, anchored by depth >= length == full traceback) around the soft forward recursion orc_dec_step_soft.
+ * soft: n int8 per segment.  Returns the number of bits written (total - S) or -1.
+ */
+int orc_decode_window_soft(int K, int n, const uint64_t *g, const int8_t *soft, int totalSegs, int callSegs, int depth,
+                           uint8_t *out)
+{
+    if (callSegs <= 0 || depth < 0 || totalSegs <= K - 1)
+        return -1;
+    orc_soft_decoder_t *d = orc_soft_new(K, n, g, totalSegs);
+    if (!d)
+        return -1;
+    const int N = d->N, S = d->S;
+    memset(out, 0, (size_t)(totalSegs - S + 7) / 8);
+    int emitted = 0;
+    for (int P0 = 0; P0 < totalSegs;) {
+        const int P = (totalSegs - P0 <= callSegs) ? totalSegs : P0 + callSegs;
+        const int lastCall = P == totalSegs;
+        orc_dec_step_soft(d, soft + (size_t)P0 * (size_t)n, P - P0, NULL, 0);
+        uint32_t state = 0;
+        if (!lastCall)
+            for (int s2 = 1; s2 < N; s2++)
+                if (d->metric[s2] < d->metric[state])
+                    state = (uint32_t)s2;
+        const int hi = lastCall ? totalSegs - S : P - depth;
+        for (int t = P - 1; t >= emitted; t--) {
+            const uint32_t dec = d->surv[(size_t)t * (size_t)N + state];
+            if (t < hi && (state & 1u))
+                out[t / 8] |= (uint8_t)(0x80u >> (t % 8));
+            state = (state >> 1) | (dec << (S - 1));
+        }
+        if (hi > emitted)
+            emitted = hi;
+        P0 = P;
+    }
+    orc_soft_free(d);
+    return emitted;
+}
+
 int orc_decode_soft_batch(int K, int n, const uint64_t *g, const int8_t *soft, size_t softStride, int nFrames,
                           int segsPerFrame, uint8_t *out, size_t outStride)
 {

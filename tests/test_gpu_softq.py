@@ -123,6 +123,39 @@ def test_softq_host_buffers_match_device_path(torch_cuda, ctx, port):
     assert np.array_equal(out[sample], port.decode_soft_batch(7, K7, to_int8_pairs(syms[sample], T), T))
 
 
+@pytest.mark.parametrize("n_streams,total,call,depth,kind", [(3, 96 * 3 + 14, 96, 24, "3dB"), (70, 1000 // 8 * 8 + 6, 192, 48, "3dB"),
+                                                              (40, 2054, 480, 48, "noise"), (33, 2054, 96, 96, "ties"),
+                                                              (10, 4102, 960, 48, "3dB"), (5, 518, 4800, 48, "3dB")])
+def test_softq_window_decode_matches_oracle_definition(torch_cuda, ctx, port, n_streams, total, call, depth, kind):
+    """ced_decode_window_batch_softq: continuous streams of 3-bit soft symbols, slice by slice, against
+    orc_decode_window_soft on the reliabilities s = 7 - 2x (the window procedure of orc_decode_window around the soft
+    recursion); with depth >= stream length it is the full-frame soft decode."""
+    torch = torch_cuda
+    rng = np.random.default_rng(total + call + depth)
+    bits = total - 6
+    msgs = rng.integers(0, 256, (n_streams, bits // 8), dtype=np.uint8)
+    clean = port.encode_batch(7, K7, msgs)
+    if kind == "3dB":
+        bit = ((clean[..., None] >> np.arange(2)) & 1).astype(np.float64)
+        y = (1 - 2 * bit) + rng.normal(0, 10 ** (-3 / 20), bit.shape)
+        x = np.clip(3 - np.floor(y / 0.35).astype(np.int64), 0, 7)
+    elif kind == "noise":
+        x = rng.integers(0, 8, clean.shape + (2,))
+    else:
+        x = rng.integers(3, 5, clean.shape + (2,))
+    syms = (x[..., 0] | (x[..., 1] << 3)).astype(np.uint8)
+    soft = to_int8_pairs(syms, total)
+    want = np.stack([port.decode_window_soft(7, K7, soft[i], call, depth) for i in range(n_streams)])
+    d = torch.from_numpy(syms).cuda()
+    wd = ctx.window_decoder(ced.K7_DEFAULT, n_streams, depth=depth, softq=True)
+    parts = [wd.push(d[:, a:min(a + call, total)], last=a + call >= total).clone() for a in range(0, total, call)]
+    ctx.sync()
+    got = torch.cat(parts, dim=1).cpu().numpy()
+    assert np.array_equal(got, want), (n_streams, total, call, depth, kind)
+    if call >= total:      # one slice: the full-frame soft decode
+        assert np.array_equal(got, port.decode_soft_batch(7, K7, soft, total))
+
+
 def test_softq_argument_checks(torch_cuda, ctx):
     torch = torch_cuda
     d = torch.zeros((4, 64), dtype=torch.uint8, device="cuda")

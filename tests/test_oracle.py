@@ -192,3 +192,26 @@ def test_window_definition_reproduces_matlab_tblen_expectations(port):
         assert abs(full[2] / full[3] - want_full) / want_full < 0.10, (p, full[2] / full[3], want_full)
         excess.append(ber / (full[2] / full[3]))
     assert excess[0] > 1.03 and excess[1] > 1.0     # truncating the traceback at 35 steps costs errors, as in MATLAB's numbers
+
+
+def test_window_soft_definition_anchors(port):
+    """orc_decode_window_soft (semantics of ced_decode_window_batch_softq): with depth >= stream length it is the full-frame
+    soft decode, and with reliabilities of one constant magnitude it is orc_decode_window on the sliced symbols -- the
+    same two anchors that tie the hard window definition to the pinned decoder."""
+    rng = np.random.default_rng(5)
+    T = 96 * 5 + 38
+    msgs = rng.integers(0, 256, (6, (T - 6) // 8), dtype=np.uint8)
+    clean = port.encode_batch(7, oracle.K7_G, msgs)
+    soft = rng.integers(-7, 8, (6, 2 * T)).astype(np.int8)
+    full = port.decode_soft_batch(7, oracle.K7_G, soft, T)
+    for i in range(6):
+        assert np.array_equal(port.decode_window_soft(7, oracle.K7_G, soft[i], 96, 10000), full[i])
+    flips = rng.random(clean.shape + (2,)) < 0.08
+    noisy = clean ^ (flips[..., 0].astype(np.uint8) | (flips[..., 1].astype(np.uint8) << 1))
+    const = np.empty((6, 2 * T), dtype=np.int8)
+    const[:, 0::2] = np.where(noisy & 1, -5, 5)
+    const[:, 1::2] = np.where(noisy & 2, -5, 5)
+    for call, depth in ((96, 24), (192, 48), (480, 96)):
+        for i in range(6):
+            assert np.array_equal(port.decode_window_soft(7, oracle.K7_G, const[i], call, depth),
+                                  port.decode_window(7, oracle.K7_G, noisy[i], call, depth)), (call, depth, i)

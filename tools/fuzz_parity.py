@@ -48,7 +48,7 @@ t_end = time.time() + seconds
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window", "enc", "host"])
+    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window", "windowq", "enc", "host"])
     frames = int(rng.choice([1, 2, 31, 33, 64, 100, 257]))
     bits = int(rng.choice([8, 16, 40, 96, 104, 200, 512, 1000, 2048]))
     pad, off = int(rng.integers(0, 20)), int(rng.integers(0, 16))
@@ -96,6 +96,23 @@ while time.time() < t_end:
         if not np.array_equal(enc_out[:200, :T], P.encode_batch(7, g, msgs[:200])):
             print("HOST ENCODE MISMATCH", dict(frames=frames, bits=bits, pad=pad))
             sys.exit(1)
+    elif kind == "windowq":
+        g = [K7, [0o133, 0o171]][int(rng.integers(0, 2))]
+        code = ced.Code(7, g)
+        total_bits = int(rng.choice([96 * 3 - 6 + 8 * 5, 1000 // 8 * 8, 2048]))
+        Tt = total_bits + 6
+        frames = min(frames, 64)
+        x = rng.integers(0, 8, (frames, Tt, 2))
+        syms = (x[..., 0] | (x[..., 1] << 3)).astype(np.uint8)
+        s8 = np.empty((frames, 2 * Tt), dtype=np.int8)
+        s8[:, 0::2] = 7 - 2 * (syms & 7).astype(np.int16)
+        s8[:, 1::2] = 7 - 2 * ((syms >> 3) & 7).astype(np.int16)
+        call, depth = int(rng.choice([96, 192, 480])), int(rng.choice([24, 48, 96]))
+        wd = ctx.window_decoder(code, frames, depth=depth, softq=True)
+        d = torch.from_numpy(syms).cuda()
+        parts = [wd.push(d[:, a:min(a + call, Tt)], last=a + call >= Tt).clone() for a in range(0, Tt, call)]
+        got = torch.cat(parts, dim=1)
+        want = np.stack([P.decode_window_soft(7, g, s8[i], call, depth) for i in range(frames)])
     elif kind in ("k7", "packed", "soft", "softq", "window"):
         g = [K7, [0o133, 0o171], [0o171, 0o133]][int(rng.integers(0, 3 if kind in ("k7", "packed") else 2))]
         code = ced.Code(7, g)
