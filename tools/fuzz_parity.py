@@ -99,7 +99,7 @@ while time.time() < t_end:
     elif kind == "windowq":
         g = [K7, [0o133, 0o171]][int(rng.integers(0, 2))]
         code = ced.Code(7, g)
-        total_bits = int(rng.choice([96 * 3 - 6 + 8 * 5, 1000 // 8 * 8, 2048]))
+        total_bits = int(rng.choice([320, 1000, 2048]))
         Tt = total_bits + 6
         frames = min(frames, 64)
         x = rng.integers(0, 8, (frames, Tt, 2))
@@ -148,7 +148,7 @@ while time.time() < t_end:
             want = P.decode_soft_batch(7, g, s, T)
             got = ctx.decode_batch_softq(code, place(syms | (rng.integers(0, 4, syms.shape, dtype=np.uint8) << 6), pad, off), bits)
         else:
-            total_bits = int(rng.choice([96 * 3 - 6 + 8 * 5, 1000 // 8 * 8, 2048]))
+            total_bits = int(rng.choice([320, 1000, 2048]))
             msgs = rng.integers(0, 256, (frames, total_bits // 8), dtype=np.uint8)
             clean = P.encode_batch(7, g, msgs)
             rx = noisy(clean, 2, min(p, 0.06))
