@@ -128,6 +128,8 @@ def load_abi():
     lib.ced_window_carry_bytes.restype = sz
     lib.ced_decode_window_batch.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
     lib.ced_decode_window_batch_packed.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
+    lib.ced_window_carry_bytes_code.restype = sz
+    lib.ced_window_carry_bytes_code.argtypes = [codep, i, i]
     lib.ced_decode_window_batch_softq.argtypes = [vp, codep, _u8p, sz, i, i, u64, i, i, vp, _u8p, sz, vp]
     lib.ced_ber_count.argtypes = [vp, _u8p, sz, _u8p, sz, i, i, vp, vp]
     lib.ced_bsc_channel.argtypes = [vp, _u8p, sz, i, i, i, C.c_double, u64, u64, vp, vp]
@@ -164,9 +166,9 @@ class WindowDecoder:
         import torch
         self.ctx, self.code, self.n, self.depth, self.pos, self.packed = ctx, code, n_streams, depth, 0, packed
         self.softq = softq
-        nbytes = ctx.lib.ced_window_carry_bytes(n_streams, depth)
+        nbytes = ctx.lib.ced_window_carry_bytes_code(C.byref(code._c), n_streams, depth)
         if n_streams > 0 and nbytes == 0:
-            raise ValueError("depth must be a multiple of 24, at least 24")
+            raise ValueError("depth must be a multiple of 24, at least 24, and the code one the windowed decoder takes")
         self.carry = torch.empty(max(nbytes, 16), dtype=torch.uint8, device="cuda:%d" % ctx.device)
 
     def push(self, segs, last=False, out=None, stream=None, n_segments=None):

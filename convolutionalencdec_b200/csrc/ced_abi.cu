@@ -825,6 +825,13 @@ size_t ced_window_carry_bytes(int nStreams, int depth)
     return (size_t)((nStreams + 31) / 32) * windowCarryGroupBytes(depth);
 }
 
+size_t ced_window_carry_bytes_code(const ced_code_t *code, int nStreams, int depth)
+{
+    if (classify(code) != CodeId::Unsupported)
+        return ced_window_carry_bytes(nStreams, depth);
+    return cedWindowCarryBytesGeneric(code, nStreams, depth);
+}
+
 static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, WireKind kind, const uint8_t *dSegs, size_t segStride,
                             int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                             uint8_t *dOut, size_t outStride, void *stream)
@@ -840,6 +847,13 @@ static int decodeWindowImpl(ced_ctx *c, const ced_code_t *code, WireKind kind, c
     if (softq && id != CodeId::K7_0113_0171 && id != CodeId::K7_0133_0171) {
         setError("ced_decode_window_batch_softq: K=7 rate-1/2 codes 0113/0171 and 0133/0171 only");
         return CED_ERR_UNSUPPORTED;
+    }
+    if (id == CodeId::Unsupported && kind == WireKind::Bytes) {
+        /* other code parameters (K <= 7, 2 or 3 generators of any shape): the table-driven kernels (swar_generic.cu) */
+        const int rg = cedDecodeWindowGeneric(c, code, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut,
+                                              outStride, stream);
+        if (rg != CED_ERR_UNSUPPORTED)
+            return rg;
     }
     if (id == CodeId::Unsupported || (packed && id == CodeId::K7_RuntimeN3)) {
         setError("ced_decode_window_batch: K=7 codes with 2 or 3 generators that tap the newest and the oldest bit only "

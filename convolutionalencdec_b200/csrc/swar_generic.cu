@@ -16,11 +16,35 @@ struct alignas(W >= 4 ? 16 : 4 * W) SurvRow {
     uint32_t w[W];
 };
 
+/* continuous streams (cedDecodeWindowGeneric): the counterpart of FwdWindow (decode_batch.cuh) for any trellis policy */
+struct GenWindow {
+    const uint4 *metricsIn;  /* [groups][kStateU4][32] or NULL = start of the stream */
+    uint4 *metricsOut;       /* renormalised metrics after the last step, or NULL */
+    uint32_t *startPos;      /* [groups][32] position (== state: the next phase is 0) of the smallest metric */
+    int survSteps;           /* survivor rows per group in `surv` */
+    int stepOffset;          /* rows in front of this launch's first step (the carried traceback depth) */
+};
+
+/* lowest position whose metric is 0 (after a renormalisation the smallest metric is 0); position == state at phase 0 */
+template <class P>
+__device__ __forceinline__ uint32_t genBestPosition(const uint32_t (&R)[P::kRegs])
+{
+    uint32_t best = 0;
+#pragma unroll
+    for (int r = P::kRegs - 1; r >= 0; r--) {
+        const uint32_t z = (R[r] - 0x01010101u) & ~R[r] & 0x80808080u;
+        if (z)
+            best = 4u * (uint32_t)r + (uint32_t)((__ffs((int)z) - 1) >> 3);
+    }
+    return best;
+}
+
 /* Forward pass: see k7ForwardKernel (decode_batch.cuh) for the scheduler; symbols are byte-per-segment only. */
-template <class P, int V, bool ALIGNED>
+template <class P, int V, bool ALIGNED, bool CARRY = false>
 __global__ void __launch_bounds__(kFwdThreads, P::kRegs >= 64 ? 2 : 3)
 genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, int T, SurvRow<P::kWords> *__restrict__ surv,
-                 const uint8_t *__restrict__ table, int n, uint32_t minusOne, FwdSched sched, int chunksPerUnit)
+                 const uint8_t *__restrict__ table, int n, uint32_t minusOne, FwdSched sched, int chunksPerUnit,
+                 GenWindow win = GenWindow())
 {
     using G = P;
     constexpr int S = P::kPhases;   /* steps per label rotation */
@@ -61,6 +85,19 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
         uint32_t R[kRegs];
         if (su == 0) {
             P::init(R, n);
+            if constexpr (CARRY) {
+                if (win.metricsIn) {
+#pragma unroll
+                    for (int i = 0; i < kStateU4; i++) {
+                        const uint4 v = __ldcg(win.metricsIn + ((size_t)g * kStateU4 + i) * 32 + lane);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (4 * i + k < kRegs)
+                                R[4 * i + k] = w[k];
+                    }
+                }
+            }
         } else {
             if (lane == 0)
                 while (ldAcquire(sched.done + g) < (int)su)
@@ -93,7 +130,7 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
             __syncwarp();
             const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(segs) + (size_t)(frame0 + lane) * stride + (size_t)t0;
             const uint8_t *p = tile + lane * kPitch + (ALIGNED ? 0u : (rowAddr & 15u));
-            SurvRow<G::kWords> *o = surv + ((size_t)g * T + t0) * 32 + lane;
+            SurvRow<G::kWords> *o = surv + ((size_t)g * (CARRY ? win.survSteps : T) + (CARRY ? win.stepOffset : 0) + t0) * 32 + lane;
             const int steps = min(P::kChunk, T - t0);
             for (int done = 0; done < steps;) {
                 const int nr = min(G::kRenorm, steps - done);
@@ -146,6 +183,23 @@ genForwardKernel(const uint8_t *__restrict__ segs, size_t stride, int nFrames, i
             __syncwarp();
             if (lane == 0)
                 stRelease(sched.done + g, (int)su + 1);
+        } else if constexpr (CARRY) {
+            if (win.metricsOut) {
+                P::renorm(R);   /* a slice is a whole number of label rotations: the next phase is 0, position == state */
+                const uint32_t best = genBestPosition<P>(R);
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < kStateU4; i++) {
+                        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            if (4 * i + k < kRegs)
+                                w[k] = R[4 * i + k];
+                        __stcg(win.metricsOut + ((size_t)g * kStateU4 + i) * 32 + lane, make_uint4(w[0], w[1], w[2], w[3]));
+                    }
+                    win.startPos[(size_t)g * 32 + lane] = best;
+                }
+            }
         }
         u = un;
     }
@@ -234,25 +288,33 @@ genTracebackKernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, int
 template <class P>
 __host__ __device__ constexpr int genTb24Threads() { return sizeof(SurvRow<P::kWords>) >= 16 ? 32 : 64; }
 
-template <class P, int I>
-__device__ __forceinline__ void genWalk24(uint32_t &p, uint32_t &acc, const SurvRow<P::kWords> *rows, int stride, uint8_t *dst, int blk)
+/* CHECK: the block reaches above step L (steps >= L carry no output): test every step instead of none */
+template <class P, int I, bool CHECK>
+__device__ __forceinline__ void genWalk24(uint32_t &p, uint32_t &acc, const SurvRow<P::kWords> *rows, int stride, uint8_t *dst, int blk,
+                                          int L)
 {
     if constexpr (I >= 0) {
         constexpr int kb = P::kStepBits, spb = 8 / kb;
         const SurvRow<P::kWords> row = rows[(size_t)I * stride];
         const uint32_t v = P::template tbStepC<I % P::kPhases>(p, row.w);
-        acc = (acc >> kb) | (v << (8 - kb));
-        if constexpr (I % spb == 0) {
-            dst[(24 * blk + I) / spb] = (uint8_t)acc;
-            acc = 0;
+        if (!CHECK || 24 * blk + I < L) {
+            acc = (acc >> kb) | (v << (8 - kb));
+            if constexpr (I % spb == 0) {
+                dst[(24 * blk + I) / spb] = (uint8_t)acc;
+                acc = 0;
+            }
         }
-        genWalk24<P, I - 1>(p, acc, rows, stride, dst, blk);
+        genWalk24<P, I - 1, CHECK>(p, acc, rows, stride, dst, blk, L);
     }
 }
 
+/* startPos (continuous streams): position to start the walk from instead of state 0; `skip` top steps carry no output
+ * (the tail of a terminated frame, or the traceback depth of a slice); steps below `emitLo` (a multiple of 24) are not
+ * walked: their bits were emitted by an earlier slice.  Output byte 0 holds step emitLo. */
 template <class P>
 __global__ void __launch_bounds__(genTb24Threads<P>())
-genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride)
+genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, int T, uint8_t *__restrict__ out, size_t outStride,
+                     const uint32_t *__restrict__ startPos = nullptr, int skip = P::kTail, int emitLo = 0)
 {
     using Row = SurvRow<P::kWords>;
     constexpr int kb = P::kStepBits, spb = 8 / kb, kThreads = genTb24Threads<P>();
@@ -262,8 +324,8 @@ genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, i
     if (frame >= nFrames)
         return;
     const Row *s = surv + ((size_t)(frame / 32) * T) * 32 + (frame & 31);
-    uint8_t *dst = out + (size_t)frame * outStride;
-    const int L = T - P::kTail, nBlocks = L / 24, tid = threadIdx.x;
+    uint8_t *dst = out + (size_t)frame * outStride - emitLo / spb;   /* dst[t / spb] for t >= emitLo */
+    const int L = T - skip, nBlocks = T / 24, blkLo = emitLo / 24, tid = threadIdx.x;   /* output steps [emitLo, L) */
     auto prefetch = [&](int blk, int buf) {
 #pragma unroll
         for (int i = 0; i < 24; i++) {
@@ -278,9 +340,9 @@ genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, i
         }
         asm volatile("cp.async.commit_group;");
     };
-    if (nBlocks > 0)
+    if (nBlocks > blkLo)
         prefetch(nBlocks - 1, 0);
-    uint32_t p = 0, acc = 0;
+    uint32_t p = startPos ? startPos[frame] : 0u, acc = 0;
     for (int t = T - 1; t >= 24 * nBlocks; t--) {   /* tail steps (no output, :208-223) and the ragged top */
         const Row row = s[(size_t)t * 32];
         const uint32_t v = P::tbStep(p, row.w, t);
@@ -293,18 +355,33 @@ genTraceback24Kernel(const SurvRow<P::kWords> *__restrict__ surv, int nFrames, i
         }
     }
     int buf = 0;
-    for (int blk = nBlocks - 1; blk >= 0; blk--, buf ^= 1) {
-        if (blk > 0) {
+    for (int blk = nBlocks - 1; blk >= blkLo; blk--, buf ^= 1) {
+        if (blk > blkLo) {
             prefetch(blk - 1, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        genWalk24<P, 23>(p, acc, &sW[buf][0][tid], kThreads, dst, blk);
+        if (24 * blk + 24 <= L)
+            genWalk24<P, 23, false>(p, acc, &sW[buf][0][tid], kThreads, dst, blk, L);
+        else
+            genWalk24<P, 23, true>(p, acc, &sW[buf][0][tid], kThreads, dst, blk, L);
     }
 }
 
 } // namespace ced
+
+template <class P>
+using GenKernelPtr = void (*)(const uint8_t *, size_t, int, int, ced::SurvRow<P::kWords> *, const uint8_t *, int, uint32_t,
+                              ced::FwdSched, int, ced::GenWindow);
+
+template <class P, bool CARRY>
+static GenKernelPtr<P> genKernelFor(int n, bool aligned)
+{
+    if (n == 2)
+        return aligned ? ced::genForwardKernel<P, 4, true, CARRY> : ced::genForwardKernel<P, 4, false, CARRY>;
+    return aligned ? ced::genForwardKernel<P, 8, true, CARRY> : ced::genForwardKernel<P, 8, false, CARRY>;
+}
 
 /* table and launch for one call of a trellis policy P; T = trellis steps per frame, V = 2^n received symbols */
 template <class P, class BuildTable>
@@ -339,12 +416,7 @@ static int launchGen(ced_ctx *c, int n, int T, BuildTable buildTable, const uint
     const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0 && P::kChunk % 16 == 0;
     const size_t pitchA = ced::TileGeom<ced::ByteSymbols, true>::kPitch, pitchU = ced::TileGeom<ced::ByteSymbols, false>::kPitch;
     const size_t smem = tabBytes + 4 * 32 * (aligned16 ? pitchA : pitchU);
-    auto kernelFor = [&](bool al) -> void (*)(const uint8_t *, size_t, int, int, Row *, const uint8_t *, int, uint32_t, ced::FwdSched, int) {
-        if (n == 2)
-            return al ? ced::genForwardKernel<P, 4, true> : ced::genForwardKernel<P, 4, false>;
-        return al ? ced::genForwardKernel<P, 8, true> : ced::genForwardKernel<P, 8, false>;
-    };
-    auto kernel = kernelFor(aligned16);
+    auto kernel = genKernelFor<P, false>(n, aligned16);
     CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int resident = 0;
     CED_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, ced::kFwdThreads, smem));
@@ -360,7 +432,7 @@ static int launchGen(ced_ctx *c, int n, int T, BuildTable buildTable, const uint
         sched.state = wk.schedState.p;
         CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
         kernel<<<blocks, ced::kFwdThreads, smem, s>>>(dSegs + f0 * segStride, segStride, wave, T, reinterpret_cast<Row *>(wk.scratch.p),
-                                                     dTable, n, c->bm0113.minusOne, sched, 2);
+                                                     dTable, n, c->bm0113.minusOne, sched, 2, ced::GenWindow());
         if constexpr (sizeof(Row) <= 16 && 24 % P::kPhases == 0) {
             constexpr int tbT = ced::genTb24Threads<P>();
             ced::genTraceback24Kernel<P><<<(wave + tbT - 1) / tbT, tbT, 0, s>>>(reinterpret_cast<const Row *>(wk.scratch.p), wave, T,
@@ -420,6 +492,162 @@ int cedDecodeBatchSwarGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t 
                                             dOut, outStride, s, slot);
     }
 #undef CED_GEN_CASE
+}
+
+/*
+ * Continuous streams with windowed traceback (ced_decode_window_batch) for the codes of these kernels with K <= 7: the
+ * procedure of decodeWindowImpl (ced_abi.cu) -- carried metrics, the newest `depth` survivor rows kept between calls,
+ * traceback from the best-metric state with the top `depth` steps discarded -- on GenPolicy<S> kernels.
+ * Carry block per 32 streams: kStateU4 x 32 uint4 metrics, 32 start positions, depth x 32 survivor rows.
+ */
+template <int S>
+static size_t genWindowCarryGroupBytes(int depth)
+{
+    using P = ced::GenPolicy<S>;
+    constexpr int kStateU4 = (P::kRegs + 3) / 4;
+    return (size_t)kStateU4 * 32 * sizeof(uint4) + 32 * sizeof(uint32_t) + (size_t)depth * 32 * sizeof(ced::SurvRow<P::kWords>);
+}
+
+template <int S>
+static int windowGen(ced_ctx *c, const ced::GenCode &gc, const uint8_t *dSegs, size_t segStride, int nStreams, int nSegments,
+                     uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut, size_t outStride, cudaStream_t s)
+{
+    using P = ced::GenPolicy<S>;
+    using Row = ced::SurvRow<P::kWords>;
+    static_assert(sizeof(Row) <= 16 && 24 % S == 0, "windowed decoding: K <= 7");
+    constexpr int kStateU4 = (P::kRegs + 3) / 4;
+    const int n = gc.n, V = 1 << n;
+    const int emitLo = (int)std::max<int64_t>(0, (int64_t)depth - (int64_t)streamPos);
+    const int Tl = depth + nSegments;
+    const int emitHi = last ? Tl - S : nSegments;
+    const int bytesOut = emitHi > emitLo ? (emitHi - emitLo) / 8 : 0;
+    if (outStride < (size_t)bytesOut) {
+        setError("ced_decode_window_batch: stride shorter than a slice");
+        return CED_ERR_ARG;
+    }
+    if (nStreams == 0)
+        return bytesOut;
+    ced_ctx::Work &wk = c->work[0];
+    const size_t perFrame = (size_t)Tl * sizeof(Row);
+    const size_t waveMax = std::max<size_t>(64, std::min<size_t>(c->maxWaveFrames, kMaxScratchBytes / perFrame) / 64 * 64);
+    const size_t g0n = (std::min<size_t>((size_t)nStreams, waveMax) + 31) / 32;
+    const size_t tabBytes = ((size_t)P::tableBytes(V) + 15) / 16 * 16;
+    const size_t stateBytes = g0n * kStateU4 * 32 * sizeof(uint4) + tabBytes + 512, flagBytes = (g0n + 1) * sizeof(int);
+    if (wk.scratch.bytes < g0n * 32 * perFrame || wk.schedState.bytes < stateBytes || wk.schedFlags.bytes < flagBytes) {
+        CED_CUDA(cudaDeviceSynchronize());
+        int rc = wk.scratch.ensure(g0n * 32 * perFrame);
+        if (rc == CED_OK) rc = wk.schedState.ensure(stateBytes);
+        if (rc == CED_OK) rc = wk.schedFlags.ensure(flagBytes);
+        if (rc != CED_OK)
+            return rc;
+    }
+    if (wk.lastStream && wk.lastStream != s)
+        CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
+    std::vector<uint8_t> table(tabBytes);
+    ced::buildGenTable<S>(gc, table.data());
+    uint8_t *dTable = reinterpret_cast<uint8_t *>(wk.schedState.p) + (g0n * kStateU4 * 32 * sizeof(uint4) + 255) / 256 * 256;
+    CED_CUDA(cudaMemcpyAsync(dTable, table.data(), tabBytes, cudaMemcpyHostToDevice, s));
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(dSegs) & 15u) == 0 && (segStride & 15u) == 0 && P::kChunk % 16 == 0;
+    const size_t smem = tabBytes + 4 * 32 * (aligned16 ? ced::TileGeom<ced::ByteSymbols, true>::kPitch
+                                                       : ced::TileGeom<ced::ByteSymbols, false>::kPitch);
+    auto kernel = genKernelFor<P, true>(n, aligned16);
+    CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t allGroups = (size_t)(nStreams + 31) / 32;
+    uint8_t *carry = static_cast<uint8_t *>(dCarry);
+    uint4 *carryMetrics = reinterpret_cast<uint4 *>(carry);
+    uint32_t *carryStart = reinterpret_cast<uint32_t *>(carry + allGroups * kStateU4 * 32 * sizeof(uint4));
+    uint8_t *carrySurv = carry + allGroups * ((size_t)kStateU4 * 32 * sizeof(uint4) + 32 * sizeof(uint32_t));
+    const size_t tailBytes = (size_t)depth * 32 * sizeof(Row);   /* per group */
+    const size_t rowBytes = (size_t)Tl * 32 * sizeof(Row);       /* per group in the scratch */
+    for (size_t f0 = 0; f0 < (size_t)nStreams; f0 += waveMax) {
+        const int wave = (int)std::min<size_t>(waveMax, (size_t)nStreams - f0);
+        const int groups = (wave + 31) / 32;
+        const size_t gFirst = f0 / 32;
+        if (streamPos > 0)
+            CED_CUDA(cudaMemcpy2DAsync(wk.scratch.p, rowBytes, carrySurv + gFirst * tailBytes, tailBytes, tailBytes, (size_t)groups,
+                                       cudaMemcpyDeviceToDevice, s));
+        const int blocks = std::max(1, std::min(c->sms * 3, (groups + 3) / 4));
+        ced::FwdSched sched;
+        sched.counter = reinterpret_cast<unsigned int *>(wk.schedFlags.p);
+        sched.done = wk.schedFlags.p + 1;
+        sched.state = wk.schedState.p;
+        CED_CUDA(cudaMemsetAsync(wk.schedFlags.p, 0, (size_t)(groups + 1) * sizeof(int), s));
+        ced::GenWindow win;
+        win.metricsIn = streamPos > 0 ? carryMetrics + gFirst * kStateU4 * 32 : nullptr;
+        win.metricsOut = last ? nullptr : carryMetrics + gFirst * kStateU4 * 32;
+        win.startPos = carryStart + gFirst * 32;
+        win.survSteps = Tl;
+        win.stepOffset = depth;
+        kernel<<<blocks, ced::kFwdThreads, smem, s>>>(dSegs + f0 * segStride, segStride, wave, nSegments,
+                                                     reinterpret_cast<Row *>(wk.scratch.p), dTable, n, c->bm0113.minusOne, sched, 2, win);
+        c->launches += 1;
+        if (bytesOut > 0) {
+            constexpr int tbT = ced::genTb24Threads<P>();
+            ced::genTraceback24Kernel<P><<<(wave + tbT - 1) / tbT, tbT, 0, s>>>(
+                reinterpret_cast<const Row *>(wk.scratch.p), wave, Tl, dOut + f0 * outStride, outStride,
+                last ? nullptr : win.startPos, last ? S : depth, emitLo);
+            c->launches += 1;
+        }
+        if (!last)
+            CED_CUDA(cudaMemcpy2DAsync(carrySurv + gFirst * tailBytes, tailBytes,
+                                       reinterpret_cast<uint8_t *>(wk.scratch.p) + (size_t)nSegments * 32 * sizeof(Row), rowBytes,
+                                       tailBytes, (size_t)groups, cudaMemcpyDeviceToDevice, s));
+    }
+    CED_CUDA(cudaEventRecord(wk.idle, s));
+    wk.lastStream = s;
+    CED_CUDA(cudaGetLastError());
+    return bytesOut;
+}
+
+/* bytes of carry block for `code` on this path, 0 if the code is not one of these kernels' (K <= 7, n = 2 or 3) */
+size_t cedWindowCarryBytesGeneric(const ced_code_t *code, int nStreams, int depth)
+{
+    if (!code || code->codedBits < 2 || code->codedBits > 3 || nStreams <= 0 || depth < 24 || depth % 24)
+        return 0;
+    const size_t groups = (size_t)(nStreams + 31) / 32;
+    switch (code->constraintLen - 1) {
+    case 2: return groups * genWindowCarryGroupBytes<2>(depth);
+    case 3: return groups * genWindowCarryGroupBytes<3>(depth);
+    case 4: return groups * genWindowCarryGroupBytes<4>(depth);
+    case 6: return groups * genWindowCarryGroupBytes<6>(depth);
+    default: return 0;
+    }
+}
+
+int cedDecodeWindowGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nStreams, int nSegments,
+                           uint64_t streamPos, int depth, int last, void *dCarry, uint8_t *dOut, size_t outStride, void *stream)
+{
+    const int K = code ? code->constraintLen : 0, S = K - 1;
+    if (!code || code->codedBits < 2 || code->codedBits > 3 || !(S == 2 || S == 3 || S == 4 || S == 6))
+        return CED_ERR_UNSUPPORTED;
+    if (!c || nStreams < 0 || nSegments < 0 || depth < 24 || depth % 24 || depth > 8184 || streamPos % 96 ||
+        (nStreams > 0 && (!dSegs || !dOut || !dCarry)) || (reinterpret_cast<uintptr_t>(dCarry) & 15u)) {
+        setError("ced_decode_window_batch: bad argument (depth and streamPos must be multiples of 24 / 96)");
+        return CED_ERR_ARG;
+    }
+    if (last ? (nSegments < S || (streamPos + (uint64_t)nSegments - (uint64_t)S) % 8 != 0) : (nSegments == 0 || nSegments % 96 != 0)) {
+        setError("ced_decode_window_batch: a slice must be a positive multiple of 96 segments; the last one must end the stream "
+                 "on a byte boundary plus K-1 tail segments");
+        return CED_ERR_ARG;
+    }
+    if (nSegments > (int)kStreamMaxSteps * 4 || segStride < (size_t)nSegments) {
+        setError("ced_decode_window_batch: slice too long or stride shorter than a slice");
+        return CED_ERR_ARG;
+    }
+    ced::GenCode gc;
+    gc.S = S;
+    gc.n = code->codedBits;
+    for (int i = 0; i < 3; i++)
+        gc.tap[i] = i < gc.n ? reverseBits(code->gen[i], K) : 0u;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    switch (S) {
+    case 2: return windowGen<2>(c, gc, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut, outStride, s);
+    case 3: return windowGen<3>(c, gc, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut, outStride, s);
+    case 4: return windowGen<4>(c, gc, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut, outStride, s);
+    default: return windowGen<6>(c, gc, dSegs, segStride, nStreams, nSegments, streamPos, depth, last, dCarry, dOut, outStride, s);
+    }
 }
 
 /* rate-2/n codes (k = 2), n = 2 or 3, 4 .. 256 states: radix-4 SIMD-in-word kernels; CED_ERR_UNSUPPORTED = not a code

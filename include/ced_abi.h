@@ -219,6 +219,10 @@ size_t ced_decode_scratch_bytes(int nFrames, int frameBits);
  * reference's full traceback.
  */
 size_t ced_window_carry_bytes(int nStreams, int depth);
+/* ... for any code ced_decode_window_batch takes: the K=7 codes above, and -- byte format -- every other code with K = 3, 4, 5
+ * or 7 and 2 or 3 generators of any shape (table-driven kernels; their carry block depends on the number of states).
+ * 0 = not a code the windowed decoder takes. */
+size_t ced_window_carry_bytes_code(const ced_code_t *code, int nStreams, int depth);
 int ced_decode_window_batch(ced_ctx *ctx, const ced_code_t *code, const uint8_t *dSegs, size_t segStride,
                             int nStreams, int nSegments, uint64_t streamPos, int depth, int last, void *dCarry,
                             uint8_t *dOut, size_t outStride, void *stream);

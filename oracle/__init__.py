@@ -84,6 +84,8 @@ class Port:
         lib.orc_decode_soft_batch.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_size_t, C.c_int, C.c_int,
                                               _u8p, C.c_size_t]
 
+        lib.orc_decode_window2.restype = C.c_int
+        lib.orc_decode_window2.argtypes = [C.c_int, C.c_int, _u64p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, _u8p]
         lib.orc_decode_window_soft.restype = C.c_int
         lib.orc_decode_window_soft.argtypes = [C.c_int, C.c_int, _u64p, C.c_void_p, C.c_int, C.c_int, C.c_int, _u8p]
         _u32p = C.POINTER(C.c_uint32)
@@ -191,12 +193,14 @@ class Port:
         assert rc == total - (K - 1)
         return out
 
-    def decode_window(self, K, g, segs, call_segs, depth):
-        """One terminated stream decoded with windowed traceback (orc_decode_window: semantics defined there)."""
+    def decode_window(self, K, g, segs, call_segs, depth, symmetric=True):
+        """One terminated stream decoded with windowed traceback (orc_decode_window: semantics defined there);
+        symmetric=False: the general branch costs, for generators that do not tap both ends."""
         segs = np.ascontiguousarray(segs, dtype=np.uint8)
         T = segs.size
         out = np.zeros((T - (K - 1) + 7) // 8, dtype=np.uint8)
-        rc = self.lib.orc_decode_window(K, len(g), self._g(g), _p(segs), T, int(call_segs), int(depth), _p(out))
+        rc = self.lib.orc_decode_window2(K, len(g), self._g(g), int(symmetric), _p(segs), T, int(call_segs), int(depth),
+                                         _p(out))
         assert rc == T - (K - 1), rc
         return out
 

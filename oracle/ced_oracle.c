@@ -281,12 +281,22 @@ int orc_dec_step(orc_decoder_t *d, const uint8_t *segs, int segmentsIn, uint8_t 
  * Output bit t is bit 0 of the survivor state after step t, MSb-first (:244-249).  Returns the number
  * of bits written (total - S) or -1.
  */
+int orc_decode_window2(int K, int n, const uint64_t *g, int symmetric, const uint8_t *segs, int totalSegs, int callSegs,
+                       int depth, uint8_t *out);
+
 int orc_decode_window(int K, int n, const uint64_t *g, const uint8_t *segs, int totalSegs, int callSegs,
                       int depth, uint8_t *out)
 {
+    return orc_decode_window2(K, n, g, 1, segs, totalSegs, callSegs, depth, out);
+}
+
+/* the same with the general (non-symmetric) branch costs of orc_dec_step for any code */
+int orc_decode_window2(int K, int n, const uint64_t *g, int symmetric, const uint8_t *segs, int totalSegs, int callSegs,
+                       int depth, uint8_t *out)
+{
     if (callSegs <= 0 || depth < 0 || totalSegs <= K - 1)
         return -1;
-    orc_decoder_t *d = orc_dec_new(K, n, g, 1, totalSegs);
+    orc_decoder_t *d = orc_dec_new(K, n, g, symmetric, totalSegs);
     if (!d)
         return -1;
     const int N = d->N, S = d->S;

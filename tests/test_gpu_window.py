@@ -106,9 +106,10 @@ def test_window_argument_checks(ctx):
         dec.push(segs[:, :100])                            # slices are multiples of 96
     with pytest.raises(ced.CedError):
         dec.push(segs[:, :96 + 7], last=True)              # stream must end on a byte boundary + tail
-    k3 = ced.Code(3, [7, 6])
+    with pytest.raises(ValueError):
+        ctx.window_decoder(ced.Code(9, [0o561, 0o753]), 4, 48)   # K <= 7 only (the carry block has no size for it)
     with pytest.raises(ced.CedError):
-        ctx.window_decoder(k3, 4, 48).push(segs[:, :96])   # SWAR codes only
+        ctx.window_decoder(ced.Code(3, [7, 6]), 4, 48, packed=True).push(segs[:, :96])   # packed format: K=7 family only
 
 
 def test_outputs_stay_inside_their_rows(ctx, port):
@@ -216,3 +217,35 @@ def test_window_ber_meets_the_reference_held_expectations(ctx, port):
         if pkts == 1 << 13:
             assert np.array_equal(run_window_packed(ctx, code, segs[:512, :T].cpu().numpy(), 192, 48),
                                   np.stack([port.decode_window(7, g, r, 192, 48) for r in segs[:512, :T].cpu().numpy()]))
+
+
+@pytest.mark.parametrize("K,g", [(3, (0b111, 0b110)), (3, (0b111, 0b101, 0b011)), (4, (0o15, 0o17)), (5, (0o23, 0o35)),
+                                 (5, (0o25, 0o33, 0o37)), (7, (0o133, 0o170)), (7, (0o133, 0o145, 0o174))])
+def test_window_decode_other_code_parameters(ctx, port, K, g):
+    """ced_decode_window_batch for codes outside the symmetric K=7 family (table-driven kernels, K <= 7, 2 or 3 generators
+    of any shape): bit-exact against the window definition with the general branch costs; with depth >= stream length it
+    is the full-frame decode of the same code."""
+    import torch
+    rng = np.random.default_rng(K * 31 + sum(g))
+    n, S = len(g), K - 1
+    code = ced.Code(K, g)
+    for n_streams, bits, call, depth, p in ((3, 96 * 3 + 40, 96, 24, 0.0), (70, 1000 // 8 * 8, 192, 48, 0.03),
+                                            (40, 2048, 480, 96, 0.08), (33, 512, 96, 48, 0.5), (5, 512, 4800, 48, 0.03)):
+        total = bits + S
+        msgs = rng.integers(0, 256, (n_streams, bits // 8), dtype=np.uint8)
+        clean = port.encode_batch(K, list(g), msgs)
+        flips = rng.random(clean.shape + (n,)) < p
+        noisy = clean.copy()
+        for j in range(n):
+            noisy ^= (flips[..., j].astype(np.uint8) << j)
+        want = np.stack([port.decode_window(K, list(g), noisy[i], call, depth, symmetric=False) for i in range(n_streams)])
+        d = torch.from_numpy(noisy).cuda()
+        wd = ctx.window_decoder(code, n_streams, depth=depth)
+        parts = [wd.push(d[:, a:min(a + call, total)], last=a + call >= total).clone() for a in range(0, total, call)]
+        ctx.sync()
+        got = torch.cat(parts, dim=1).cpu().numpy()
+        assert np.array_equal(got, want), (K, g, n_streams, bits, call, depth, p)
+        if call >= total:
+            assert np.array_equal(got, port.decode_batch(K, list(g), noisy, total, symmetric=False))
+        if p == 0.0:
+            assert np.array_equal(got, msgs)

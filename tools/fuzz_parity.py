@@ -48,7 +48,7 @@ t_end = time.time() + seconds
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window", "windowq", "enc", "host"])
+    kind = rng.choice(["k7", "k7rt", "generic", "packed", "soft", "softq", "k2", "window", "windowq", "windowgen", "enc", "host"])
     frames = int(rng.choice([1, 2, 31, 33, 64, 100, 257]))
     bits = int(rng.choice([8, 16, 40, 96, 104, 200, 512, 1000, 2048]))
     pad, off = int(rng.integers(0, 20)), int(rng.integers(0, 16))
@@ -160,6 +160,23 @@ while time.time() < t_end:
             got = torch.cat(parts, dim=1)
             want = np.stack([P.decode_window(7, g, rx[i], call, depth) for i in range(frames)])
             bits = total_bits
+    elif kind == "windowgen":
+        K = int(rng.choice([3, 4, 5, 7]))
+        n = int(rng.integers(2, 4))
+        g = [rand_gen(K, rng, False) for _ in range(n)]
+        code = ced.Code(K, g)
+        total_bits = int(rng.choice([320, 1000, 2048]))
+        msgs = rng.integers(0, 256, (frames, total_bits // 8), dtype=np.uint8)
+        rx = noisy(P.encode_batch(K, g, msgs), n, min(p, 0.2))
+        Tt = total_bits + K - 1
+        call, depth = int(rng.choice([96, 192, 480])), int(rng.choice([24, 48, 96]))
+        wd = ctx.window_decoder(code, frames, depth=depth)
+        d = place(rx, pad, off)
+        parts = [wd.push(d[:, a:min(a + call, Tt)], last=a + call >= Tt).clone() for a in range(0, Tt, call)]
+        got = torch.cat(parts, dim=1)
+        want = np.stack([P.decode_window(K, g, rx[i], call, depth, symmetric=False) for i in range(frames)])
+        bits = total_bits
+        tag = "windowgen K=%d" % K
     elif kind == "k7rt":
         n = int(rng.integers(2, 4))
         g = [rand_gen(7, rng, True) for _ in range(n)]
