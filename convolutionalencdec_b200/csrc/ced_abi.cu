@@ -434,6 +434,12 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         setError("ced_decode_batch: bad argument (frameBits must be a positive multiple of 8)");
         return CED_ERR_ARG;
     }
+    /* small batches: one warp per frame, decisions in shared memory (warp_frame.cu) */
+    if (!packed && nFrames > 0 && nFrames <= cedWarpFrameMaxFrames(c, frameBits)) {
+        const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+        if (rc != CED_ERR_UNSUPPORTED)
+            return rc;
+    }
     CodeId id = classify(code);
     /* the compiled-in codes with their two generators written the other way round ((0171, 0133) is how the NASA standard
      * code is often given): the same kernel with the rows of its branch-cost table for the received symbols 01 and 10
@@ -1517,6 +1523,29 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
     }
     if (nFrames == 0)
         return CED_OK;
+    /* small batches (speedDecode's 16 packets, speedDecode/speedDecode.c:18-19): one copy in, the warp-per-frame kernel
+     * (warp_frame.cu), one copy out -- no chunk pipeline, no host-side packing */
+    if (nFrames <= cedWarpFrameMaxFrames(c, frameBits)) {
+        std::lock_guard<std::recursive_mutex> lock(c->mu);
+        CED_CUDA(cudaSetDevice(c->device));
+        const size_t T = (size_t)frameBits + code->constraintLen - 1;
+        const size_t inBytes = (size_t)(nFrames - 1) * segStride + T, outBytes = (size_t)(nFrames - 1) * outStride + (size_t)frameBits / 8;
+        int rc = c->hostIn[0].ensure(inBytes + 16);
+        if (rc == CED_OK)
+            rc = c->hostOut[0].ensure(outBytes + 16);
+        if (rc != CED_OK)
+            return rc;
+        CED_CUDA(cudaMemcpyAsync(c->hostIn[0].p, hSegs, inBytes, cudaMemcpyHostToDevice, c->stream));
+        rc = cedDecodeBatchWarpFrame(c, code, c->hostIn[0].p, segStride, nFrames, frameBits, c->hostOut[0].p, outStride, c->stream);
+        if (rc == CED_OK) {
+            CED_CUDA(cudaMemcpyAsync(hOut, c->hostOut[0].p, outBytes, cudaMemcpyDeviceToHost, c->stream));
+            CED_CUDA(cudaStreamSynchronize(c->stream));
+            return CED_OK;
+        }
+        CED_CUDA(cudaStreamSynchronize(c->stream));   /* not a case for that kernel: the general pipeline below */
+        if (rc != CED_ERR_UNSUPPORTED)
+            return rc;
+    }
     /* Transfer compression: worker threads pack the symbols to 2 bits into page-locked staging and a quarter of
      * the bytes crosses PCIe.  CED_HOST_PACK forces 0 = never, 1 = every chunk, 2 = adaptive; the default is
      *  - page-locked caller buffers: adaptive, if this machine gains from it (PackTuner above measures that during

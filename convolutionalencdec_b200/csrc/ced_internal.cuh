@@ -236,6 +236,12 @@ int cedDecodeBatchSoftQ(ced_ctx *c, const ced_code_t *code, const uint8_t *dSyms
 int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, int blocks, cudaStream_t s, const uint8_t *in,
                           size_t symStride, int wave, int nSegments, uint4 *scratch, ced::FwdSched sched, ced::FwdWindow win);
 
+/* warp_frame.cu: small batches, one warp per frame (k = 1 codes with <= 64 states, n <= 3, byte format);
+ * CED_ERR_UNSUPPORTED = not a case for it */
+int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream);
+int cedWarpFrameMaxFrames(const ced_ctx *c, int frameBits);
+
 /* swar_generic.cu: continuous streams for the table-driven kernels (K <= 7); CED_ERR_UNSUPPORTED / 0 = not their code */
 size_t cedWindowCarryBytesGeneric(const ced_code_t *code, int nStreams, int depth);
 int cedDecodeWindowGeneric(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nStreams, int nSegments,

@@ -1,0 +1,397 @@
+/*
+ * warp_frame.cu -- ced_decode_batch for SMALL batches: one warp per frame, the trellis states spread over the lanes.
+ *
+ * The thread-per-frame kernels (decode_batch.cuh, swar_generic.cu) need >= 2^11 frames before every sub-partition of the
+ * GPU has a warp, and a frame is a chain of T dependent steps of ~121 instructions: 73 ns per step, however few frames
+ * there are (the reference's own shapes are 16 packets, speedDecode/speedDecode.c:18-19, and 10,000 packets one by one,
+ * berTestK7/berTestK7.c:109-165).  Here a frame belongs to ONE warp and a step is a handful of instructions deep:
+ *
+ *  forward (src/viterbiDecoderButterflyk1.c:85-196).  Metrics are exact 16-bit integers, two per register.
+ *    radix 2 (any k = 1 code with <= 64 states): lane j is butterfly j -- it holds m[j], m[j+H] and produces m'[2j],
+ *    m'[2j+1]: A = (m[j], m[j]) + (c(j->2j), c(j->2j+1)), B = (m[j+H], m[j+H]) + (...), m' = min(A, B) per half
+ *    (VIMNMX.U16x2), decision = A != min (the lower predecessor wins a tie, :129-130); two independent shuffles and
+ *    two PRMT re-gather the operands of the next step.
+ *    radix 4 (64 states): two trellis steps per gather.  Lane l = 2q + h holds (m[q], m[q+16]) and (m[q+32], m[q+48]);
+ *    step t gives the two intermediate states l and l + 32 (each of the 64 is computed by exactly one lane), step t+1 is
+ *    the radix-2 butterfly of those two inside the lane: m''[2l], m''[2l+1].  Four independent shuffles + two PRMT per
+ *    TWO steps, so the dependent chain per step is ~26 cycles instead of ~40.
+ *    Branch costs come from a per-lane table in shared memory indexed by the received symbol (one LDS.64 per step,
+ *    fetched a block of four steps ahead); the frame's symbols are staged in shared memory with 16-byte loads first.
+ *  decisions: __ballot_sync-packed, one 8-byte row per step, kept in SHARED memory (never written to HBM).
+ *  traceback (:200-256): warp-parallel and exact.  The T steps are cut into 32 segments; lane i walks segment i after a
+ *    warm-up of one segment length from state 0 above it.  Paths merge, so nearly always every lane enters its segment
+ *    in the state the lane above leaves in; where it does not, that lane walks its segment again from the right state,
+ *    until every hand-over agrees (the top lane starts in state 0 at the last step and is exact by construction, so the
+ *    loop ends after at most 32 rounds and the result is the sequential walk's, bit for bit).  Bytes are packed MSb
+ *    first (:244-249) in shared memory and leave as one row.
+ *
+ * No global scratch: a CTA is one warp with (9 T + 4.5 K) bytes of shared memory.
+ */
+#include "ced_internal.cuh"
+
+#include <type_traits>
+
+namespace ced {
+
+constexpr int kWfMaxV = 8;          /* received symbols: n <= 3 */
+constexpr int kWfCostBytes = 16 * 32 * (int)sizeof(uint4);   /* radix 4: [rx1 | rx2 << 2][lane] uint4; radix 2: [rx][lane] uint2 */
+
+struct WfArgs {
+    const uint8_t *segs;
+    size_t segStride;
+    uint8_t *out;
+    size_t outStride;
+    int nFrames, T, S, n;
+    int seg;               /* traceback: steps per lane, a multiple of 8 */
+    int survRows;          /* >= T + T / seg, even */
+    int outPad;            /* bytes of the output row in shared memory, a multiple of 16 */
+    uint32_t initMetric;   /* (uint8_t)(NUM_STATES + 1), :59-67 */
+    uint32_t cost[2][kWfMaxV][32]; /* [second step of a radix-4 pair / radix-2 step = 1, first = 0][rx][lane]: 4 costs as bytes */
+};
+
+/* one step back from state s over a row in the radix-2 format (x: successors 2j, y: successors 2j+1; bit j) */
+template <int S>
+__device__ __forceinline__ void wfBackOdd(uint32_t &s, const uint2 w)
+{
+    const uint32_t word = (s & 1u) ? w.y : w.x;
+    const uint32_t dec = (word >> (s >> 1)) & 1u;
+    s = (s >> 1) | (dec << (S - 1));
+}
+__device__ __forceinline__ void wfBackOddRt(uint32_t &s, const uint2 w, int S)
+{
+    const uint32_t word = (s & 1u) ? w.y : w.x;
+    const uint32_t dec = (word >> (s >> 1)) & 1u;
+    s = (s >> 1) | (dec << (S - 1));
+}
+/* ... over a row in the state-indexed format of the first step of a radix-4 pair (x: states 0..31, y: 32..63) */
+__device__ __forceinline__ void wfBackEven(uint32_t &s, const uint2 w)
+{
+    const uint32_t word = (s & 32u) ? w.y : w.x;
+    const uint32_t dec = (word >> (s & 31u)) & 1u;
+    s = (s >> 1) | (dec << 5);
+}
+
+/* walk steps [tLo, tHi) downwards from state s (tLo a multiple of 8); EMIT: bits of steps < L go to sOut, MSb first */
+template <bool R4, bool EMIT>
+__device__ __forceinline__ uint32_t wfWalk(uint32_t s, int tHi, int tLo, const uint2 *rows, int S, int L, uint8_t *sOut)
+{
+    int t = tHi - 1;
+    uint32_t acc = 0;
+    for (; t >= tLo && (t & 7) != 7; t--) {   /* ragged top: only where a walk starts at the end of the frame */
+        const uint32_t bit = s & 1u;
+        if (R4 && !(t & 1))
+            wfBackEven(s, rows[t - tLo]);
+        else
+            wfBackOddRt(s, rows[t - tLo], S);
+        if (EMIT && t < L) {
+            acc = (acc >> 1) | (bit << 7);
+            if ((t & 7) == 0) {
+                sOut[t >> 3] = (uint8_t)acc;
+                acc = 0;
+            }
+        }
+    }
+    for (; t >= tLo; t -= 8) {   /* t + 1 is a multiple of 8: whole bytes; the rows do not depend on the path */
+        const int tb = t - 7;
+        uint2 w[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            w[q] = rows[tb - tLo + q];
+        uint32_t byte = 0;
+#pragma unroll
+        for (int q = 7; q >= 0; q--) {
+            byte |= (s & 1u) << (7 - q);   /* step tb + q is bit 7 - q of byte tb / 8 (:249) */
+            if (R4 && !(q & 1))
+                wfBackEven(s, w[q]);
+            else if (R4)
+                wfBackOdd<6>(s, w[q]);
+            else
+                wfBackOddRt(s, w[q], S);
+        }
+        if (EMIT && tb < L)
+            sOut[tb >> 3] = (uint8_t)byte;
+    }
+    return s;
+}
+
+template <bool R4>
+__global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfArgs a)
+{
+    extern __shared__ __align__(16) uint8_t wfSmem[];
+    uint2 *sSurv = reinterpret_cast<uint2 *>(wfSmem + kWfCostBytes);        /* row of step t at t + t / seg */
+    uint8_t *sOut = reinterpret_cast<uint8_t *>(sSurv + a.survRows);
+    uint32_t *sOffs = reinterpret_cast<uint32_t *>(sOut + a.outPad);        /* table offset of every unit (+ 12 of padding) */
+
+    const int lane = threadIdx.x, T = a.T, S = a.S, L = T - S, seg = a.seg;
+    const int H = 1 << (S - 1);
+    const uint32_t rxMask = (1u << a.n) - 1u;
+    auto spread = [](uint32_t u) { return make_uint2((u & 0xFFu) | ((u >> 8 & 0xFFu) << 16), (u >> 16 & 0xFFu) | ((u >> 24) << 16)); };
+    if (R4) {
+        for (int i = lane; i < 16 * 32; i += 32) {
+            const uint2 c1 = spread(a.cost[0][(i >> 5) & 3][lane]), c2 = spread(a.cost[1][i >> 7][lane]);
+            reinterpret_cast<uint4 *>(wfSmem)[i] = make_uint4(c1.x, c1.y, c2.x, c2.y);
+        }
+    } else {
+        for (int i = lane; i < kWfMaxV * 32; i += 32)
+            reinterpret_cast<uint2 *>(wfSmem)[i] = spread(a.cost[1][i >> 5][lane]);
+    }
+
+    /* operands of the next step: which lane holds them, which half */
+    uint32_t src0, src1, src2 = 0, src3 = 0, sel0, sel1;
+    if (R4) {
+        const uint32_t q = (uint32_t)lane >> 1;
+        src0 = q >> 1;
+        src1 = src0 + 8;
+        src2 = src0 + 16;
+        src3 = src0 + 24;
+        sel0 = sel1 = (q & 1u) ? 0x7632u : 0x5410u;
+    } else {
+        const uint32_t j = (uint32_t)lane & (uint32_t)(H - 1);   /* lanes >= H (fewer than 64 states) mirror a butterfly */
+        src0 = j >> 1;
+        src1 = (j + (uint32_t)H) >> 1;
+        sel0 = (j & 1u) ? 0x3232u : 0x1010u;
+        sel1 = ((j + (uint32_t)H) & 1u) ? 0x3232u : 0x1010u;
+    }
+
+    for (int f = blockIdx.x; f < a.nFrames; f += gridDim.x) {
+        /* stage the symbols (whole 16-byte pieces around the row) where the decisions will go, then turn them into the
+         * table offset of every unit -- a unit is a pair of steps (radix 4: 16 B of costs per lane and symbol pair) or a
+         * step (radix 2: 8 B per lane and symbol) -- so that the dependent loop below spends one add and one load on it */
+        const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(a.segs) + (size_t)f * a.segStride;
+        const uint32_t off = (uint32_t)(rowAddr & 15u);
+        const uint4 *src = reinterpret_cast<const uint4 *>(rowAddr - off);
+        const int nq = (int)(off + (uint32_t)T + 15u) >> 4;
+        __syncwarp();
+        for (int q = lane; q < nq; q += 32)
+            reinterpret_cast<uint4 *>(sSurv)[q] = __ldg(src + q);
+        __syncwarp();
+        const uint8_t *sym = reinterpret_cast<const uint8_t *>(sSurv) + off;
+        const int units = R4 ? T >> 1 : T;
+        for (int u = lane; u < units + 12; u += 32) {
+            uint32_t o = 0;
+            if (u < units)
+                o = R4 ? ((sym[2 * u] & 3u) | ((sym[2 * u + 1] & 3u) << 2)) * 512u : (sym[u] & rxMask) * 256u;
+            sOffs[u] = o;
+        }
+        __syncwarp();
+
+        uint32_t X, Y;
+        const uint32_t m0 = a.initMetric;
+        if (R4) {
+            const uint32_t q = (uint32_t)lane >> 1;
+            X = (q == 0 ? 0u : m0) | (m0 << 16);
+            Y = m0 | (m0 << 16);
+        } else {
+            const uint32_t lo = (lane & (H - 1)) == 0 ? 0u : m0;
+            X = lo | (lo << 16);
+            Y = m0 | (m0 << 16);
+        }
+        using Cost = typename std::conditional<R4, uint4, uint2>::type;
+        const uint8_t *costBase = wfSmem + lane * sizeof(Cost);
+        auto costAt = [&](uint32_t o) -> Cost { return *reinterpret_cast<const Cost *>(costBase + o); };
+        uint2 *rowPtr = sSurv;
+        auto unit = [&](const Cost cc) {
+            if constexpr (R4) {   /* two steps */
+                bool h1, l1, h2, l2;
+                const uint32_t A = X + cc.x, B = Y + cc.y;
+                const uint32_t I = __vibmin_u16x2(A, B, &h1, &l1);   /* predicate: the first operand is the minimum */
+                const uint32_t w0 = __ballot_sync(0xFFFFFFFFu, !l1);
+                const uint32_t w1 = __ballot_sync(0xFFFFFFFFu, !h1);
+                const uint32_t A2 = __byte_perm(I, 0, 0x1010) + cc.z, B2 = __byte_perm(I, 0, 0x3232) + cc.w;
+                const uint32_t O = __vibmin_u16x2(A2, B2, &h2, &l2);
+                const uint32_t v0 = __shfl_sync(0xFFFFFFFFu, O, src0);
+                const uint32_t v1 = __shfl_sync(0xFFFFFFFFu, O, src1);
+                const uint32_t v2 = __shfl_sync(0xFFFFFFFFu, O, src2);
+                const uint32_t v3 = __shfl_sync(0xFFFFFFFFu, O, src3);
+                const uint32_t wa = __ballot_sync(0xFFFFFFFFu, !l2);
+                const uint32_t wb = __ballot_sync(0xFFFFFFFFu, !h2);
+                if (lane == 0) {
+                    rowPtr[0] = make_uint2(w0, w1);
+                    rowPtr[1] = make_uint2(wa, wb);
+                }
+                rowPtr += 2;
+                X = __byte_perm(v0, v1, sel0);
+                Y = __byte_perm(v2, v3, sel0);
+            } else {
+                bool h1, l1;
+                const uint32_t A = X + cc.x, B = Y + cc.y;
+                const uint32_t N = __vibmin_u16x2(A, B, &h1, &l1);
+                const uint32_t v = __shfl_sync(0xFFFFFFFFu, N, src0);
+                const uint32_t w = __shfl_sync(0xFFFFFFFFu, N, src1);
+                const uint32_t wa = __ballot_sync(0xFFFFFFFFu, !l1);
+                const uint32_t wb = __ballot_sync(0xFFFFFFFFu, !h1);
+                if (lane == 0)
+                    rowPtr[0] = make_uint2(wa, wb);
+                rowPtr += 1;
+                X = __byte_perm(v, 0, sel0);
+                Y = __byte_perm(w, 0, sel1);
+            }
+        };
+        /* blocks of four units; the offsets are fetched two blocks ahead, the costs one */
+        const int blocks = units >> 2, blocksPerSeg = seg / (R4 ? 8 : 4);
+        int untilBoundary = blocksPerSeg;
+        const uint4 *offs4 = reinterpret_cast<const uint4 *>(sOffs);
+        uint4 oNext = offs4[1];
+        Cost cA[4], cB[4];
+        {
+            const uint4 o0 = offs4[0];
+            cA[0] = costAt(o0.x);
+            cA[1] = costAt(o0.y);
+            cA[2] = costAt(o0.z);
+            cA[3] = costAt(o0.w);
+        }
+        auto block = [&](int b, const Cost (&cur)[4], Cost (&nxt)[4]) {
+            const uint4 o2 = offs4[b + 2];   /* padded: stays inside the array */
+            nxt[0] = costAt(oNext.x);
+            nxt[1] = costAt(oNext.y);
+            nxt[2] = costAt(oNext.z);
+            nxt[3] = costAt(oNext.w);
+            unit(cur[0]);
+            unit(cur[1]);
+            unit(cur[2]);
+            unit(cur[3]);
+            oNext = o2;
+            if (--untilBoundary == 0) {   /* the next segment's rows start one slot further on */
+                rowPtr++;
+                untilBoundary = blocksPerSeg;
+            }
+        };
+        int b = 0;
+        for (; b + 2 <= blocks; b += 2) {
+            block(b, cA, cB);
+            block(b + 1, cB, cA);
+        }
+        if (b < blocks) {
+            block(b, cA, cB);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                cA[k] = cB[k];
+            b++;
+        }
+        for (int u = 4 * b, k = 0; u < units; u++, k++)   /* at most three units; cA holds their costs */
+            unit(k == 0 ? cA[0] : k == 1 ? cA[1] : cA[2]);
+        __syncwarp();
+
+        /* warp-parallel traceback */
+        const int top = (T - 1) / seg;
+        const int lo = lane * seg, hi = min(T, lo + seg);
+        const uint2 *myRows = sSurv + lo + lane;   /* row of step t at t + t / seg */
+        uint32_t sIn = 0;
+        if (lane < top) {
+            const int wHi = min(T, hi + seg);      /* warm-up over the steps of the lane above, from state 0 */
+            sIn = wfWalk<R4, false>(0u, wHi, hi, sSurv + hi + lane + 1, S, L, sOut);
+        }
+        uint32_t sLeave = 0;
+        if (lane <= top)
+            sLeave = wfWalk<R4, true>(sIn, hi, lo, myRows, S, L, sOut);
+        for (;;) {
+            const uint32_t above = __shfl_down_sync(0xFFFFFFFFu, sLeave, 1);
+            const bool redo = lane < top && above != sIn;
+            if (!__any_sync(0xFFFFFFFFu, redo))
+                break;
+            if (redo) {
+                sIn = above;
+                sLeave = wfWalk<R4, true>(sIn, hi, lo, myRows, S, L, sOut);
+            }
+        }
+        __syncwarp();
+        uint8_t *dst = a.out + (size_t)f * a.outStride;
+        for (int i = lane; i < (L >> 3); i += 32)
+            dst[i] = sOut[i];
+    }
+}
+
+} // namespace ced
+
+/* bytes of shared memory a frame of T steps needs */
+static size_t wfSmemBytes(int T, int seg, bool r4, int *survRows, int *outPad)
+{
+    *survRows = (T + T / seg + 9) & ~1;   /* even: what follows stays 16-byte aligned; also holds the staged symbols (T + 46 bytes) */
+    *outPad = ((T >> 3) + 15) / 16 * 16 + 16;
+    const size_t units = r4 ? (size_t)T / 2 : (size_t)T;
+    return (size_t)ced::kWfCostBytes + (size_t)*survRows * sizeof(uint2) + (size_t)*outPad + (units + 12 + 3) / 4 * 16;
+}
+
+/*
+ * ced_decode_batch for at most `maxFrames` frames of a k = 1 code with <= 64 states and n <= 3 (byte format).
+ * CED_ERR_UNSUPPORTED = not a case for this kernel (the caller goes on to the thread-per-frame kernels).
+ */
+int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+{
+    if (!c || !code || code->constraintLen < 3 || code->constraintLen > 7 || code->codedBits < 1 || code->codedBits > 3)
+        return CED_ERR_UNSUPPORTED;
+    const int K = code->constraintLen, S = K - 1, n = code->codedBits, N = 1 << S, H = N / 2;
+    const int T = frameBits + S;
+    const uint32_t init = (uint32_t)(uint8_t)(N + 1);
+    if ((size_t)init + (size_t)n * (size_t)T > 65535u)   /* exact 16-bit metrics without renormalisation */
+        return CED_ERR_UNSUPPORTED;
+    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+        setError("ced_decode_batch: stride shorter than a frame");
+        return CED_ERR_ARG;
+    }
+    ced::WfArgs a;
+    a.seg = (((T + 31) / 32) + 7) & ~7;
+    const char *envRadix = getenv("CED_WARP_FRAME_RADIX");   /* read per call: tests flip it */
+    const bool r4 = K == 7 && n == 2 && !(envRadix && atoi(envRadix) == 2);
+    const size_t smem = wfSmemBytes(T, a.seg, r4, &a.survRows, &a.outPad);
+    if (smem > 200 * 1024)
+        return CED_ERR_UNSUPPORTED;
+    if (nFrames == 0)
+        return CED_OK;
+    /* trellis labels as viterbiInit builds them (src/viterbiDecoder.c:32-50): edge[b][st] = coded segment of the branch
+     * that leaves state st with input bit b */
+    uint32_t taps[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++)
+        taps[i] = reverseBits(code->gen[i], K);
+    auto edge = [&](int b, int st) -> uint32_t {
+        const uint32_t reg = (((uint32_t)st << 1) | (uint32_t)b) & ((1u << K) - 1u);
+        uint32_t segv = 0;
+        for (int i = 0; i < n; i++)
+            segv |= (uint32_t)(__builtin_popcount(reg & taps[i]) & 1) << i;
+        return segv;
+    };
+    auto hd = [&](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & ((1u << n) - 1u)); };
+    memset(a.cost, 0, sizeof(a.cost));
+    for (int rx = 0; rx < (1 << n); rx++)
+        for (int l = 0; l < 32; l++) {
+            /* second step of a pair / the radix-2 step: butterfly j = l: (j -> 2j, j -> 2j+1), (j+H -> 2j, j+H -> 2j+1) */
+            const int j = l & (H - 1);
+            a.cost[1][rx][l] = hd(edge(0, j), rx) | hd(edge(1, j), rx) << 8 | hd(edge(0, j + H), rx) << 16 | hd(edge(1, j + H), rx) << 24;
+            if (r4) {
+                /* first step: lane l = 2q + h makes states l (from q, q+32) and l + 32 (from q+16, q+48); input bit h */
+                const int q = l >> 1, h = l & 1;
+                a.cost[0][rx][l] = hd(edge(h, q), rx) | hd(edge(h, q + 16), rx) << 8 | hd(edge(h, q + 32), rx) << 16 |
+                                   hd(edge(h, q + 48), rx) << 24;
+            }
+        }
+    a.segs = dSegs;
+    a.segStride = segStride;
+    a.out = dOut;
+    a.outStride = outStride;
+    a.nFrames = nFrames;
+    a.T = T;
+    a.S = S;
+    a.n = n;
+    a.initMetric = init;
+    std::lock_guard<std::recursive_mutex> lock(c->mu);
+    CED_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+    auto kernel = r4 ? ced::wfDecodeKernel<true> : ced::wfDecodeKernel<false>;
+    CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int perSm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(220 * 1024) / (smem + 1024)));
+    const int blocks = std::min(nFrames, c->sms * perSm);
+    kernel<<<blocks, 32, smem, s>>>(a);
+    c->launches += 1;
+    CED_CUDA(cudaGetLastError());
+    return CED_OK;
+}
+
+/* largest batch the warp-per-frame kernel takes for frames of frameBits bits (0 = never): CED_WARP_FRAME_MAX overrides */
+int cedWarpFrameMaxFrames(const ced_ctx *c, int frameBits)
+{
+    if (const char *e = getenv("CED_WARP_FRAME_MAX"))   /* read per call: tests flip it */
+        return atoi(e);
+    (void)frameBits;
+    return c ? 4 * c->sms : 0;
+}
