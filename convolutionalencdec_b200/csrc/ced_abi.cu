@@ -435,7 +435,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         return CED_ERR_ARG;
     }
     /* small batches: one warp per frame, decisions in shared memory (warp_frame.cu) */
-    if (!packed && nFrames > 0 && nFrames <= cedWarpFrameMaxFrames(c, frameBits)) {
+    if (!packed && cedWarpFrameTakes(c, code, nFrames, frameBits)) {
         const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
         if (rc != CED_ERR_UNSUPPORTED)
             return rc;
@@ -1525,7 +1525,7 @@ int ced_decode_batch_host(ced_ctx *c, const ced_code_t *code, const uint8_t *hSe
         return CED_OK;
     /* small batches (speedDecode's 16 packets, speedDecode/speedDecode.c:18-19): one copy in, the warp-per-frame kernel
      * (warp_frame.cu), one copy out -- no chunk pipeline, no host-side packing */
-    if (nFrames <= cedWarpFrameMaxFrames(c, frameBits)) {
+    if (cedWarpFrameTakes(c, code, nFrames, frameBits)) {
         std::lock_guard<std::recursive_mutex> lock(c->mu);
         CED_CUDA(cudaSetDevice(c->device));
         const size_t T = (size_t)frameBits + code->constraintLen - 1;

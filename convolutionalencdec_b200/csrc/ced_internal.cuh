@@ -240,7 +240,7 @@ int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, in
  * CED_ERR_UNSUPPORTED = not a case for it */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                             int frameBits, uint8_t *dOut, size_t outStride, void *stream);
-int cedWarpFrameMaxFrames(const ced_ctx *c, int frameBits);
+bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits);
 
 /* swar_generic.cu: continuous streams for the table-driven kernels (K <= 7); CED_ERR_UNSUPPORTED / 0 = not their code */
 size_t cedWindowCarryBytesGeneric(const ced_code_t *code, int nStreams, int depth);

@@ -312,31 +312,76 @@ static size_t wfSmemBytes(int T, int seg, bool r4, int *survRows, int *outPad)
     return (size_t)ced::kWfCostBytes + (size_t)*survRows * sizeof(uint2) + (size_t)*outPad + (units + 12 + 3) / 4 * 16;
 }
 
+/* what a call would run as: radix, traceback segment, shared memory, resident CTAs per SM */
+struct WfPlan {
+    bool ok, r4;
+    int seg, survRows, outPad, perSm;
+    size_t smem;
+};
+
+static WfPlan wfPlan(const ced_code_t *code, int frameBits)
+{
+    WfPlan p = {};
+    if (!code || code->constraintLen < 3 || code->constraintLen > 7 || code->codedBits < 1 || code->codedBits > 3 || frameBits <= 0)
+        return p;
+    const int K = code->constraintLen, n = code->codedBits, T = frameBits + K - 1;
+    const char *envAnyK = getenv("CED_WARP_FRAME_ANY_K");   /* read per call: tests flip them */
+    /* fewer than 32 states leave most lanes idle, and the thread-per-frame kernels of such codes are short chains
+     * themselves (K = 5: ~24 ns per step against ~30 here): only K = 6 and 7 by default */
+    if (K < 6 && !(envAnyK && atoi(envAnyK) != 0))
+        return p;
+    if ((size_t)(uint8_t)((1 << (K - 1)) + 1) + (size_t)n * (size_t)T > 65535u)   /* exact 16-bit metrics without renormalisation */
+        return p;
+    const char *envRadix = getenv("CED_WARP_FRAME_RADIX");
+    p.r4 = K == 7 && n == 2 && !(envRadix && atoi(envRadix) == 2);
+    p.seg = (((T + 31) / 32) + 7) & ~7;
+    p.smem = wfSmemBytes(T, p.seg, p.r4, &p.survRows, &p.outPad);
+    if (p.smem > 200 * 1024)
+        return p;
+    p.perSm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(220 * 1024) / (p.smem + 1024)));
+    p.ok = true;
+    return p;
+}
+
 /*
- * ced_decode_batch for at most `maxFrames` frames of a k = 1 code with <= 64 states and n <= 3 (byte format).
- * CED_ERR_UNSUPPORTED = not a case for this kernel (the caller goes on to the thread-per-frame kernels).
+ * Whether ced_decode_batch hands a batch to this kernel: k = 1 codes with 32 or 64 states and n <= 3, byte format, and
+ * few enough frames -- at most three (radix 4; radix 2: two) rounds of resident one-warp CTAs.  Measured on B200
+ * (tools/small_batch_throughput.py, profiles/small_batch_r2.txt): 2048-bit frames 58 us up to 592 frames, 75 us at
+ * 1024, 135 us at 2048 against 285 .. 320 us on the thread-per-frame kernels; 4096 frames: 258 against 325 us.
+ * CED_WARP_FRAME_MAX = n overrides the frame limit (0 = never).
  */
+bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits)
+{
+    if (!c || nFrames <= 0)
+        return false;
+    const WfPlan p = wfPlan(code, frameBits);
+    if (!p.ok)
+        return false;
+    if (const char *e = getenv("CED_WARP_FRAME_MAX"))
+        return nFrames <= atoi(e);
+    return nFrames <= (p.r4 ? 3 : 2) * c->sms * p.perSm;
+}
+
+/* ced_decode_batch for a batch cedWarpFrameTakes() said yes to (CED_ERR_UNSUPPORTED otherwise) */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                             int frameBits, uint8_t *dOut, size_t outStride, void *stream)
 {
-    if (!c || !code || code->constraintLen < 3 || code->constraintLen > 7 || code->codedBits < 1 || code->codedBits > 3)
+    const WfPlan plan = wfPlan(code, frameBits);
+    if (!c || !plan.ok)
         return CED_ERR_UNSUPPORTED;
     const int K = code->constraintLen, S = K - 1, n = code->codedBits, N = 1 << S, H = N / 2;
     const int T = frameBits + S;
     const uint32_t init = (uint32_t)(uint8_t)(N + 1);
-    if ((size_t)init + (size_t)n * (size_t)T > 65535u)   /* exact 16-bit metrics without renormalisation */
-        return CED_ERR_UNSUPPORTED;
     if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
         setError("ced_decode_batch: stride shorter than a frame");
         return CED_ERR_ARG;
     }
     ced::WfArgs a;
-    a.seg = (((T + 31) / 32) + 7) & ~7;
-    const char *envRadix = getenv("CED_WARP_FRAME_RADIX");   /* read per call: tests flip it */
-    const bool r4 = K == 7 && n == 2 && !(envRadix && atoi(envRadix) == 2);
-    const size_t smem = wfSmemBytes(T, a.seg, r4, &a.survRows, &a.outPad);
-    if (smem > 200 * 1024)
-        return CED_ERR_UNSUPPORTED;
+    a.seg = plan.seg;
+    a.survRows = plan.survRows;
+    a.outPad = plan.outPad;
+    const bool r4 = plan.r4;
+    const size_t smem = plan.smem;
     if (nFrames == 0)
         return CED_OK;
     /* trellis labels as viterbiInit builds them (src/viterbiDecoder.c:32-50): edge[b][st] = coded segment of the branch
@@ -379,19 +424,10 @@ int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     auto kernel = r4 ? ced::wfDecodeKernel<true> : ced::wfDecodeKernel<false>;
     CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int perSm = (int)std::max<size_t>(1, std::min<size_t>(32, (size_t)(220 * 1024) / (smem + 1024)));
-    const int blocks = std::min(nFrames, c->sms * perSm);
+    const int blocks = std::min(nFrames, c->sms * plan.perSm);
     kernel<<<blocks, 32, smem, s>>>(a);
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
 }
 
-/* largest batch the warp-per-frame kernel takes for frames of frameBits bits (0 = never): CED_WARP_FRAME_MAX overrides */
-int cedWarpFrameMaxFrames(const ced_ctx *c, int frameBits)
-{
-    if (const char *e = getenv("CED_WARP_FRAME_MAX"))   /* read per call: tests flip it */
-        return atoi(e);
-    (void)frameBits;
-    return c ? 4 * c->sms : 0;
-}

@@ -24,7 +24,7 @@ def ctx():
 
 @pytest.fixture
 def env():
-    saved = {k: os.environ.get(k) for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX")}
+    saved = {k: os.environ.get(k) for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K")}
     yield os.environ
     for k, v in saved.items():
         if v is None:
@@ -86,9 +86,10 @@ def test_small_batches_of_other_codes(ctx, port, env, K, g):
     rng = np.random.default_rng(K * 131 + sum(g))
     n = len(g)
     code = ced.Code(K, g)
-    for radix in ((4, 2) if K == 7 else (2,)):
+    env["CED_WARP_FRAME_ANY_K"] = "1"   # by default only K = 6 and 7 come here (fewer states leave most lanes idle)
+    for radix in ((4, 2) if K == 7 and n == 2 else (2,)):
         env["CED_WARP_FRAME_RADIX"] = str(radix)
-        for frames, bits, p in ((1, 16, 0.0), (20, 2048, 0.03), (70, 512, 0.5), (9, 4096, 0.1)):
+        for frames, bits, p in ((1, 16, 0.0), (20, 2048, 0.03), (70, 512, 0.5), (9, 4096, 0.1)):  # noqa
             msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
             rx = noisy(rng, port.encode_batch(K, list(g), msgs), n, p)
             want = port.decode_batch(K, list(g), rx, bits + K - 1, symmetric=False)
@@ -140,3 +141,27 @@ def test_small_host_batches_take_the_direct_route(ctx, port, env):
         ctx.decode_batch_host(ced.K7_DEFAULT, h_in, bits, h_out)
         assert ctx.launches - before == 1
         assert np.array_equal(h_out, port.decode_batch(7, K7, rx, T)), (frames, bits, pad, pinned)
+
+
+def test_which_batches_take_the_warp_per_frame_kernel(ctx, env):
+    """Default selection: K = 6 and 7 only, a few rounds of resident CTAs at most; CED_WARP_FRAME_MAX overrides."""
+    import torch
+    for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K"):
+        env.pop(k, None)
+
+    def launches(code, frames, bits):
+        segs = torch.zeros((frames, bits + 16), dtype=torch.uint8, device="cuda")
+        before = ctx.launches
+        ctx.decode_batch(code, segs, bits)
+        ctx.sync()
+        return ctx.launches - before
+
+    assert launches(ced.K7_DEFAULT, 16, 2048) == 1
+    assert launches(ced.K7_DEFAULT, 2048, 2048) == 1
+    assert launches(ced.K7_DEFAULT, 8192, 2048) == 2          # forward + traceback of the thread-per-frame path
+    assert launches(ced.Code(7, (0o133, 0o145, 0o175)), 64, 1024) == 1
+    assert launches(ced.Code(6, (0o53, 0o75)), 64, 1024) == 1
+    assert launches(ced.Code(5, (0o23, 0o35)), 64, 1024) == 2
+    assert launches(ced.Code(3, (7, 6)), 64, 1024) == 2
+    env["CED_WARP_FRAME_MAX"] = "0"
+    assert launches(ced.K7_DEFAULT, 16, 2048) == 2

@@ -55,6 +55,12 @@ while time.time() < t_end:
     p = float(rng.choice([0.0, 0.02, 0.06, 0.2, 0.5]))
     msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
     tag = kind
+    # small batches of K = 6, 7 codes: the warp-per-frame kernel (the library's default) or the thread-per-frame kernels
+    if rng.integers(0, 2):
+        os.environ["CED_WARP_FRAME_MAX"] = "0"
+    else:
+        os.environ.pop("CED_WARP_FRAME_MAX", None)
+    os.environ["CED_WARP_FRAME_RADIX"] = str(int(rng.choice([2, 4])))
     if kind == "enc":
         k = int(rng.choice([1, 1, 2]))
         K = int(rng.integers(2, 10)) if k == 1 else int(rng.integers(2, 6))
