@@ -209,6 +209,31 @@ def per_packet_rate(seconds, bits=2048):
                    "(the call speedDecode.c:79 makes); whole packet decoded at once by fpBlockKernel + fpSelectKernel"}
 
 
+def small_batch_rate(ctx, seconds, packets=16, bits=2048):
+    """speedDecode's shape -- 16 packets of 2048 bits (speedDecode.c:18-19) -- as ONE ced_decode_batch_host call from
+    pageable host buffers: one copy in, the warp-per-frame kernel (csrc/warp_frame.cu), one copy out."""
+    import numpy as np
+    import convolutionalencdec_b200 as ced
+    rng = np.random.default_rng(314)
+    msgs = rng.integers(0, 256, (packets, bits // 8), dtype=np.uint8)
+    segs = np.zeros((packets, bits + 6), dtype=np.uint8)
+    ctx.encode_batch_host(ced.K7_DEFAULT, msgs, segs)
+    out = np.zeros((packets, bits // 8), dtype=np.uint8)
+    launches0 = ctx.launches
+    for _ in range(10):
+        ctx.decode_batch_host(ced.K7_DEFAULT, segs, bits, out)
+    ok = bool(np.array_equal(out, msgs))
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        ctx.decode_batch_host(ced.K7_DEFAULT, segs, bits, out)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * packets * bits / dt / 1e6, "unit": "Mbit/s", "us_per_call": dt / n * 1e6, "packets_per_call": packets,
+            "packet_bits": bits, "calls": n, "gpu_launches": ctx.launches - launches0, "round_trip_ok": ok,
+            "api": "ced_decode_batch_host, pageable host buffers, one synchronous call per %d packets: warp-per-frame kernel "
+                   "(one warp per packet, radix-4 steps, decisions in shared memory, warp-parallel traceback)" % packets}
+
+
 def per_packet_reference_rate(seconds, bits=2048):
     """The same loop on the reference's own C decoder, one host core (oracle/_ref)."""
     import numpy as np
@@ -719,6 +744,7 @@ def main():
         # the reference's own driver shape: ONE 2048-bit packet per synchronous VITERBI_DECODER_HARD call
         # (speedDecode.c:18-23,79) through the drop-in host C library, next to the reference C on one core
         line["per_packet"] = per_packet_rate(1.0)
+        line["small_batch"] = small_batch_rate(ctx, 1.0)
         line["cpu_baseline"]["one_core_2048_bit_packets"] = per_packet_reference_rate(1.0)
 
     if rank == 0:

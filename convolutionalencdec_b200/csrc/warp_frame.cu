@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
     const uint32_t rxMask = (1u << a.n) - 1u;
     auto spread = [](uint32_t u) { return make_uint2((u & 0xFFu) | ((u >> 8 & 0xFFu) << 16), (u >> 16 & 0xFFu) | ((u >> 24) << 16)); };
     if (R4) {
+#pragma unroll 4
         for (int i = lane; i < 16 * 32; i += 32) {
             const uint2 c1 = spread(a.cost[0][(i >> 5) & 3][lane]), c2 = spread(a.cost[1][i >> 7][lane]);
             reinterpret_cast<uint4 *>(wfSmem)[i] = make_uint4(c1.x, c1.y, c2.x, c2.y);
@@ -165,13 +166,29 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
         for (int q = lane; q < nq; q += 32)
             reinterpret_cast<uint4 *>(sSurv)[q] = __ldg(src + q);
         __syncwarp();
-        const uint8_t *sym = reinterpret_cast<const uint8_t *>(sSurv) + off;
+        const uint32_t *symW = reinterpret_cast<const uint32_t *>(sSurv) + (off >> 2);
+        const uint32_t sh = (off & 3u) * 8u;
         const int units = R4 ? T >> 1 : T;
-        for (int u = lane; u < units + 12; u += 32) {
-            uint32_t o = 0;
-            if (u < units)
-                o = R4 ? ((sym[2 * u] & 3u) | ((sym[2 * u + 1] & 3u) << 2)) * 512u : (sym[u] & rxMask) * 256u;
-            sOffs[u] = o;
+        for (int g = lane; 4 * g < units + 12; g += 32) {   /* four units per lane and round; padding units get offset 0 */
+            uint32_t o[4];
+            if (R4) {
+                const uint32_t w0 = __funnelshift_r(symW[2 * g], symW[2 * g + 1], sh);
+                const uint32_t w1 = __funnelshift_r(symW[2 * g + 1], symW[2 * g + 2], sh);
+                o[0] = ((w0 & 3u) | ((w0 >> 6) & 12u)) * 512u;
+                o[1] = (((w0 >> 16) & 3u) | ((w0 >> 22) & 12u)) * 512u;
+                o[2] = ((w1 & 3u) | ((w1 >> 6) & 12u)) * 512u;
+                o[3] = (((w1 >> 16) & 3u) | ((w1 >> 22) & 12u)) * 512u;
+            } else {
+                const uint32_t w0 = __funnelshift_r(symW[g], symW[g + 1], sh);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    o[k] = ((w0 >> (8 * k)) & rxMask) * 256u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (4 * g + k >= units)
+                    o[k] = 0;
+            reinterpret_cast<uint4 *>(sOffs)[g] = make_uint4(o[0], o[1], o[2], o[3]);
         }
         __syncwarp();
 

@@ -13,8 +13,9 @@ BASE_KEYS = ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def _run(args, timeout):
+    env = {k: v for k, v in os.environ.items() if not k.startswith("CED_WARP_FRAME")}   # bench.py runs the library as shipped
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
-                       timeout=timeout, cwd=ROOT)
+                       timeout=timeout, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout[-2000:]           # ONE line, nothing else on stdout
@@ -63,3 +64,5 @@ def test_our_arm_line():
     assert soft["roofline"]["kernel"] == "k7SoftForwardKernel" and soft["value"] > 1.0 and soft["check"]["ber"] < 2e-3
     pp = d["per_packet"]                       # one 2048-bit packet per call: the two frame-parallel kernels each time
     assert pp["round_trip_ok"] is True and pp["gpu_launches"] == 2 * (pp["calls"] + 64) and pp["value"] > 0
+    sb = d["small_batch"]                      # 16 such packets per call: ONE launch of the warp-per-frame kernel each time
+    assert sb["round_trip_ok"] is True and sb["gpu_launches"] == sb["calls"] + 10 and sb["value"] > pp["value"]
