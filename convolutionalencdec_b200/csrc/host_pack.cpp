@@ -10,6 +10,7 @@
  */
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -61,6 +62,23 @@ __attribute__((target("avx2"))) static void packRowAvx2(const uint8_t *in, int s
     if (t < segs)
         packRowScalar(in + t, segs - t, out + o);
 }
+
+/* 64 segments -> 16 bytes per round: two multiply-adds and one narrowing move (VPMOVDB) */
+__attribute__((target("avx512f,avx512bw"))) static void packRowAvx512(const uint8_t *in, int segs, uint8_t *out)
+{
+    const __m512i three = _mm512_set1_epi8(3);
+    const __m512i mul1 = _mm512_set1_epi16(0x0401);
+    const __m512i mul2 = _mm512_set1_epi32(0x00100001);
+    int t = 0, o = 0;
+    for (; t + 64 <= segs; t += 64, o += 16) {
+        __m512i v = _mm512_and_si512(_mm512_loadu_si512(reinterpret_cast<const void *>(in + t)), three);
+        v = _mm512_maddubs_epi16(v, mul1);
+        v = _mm512_madd_epi16(v, mul2);                  /* 16 x int32, each one packed byte */
+        _mm_storeu_si128(reinterpret_cast<__m128i *>(out + o), _mm512_cvtepi32_epi8(v));
+    }
+    if (t < segs)
+        packRowAvx2(in + t, segs - t, out + o);
+}
 #endif
 
 using PackRowFn = void (*)(const uint8_t *, int, uint8_t *);
@@ -68,6 +86,9 @@ using PackRowFn = void (*)(const uint8_t *, int, uint8_t *);
 static PackRowFn pickPackRow()
 {
 #if defined(__x86_64__)
+    const char *env = getenv("CED_HOST_PACK_ISA");   /* "avx2" keeps the 256-bit loop on an AVX-512 host */
+    if (__builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") && !(env && !strcmp(env, "avx2")))
+        return packRowAvx512;
     if (__builtin_cpu_supports("avx2"))
         return packRowAvx2;
 #endif
