@@ -436,7 +436,7 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
     }
     /* small batches: one warp per frame, decisions in shared memory (warp_frame.cu) */
     if (!packed && cedWarpFrameTakes(c, code, nFrames, frameBits)) {
-        const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream);
+        const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
         if (rc != CED_ERR_UNSUPPORTED)
             return rc;
     }

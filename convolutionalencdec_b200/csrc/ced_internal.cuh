@@ -239,7 +239,10 @@ int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, in
 /* warp_frame.cu: small batches, one warp per frame (k = 1 codes with <= 64 states, n <= 3, byte format);
  * CED_ERR_UNSUPPORTED = not a case for it */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream);
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0);
+/* warp_split.cu: the same for so few frames of a 64-state rate-1/2 code that they are cut into blocks in time as well */
+int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
 bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits);
 
 /* swar_generic.cu: continuous streams for the table-driven kernels (K <= 7); CED_ERR_UNSUPPORTED / 0 = not their code */

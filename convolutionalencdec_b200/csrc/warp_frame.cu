@@ -27,92 +27,9 @@
  *
  * No global scratch: a CTA is one warp with (9 T + 4.5 K) bytes of shared memory.
  */
-#include "ced_internal.cuh"
-
-#include <type_traits>
+#include "warp_frame.cuh"
 
 namespace ced {
-
-constexpr int kWfMaxV = 8;          /* received symbols: n <= 3 */
-constexpr int kWfCostBytes = 16 * 32 * (int)sizeof(uint4);   /* radix 4: [rx1 | rx2 << 2][lane] uint4; radix 2: [rx][lane] uint2 */
-
-struct WfArgs {
-    const uint8_t *segs;
-    size_t segStride;
-    uint8_t *out;
-    size_t outStride;
-    int nFrames, T, S, n;
-    int seg;               /* traceback: steps per lane, a multiple of 8 */
-    int survRows;          /* >= T + T / seg, even */
-    int outPad;            /* bytes of the output row in shared memory, a multiple of 16 */
-    uint32_t initMetric;   /* (uint8_t)(NUM_STATES + 1), :59-67 */
-    uint32_t cost[2][kWfMaxV][32]; /* [second step of a radix-4 pair / radix-2 step = 1, first = 0][rx][lane]: 4 costs as bytes */
-};
-
-/* one step back from state s over a row in the radix-2 format (x: successors 2j, y: successors 2j+1; bit j) */
-template <int S>
-__device__ __forceinline__ void wfBackOdd(uint32_t &s, const uint2 w)
-{
-    const uint32_t word = (s & 1u) ? w.y : w.x;
-    const uint32_t dec = (word >> (s >> 1)) & 1u;
-    s = (s >> 1) | (dec << (S - 1));
-}
-__device__ __forceinline__ void wfBackOddRt(uint32_t &s, const uint2 w, int S)
-{
-    const uint32_t word = (s & 1u) ? w.y : w.x;
-    const uint32_t dec = (word >> (s >> 1)) & 1u;
-    s = (s >> 1) | (dec << (S - 1));
-}
-/* ... over a row in the state-indexed format of the first step of a radix-4 pair (x: states 0..31, y: 32..63) */
-__device__ __forceinline__ void wfBackEven(uint32_t &s, const uint2 w)
-{
-    const uint32_t word = (s & 32u) ? w.y : w.x;
-    const uint32_t dec = (word >> (s & 31u)) & 1u;
-    s = (s >> 1) | (dec << 5);
-}
-
-/* walk steps [tLo, tHi) downwards from state s (tLo a multiple of 8); EMIT: bits of steps < L go to sOut, MSb first */
-template <bool R4, bool EMIT>
-__device__ __forceinline__ uint32_t wfWalk(uint32_t s, int tHi, int tLo, const uint2 *rows, int S, int L, uint8_t *sOut)
-{
-    int t = tHi - 1;
-    uint32_t acc = 0;
-    for (; t >= tLo && (t & 7) != 7; t--) {   /* ragged top: only where a walk starts at the end of the frame */
-        const uint32_t bit = s & 1u;
-        if (R4 && !(t & 1))
-            wfBackEven(s, rows[t - tLo]);
-        else
-            wfBackOddRt(s, rows[t - tLo], S);
-        if (EMIT && t < L) {
-            acc = (acc >> 1) | (bit << 7);
-            if ((t & 7) == 0) {
-                sOut[t >> 3] = (uint8_t)acc;
-                acc = 0;
-            }
-        }
-    }
-    for (; t >= tLo; t -= 8) {   /* t + 1 is a multiple of 8: whole bytes; the rows do not depend on the path */
-        const int tb = t - 7;
-        uint2 w[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            w[q] = rows[tb - tLo + q];
-        uint32_t byte = 0;
-#pragma unroll
-        for (int q = 7; q >= 0; q--) {
-            byte |= (s & 1u) << (7 - q);   /* step tb + q is bit 7 - q of byte tb / 8 (:249) */
-            if (R4 && !(q & 1))
-                wfBackEven(s, w[q]);
-            else if (R4)
-                wfBackOdd<6>(s, w[q]);
-            else
-                wfBackOddRt(s, w[q], S);
-        }
-        if (EMIT && tb < L)
-            sOut[tb >> 3] = (uint8_t)byte;
-    }
-    return s;
-}
 
 template <bool R4>
 __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfArgs a)
@@ -125,17 +42,7 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
     const int lane = threadIdx.x, T = a.T, S = a.S, L = T - S, seg = a.seg;
     const int H = 1 << (S - 1);
     const uint32_t rxMask = (1u << a.n) - 1u;
-    auto spread = [](uint32_t u) { return make_uint2((u & 0xFFu) | ((u >> 8 & 0xFFu) << 16), (u >> 16 & 0xFFu) | ((u >> 24) << 16)); };
-    if (R4) {
-#pragma unroll 4
-        for (int i = lane; i < 16 * 32; i += 32) {
-            const uint2 c1 = spread(a.cost[0][(i >> 5) & 3][lane]), c2 = spread(a.cost[1][i >> 7][lane]);
-            reinterpret_cast<uint4 *>(wfSmem)[i] = make_uint4(c1.x, c1.y, c2.x, c2.y);
-        }
-    } else {
-        for (int i = lane; i < kWfMaxV * 32; i += 32)
-            reinterpret_cast<uint2 *>(wfSmem)[i] = spread(a.cost[1][i >> 5][lane]);
-    }
+    wfBuildCostTable<R4>(a.cost, wfSmem, lane);
 
     /* operands of the next step: which lane holds them, which half */
     uint32_t src0, src1, src2 = 0, src3 = 0, sel0, sel1;
@@ -289,28 +196,7 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
             unit(k == 0 ? cA[0] : k == 1 ? cA[1] : cA[2]);
         __syncwarp();
 
-        /* warp-parallel traceback */
-        const int top = (T - 1) / seg;
-        const int lo = lane * seg, hi = min(T, lo + seg);
-        const uint2 *myRows = sSurv + lo + lane;   /* row of step t at t + t / seg */
-        uint32_t sIn = 0;
-        if (lane < top) {
-            const int wHi = min(T, hi + seg);      /* warm-up over the steps of the lane above, from state 0 */
-            sIn = wfWalk<R4, false>(0u, wHi, hi, sSurv + hi + lane + 1, S, L, sOut);
-        }
-        uint32_t sLeave = 0;
-        if (lane <= top)
-            sLeave = wfWalk<R4, true>(sIn, hi, lo, myRows, S, L, sOut);
-        for (;;) {
-            const uint32_t above = __shfl_down_sync(0xFFFFFFFFu, sLeave, 1);
-            const bool redo = lane < top && above != sIn;
-            if (!__any_sync(0xFFFFFFFFu, redo))
-                break;
-            if (redo) {
-                sIn = above;
-                sLeave = wfWalk<R4, true>(sIn, hi, lo, myRows, S, L, sOut);
-            }
-        }
+        wfTraceback<R4>(sSurv, T, S, seg, sOut, lane);   /* warp-parallel, exact */
         __syncwarp();
         uint8_t *dst = a.out + (size_t)f * a.outStride;
         for (int i = lane; i < (L >> 3); i += 32)
@@ -360,6 +246,38 @@ static WfPlan wfPlan(const ced_code_t *code, int frameBits)
     return p;
 }
 
+/* branch costs per lane and received symbol, four bytes per entry (WfArgs::cost) */
+void cedWarpFrameCosts(const ced_code_t *code, bool r4, uint32_t (&cost)[2][ced::kWfMaxV][32])
+{
+    const int K = code->constraintLen, n = code->codedBits, H = (1 << (K - 1)) / 2;
+    /* trellis labels as viterbiInit builds them (src/viterbiDecoder.c:32-50): edge[b][st] = coded segment of the branch
+     * that leaves state st with input bit b */
+    uint32_t taps[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++)
+        taps[i] = reverseBits(code->gen[i], K);
+    auto edge = [&](int b, int st) -> uint32_t {
+        const uint32_t reg = (((uint32_t)st << 1) | (uint32_t)b) & ((1u << K) - 1u);
+        uint32_t segv = 0;
+        for (int i = 0; i < n; i++)
+            segv |= (uint32_t)(__builtin_popcount(reg & taps[i]) & 1) << i;
+        return segv;
+    };
+    auto hd = [&](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & ((1u << n) - 1u)); };
+    memset(cost, 0, sizeof(cost));
+    for (int rx = 0; rx < (1 << n); rx++)
+        for (int l = 0; l < 32; l++) {
+            /* second step of a pair / the radix-2 step: butterfly j = l: (j -> 2j, j -> 2j+1), (j+H -> 2j, j+H -> 2j+1) */
+            const int j = l & (H - 1);
+            cost[1][rx][l] = hd(edge(0, j), rx) | hd(edge(1, j), rx) << 8 | hd(edge(0, j + H), rx) << 16 | hd(edge(1, j + H), rx) << 24;
+            if (r4) {
+                /* first step: lane l = 2q + h makes states l (from q, q+32) and l + 32 (from q+16, q+48); input bit h */
+                const int q = l >> 1, h = l & 1;
+                cost[0][rx][l] = hd(edge(h, q), rx) | hd(edge(h, q + 16), rx) << 8 | hd(edge(h, q + 32), rx) << 16 |
+                                   hd(edge(h, q + 48), rx) << 24;
+            }
+        }
+}
+
 /*
  * Whether ced_decode_batch hands a batch to this kernel: k = 1 codes with 32 or 64 states and n <= 3, byte format, and
  * few enough frames -- at most three (radix 4; radix 2: two) rounds of resident one-warp CTAs.  Measured on B200
@@ -381,12 +299,17 @@ bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, in
 
 /* ced_decode_batch for a batch cedWarpFrameTakes() said yes to (CED_ERR_UNSUPPORTED otherwise) */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream)
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
 {
     const WfPlan plan = wfPlan(code, frameBits);
     if (!c || !plan.ok)
         return CED_ERR_UNSUPPORTED;
-    const int K = code->constraintLen, S = K - 1, n = code->codedBits, N = 1 << S, H = N / 2;
+    if (plan.r4) {   /* so few frames that cutting them in time as well pays (warp_split.cu) */
+        const int rc = cedDecodeBatchWarpSplit(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
+        if (rc != CED_ERR_UNSUPPORTED)
+            return rc;
+    }
+    const int K = code->constraintLen, S = K - 1, n = code->codedBits, N = 1 << S;
     const int T = frameBits + S;
     const uint32_t init = (uint32_t)(uint8_t)(N + 1);
     if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
@@ -401,32 +324,7 @@ int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     const size_t smem = plan.smem;
     if (nFrames == 0)
         return CED_OK;
-    /* trellis labels as viterbiInit builds them (src/viterbiDecoder.c:32-50): edge[b][st] = coded segment of the branch
-     * that leaves state st with input bit b */
-    uint32_t taps[3] = {0, 0, 0};
-    for (int i = 0; i < n; i++)
-        taps[i] = reverseBits(code->gen[i], K);
-    auto edge = [&](int b, int st) -> uint32_t {
-        const uint32_t reg = (((uint32_t)st << 1) | (uint32_t)b) & ((1u << K) - 1u);
-        uint32_t segv = 0;
-        for (int i = 0; i < n; i++)
-            segv |= (uint32_t)(__builtin_popcount(reg & taps[i]) & 1) << i;
-        return segv;
-    };
-    auto hd = [&](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & ((1u << n) - 1u)); };
-    memset(a.cost, 0, sizeof(a.cost));
-    for (int rx = 0; rx < (1 << n); rx++)
-        for (int l = 0; l < 32; l++) {
-            /* second step of a pair / the radix-2 step: butterfly j = l: (j -> 2j, j -> 2j+1), (j+H -> 2j, j+H -> 2j+1) */
-            const int j = l & (H - 1);
-            a.cost[1][rx][l] = hd(edge(0, j), rx) | hd(edge(1, j), rx) << 8 | hd(edge(0, j + H), rx) << 16 | hd(edge(1, j + H), rx) << 24;
-            if (r4) {
-                /* first step: lane l = 2q + h makes states l (from q, q+32) and l + 32 (from q+16, q+48); input bit h */
-                const int q = l >> 1, h = l & 1;
-                a.cost[0][rx][l] = hd(edge(h, q), rx) | hd(edge(h, q + 16), rx) << 8 | hd(edge(h, q + 32), rx) << 16 |
-                                   hd(edge(h, q + 48), rx) << 24;
-            }
-        }
+    cedWarpFrameCosts(code, r4, a.cost);
     a.segs = dSegs;
     a.segStride = segStride;
     a.out = dOut;

@@ -24,7 +24,10 @@ def ctx():
 
 @pytest.fixture
 def env():
-    saved = {k: os.environ.get(k) for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K")}
+    keys = ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K", "CED_WARP_SPLIT", "CED_WARP_SPLIT_WARMUP",
+            "CED_WARP_SPLIT_LEN")
+    saved = {k: os.environ.get(k) for k in keys}
+    os.environ["CED_WARP_SPLIT"] = "0"    # the tests of the one-warp-per-frame kernel; the split tests switch it on
     yield os.environ
     for k, v in saved.items():
         if v is None:
@@ -146,7 +149,7 @@ def test_small_host_batches_take_the_direct_route(ctx, port, env):
 def test_which_batches_take_the_warp_per_frame_kernel(ctx, env):
     """Default selection: K = 6 and 7 only, a few rounds of resident CTAs at most; CED_WARP_FRAME_MAX overrides."""
     import torch
-    for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K"):
+    for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_FRAME_ANY_K", "CED_WARP_SPLIT"):
         env.pop(k, None)
 
     def launches(code, frames, bits):
@@ -156,7 +159,9 @@ def test_which_batches_take_the_warp_per_frame_kernel(ctx, env):
         ctx.sync()
         return ctx.launches - before
 
-    assert launches(ced.K7_DEFAULT, 16, 2048) == 1
+    assert launches(ced.K7_DEFAULT, 16, 2048) == 2            # cut in time as well: block kernel + join kernel
+    assert launches(ced.K7_DEFAULT, 200, 4096) == 2
+    assert launches(ced.K7_DEFAULT, 400, 2048) == 1           # one warp per frame
     assert launches(ced.K7_DEFAULT, 2048, 2048) == 1
     assert launches(ced.K7_DEFAULT, 8192, 2048) == 2          # forward + traceback of the thread-per-frame path
     assert launches(ced.Code(7, (0o133, 0o145, 0o175)), 64, 1024) == 1
@@ -165,3 +170,30 @@ def test_which_batches_take_the_warp_per_frame_kernel(ctx, env):
     assert launches(ced.Code(3, (7, 6)), 64, 1024) == 2
     env["CED_WARP_FRAME_MAX"] = "0"
     assert launches(ced.K7_DEFAULT, 16, 2048) == 2
+
+
+@pytest.mark.parametrize("warmup,length", [(None, None), (8, 64), (96, 8), (24, 200), (4096, 64)])
+def test_frames_cut_in_time(ctx, port, env, warmup, length):
+    """warp_split.cu: every (frame, block) on its own warp from guessed metrics, hand-overs checked, blocks whose guess
+    was wrong run again.  Short warm-ups and pure-noise frames make wrong guesses the rule, a warm-up longer than the
+    frame makes every block start from step 0; the result is the oracle's bit for bit either way."""
+    env.pop("CED_WARP_SPLIT")
+    if warmup:
+        env["CED_WARP_SPLIT_WARMUP"], env["CED_WARP_SPLIT_LEN"] = str(warmup), str(length)
+    rng = np.random.default_rng(77 + (warmup or 0))
+    for g in (K7, [0o133, 0o171], [0o133, 0o170]):
+        code = ced.Code(7, g)
+        for frames, bits, p, pad, off in ((1, 2048, 0.0, 0, 0), (1, 2048, 0.04, 0, 3), (16, 2048, 0.0377, 0, 0), (16, 2048, 0.5, 3, 5),
+                                          (3, 8192, 0.08, 1, 9), (40, 512, 0.5, 0, 0), (7, 128, 0.1, 2, 1), (2, 16384, 0.5, 0, 0),
+                                          (100, 4096, 0.03, 16, 0)):
+            msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+            rx = noisy(rng, port.encode_batch(7, g, msgs), 2, p, junk=True)
+            want = port.decode_batch(7, g, rx & 3, bits + 6, symmetric=False)
+            before = ctx.launches
+            got = ctx.decode_batch(code, place(rx, pad, off), bits)
+            ctx.sync()
+            if bits + 6 > (length or 64):          # a frame of one block is not cut
+                assert ctx.launches - before == 2, "not the block + join kernels"
+            assert np.array_equal(got.cpu().numpy(), want), (g, frames, bits, p, pad, off)
+            if p == 0.0:
+                assert np.array_equal(want, msgs)

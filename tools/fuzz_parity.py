@@ -61,6 +61,8 @@ while time.time() < t_end:
     else:
         os.environ.pop("CED_WARP_FRAME_MAX", None)
     os.environ["CED_WARP_FRAME_RADIX"] = str(int(rng.choice([2, 4])))
+    os.environ["CED_WARP_SPLIT"] = str(int(rng.integers(0, 2)))             # frames cut in time as well (warp_split.cu)
+    os.environ["CED_WARP_SPLIT_WARMUP"] = str(int(rng.choice([8, 48, 96])))
     if kind == "enc":
         k = int(rng.choice([1, 1, 2]))
         K = int(rng.integers(2, 10)) if k == 1 else int(rng.integers(2, 6))

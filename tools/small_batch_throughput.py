@@ -37,7 +37,7 @@ def timed(fn, reps):
     return float(np.median(ts))
 
 
-print("frames  bits   thread-per-frame us   warp-per-frame us (radix 2)   (radix 4)   gain   Gbit/s")
+print("frames  bits   thread-per-frame us   warp-per-frame us (radix 2)   (radix 4)   cut in time   gain   Gbit/s")
 for bits in (2048, 4096):
     for frames in (1, 16, 64, 148, 296, 592, 1024, 2048, 4096):
         msgs = torch.from_numpy(rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)).cuda()
@@ -46,16 +46,20 @@ for bits in (2048, 4096):
         ctx.bsc_channel(segs, bits + 6, 2, 0.0377, seed=2)
         out = torch.zeros((frames, bits // 8), dtype=torch.uint8, device="cuda")
         res = {}
-        for name, env in (("tpf", {"CED_WARP_FRAME_MAX": "0"}), ("r2", {"CED_WARP_FRAME_MAX": "100000", "CED_WARP_FRAME_RADIX": "2"}),
-                          ("r4", {"CED_WARP_FRAME_MAX": "100000", "CED_WARP_FRAME_RADIX": "4"})):
+        for name, env in (("tpf", {"CED_WARP_FRAME_MAX": "0", "CED_WARP_SPLIT": "0"}),
+                          ("r2", {"CED_WARP_FRAME_MAX": "100000", "CED_WARP_FRAME_RADIX": "2"}),
+                          ("r4", {"CED_WARP_FRAME_MAX": "100000", "CED_WARP_FRAME_RADIX": "4"}),
+                          ("split", {"CED_WARP_SPLIT": "1"})):
             os.environ.update(env)
             res[name] = timed(lambda: ctx.decode_batch(code, segs, bits, out=out), reps)
             res[name + "_out"] = out.clone()
         assert torch.equal(res["tpf_out"], res["r2_out"]) and torch.equal(res["tpf_out"], res["r4_out"])
-        print("%6d %5d %12.1f %22.1f %18.1f %9.2f %8.2f" % (frames, bits, res["tpf"], res["r2"], res["r4"],
-                                                             res["tpf"] / res["r4"], frames * bits / res["r4"] / 1e3))
-os.environ.pop("CED_WARP_FRAME_MAX")
-os.environ.pop("CED_WARP_FRAME_RADIX")
+        assert torch.equal(res["tpf_out"], res["split_out"])
+        best = min(res["r4"], res["split"])
+        print("%6d %5d %12.1f %22.1f %18.1f %12.1f %9.2f %8.2f" % (frames, bits, res["tpf"], res["r2"], res["r4"], res["split"],
+                                                                    res["tpf"] / best, frames * bits / best / 1e3))
+for k in ("CED_WARP_FRAME_MAX", "CED_WARP_FRAME_RADIX", "CED_WARP_SPLIT"):
+    os.environ.pop(k, None)
 
 # speedDecode's shape from host buffers
 bits, T = 2048, 2054
