@@ -211,7 +211,7 @@ def per_packet_rate(seconds, bits=2048):
 
 def small_batch_rate(ctx, seconds, packets=16, bits=2048):
     """speedDecode's shape -- 16 packets of 2048 bits (speedDecode.c:18-19) -- as ONE ced_decode_batch_host call from
-    pageable host buffers: one copy in, the warp-per-frame kernel (csrc/warp_frame.cu), one copy out."""
+    pageable host buffers: one copy in, the small-batch kernels (csrc/warp_split.cu, warp_frame.cu), one copy out."""
     import numpy as np
     import convolutionalencdec_b200 as ced
     rng = np.random.default_rng(314)
@@ -230,8 +230,9 @@ def small_batch_rate(ctx, seconds, packets=16, bits=2048):
     dt = time.perf_counter() - t0
     return {"value": n * packets * bits / dt / 1e6, "unit": "Mbit/s", "us_per_call": dt / n * 1e6, "packets_per_call": packets,
             "packet_bits": bits, "calls": n, "gpu_launches": ctx.launches - launches0, "round_trip_ok": ok,
-            "api": "ced_decode_batch_host, pageable host buffers, one synchronous call per %d packets: warp-per-frame kernel "
-                   "(one warp per packet, radix-4 steps, decisions in shared memory, warp-parallel traceback)" % packets}
+            "api": "ced_decode_batch_host, pageable host buffers, one synchronous call per %d packets: packets cut into "
+                   "blocks in time, one warp per block from speculative start metrics (radix-4 steps), hand-overs checked and "
+                   "wrong guesses re-run by the join kernel, warp-parallel traceback" % packets}
 
 
 def per_packet_reference_rate(seconds, bits=2048):
