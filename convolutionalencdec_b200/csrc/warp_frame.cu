@@ -338,7 +338,7 @@ int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     auto kernel = r4 ? ced::wfDecodeKernel<true> : ced::wfDecodeKernel<false>;
-    CED_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CED_CUDA(cedWarpEnsureSmem(c->device, r4 ? 0 : 1, kernel, smem));
     const int blocks = std::min(nFrames, c->sms * plan.perSm);
     kernel<<<blocks, 32, smem, s>>>(a);
     c->launches += 1;

@@ -138,5 +138,21 @@ __device__ __forceinline__ void wfBuildCostTable(const uint32_t (&cost)[2][kWfMa
 
 } // namespace ced
 
+/* host: cudaFuncAttributeMaxDynamicSharedMemorySize once per (device, kernel, size reached) instead of on every call;
+ * `slot` names the kernel (0 .. 3) */
+#include <atomic>
+template <class Kernel>
+static inline cudaError_t cedWarpEnsureSmem(int device, int slot, Kernel kernel, size_t bytes)
+{
+    static std::atomic<int> reached[32][4];
+    std::atomic<int> &r = reached[device & 31][slot & 3];
+    if ((int)bytes <= r.load(std::memory_order_relaxed))
+        return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess)
+        r.store((int)bytes, std::memory_order_relaxed);
+    return e;
+}
+
 /* host: branch costs of `code` in the byte form the kernels take (warp_frame.cu) */
 void cedWarpFrameCosts(const ced_code_t *code, bool r4, uint32_t (&cost)[2][ced::kWfMaxV][32]);

@@ -375,8 +375,8 @@ int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     a.rows = reinterpret_cast<uint2 *>(wk.scratch.p);
     a.vecs = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(wk.scratch.p) + rowBytes);
     a.initMetric = 65;
-    CED_CUDA(cudaFuncSetAttribute(ced::wsBlockKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBlock));
-    CED_CUDA(cudaFuncSetAttribute(ced::wsJoinKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemJoin));
+    CED_CUDA(cedWarpEnsureSmem(c->device, 2, ced::wsBlockKernel, smemBlock));
+    CED_CUDA(cedWarpEnsureSmem(c->device, 3, ced::wsJoinKernel, smemJoin));
     ced::wsBlockKernel<<<std::min(nFrames * B, c->sms * 8), 32, smemBlock, s>>>(a);
     ced::wsJoinKernel<<<std::min(nFrames, c->sms * 4), ced::kWsJoinThreads, smemJoin, s>>>(a);
     c->launches += 2;
