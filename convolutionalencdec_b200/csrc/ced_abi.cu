@@ -217,6 +217,7 @@ void ced_ctx_destroy(ced_ctx *c)
     c->sOut.release();
     c->sSurv.release();
     c->sParallel.release();
+    c->sSplit.release();
     if (c->fpGraph)
         cudaGraphExecDestroy(c->fpGraph);
     c->sPinIn.release();
@@ -1760,6 +1761,14 @@ static bool streamParallelEnabled()
     return on;
 }
 
+/* CED_STREAM_SPLIT: one-shot K=7 packets of at least that many segments run on the time-split kernels (warp_split.cu)
+ * instead of the frame-parallel ones; 0 = never.  Read per call: tests flip it. */
+static int streamSplitMinSegments()
+{
+    const char *e = getenv("CED_STREAM_SPLIT");
+    return e ? atoi(e) : kStreamSplitMinSegments;
+}
+
 /* ------------------------------------------------ resident packet decoder (frame_server.cuh) */
 /* CED_STREAM_SERVER=1: the resident kernel instead of one graph launch per packet.  Off by default: measured on B200 it
  * takes the host-visible overhead of a call from ~20 us to 2.5 us, but the device-side phases of a 2048-bit packet then
@@ -1973,6 +1982,11 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         if (rc == CED_OK)
             CED_CUDA(cudaMemsetAsync(c->sParallel.p + lay.tickets, 0, 16, c->stream));
     }
+    const int splitMin = streamSplitMinSegments();
+    const bool split = parallel && splitMin > 0 && segmentsIn >= splitMin && !(streamServerEnabled() && !c->fsDisabled) &&
+                       cedStreamDecodeSplitTakes(c, segmentsIn);   /* the resident decoder is opt-in and keeps its packets */
+    if (rc == CED_OK && split)
+        rc = c->sSplit.ensure(cedStreamDecodeSplitScratchBytes(kStreamMaxSteps));
     if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
     if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
@@ -2054,11 +2068,21 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
         /* the 64 passes over a block all read its segments: those reads stay on the device (one small copy) */
         auto issue = [&]() -> cudaError_t {
-            cudaError_t e = cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream);
+            cudaError_t e = cudaSuccess;
+            if (split) {
+                /* warp_split.cu: blocks of 64 steps from guessed metrics, checked hand-overs; the symbols are read from
+                 * the pinned mailbox directly (every block reads its own 160 bytes once) */
+                const int rs = cedStreamDecodeSplit(c, edge, metrics, c->sPinIn.p + 1024, segmentsIn, a.out, c->sSplit.p,
+                                                    c->sSplit.bytes, c->stream);
+                if (rs != CED_OK)
+                    return cudaErrorNotSupported;
+            } else {
+            e = cudaMemcpyAsync(c->sIn.p, c->sPinIn.p, inBytes, cudaMemcpyHostToDevice, c->stream);
             if (e != cudaSuccess)
                 return e;
             ced::fpBlockKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
             ced::fpSelectKernel<<<grid, ced::kFpThreads, 0, c->stream>>>(f);
+            }
             if (!zcOut)
                 e = cudaMemcpyAsync(c->sPinOut.p, c->sOut.p, 272 + decodedBytes, cudaMemcpyDeviceToHost, c->stream);
             return e != cudaSuccess ? e : cudaGetLastError();
@@ -2067,8 +2091,13 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
             /* per-packet loops call with one packet length: the three submissions become one graph launch */
             /* the graph holds raw pointers into the staging buffers, which ced_stream_encode may have regrown
              * (ensure() frees and reallocates): the cache is keyed on them as well as on the packet length */
-            const void *key[5] = {c->sIn.p, c->sOut.p, c->sParallel.p, c->sPinIn.p, c->sPinOut.p};
-            if (!c->fpGraph || c->fpGraphSegs != segmentsIn || memcmp(key, c->fpGraphKey, sizeof(key)) != 0) {
+            const void *key[5] = {c->sIn.p, c->sOut.p, split ? c->sSplit.p : c->sParallel.p, c->sPinIn.p, c->sPinOut.p};
+            /* the split kernels take the labels and the start metrics as kernel arguments: part of the key */
+            uint8_t tables[192];
+            memcpy(tables, edge, 128);
+            memcpy(tables + 128, metrics, 64);
+            if (!c->fpGraph || c->fpGraphSegs != segmentsIn || memcmp(key, c->fpGraphKey, sizeof(key)) != 0 ||
+                c->fpGraphSplit != split || (split && memcmp(tables, c->fpGraphTables, sizeof(tables)) != 0)) {
                 if (c->fpGraph)
                     cudaGraphExecDestroy(c->fpGraph);
                 c->fpGraph = nullptr;
@@ -2082,6 +2111,8 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                 cudaGraphDestroy(g);
                 CED_CUDA(e3);
                 c->fpGraphSegs = segmentsIn;
+                c->fpGraphSplit = split;
+                memcpy(c->fpGraphTables, tables, sizeof(tables));
                 memcpy(c->fpGraphKey, key, sizeof(key));
             }
             CED_CUDA(cudaGraphLaunch(c->fpGraph, c->stream));

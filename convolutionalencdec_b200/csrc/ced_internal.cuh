@@ -37,6 +37,7 @@ constexpr size_t kMaxScratchBytes = 12ull << 30;  /* survivor scratch per wave  
 constexpr size_t kMaxWaveFrames = 1u << 20;       /* bounds the scheduler state (2 KB per 32 frames) */
 constexpr int kHostChunkFrames = 8192;            /* frames per H2D/kernel/D2H pipeline stage */
 constexpr int kPipeDepth = 4;                     /* chunks in flight in the host pipeline      */
+constexpr int kStreamSplitMinSegments = 134;       /* one-shot packets from this length on: warp_split.cu (ced_stream_decode) */
 constexpr uint32_t kStreamMaxSteps = 16384 + 8;   /* MAX_PKT_LEN_SEGMENTS (src/viterbiDecoder.h:18,45) */
 
 template <typename T>
@@ -163,6 +164,9 @@ struct ced_ctx {
     DeviceBuf<uint8_t> sIn, sOut;
     DeviceBuf<uint32_t> sSurv;
     DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
+    DeviceBuf<uint8_t> sSplit;       /* warp_split.cu scratch of the same calls */
+    uint8_t fpGraphTables[192] = {}; /* edge labels + start metrics baked into a graph of the split kernels */
+    bool fpGraphSplit = false;
     cudaGraphExec_t fpGraph = nullptr; /* copy in + fpBlockKernel + fpSelectKernel for packets of fpGraphSegs segments */
     int fpGraphSegs = 0;
     const void *fpGraphKey[5] = {};  /* staging pointers baked into fpGraph */
@@ -244,6 +248,12 @@ int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *d
 int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
                             int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
 bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits);
+
+/* warp_split.cu: the one-packet call of the reference-named API on the same kernels (labels and start metrics are the caller's) */
+int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics, const uint8_t *dSegs, int T, uint8_t *dOut,
+                         void *scratch, size_t scratchBytes, cudaStream_t s);
+size_t cedStreamDecodeSplitScratchBytes(int maxSteps);
+bool cedStreamDecodeSplitTakes(const ced_ctx *c, int T);
 
 /* swar_generic.cu: continuous streams for the table-driven kernels (K <= 7); CED_ERR_UNSUPPORTED / 0 = not their code */
 size_t cedWindowCarryBytesGeneric(const ced_code_t *code, int nStreams, int depth);

@@ -35,7 +35,7 @@ struct WsArgs {
     int rowPitch;           /* decision rows per frame in `rows` */
     uint2 *rows;            /* [nFrames][rowPitch] */
     uint2 *vecs;            /* [nFrames][B][2][32]: (X, Y) of every lane at the block start / at the block end, minimum 0 */
-    uint32_t initMetric;
+    uint2 start[32];        /* (X, Y) of every lane at step 0: the frame's initial metrics (:59-67, or the caller's) */
     uint32_t cost[2][kWfMaxV][32];
 };
 
@@ -55,11 +55,6 @@ struct WsForward {
         src3 = src0 + 24;
         sel = (q & 1u) ? 0x7632u : 0x5410u;
         costBase = costTable + l * sizeof(uint4);
-    }
-    __device__ __forceinline__ void startOfFrame(uint32_t m0)   /* :59-67 */
-    {
-        X = ((lane >> 1) == 0 ? 0u : m0) | (m0 << 16);
-        Y = m0 | (m0 << 16);
     }
     __device__ __forceinline__ uint4 costAt(uint32_t o) const { return *reinterpret_cast<const uint4 *>(costBase + o); }
 
@@ -193,10 +188,12 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
         const int f = w / a.B, c = w - f * a.B;
         const int s = c * a.len, e = min(a.T, s + a.len), lo = max(0, s - a.D);
         wsOffsets(a.segs + (size_t)f * a.segStride, lo, e - lo, stage, offs, lane);
-        if (lo == 0)
-            fwd.startOfFrame(a.initMetric);
-        else
+        if (lo == 0) {
+            fwd.X = a.start[lane].x;
+            fwd.Y = a.start[lane].y;
+        } else {
             fwd.X = fwd.Y = 0;
+        }
         uint2 *rowPtr = a.rows + (size_t)f * a.rowPitch + s;
         uint2 *vec = a.vecs + ((size_t)f * a.B + c) * 64;
         if (s > lo)
@@ -305,12 +302,80 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
             wfTraceback<true>(sSurv, T, 6, a.seg, sOut, lane);
         __syncthreads();
         uint8_t *dst = a.out + (size_t)f * a.outStride;
-        for (int i = tid; i < ((T - 6) >> 3); i += kWsJoinThreads)
+        const int nOut = (T - 6) >> 3;
+        const int nVec = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0 ? nOut >> 4 : 0;   /* whole 16-byte pieces of an aligned row */
+        for (int i = tid; i < nVec; i += kWsJoinThreads)
+            reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(sOut)[i];
+        for (int i = 16 * nVec + tid; i < nOut; i += kWsJoinThreads)
             dst[i] = sOut[i];
     }
 }
 
 } // namespace ced
+
+/* block geometry, shared memory and scratch of a call; ok = false: not a case for these kernels */
+struct WsPlan {
+    bool ok;
+    int T, len, B, D, seg, survRows, outPad, rowPitch;
+    size_t smemBlock, smemJoin, rowBytes, vecBytes;
+};
+
+static WsPlan wsPlan(const ced_ctx *c, int nFrames, int T)
+{
+    WsPlan p = {};
+    const char *envOn = getenv("CED_WARP_SPLIT");   /* read per call: tests flip them */
+    if (!c || nFrames <= 0 || T < 16 || (T & 1) || ((T - 6) & 7) || (envOn && atoi(envOn) == 0))
+        return p;
+    const char *envD = getenv("CED_WARP_SPLIT_WARMUP"), *envLen = getenv("CED_WARP_SPLIT_LEN");
+    p.T = T;
+    p.D = envD && atoi(envD) >= 8 ? atoi(envD) / 8 * 8 : 96;
+    const int maxBlocks = std::max(1, 4 * c->sms / nFrames);
+    p.len = std::max(64, ((T + maxBlocks - 1) / maxBlocks + 7) / 8 * 8);
+    if (envLen && atoi(envLen) >= 8)
+        p.len = atoi(envLen) / 8 * 8;
+    p.B = (T + p.len - 1) / p.len;
+    if (p.B < 2 || (size_t)65 + 2u * (size_t)T > 65535u)
+        return p;
+    p.seg = (((T + 31) / 32) + 7) & ~7;
+    p.survRows = (T + T / p.seg + 9) & ~1;
+    p.outPad = ((T >> 3) + 15) / 16 * 16 + 16;
+    p.rowPitch = (T + 15) / 8 * 8;
+    p.smemBlock = (size_t)ced::kWfCostBytes + (size_t)((p.D + p.len + 64 + 15) / 16) * 16 + (size_t)((p.D + p.len) / 2 + 12 + 3) / 4 * 16;
+    p.smemJoin = (size_t)ced::kWfCostBytes + (size_t)p.survRows * sizeof(uint2) + (size_t)p.outPad +
+                 (size_t)(p.len / 2 + 12 + 3) / 4 * 16 + (size_t)(p.B + 15) / 16 * 16;
+    if (p.smemJoin > 200 * 1024 || p.smemBlock > 200 * 1024 || (size_t)p.survRows * sizeof(uint2) < (size_t)p.len + 64)
+        return p;
+    p.rowBytes = (size_t)nFrames * p.rowPitch * sizeof(uint2);
+    p.vecBytes = (size_t)nFrames * p.B * 64 * sizeof(uint2);
+    p.ok = true;
+    return p;
+}
+
+/* the two launches; `scratch` holds rowBytes + vecBytes */
+static int wsLaunch(ced_ctx *c, const WsPlan &p, ced::WsArgs &a, const uint8_t *dSegs, size_t segStride, int nFrames, uint8_t *dOut,
+                    size_t outStride, void *scratch, cudaStream_t s)
+{
+    a.segs = dSegs;
+    a.segStride = segStride;
+    a.out = dOut;
+    a.outStride = outStride;
+    a.nFrames = nFrames;
+    a.T = p.T;
+    a.len = p.len;
+    a.B = p.B;
+    a.D = p.D;
+    a.seg = p.seg;
+    a.survRows = p.survRows;
+    a.outPad = p.outPad;
+    a.rowPitch = p.rowPitch;
+    a.rows = reinterpret_cast<uint2 *>(scratch);
+    a.vecs = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(scratch) + p.rowBytes);
+    CED_CUDA(cedWarpEnsureSmem(c->device, 2, ced::wsBlockKernel, p.smemBlock));
+    CED_CUDA(cedWarpEnsureSmem(c->device, 3, ced::wsJoinKernel, p.smemJoin));
+    ced::wsBlockKernel<<<std::min(nFrames * p.B, c->sms * 8), 32, p.smemBlock, s>>>(a);
+    ced::wsJoinKernel<<<std::min(nFrames, c->sms * 4), ced::kWsJoinThreads, p.smemJoin, s>>>(a);
+    return CED_OK;
+}
 
 /*
  * ced_decode_batch for so few frames of a 64-state rate-1/2 code that cutting them in time pays (called by
@@ -322,66 +387,75 @@ int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *d
 {
     if (!c || !code || code->constraintLen != 7 || code->codedBits != 2 || nFrames <= 0 || frameBits <= 0)
         return CED_ERR_UNSUPPORTED;
-    const char *envOn = getenv("CED_WARP_SPLIT");   /* read per call: tests flip them */
-    if (envOn && atoi(envOn) == 0)
+    const WsPlan p = wsPlan(c, nFrames, frameBits + 6);
+    if (!p.ok)
         return CED_ERR_UNSUPPORTED;
-    const int T = frameBits + 6;
-    const char *envD = getenv("CED_WARP_SPLIT_WARMUP"), *envLen = getenv("CED_WARP_SPLIT_LEN");
-    const int D = envD && atoi(envD) >= 8 ? atoi(envD) / 8 * 8 : 96;
-    const int maxBlocks = std::max(1, 4 * c->sms / nFrames);
-    int len = std::max(64, ((T + maxBlocks - 1) / maxBlocks + 7) / 8 * 8);
-    if (envLen && atoi(envLen) >= 8)
-        len = atoi(envLen) / 8 * 8;
-    const int B = (T + len - 1) / len;
-    if (B < 2 || (size_t)65 + 2u * (size_t)T > 65535u)
-        return CED_ERR_UNSUPPORTED;
-    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+    if (segStride < (size_t)p.T || outStride < (size_t)(frameBits / 8)) {
         setError("ced_decode_batch: stride shorter than a frame");
         return CED_ERR_ARG;
     }
-    ced::WsArgs a;
-    a.seg = (((T + 31) / 32) + 7) & ~7;
-    a.survRows = (T + T / a.seg + 9) & ~1;
-    a.outPad = ((T >> 3) + 15) / 16 * 16 + 16;
-    a.rowPitch = (T + 15) / 8 * 8;
-    const size_t smemBlock = (size_t)ced::kWfCostBytes + (size_t)((D + len + 64 + 15) / 16) * 16 + (size_t)((D + len) / 2 + 12 + 3) / 4 * 16;
-    const size_t smemJoin = (size_t)ced::kWfCostBytes + (size_t)a.survRows * sizeof(uint2) + (size_t)a.outPad +
-                            (size_t)(len / 2 + 12 + 3) / 4 * 16 + (size_t)(B + 15) / 16 * 16;
-    if (smemJoin > 200 * 1024 || smemBlock > 200 * 1024 || (size_t)a.survRows * sizeof(uint2) < (size_t)len + 64)
-        return CED_ERR_UNSUPPORTED;
-    const size_t rowBytes = (size_t)nFrames * a.rowPitch * sizeof(uint2), vecBytes = (size_t)nFrames * B * 64 * sizeof(uint2);
     std::lock_guard<std::recursive_mutex> lock(c->mu);
     CED_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
     ced_ctx::Work &wk = c->work[slot];
-    if (wk.scratch.bytes < rowBytes + vecBytes) {
+    if (wk.scratch.bytes < p.rowBytes + p.vecBytes) {
         CED_CUDA(cudaDeviceSynchronize());   /* growing means freeing: nothing may still use the old block */
-        const int rc = wk.scratch.ensure(rowBytes + vecBytes);
+        const int rc = wk.scratch.ensure(p.rowBytes + p.vecBytes);
         if (rc != CED_OK)
             return rc;
     }
     if (wk.lastStream && wk.lastStream != s)
         CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
+    ced::WsArgs a;
     cedWarpFrameCosts(code, true, a.cost);
-    a.segs = dSegs;
-    a.segStride = segStride;
-    a.out = dOut;
-    a.outStride = outStride;
-    a.nFrames = nFrames;
-    a.T = T;
-    a.len = len;
-    a.B = B;
-    a.D = D;
-    a.rows = reinterpret_cast<uint2 *>(wk.scratch.p);
-    a.vecs = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(wk.scratch.p) + rowBytes);
-    a.initMetric = 65;
-    CED_CUDA(cedWarpEnsureSmem(c->device, 2, ced::wsBlockKernel, smemBlock));
-    CED_CUDA(cedWarpEnsureSmem(c->device, 3, ced::wsJoinKernel, smemJoin));
-    ced::wsBlockKernel<<<std::min(nFrames * B, c->sms * 8), 32, smemBlock, s>>>(a);
-    ced::wsJoinKernel<<<std::min(nFrames, c->sms * 4), ced::kWsJoinThreads, smemJoin, s>>>(a);
+    for (int l = 0; l < 32; l++)   /* :59-67: state 0 starts at 0, every other state at NUM_STATES + 1 */
+        a.start[l] = make_uint2((l >> 1) == 0 ? 65u << 16 : 65u | 65u << 16, 65u | 65u << 16);
+    const int rc = wsLaunch(c, p, a, dSegs, segStride, nFrames, dOut, outStride, wk.scratch.p, s);
+    if (rc != CED_OK)
+        return rc;
     c->launches += 2;
     CED_CUDA(cudaEventRecord(wk.idle, s));
     wk.lastStream = s;
     CED_CUDA(cudaGetLastError());
     return CED_OK;
+}
+
+/*
+ * The one-packet call of the reference-named API (ced_stream_decode, last = true from reset-like metrics): the same two
+ * kernels on ONE frame whose trellis labels and initial metrics are the caller's (edge[b * 64 + st], metrics[st] <= 65).
+ * dSegs / dOut are device-accessible (the pinned mailboxes); nothing is synchronised here, so the pair can be captured
+ * in a graph.  CED_ERR_UNSUPPORTED = not a case (odd length, a length that is not whole bytes + 6, too short).
+ */
+int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics, const uint8_t *dSegs, int T, uint8_t *dOut,
+                         void *scratch, size_t scratchBytes, cudaStream_t s)
+{
+    const WsPlan p = wsPlan(c, 1, T);
+    if (!p.ok || p.rowBytes + p.vecBytes > scratchBytes)
+        return CED_ERR_UNSUPPORTED;
+    ced::WsArgs a;
+    auto hd = [](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & 3u); };
+    memset(a.cost, 0, sizeof(a.cost));
+    for (uint32_t rx = 0; rx < 4; rx++)
+        for (int l = 0; l < 32; l++) {   /* as cedWarpFrameCosts, labels from the caller's table */
+            const int q = l >> 1, h = l & 1;
+            a.cost[1][rx][l] = hd(edge[l], rx) | hd(edge[64 + l], rx) << 8 | hd(edge[l + 32], rx) << 16 | hd(edge[64 + l + 32], rx) << 24;
+            a.cost[0][rx][l] = hd(edge[h * 64 + q], rx) | hd(edge[h * 64 + q + 16], rx) << 8 | hd(edge[h * 64 + q + 32], rx) << 16 |
+                               hd(edge[h * 64 + q + 48], rx) << 24;
+        }
+    for (int l = 0; l < 32; l++) {
+        const int q = l >> 1;
+        a.start[l] = make_uint2((uint32_t)metrics[q] | (uint32_t)metrics[q + 16] << 16, (uint32_t)metrics[q + 32] | (uint32_t)metrics[q + 48] << 16);
+    }
+    return wsLaunch(c, p, a, dSegs, (size_t)T, 1, dOut, 0, scratch, s);
+}
+
+bool cedStreamDecodeSplitTakes(const ced_ctx *c, int T)
+{
+    return wsPlan(c, 1, T).ok;
+}
+
+size_t cedStreamDecodeSplitScratchBytes(int maxSteps)
+{
+    /* one frame: rows + at most maxSteps / 64 + 1 blocks of two 256-byte vectors (smaller blocks only by experiment switch) */
+    return (size_t)(maxSteps + 16) * sizeof(uint2) + (size_t)(maxSteps / 8 + 2) * 64 * sizeof(uint2);
 }
