@@ -206,7 +206,8 @@ def per_packet_rate(seconds, bits=2048):
     return {"value": n * bits / dt / 1e6, "unit": "Mbit/s", "us_per_call": dt / n * 1e6, "packet_bits": bits,
             "calls": n, "gpu_launches": launches, "round_trip_ok": ok,
             "api": "viterbiDecoderHardButterflyk1(last=true), one packet per synchronous call, host buffers "
-                   "(the call speedDecode.c:79 makes); whole packet decoded at once by fpBlockKernel + fpSelectKernel"}
+                   "(the call speedDecode.c:79 makes); the packet's 64-step blocks decoded at once by wsBlockKernel (speculative start "
+                   "metrics), checked, repaired and walked back by wsJoinKernel (csrc/warp_split.cu)"}
 
 
 def small_batch_rate(ctx, seconds, packets=16, bits=2048):
