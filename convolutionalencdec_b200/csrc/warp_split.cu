@@ -142,14 +142,26 @@ struct WsForward {
 
 /* stage the symbols of steps [lo, lo + nSteps) of a row in `stage` (16-byte aligned shared memory of nSteps + 64 bytes)
  * and write the table offset of every pair of steps to offs (nSteps / 2 entries + 12 zeros) */
-__device__ __forceinline__ void wsOffsets(const uint8_t *row, int lo, int nSteps, uint32_t *stage, uint32_t *offs, int lane)
+/* first: the lane's first 16-byte piece of those symbols, fetched by the caller ahead of time (wsFirstPiece), or NULL */
+__device__ __forceinline__ uint4 wsFirstPiece(const uint8_t *row, int lo, int nSteps, int lane)
+{
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)lo;
+    const uint32_t off = (uint32_t)(addr & 15u);
+    const int nq = (int)(off + (uint32_t)nSteps + 15u) >> 4;
+    return lane < nq ? __ldg(reinterpret_cast<const uint4 *>(addr - off) + lane) : make_uint4(0, 0, 0, 0);
+}
+
+__device__ __forceinline__ void wsOffsets(const uint8_t *row, int lo, int nSteps, uint32_t *stage, uint32_t *offs, int lane,
+                                          const uint4 *first = nullptr)
 {
     const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)lo;
     const uint32_t off = (uint32_t)(addr & 15u);
     const uint4 *src = reinterpret_cast<const uint4 *>(addr - off);
     const int nq = (int)(off + (uint32_t)nSteps + 15u) >> 4;
     __syncwarp();
-    for (int q = lane; q < nq; q += 32)
+    if (first && lane < nq)
+        reinterpret_cast<uint4 *>(stage)[lane] = *first;
+    for (int q = lane + (first ? 32 : 0); q < nq; q += 32)
         reinterpret_cast<uint4 *>(stage)[q] = __ldg(src + q);
     __syncwarp();
     const uint32_t *symW = stage + (off >> 2);
@@ -180,14 +192,20 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
     const int span = a.D + a.len;                                        /* most steps a block runs */
     uint32_t *stage = reinterpret_cast<uint32_t *>(wsSmem + kWfCostBytes);   /* span + 64 bytes */
     uint32_t *offs = stage + ((span + 64 + 15) / 16) * 4;                 /* span / 2 + 12 entries */
+    const int total = a.nFrames * a.B;
+    uint4 first = make_uint4(0, 0, 0, 0);
+    if ((int)blockIdx.x < total) {   /* the first block's symbols are on their way while the cost table is built */
+        const int f = blockIdx.x / a.B, c = blockIdx.x - f * a.B;
+        const int s = c * a.len, e = min(a.T, s + a.len), lo = max(0, s - a.D);
+        first = wsFirstPiece(a.segs + (size_t)f * a.segStride, lo, e - lo, lane);
+    }
     wfBuildCostTable<true>(a.cost, wsSmem, lane);
     WsForward fwd;
     fwd.setup(lane, wsSmem);
-    const int total = a.nFrames * a.B;
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int f = w / a.B, c = w - f * a.B;
         const int s = c * a.len, e = min(a.T, s + a.len), lo = max(0, s - a.D);
-        wsOffsets(a.segs + (size_t)f * a.segStride, lo, e - lo, stage, offs, lane);
+        wsOffsets(a.segs + (size_t)f * a.segStride, lo, e - lo, stage, offs, lane, w == (int)blockIdx.x ? &first : nullptr);
         if (lo == 0) {
             fwd.X = a.start[lane].x;
             fwd.Y = a.start[lane].y;
@@ -206,7 +224,8 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
     }
 }
 
-constexpr int kWsJoinThreads = 128;   /* warp 0 checks, repairs and walks back; all four warps move the rows */
+constexpr int kWsJoinThreads = 256;   /* all warps compare the hand-overs and move the rows; warp 0 repairs and walks back */
+constexpr int kWsJoinLoads = 6;       /* 16-byte loads a thread keeps in flight */
 
 __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_constant__ WsArgs a)
 {
@@ -221,28 +240,34 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
     WsForward fwd;
     for (int f = blockIdx.x; f < a.nFrames; f += gridDim.x) {
         __syncthreads();
-        if (warp == 0) {
-            uint2 *vecs = a.vecs + (size_t)f * B * 64;
-            /* all hand-overs at once: lane c compares what block c started with against what block c-1 ended with */
-            for (int c0 = 0; c0 < B; c0 += 32) {
-                const int c = c0 + lane;
-                bool bad = false;
-                if (c >= 1 && c < B && c * a.len - a.D > 0) {
-                    const uint4 *p = reinterpret_cast<const uint4 *>(vecs + (size_t)c * 64);
-                    const uint4 *q = reinterpret_cast<const uint4 *>(vecs + (size_t)(c - 1) * 64 + 32);
-                    uint4 u[16], v[16];
+        uint2 *vecs = a.vecs + (size_t)f * B * 64;
+        /* all hand-overs at once: what block c started with against what block c-1 ended with, 16 bytes per thread and
+         * piece (a block that reaches back to step 0 started from the true metrics: nothing to compare) */
+        for (int c = tid; c < B; c += kWsJoinThreads)
+            sBad[c] = 0;
+        __syncthreads();
+        const int cFirst = a.D / a.len + 1;   /* first block with c * len - D > 0 */
+        const int pieces = B > cFirst ? (B - cFirst) * 16 : 0;
+        for (int k0 = tid; k0 < pieces; k0 += kWsJoinLoads * kWsJoinThreads) {
+            uint4 u[kWsJoinLoads], v[kWsJoinLoads];
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        u[i] = __ldcg(p + i);
-                        v[i] = __ldcg(q + i);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        bad |= (u[i].x != v[i].x) | (u[i].y != v[i].y) | (u[i].z != v[i].z) | (u[i].w != v[i].w);
+            for (int j = 0; j < kWsJoinLoads; j++) {
+                const int k = k0 + j * kWsJoinThreads;
+                if (k < pieces) {
+                    const int c = cFirst + (k >> 4), i = k & 15;
+                    u[j] = __ldcg(reinterpret_cast<const uint4 *>(vecs + (size_t)c * 64) + i);
+                    v[j] = __ldcg(reinterpret_cast<const uint4 *>(vecs + (size_t)(c - 1) * 64 + 32) + i);
                 }
-                if (c < B)
-                    sBad[c] = bad ? 1 : 0;
             }
+#pragma unroll
+            for (int j = 0; j < kWsJoinLoads; j++) {
+                const int k = k0 + j * kWsJoinThreads;
+                if (k < pieces && ((u[j].x != v[j].x) | (u[j].y != v[j].y) | (u[j].z != v[j].z) | (u[j].w != v[j].w)))
+                    sBad[cFirst + (k >> 4)] = 1;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
             __syncwarp();
             for (int c = 1; c < B; c++) {
                 if (!sBad[c])
@@ -277,18 +302,18 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
             __threadfence_block();
         }
         __syncthreads();
-        /* the frame's decisions into shared memory, two rows per load, four loads in flight per thread; the rows of
+        /* the frame's decisions into shared memory, two rows per load, six loads in flight per thread; the rows of
          * segment i are skewed by i slots (wfTraceback) */
         const uint4 *rows2 = reinterpret_cast<const uint4 *>(a.rows + (size_t)f * a.rowPitch);
         const int pairs = (T + 1) >> 1;
-        for (int i0 = tid; i0 < pairs; i0 += 4 * kWsJoinThreads) {
-            uint4 r[4];
+        for (int i0 = tid; i0 < pairs; i0 += kWsJoinLoads * kWsJoinThreads) {
+            uint4 r[kWsJoinLoads];
 #pragma unroll
-            for (int k = 0; k < 4; k++)
+            for (int k = 0; k < kWsJoinLoads; k++)
                 if (i0 + k * kWsJoinThreads < pairs)
                     r[k] = __ldcg(rows2 + i0 + k * kWsJoinThreads);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < kWsJoinLoads; k++) {
                 const int i = i0 + k * kWsJoinThreads;
                 if (i < pairs) {
                     const int t = 2 * i, sg = (int)(((uint64_t)t * segMagic) >> 32);   /* seg is even: both rows in one segment */
