@@ -503,13 +503,19 @@ def test_streaming_api_matches_reference_metrics_and_chunking(golden, port):
     assert np.array_equal(dec.VITERBI_DECODER_HARD(big[:0], True, max_bytes=4096), want)
 
 
+@pytest.mark.parametrize("split", ["default", "0", "134", "16"])
 @pytest.mark.parametrize("T", [13, 14, 33, 38, 39, 65, 70, 129, 130, 133, 134, 262, 1030, 2054, 2055, 4102, 16390])
-def test_one_shot_packets_take_the_frame_parallel_kernels(port, T, monkeypatch):
-    """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs fpBlockKernel / fpSelectKernel
-    (csrc/frame_parallel.cuh; one graph launch per packet, the default): same bytes as the sequential decoder for
-    clean, noisy, all-zero and pure-noise packets, for lengths that leave a short last block or a partial last byte,
-    and the decoder is usable for chunked packets afterwards."""
+def test_one_shot_packets_take_the_frame_parallel_kernels(port, T, split, monkeypatch):
+    """A whole K=7 packet in ONE VITERBI_DECODER_HARD(last=true) call runs two parallel kernels in one graph launch:
+    wsBlockKernel / wsJoinKernel (csrc/warp_split.cu: the packet cut into blocks that start from guessed metrics, the
+    hand-overs checked -- the default from 134 segments on when the length is whole bytes + 6) or fpBlockKernel /
+    fpSelectKernel (csrc/frame_parallel.cuh; CED_STREAM_SPLIT=0 and every other length).  Same bytes as the sequential
+    decoder for clean, noisy, all-zero and pure-noise packets, for lengths that leave a short last block or a partial
+    last byte, and the decoder is usable for chunked packets afterwards."""
     monkeypatch.setenv("CED_STREAM_SERVER", "0")
+    monkeypatch.delenv("CED_WARP_SPLIT", raising=False)
+    if split != "default":
+        monkeypatch.setenv("CED_STREAM_SPLIT", split)
     api = ced.RefApi("k7")
     dec = api.decoder()
     dec.VITERBI_RESET()
