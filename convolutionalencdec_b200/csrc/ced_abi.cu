@@ -218,6 +218,8 @@ void ced_ctx_destroy(ced_ctx *c)
     c->sSurv.release();
     c->sParallel.release();
     c->sSplit.release();
+    c->sSplitSeq.release();
+    c->sDoorbell.release();
     if (c->fpGraph)
         cudaGraphExecDestroy(c->fpGraph);
     c->sPinIn.release();
@@ -1987,6 +1989,15 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                        cedStreamDecodeSplitTakes(c, segmentsIn);   /* the resident decoder is opt-in and keeps its packets */
     if (rc == CED_OK && split)
         rc = c->sSplit.ensure(cedStreamDecodeSplitScratchBytes(kStreamMaxSteps));
+    if (rc == CED_OK && split && !c->sSplitSeq.p) {
+        rc = c->sSplitSeq.ensure(64);
+        if (rc == CED_OK) rc = c->sDoorbell.ensure(64);
+        if (rc == CED_OK) {
+            CED_CUDA(cudaMemsetAsync(c->sSplitSeq.p, 0, 64, c->stream));
+            memset(c->sDoorbell.p, 0, 64);
+            c->splitSeq = 0;
+        }
+    }
     if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
     if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
@@ -2027,6 +2038,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         CED_CUDA(cudaMemcpyAsync(c->sSurv.p, surv, (size_t)it0 * W * sizeof(uint32_t), cudaMemcpyHostToDevice,
                                  c->stream));
     const size_t decodedBytes = last ? (size_t)((total - S - 1) / 8 + 1) : 0;
+    bool doorbell = false;
     ced::StreamArgs a;
     a.K = K;
     a.n = n;
@@ -2066,6 +2078,10 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
             f.stamps[1] = f.stamps[6] = 0;
         }
         const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
+        /* the join kernel writes the packet's bytes to the pinned mailbox and then a count to a doorbell word: the host
+         * waits for that word instead of for the stream (CED_STREAM_DOORBELL=0: cudaStreamSynchronize as everywhere else) */
+        static const bool doorbellOn = !getenv("CED_STREAM_DOORBELL") || atoi(getenv("CED_STREAM_DOORBELL")) != 0;
+        doorbell = split && zcOut && doorbellOn;
         /* the 64 passes over a block all read its segments: those reads stay on the device (one small copy) */
         auto issue = [&]() -> cudaError_t {
             cudaError_t e = cudaSuccess;
@@ -2073,7 +2089,8 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                 /* warp_split.cu: blocks of 64 steps from guessed metrics, checked hand-overs; the symbols are read from
                  * the pinned mailbox directly (every block reads its own 160 bytes once) */
                 const int rs = cedStreamDecodeSplit(c, edge, metrics, c->sPinIn.p + 1024, segmentsIn, a.out, c->sSplit.p,
-                                                    c->sSplit.bytes, c->stream);
+                                                    c->sSplit.bytes, c->stream, doorbell ? c->sSplitSeq.p : nullptr,
+                                                    doorbell ? reinterpret_cast<volatile unsigned int *>(c->sDoorbell.p) : nullptr);
                 if (rs != CED_OK)
                     return cudaErrorNotSupported;
             } else {
@@ -2097,7 +2114,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
             memcpy(tables, edge, 128);
             memcpy(tables + 128, metrics, 64);
             if (!c->fpGraph || c->fpGraphSegs != segmentsIn || memcmp(key, c->fpGraphKey, sizeof(key)) != 0 ||
-                c->fpGraphSplit != split || (split && memcmp(tables, c->fpGraphTables, sizeof(tables)) != 0)) {
+                c->fpGraphSplit != split || c->fpGraphDoorbell != doorbell || (split && memcmp(tables, c->fpGraphTables, sizeof(tables)) != 0)) {
                 if (c->fpGraph)
                     cudaGraphExecDestroy(c->fpGraph);
                 c->fpGraph = nullptr;
@@ -2112,6 +2129,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                 CED_CUDA(e3);
                 c->fpGraphSegs = segmentsIn;
                 c->fpGraphSplit = split;
+                c->fpGraphDoorbell = doorbell;
                 memcpy(c->fpGraphTables, tables, sizeof(tables));
                 memcpy(c->fpGraphKey, key, sizeof(key));
             }
@@ -2131,7 +2149,25 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     if (!last && segmentsIn)
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 4096, c->sSurv.p + (size_t)it0 * W,
                                  (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CED_CUDA(cudaStreamSynchronize(c->stream));
+    bool rung = false;
+    if (doorbell) {
+        /* spin on the doorbell word; a packet that takes longer than 5 ms has gone wrong: let the stream say how */
+        const unsigned int expect = ++c->splitSeq;
+        volatile unsigned int *bell = reinterpret_cast<volatile unsigned int *>(c->sDoorbell.p);
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned int spins = 0; !(rung = *bell == expect);) {
+            if ((++spins & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5))
+                break;
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (!rung) {
+            const cudaError_t es = cudaStreamSynchronize(c->stream);
+            c->splitSeq = *bell;   /* whatever was counted is what the next call starts from */
+            CED_CUDA(es);
+        }
+    }
+    if (!rung)
+        CED_CUDA(cudaStreamSynchronize(c->stream));
     if (parallel && fpStamps()) {
         static unsigned long long calls = 0;
         const unsigned long long *st = fpStamps();

@@ -165,8 +165,11 @@ struct ced_ctx {
     DeviceBuf<uint32_t> sSurv;
     DeviceBuf<uint8_t> sParallel;    /* frame_parallel.cuh scratch (one-shot K=7 packets) */
     DeviceBuf<uint8_t> sSplit;       /* warp_split.cu scratch of the same calls */
+    DeviceBuf<unsigned int> sSplitSeq;   /* its doorbell: device counter ... */
+    PinnedBuf sDoorbell;             /* ... and the host-visible word the join kernel writes the count to */
+    unsigned int splitSeq = 0;       /* count the host expects next */
     uint8_t fpGraphTables[192] = {}; /* edge labels + start metrics baked into a graph of the split kernels */
-    bool fpGraphSplit = false;
+    bool fpGraphSplit = false, fpGraphDoorbell = false;
     cudaGraphExec_t fpGraph = nullptr; /* copy in + fpBlockKernel + fpSelectKernel for packets of fpGraphSegs segments */
     int fpGraphSegs = 0;
     const void *fpGraphKey[5] = {};  /* staging pointers baked into fpGraph */
@@ -251,7 +254,8 @@ bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, in
 
 /* warp_split.cu: the one-packet call of the reference-named API on the same kernels (labels and start metrics are the caller's) */
 int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics, const uint8_t *dSegs, int T, uint8_t *dOut,
-                         void *scratch, size_t scratchBytes, cudaStream_t s);
+                         void *scratch, size_t scratchBytes, cudaStream_t s, unsigned int *doneCounter,
+                         volatile unsigned int *doneFlag);
 size_t cedStreamDecodeSplitScratchBytes(int maxSteps);
 bool cedStreamDecodeSplitTakes(const ced_ctx *c, int T);
 

@@ -35,6 +35,8 @@ struct WsArgs {
     int rowPitch;           /* decision rows per frame in `rows` */
     uint2 *rows;            /* [nFrames][rowPitch] */
     uint2 *vecs;            /* [nFrames][B][2][32]: (X, Y) of every lane at the block start / at the block end, minimum 0 */
+    unsigned int *doneCounter;            /* one-packet calls: device counter and the host-visible word that receives its */
+    volatile unsigned int *doneFlag;      /* new value when the packet's bytes are out (NULL: no doorbell) */
     uint2 start[32];        /* (X, Y) of every lane at step 0: the frame's initial metrics (:59-67, or the caller's) */
     uint32_t cost[2][kWfMaxV][32];
 };
@@ -334,6 +336,14 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
         for (int i = 16 * nVec + tid; i < nOut; i += kWsJoinThreads)
             dst[i] = sOut[i];
     }
+    if (a.doneFlag) {   /* one frame, one CTA: ring the doorbell once every byte is on its way */
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            *a.doneFlag = atomicAdd(a.doneCounter, 1u) + 1u;
+            __threadfence_system();
+        }
+    }
 }
 
 } // namespace ced
@@ -393,6 +403,8 @@ static int wsLaunch(ced_ctx *c, const WsPlan &p, ced::WsArgs &a, const uint8_t *
     a.survRows = p.survRows;
     a.outPad = p.outPad;
     a.rowPitch = p.rowPitch;
+    if (nFrames != 1)
+        a.doneFlag = nullptr;
     a.rows = reinterpret_cast<uint2 *>(scratch);
     a.vecs = reinterpret_cast<uint2 *>(reinterpret_cast<uint8_t *>(scratch) + p.rowBytes);
     CED_CUDA(cedWarpEnsureSmem(c->device, 2, ced::wsBlockKernel, p.smemBlock));
@@ -432,6 +444,8 @@ int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     if (wk.lastStream && wk.lastStream != s)
         CED_CUDA(cudaStreamWaitEvent(s, wk.idle, 0));
     ced::WsArgs a;
+    a.doneCounter = nullptr;
+    a.doneFlag = nullptr;
     cedWarpFrameCosts(code, true, a.cost);
     for (int l = 0; l < 32; l++)   /* :59-67: state 0 starts at 0, every other state at NUM_STATES + 1 */
         a.start[l] = make_uint2((l >> 1) == 0 ? 65u << 16 : 65u | 65u << 16, 65u | 65u << 16);
@@ -452,12 +466,14 @@ int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *d
  * in a graph.  CED_ERR_UNSUPPORTED = not a case (odd length, a length that is not whole bytes + 6, too short).
  */
 int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics, const uint8_t *dSegs, int T, uint8_t *dOut,
-                         void *scratch, size_t scratchBytes, cudaStream_t s)
+                         void *scratch, size_t scratchBytes, cudaStream_t s, unsigned int *doneCounter, volatile unsigned int *doneFlag)
 {
     const WsPlan p = wsPlan(c, 1, T);
     if (!p.ok || p.rowBytes + p.vecBytes > scratchBytes)
         return CED_ERR_UNSUPPORTED;
     ced::WsArgs a;
+    a.doneCounter = doneCounter;
+    a.doneFlag = doneFlag;
     auto hd = [](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & 3u); };
     memset(a.cost, 0, sizeof(a.cost));
     for (uint32_t rx = 0; rx < 4; rx++)
