@@ -146,6 +146,35 @@ dec.VITERBI_DECODER_HARD(s[:100], False)
 out = dec.VITERBI_DECODER_HARD(s[100:], True)
 ok &= bool(np.array_equal(out, msg))
 print("per-frame chunked round trip:", bool(np.array_equal(out, msg)))
+# small batches: the warp-per-frame kernel (radix 4 and 2) and the time-split kernels, exactly sized and misaligned
+# input rows, output rows between canary bytes; the same calls on the thread-per-frame kernels as the yardstick
+for frames, bits, pad, off in ((1, 8, 0, 0), (3, 2048, 0, 5), (16, 2048, 3, 0), (33, 4096, 1, 9), (5, 16384, 0, 1)):
+    T = bits + 6
+    msgs = torch.empty((frames, bits // 8), dtype=torch.uint8, device="cuda")
+    ctx.random_bytes(msgs, seed=bits + frames)
+    stride = T + pad
+    flat = torch.zeros(frames * stride + off, dtype=torch.uint8, device="cuda")
+    segs = flat[off:off + frames * stride].view(frames, stride)
+    ctx.encode_batch(code, msgs, out=segs)
+    ctx.bsc_channel(segs, T, 2, 0.03, seed=2)
+    os.environ["CED_WARP_FRAME_MAX"] = "0"
+    want = ctx.decode_batch(code, segs, bits).clone()
+    ctx.sync()
+    os.environ.pop("CED_WARP_FRAME_MAX")
+    for mode in ({"CED_WARP_SPLIT": "0", "CED_WARP_FRAME_RADIX": "4"}, {"CED_WARP_SPLIT": "0", "CED_WARP_FRAME_RADIX": "2"},
+                 {"CED_WARP_SPLIT": "1"}, {"CED_WARP_SPLIT": "1", "CED_WARP_SPLIT_WARMUP": "8", "CED_WARP_SPLIT_LEN": "16"}):
+        os.environ.update(mode)
+        ostride = bits // 8 + 5
+        guard = torch.full((frames * ostride + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        out = guard[32:32 + frames * ostride].view(frames, ostride)
+        ctx.decode_batch(code, segs, bits, out=out)
+        ctx.sync()
+        good = bool(torch.equal(out[:, :bits // 8], want)) and bool((out[:, bits // 8:] == 0xA5).all()) and \
+            bool((guard[:32] == 0xA5).all()) and bool((guard[32 + frames * ostride:] == 0xA5).all())
+        ok &= good
+        print("small batch %3d x %5d bits, %s:" % (frames, bits, mode), good)
+        for k in mode:
+            os.environ.pop(k)
 ctx.close()
 print("ALL OK" if ok else "FAILED")
 sys.exit(0 if ok else 1)
