@@ -191,6 +191,9 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
 {
     extern __shared__ __align__(16) uint8_t wsSmem[];
     const int lane = threadIdx.x;
+    /* programmatic dependent launch: the join kernel may be scheduled now; its griddepcontrol.wait still holds it until
+     * this grid has finished and its writes are visible */
+    asm volatile("griddepcontrol.launch_dependents;");
     const int span = a.D + a.len;                                        /* most steps a block runs */
     uint32_t *stage = reinterpret_cast<uint32_t *>(wsSmem + kWfCostBytes);   /* span + 64 bytes */
     uint32_t *offs = stage + ((span + 64 + 15) / 16) * 4;                 /* span / 2 + 12 entries */
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
     uint32_t *offs = reinterpret_cast<uint32_t *>(sOut + a.outPad);       /* len / 2 + 12 entries */
     uint8_t *sBad = reinterpret_cast<uint8_t *>(offs + ((a.len / 2 + 12 + 3) / 4) * 4);   /* B flags */
     const uint64_t segMagic = ((1ull << 32) + (uint64_t)a.seg - 1) / (uint64_t)a.seg;   /* t / seg = (t * magic) >> 32 for t < 2^16 */
+    asm volatile("griddepcontrol.wait;" ::: "memory");   /* the block kernel's rows and vectors (no-op without the launch attribute) */
     bool haveTable = false;
     WsForward fwd;
     for (int f = blockIdx.x; f < a.nFrames; f += gridDim.x) {
@@ -410,7 +414,20 @@ static int wsLaunch(ced_ctx *c, const WsPlan &p, ced::WsArgs &a, const uint8_t *
     CED_CUDA(cedWarpEnsureSmem(c->device, 2, ced::wsBlockKernel, p.smemBlock));
     CED_CUDA(cedWarpEnsureSmem(c->device, 3, ced::wsJoinKernel, p.smemJoin));
     ced::wsBlockKernel<<<std::min(nFrames * p.B, c->sms * 8), 32, p.smemBlock, s>>>(a);
-    ced::wsJoinKernel<<<std::min(nFrames, c->sms * 4), ced::kWsJoinThreads, p.smemJoin, s>>>(a);
+    /* the join kernel is launched as a programmatic dependent of the block kernel: it is resident and past its
+     * prologue when the last block finishes (CED_WARP_SPLIT_PDL=0: an ordinary launch) */
+    static const bool pdl = !getenv("CED_WARP_SPLIT_PDL") || atoi(getenv("CED_WARP_SPLIT_PDL")) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::min(nFrames, c->sms * 4));
+    cfg.blockDim = dim3(ced::kWsJoinThreads);
+    cfg.dynamicSmemBytes = p.smemJoin;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CED_CUDA(cudaLaunchKernelEx(&cfg, ced::wsJoinKernel, a));
     return CED_OK;
 }
 
