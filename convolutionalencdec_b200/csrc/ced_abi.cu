@@ -1937,6 +1937,48 @@ int ced_stream_surv_words(int nStates)
     return 2 * ((H + 31) / 32);
 }
 
+/* The doorbell of the per-packet calls: a device counter and a pinned word the last kernel of a call writes the new
+ * count to once its results are in the pinned mailbox; the host spins on the word instead of synchronising the stream. */
+static int ensureDoorbell(ced_ctx *c)
+{
+    if (c->sSplitSeq.p)
+        return CED_OK;
+    int rc = c->sSplitSeq.ensure(64);
+    if (rc == CED_OK) rc = c->sDoorbell.ensure(64);
+    if (rc != CED_OK)
+        return rc;
+    CED_CUDA(cudaMemsetAsync(c->sSplitSeq.p, 0, 64, c->stream));
+    memset(c->sDoorbell.p, 0, 64);
+    c->splitSeq = 0;
+    return CED_OK;
+}
+
+/* wait for the next count; after 5 ms without it the stream is asked instead, so a failed launch is still reported */
+static int waitDoorbell(ced_ctx *c)
+{
+    const unsigned int expect = ++c->splitSeq;
+    volatile unsigned int *bell = reinterpret_cast<volatile unsigned int *>(c->sDoorbell.p);
+    const auto t0 = std::chrono::steady_clock::now();
+    bool rung = false;
+    for (unsigned int spins = 0; !(rung = *bell == expect);) {
+        if ((++spins & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5))
+            break;
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (!rung) {
+        const cudaError_t es = cudaStreamSynchronize(c->stream);
+        c->splitSeq = *bell;   /* whatever was counted is what the next call starts from */
+        CED_CUDA(es);
+    }
+    return CED_OK;
+}
+
+static bool streamDoorbellEnabled()
+{
+    static const bool on = !getenv("CED_STREAM_DOORBELL") || atoi(getenv("CED_STREAM_DOORBELL")) != 0;
+    return on;
+}
+
 int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint32_t *iteration,
                       uint32_t *renormCounter, uint32_t *surv, uint32_t survCapacitySteps, const uint8_t *segs,
                       int segmentsIn, uint8_t *uncoded, int last)
@@ -1989,15 +2031,8 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
                        cedStreamDecodeSplitTakes(c, segmentsIn);   /* the resident decoder is opt-in and keeps its packets */
     if (rc == CED_OK && split)
         rc = c->sSplit.ensure(cedStreamDecodeSplitScratchBytes(kStreamMaxSteps));
-    if (rc == CED_OK && split && !c->sSplitSeq.p) {
-        rc = c->sSplitSeq.ensure(64);
-        if (rc == CED_OK) rc = c->sDoorbell.ensure(64);
-        if (rc == CED_OK) {
-            CED_CUDA(cudaMemsetAsync(c->sSplitSeq.p, 0, 64, c->stream));
-            memset(c->sDoorbell.p, 0, 64);
-            c->splitSeq = 0;
-        }
-    }
+    if (rc == CED_OK && split)
+        rc = ensureDoorbell(c);
     if (rc == CED_OK) rc = c->sSurv.ensure(survBytes);
     if (rc == CED_OK) rc = c->sPinIn.ensure(1024 + kStreamMaxSteps);
     if (rc == CED_OK) rc = c->sPinOut.ensure(outBytes);
@@ -2080,8 +2115,7 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
         const int grid = f.nBlocks * 64 / (ced::kFpThreads / 32);
         /* the join kernel writes the packet's bytes to the pinned mailbox and then a count to a doorbell word: the host
          * waits for that word instead of for the stream (CED_STREAM_DOORBELL=0: cudaStreamSynchronize as everywhere else) */
-        static const bool doorbellOn = !getenv("CED_STREAM_DOORBELL") || atoi(getenv("CED_STREAM_DOORBELL")) != 0;
-        doorbell = split && zcOut && doorbellOn;
+        doorbell = split && zcOut && streamDoorbellEnabled();
         /* the 64 passes over a block all read its segments: those reads stay on the device (one small copy) */
         auto issue = [&]() -> cudaError_t {
             cudaError_t e = cudaSuccess;
@@ -2149,25 +2183,13 @@ int ced_stream_decode(int K, int n, const uint8_t *edge, uint8_t *metrics, uint3
     if (!last && segmentsIn)
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p + 4096, c->sSurv.p + (size_t)it0 * W,
                                  (size_t)segmentsIn * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    bool rung = false;
     if (doorbell) {
-        /* spin on the doorbell word; a packet that takes longer than 5 ms has gone wrong: let the stream say how */
-        const unsigned int expect = ++c->splitSeq;
-        volatile unsigned int *bell = reinterpret_cast<volatile unsigned int *>(c->sDoorbell.p);
-        const auto t0 = std::chrono::steady_clock::now();
-        for (unsigned int spins = 0; !(rung = *bell == expect);) {
-            if ((++spins & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(5))
-                break;
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        if (!rung) {
-            const cudaError_t es = cudaStreamSynchronize(c->stream);
-            c->splitSeq = *bell;   /* whatever was counted is what the next call starts from */
-            CED_CUDA(es);
-        }
-    }
-    if (!rung)
+        const int rw = waitDoorbell(c);
+        if (rw != CED_OK)
+            return rw;
+    } else {
         CED_CUDA(cudaStreamSynchronize(c->stream));
+    }
     if (parallel && fpStamps()) {
         static unsigned long long calls = 0;
         const unsigned long long *st = fpStamps();
@@ -2231,14 +2253,30 @@ int ced_stream_encode(int K, int n, const uint32_t *taps, uint32_t *reg, const u
     ced::EncTaps t;
     for (int i = 0; i < 8; i++)
         t.tap[i] = i < n ? taps[i] : 0u;
-    ced::encodeBatchKernel<0, 0><<<1, ced::kEncThreads, 0, c->stream>>>(
-        zeroCopy ? c->sPinIn.p : c->hostIn[0].p, (size_t)std::max(bytesIn, 1), 1, bytesIn,
-        zeroCopy ? c->sPinOut.p : c->hostOut[0].p, (size_t)T + 16, tail, K, n, t, *reg, 1);
+    const bool doorbell = zeroCopy && streamDoorbellEnabled();
+    if (doorbell) {
+        rc = ensureDoorbell(c);
+        if (rc != CED_OK)
+            return rc;
+        ced::encodeStreamKernel<<<1, ced::kEncThreads, 0, c->stream>>>(c->sPinIn.p, bytesIn, c->sPinOut.p, (size_t)T + 16, tail, K, n, t,
+                                                                         *reg, c->sSplitSeq.p,
+                                                                         reinterpret_cast<volatile unsigned int *>(c->sDoorbell.p));
+    } else {
+        ced::encodeBatchKernel<0, 0><<<1, ced::kEncThreads, 0, c->stream>>>(
+            zeroCopy ? c->sPinIn.p : c->hostIn[0].p, (size_t)std::max(bytesIn, 1), 1, bytesIn,
+            zeroCopy ? c->sPinOut.p : c->hostOut[0].p, (size_t)T + 16, tail, K, n, t, *reg, 1);
+    }
     c->launches += 1;
     CED_CUDA(cudaGetLastError());
     if (!zeroCopy)
         CED_CUDA(cudaMemcpyAsync(c->sPinOut.p, c->hostOut[0].p, (size_t)T, cudaMemcpyDeviceToHost, c->stream));
-    CED_CUDA(cudaStreamSynchronize(c->stream));
+    if (doorbell) {
+        rc = waitDoorbell(c);
+        if (rc != CED_OK)
+            return rc;
+    } else {
+        CED_CUDA(cudaStreamSynchronize(c->stream));
+    }
     memcpy(segs, c->sPinOut.p, (size_t)T);
     /* shift-register bookkeeping only (src/convEncode.c:93,122): which input bits are still in the window */
     uint32_t r = *reg;

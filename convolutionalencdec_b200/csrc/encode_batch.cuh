@@ -88,10 +88,10 @@ __device__ __forceinline__ uint32_t encode16Packed(uint32_t win, const EncTaps &
  * number of generators at compile time (the K=7 n=2 production code), 0 = run-time values.
  */
 template <int KK, int NN, bool PACKED = false, bool FIXED = false>
-__global__ void __launch_bounds__(kEncThreads)
-encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
-                  uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
-                  uint32_t hist, int aligned16)
+__device__ __forceinline__ void
+encodeBatchBody(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
+                uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, const EncTaps &taps,
+                uint32_t hist, int aligned16)
 {
     const int T = 8 * frameBytes + tailSegs;
     const unsigned chunksPerFrame = (unsigned)(T + 15) / 16;
@@ -133,6 +133,30 @@ encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames
             for (int s2 = 0; s2 < 16 && 16 * c + s2 < T; s2++)
                 dst[s2] = (uint8_t)(w[s2 >> 2] >> (8 * (s2 & 3)));
         }
+    }
+}
+
+template <int KK, int NN, bool PACKED = false, bool FIXED = false>
+__global__ void __launch_bounds__(kEncThreads)
+encodeBatchKernel(const uint8_t *__restrict__ msg, size_t msgStride, int nFrames, int frameBytes,
+                  uint8_t *__restrict__ segs, size_t segStride, int tailSegs, int K, int n, EncTaps taps,
+                  uint32_t hist, int aligned16)
+{
+    encodeBatchBody<KK, NN, PACKED, FIXED>(msg, msgStride, nFrames, frameBytes, segs, segStride, tailSegs, K, n, taps, hist, aligned16);
+}
+
+/* The per-packet call (ced_stream_encode): one CTA, message and segments in the pinned mailboxes; when the segments
+ * are out it writes a running count to a doorbell word the host spins on instead of synchronising the stream. */
+__global__ void __launch_bounds__(kEncThreads)
+encodeStreamKernel(const uint8_t *__restrict__ msg, int frameBytes, uint8_t *__restrict__ segs, size_t segStride, int tailSegs,
+                   int K, int n, EncTaps taps, uint32_t hist, unsigned int *doneCounter, volatile unsigned int *doneFlag)
+{
+    encodeBatchBody<0, 0>(msg, (size_t)max(frameBytes, 1), 1, frameBytes, segs, segStride, tailSegs, K, n, taps, hist, 1);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *doneFlag = atomicAdd(doneCounter, 1u) + 1u;
+        __threadfence_system();
     }
 }
 
