@@ -438,8 +438,10 @@ static int decodeBatchImpl(ced_ctx *c, const ced_code_t *code, bool packed, cons
         return CED_ERR_ARG;
     }
     /* small batches: one warp per frame, decisions in shared memory (warp_frame.cu) */
-    if (!packed && cedWarpFrameTakes(c, code, nFrames, frameBits)) {
-        const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
+    const CodeId idSmall = classify(code);   /* the packed format keeps the code family it has at any batch size */
+    const bool packedOk = idSmall == CodeId::K7_0113_0171 || idSmall == CodeId::K7_0133_0171 || idSmall == CodeId::K7_Runtime;
+    if ((!packed || packedOk) && cedWarpFrameTakes(c, code, nFrames, frameBits, packed)) {
+        const int rc = cedDecodeBatchWarpFrame(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot, packed);
         if (rc != CED_ERR_UNSUPPORTED)
             return rc;
     }

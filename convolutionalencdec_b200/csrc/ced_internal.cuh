@@ -246,11 +246,11 @@ int cedSoftQForwardWindow(ced_ctx *c, const ced_code_t *code, bool aligned16, in
 /* warp_frame.cu: small batches, one warp per frame (k = 1 codes with <= 64 states, n <= 3, byte format);
  * CED_ERR_UNSUPPORTED = not a case for it */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0);
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot = 0, bool packed = false);
 /* warp_split.cu: the same for so few frames of a 64-state rate-1/2 code that they are cut into blocks in time as well */
 int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot);
-bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits);
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot, bool packed = false);
+bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits, bool packed = false);
 
 /* warp_split.cu: the one-packet call of the reference-named API on the same kernels (labels and start metrics are the caller's) */
 int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics, const uint8_t *dSegs, int T, uint8_t *dOut,

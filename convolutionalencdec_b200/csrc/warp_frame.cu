@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
         const uintptr_t rowAddr = reinterpret_cast<uintptr_t>(a.segs) + (size_t)f * a.segStride;
         const uint32_t off = (uint32_t)(rowAddr & 15u);
         const uint4 *src = reinterpret_cast<const uint4 *>(rowAddr - off);
-        const int nq = (int)(off + (uint32_t)T + 15u) >> 4;
+        const int nq = (int)(off + (uint32_t)(R4 && a.packed ? (T + 3) >> 2 : T) + 15u) >> 4;
         __syncwarp();
         for (int q = lane; q < nq; q += 32)
             reinterpret_cast<uint4 *>(sSurv)[q] = __ldg(src + q);
@@ -78,7 +78,14 @@ __global__ void __launch_bounds__(32) wfDecodeKernel(const __grid_constant__ WfA
         const int units = R4 ? T >> 1 : T;
         for (int g = lane; 4 * g < units + 12; g += 32) {   /* four units per lane and round; padding units get offset 0 */
             uint32_t o[4];
-            if (R4) {
+            if (R4 && a.packed) {   /* four symbols to a byte: a nibble is a pair of symbols */
+                const uint8_t *symB = reinterpret_cast<const uint8_t *>(sSurv) + off;
+                const uint32_t b0 = symB[2 * g], b1 = symB[2 * g + 1];
+                o[0] = (b0 & 15u) * 512u;
+                o[1] = (b0 >> 4) * 512u;
+                o[2] = (b1 & 15u) * 512u;
+                o[3] = (b1 >> 4) * 512u;
+            } else if (R4) {
                 const uint32_t w0 = __funnelshift_r(symW[2 * g], symW[2 * g + 1], sh);
                 const uint32_t w1 = __funnelshift_r(symW[2 * g + 1], symW[2 * g + 2], sh);
                 o[0] = ((w0 & 3u) | ((w0 >> 6) & 12u)) * 512u;
@@ -285,12 +292,12 @@ void cedWarpFrameCosts(const ced_code_t *code, bool r4, uint32_t (&cost)[2][ced:
  * 1024, 135 us at 2048 against 285 .. 320 us on the thread-per-frame kernels; 4096 frames: 258 against 325 us.
  * CED_WARP_FRAME_MAX = n overrides the frame limit (0 = never).
  */
-bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits)
+bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, int frameBits, bool packed)
 {
     if (!c || nFrames <= 0)
         return false;
     const WfPlan p = wfPlan(code, frameBits);
-    if (!p.ok)
+    if (!p.ok || (packed && !p.r4))
         return false;
     if (const char *e = getenv("CED_WARP_FRAME_MAX"))
         return nFrames <= atoi(e);
@@ -299,24 +306,25 @@ bool cedWarpFrameTakes(const ced_ctx *c, const ced_code_t *code, int nFrames, in
 
 /* ced_decode_batch for a batch cedWarpFrameTakes() said yes to (CED_ERR_UNSUPPORTED otherwise) */
 int cedDecodeBatchWarpFrame(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot, bool packed)
 {
     const WfPlan plan = wfPlan(code, frameBits);
-    if (!c || !plan.ok)
+    if (!c || !plan.ok || (packed && !plan.r4))
         return CED_ERR_UNSUPPORTED;
     if (plan.r4) {   /* so few frames that cutting them in time as well pays (warp_split.cu) */
-        const int rc = cedDecodeBatchWarpSplit(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot);
+        const int rc = cedDecodeBatchWarpSplit(c, code, dSegs, segStride, nFrames, frameBits, dOut, outStride, stream, slot, packed);
         if (rc != CED_ERR_UNSUPPORTED)
             return rc;
     }
     const int K = code->constraintLen, S = K - 1, n = code->codedBits, N = 1 << S;
     const int T = frameBits + S;
     const uint32_t init = (uint32_t)(uint8_t)(N + 1);
-    if (segStride < (size_t)T || outStride < (size_t)(frameBits / 8)) {
+    if (segStride < (packed ? (size_t)(T + 3) / 4 : (size_t)T) || outStride < (size_t)(frameBits / 8)) {
         setError("ced_decode_batch: stride shorter than a frame");
         return CED_ERR_ARG;
     }
     ced::WfArgs a;
+    a.packed = packed ? 1 : 0;
     a.seg = plan.seg;
     a.survRows = plan.survRows;
     a.outPad = plan.outPad;

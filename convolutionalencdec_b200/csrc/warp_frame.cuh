@@ -18,6 +18,7 @@ struct WfArgs {
     uint8_t *out;
     size_t outStride;
     int nFrames, T, S, n;
+    int packed;            /* symbols four to a byte (ced_decode_batch_packed; radix 4 only) */
     int seg;               /* traceback: steps per lane, a multiple of 8 */
     int survRows;          /* >= T + T / seg, even */
     int outPad;            /* bytes of the output row in shared memory, a multiple of 16 */

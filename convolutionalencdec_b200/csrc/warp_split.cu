@@ -30,6 +30,7 @@ struct WsArgs {
     uint8_t *out;
     size_t outStride;
     int nFrames, T;
+    int packed;             /* symbols four to a byte (ced_decode_batch_packed) */
     int len, B, D;          /* steps per block (a multiple of 8), blocks per frame, warm-up steps (a multiple of 8) */
     int seg, survRows, outPad;   /* traceback geometry of the join kernel (as WfArgs) */
     int rowPitch;           /* decision rows per frame in `rows` */
@@ -145,21 +146,21 @@ struct WsForward {
 /* stage the symbols of steps [lo, lo + nSteps) of a row in `stage` (16-byte aligned shared memory of nSteps + 64 bytes)
  * and write the table offset of every pair of steps to offs (nSteps / 2 entries + 12 zeros) */
 /* first: the lane's first 16-byte piece of those symbols, fetched by the caller ahead of time (wsFirstPiece), or NULL */
-__device__ __forceinline__ uint4 wsFirstPiece(const uint8_t *row, int lo, int nSteps, int lane)
+__device__ __forceinline__ uint4 wsFirstPiece(const uint8_t *row, int lo, int nSteps, int lane, int packed)
 {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)lo;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)(packed ? lo >> 2 : lo);   /* lo is a multiple of 8 */
     const uint32_t off = (uint32_t)(addr & 15u);
-    const int nq = (int)(off + (uint32_t)nSteps + 15u) >> 4;
+    const int nq = (int)(off + (uint32_t)(packed ? (nSteps + 3) >> 2 : nSteps) + 15u) >> 4;
     return lane < nq ? __ldg(reinterpret_cast<const uint4 *>(addr - off) + lane) : make_uint4(0, 0, 0, 0);
 }
 
 __device__ __forceinline__ void wsOffsets(const uint8_t *row, int lo, int nSteps, uint32_t *stage, uint32_t *offs, int lane,
-                                          const uint4 *first = nullptr)
+                                          int packed, const uint4 *first = nullptr)
 {
-    const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)lo;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(row) + (size_t)(packed ? lo >> 2 : lo);
     const uint32_t off = (uint32_t)(addr & 15u);
     const uint4 *src = reinterpret_cast<const uint4 *>(addr - off);
-    const int nq = (int)(off + (uint32_t)nSteps + 15u) >> 4;
+    const int nq = (int)(off + (uint32_t)(packed ? (nSteps + 3) >> 2 : nSteps) + 15u) >> 4;
     __syncwarp();
     if (first && lane < nq)
         reinterpret_cast<uint4 *>(stage)[lane] = *first;
@@ -170,13 +171,22 @@ __device__ __forceinline__ void wsOffsets(const uint8_t *row, int lo, int nSteps
     const uint32_t sh = (off & 3u) * 8u;
     const int units = nSteps >> 1;
     for (int g = lane; 4 * g < units + 12; g += 32) {
-        const uint32_t w0 = __funnelshift_r(symW[2 * g], symW[2 * g + 1], sh);
-        const uint32_t w1 = __funnelshift_r(symW[2 * g + 1], symW[2 * g + 2], sh);
         uint32_t o[4];
-        o[0] = ((w0 & 3u) | ((w0 >> 6) & 12u)) * 512u;
-        o[1] = (((w0 >> 16) & 3u) | ((w0 >> 22) & 12u)) * 512u;
-        o[2] = ((w1 & 3u) | ((w1 >> 6) & 12u)) * 512u;
-        o[3] = (((w1 >> 16) & 3u) | ((w1 >> 22) & 12u)) * 512u;
+        if (packed) {   /* a nibble is a pair of symbols */
+            const uint8_t *symB = reinterpret_cast<const uint8_t *>(stage) + off;
+            const uint32_t b0 = symB[2 * g], b1 = symB[2 * g + 1];
+            o[0] = (b0 & 15u) * 512u;
+            o[1] = (b0 >> 4) * 512u;
+            o[2] = (b1 & 15u) * 512u;
+            o[3] = (b1 >> 4) * 512u;
+        } else {
+            const uint32_t w0 = __funnelshift_r(symW[2 * g], symW[2 * g + 1], sh);
+            const uint32_t w1 = __funnelshift_r(symW[2 * g + 1], symW[2 * g + 2], sh);
+            o[0] = ((w0 & 3u) | ((w0 >> 6) & 12u)) * 512u;
+            o[1] = (((w0 >> 16) & 3u) | ((w0 >> 22) & 12u)) * 512u;
+            o[2] = ((w1 & 3u) | ((w1 >> 6) & 12u)) * 512u;
+            o[3] = (((w1 >> 16) & 3u) | ((w1 >> 22) & 12u)) * 512u;
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (4 * g + k >= units)
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
     if ((int)blockIdx.x < total) {   /* the first block's symbols are on their way while the cost table is built */
         const int f = blockIdx.x / a.B, c = blockIdx.x - f * a.B;
         const int s = c * a.len, e = min(a.T, s + a.len), lo = max(0, s - a.D);
-        first = wsFirstPiece(a.segs + (size_t)f * a.segStride, lo, e - lo, lane);
+        first = wsFirstPiece(a.segs + (size_t)f * a.segStride, lo, e - lo, lane, a.packed);
     }
     wfBuildCostTable<true>(a.cost, wsSmem, lane);
     WsForward fwd;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(32) wsBlockKernel(const __grid_constant__ WsAr
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int f = w / a.B, c = w - f * a.B;
         const int s = c * a.len, e = min(a.T, s + a.len), lo = max(0, s - a.D);
-        wsOffsets(a.segs + (size_t)f * a.segStride, lo, e - lo, stage, offs, lane, w == (int)blockIdx.x ? &first : nullptr);
+        wsOffsets(a.segs + (size_t)f * a.segStride, lo, e - lo, stage, offs, lane, a.packed, w == (int)blockIdx.x ? &first : nullptr);
         if (lo == 0) {
             fwd.X = a.start[lane].x;
             fwd.Y = a.start[lane].y;
@@ -285,7 +295,7 @@ __global__ void __launch_bounds__(kWsJoinThreads) wsJoinKernel(const __grid_cons
                     haveTable = true;
                 }
                 const int s = c * a.len, e = min(T, s + a.len);
-                wsOffsets(a.segs + (size_t)f * a.segStride, s, e - s, reinterpret_cast<uint32_t *>(sSurv), offs, lane);
+                wsOffsets(a.segs + (size_t)f * a.segStride, s, e - s, reinterpret_cast<uint32_t *>(sSurv), offs, lane, a.packed);
                 const uint2 from = __ldcg(vecs + (size_t)(c - 1) * 64 + 32 + lane);
                 fwd.X = from.x;
                 fwd.Y = from.y;
@@ -437,14 +447,14 @@ static int wsLaunch(ced_ctx *c, const WsPlan &p, ced::WsArgs &a, const uint8_t *
  * CED_WARP_SPLIT = 0 switches it off, CED_WARP_SPLIT_WARMUP / CED_WARP_SPLIT_LEN set the warm-up / block length.
  */
 int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *dSegs, size_t segStride, int nFrames,
-                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot)
+                            int frameBits, uint8_t *dOut, size_t outStride, void *stream, int slot, bool packed)
 {
     if (!c || !code || code->constraintLen != 7 || code->codedBits != 2 || nFrames <= 0 || frameBits <= 0)
         return CED_ERR_UNSUPPORTED;
     const WsPlan p = wsPlan(c, nFrames, frameBits + 6);
     if (!p.ok)
         return CED_ERR_UNSUPPORTED;
-    if (segStride < (size_t)p.T || outStride < (size_t)(frameBits / 8)) {
+    if (segStride < (packed ? (size_t)(p.T + 3) / 4 : (size_t)p.T) || outStride < (size_t)(frameBits / 8)) {
         setError("ced_decode_batch: stride shorter than a frame");
         return CED_ERR_ARG;
     }
@@ -463,6 +473,7 @@ int cedDecodeBatchWarpSplit(ced_ctx *c, const ced_code_t *code, const uint8_t *d
     ced::WsArgs a;
     a.doneCounter = nullptr;
     a.doneFlag = nullptr;
+    a.packed = packed ? 1 : 0;
     cedWarpFrameCosts(code, true, a.cost);
     for (int l = 0; l < 32; l++)   /* :59-67: state 0 starts at 0, every other state at NUM_STATES + 1 */
         a.start[l] = make_uint2((l >> 1) == 0 ? 65u << 16 : 65u | 65u << 16, 65u | 65u << 16);
@@ -491,6 +502,7 @@ int cedStreamDecodeSplit(ced_ctx *c, const uint8_t *edge, const uint8_t *metrics
     ced::WsArgs a;
     a.doneCounter = doneCounter;
     a.doneFlag = doneFlag;
+    a.packed = 0;
     auto hd = [](uint32_t label, uint32_t rx) -> uint32_t { return (uint32_t)__builtin_popcount((label ^ rx) & 3u); };
     memset(a.cost, 0, sizeof(a.cost));
     for (uint32_t rx = 0; rx < 4; rx++)

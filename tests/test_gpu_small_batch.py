@@ -197,3 +197,28 @@ def test_frames_cut_in_time(ctx, port, env, warmup, length):
             assert np.array_equal(got.cpu().numpy(), want), (g, frames, bits, p, pad, off)
             if p == 0.0:
                 assert np.array_equal(want, msgs)
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_small_packed_batches(ctx, port, env, split):
+    """ced_decode_batch_packed (four 2-bit symbols per byte) with few frames: the same small-batch kernels, a nibble of
+    the packed row being a pair of symbols; other code families are refused as at any batch size."""
+    import torch
+    env["CED_WARP_SPLIT"] = split
+    rng = np.random.default_rng(40 + int(split))
+    for g in (K7, [0o133, 0o171], [0o117, 0o155]):
+        code = ced.Code(7, g)
+        for frames, bits, p in ((1, 8, 0.0), (1, 2048, 0.04), (16, 2048, 0.0377), (50, 1000 // 8 * 8, 0.5), (3, 16384, 0.06),
+                                (290, 512, 0.1)):
+            T = bits + 6
+            msgs = rng.integers(0, 256, (frames, bits // 8), dtype=np.uint8)
+            rx = noisy(rng, port.encode_batch(7, g, msgs), 2, p)
+            want = port.decode_batch(7, g, rx, T, symmetric=False)
+            packed = ctx.pack_symbols(torch.from_numpy(rx).cuda(), T, packed_stride=(T + 3) // 4 + int(rng.integers(0, 7)))
+            before = ctx.launches
+            got = ctx.decode_batch_packed(code, packed, bits)
+            ctx.sync()
+            assert ctx.launches - before == (2 if split == "1" and T > 64 else 1)
+            assert np.array_equal(got.cpu().numpy(), want), (g, frames, bits, p, split)
+    with pytest.raises(ced.CedError):
+        ctx.decode_batch_packed(ced.Code(7, [0o133, 0o170]), torch.zeros((4, 520), dtype=torch.uint8, device="cuda"), 2048)
