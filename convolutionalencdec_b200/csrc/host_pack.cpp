@@ -5,7 +5,7 @@
  * buffer of symbols crosses PCIe at 4x the necessary size (269 MB for 2^16 x 4096-bit frames: 5 ms at
  * the ~54 GB/s this link delivers, against 1.6 ms of decoding).  Before the H2D copy the host
  * pipeline therefore packs each chunk to the 4-segments-per-byte format of ced_decode_batch_packed
- * with a small pool of host threads (AVX2 when the CPU has it).  This is data movement only: no
+ * with a small pool of host threads (AVX-512 or AVX2 when the CPU has it).  This is data movement only: no
  * encode/decode arithmetic happens on the host.
  */
 #include <condition_variable>
