@@ -96,3 +96,53 @@ def test_blocks_from_guessed_metrics_reproduce_the_sequential_decisions(port, D,
         assert reruns[0.5] > 0                                   # pure noise, short warm-up: guesses fail and are repaired
     if D == 4096:
         assert sum(reruns.values()) == 0                         # every block reaches back to step 0: nothing to guess
+
+
+@pytest.mark.parametrize("p", [0.0, 0.05, 0.5])
+def test_segmented_traceback_with_handover_check_equals_the_sequential_walk(port, p):
+    """warp_frame.cuh wfTraceback: 32 lanes, lane i walks segment i after a warm-up of one segment from state 0 above it;
+    a lane that entered its segment in another state than the lane above left in walks again, until every hand-over
+    agrees.  The top lane starts in state 0 at the last step, so the loop ends and the states -- hence the bits -- are the
+    sequential walk's."""
+    rng = np.random.default_rng(int(p * 100) + 3)
+    edge = edge_labels(7, K7)
+    for bits in (8, 64, 1000 // 8 * 8, 2048):
+        T, S = bits + 6, 6
+        msg = rng.integers(0, 256, (1, bits // 8), dtype=np.uint8)
+        rx = port.encode_batch(7, K7, msg)[0, :T].copy()
+        flips = rng.random((T, 2)) < p
+        rx ^= flips[:, 0].astype(np.uint8) | (flips[:, 1].astype(np.uint8) << 1)
+        start = np.full(64, 65, dtype=np.int64)
+        start[0] = 0
+        _, dec = acs_run(start, rx, edge, 2)
+
+        def walk(s, hi, lo):                     # states entered while walking steps hi-1 .. lo; returns (state after, bits)
+            out = {}
+            for t in range(hi - 1, lo - 1, -1):
+                out[t] = s & 1
+                s = (s >> 1) | (int(dec[t, s]) << (S - 1))
+            return s, out
+
+        seg = ((T + 31) // 32 + 7) // 8 * 8
+        top = (T - 1) // seg
+        s_in, s_leave, got = [0] * 32, [0] * 32, {}
+        for lane in range(top + 1):
+            lo, hi = lane * seg, min(T, lane * seg + seg)
+            if lane < top:
+                s_in[lane], _ = walk(0, min(T, hi + seg), hi)
+            s_leave[lane], bits_l = walk(s_in[lane], hi, lo)
+            got.update(bits_l)
+        rounds = 0
+        while True:
+            redo = [lane for lane in range(top) if s_leave[lane + 1] != s_in[lane]]
+            if not redo:
+                break
+            above = list(s_leave)
+            for lane in redo:
+                s_in[lane] = above[lane + 1]
+                s_leave[lane], bits_l = walk(s_in[lane], min(T, lane * seg + seg), lane * seg)
+                got.update(bits_l)
+            rounds += 1
+            assert rounds <= 32
+        want_state, want = walk(0, T, 0)
+        assert s_leave[0] == want_state and all(got[t] == want[t] for t in range(T)), (bits, p, rounds)
